@@ -1,0 +1,217 @@
+/* libst_b200 -- C-ABI of the B200 (sm_100a) hot path of Soft-Truncation.
+ *
+ * Every entry point takes raw DEVICE pointers, explicit sizes and a cudaStream_t (passed as
+ * void*), enqueues work on that stream and returns immediately: 0 = ok, otherwise an error code
+ * whose text is available from st_last_error().  Nothing here allocates, synchronises or throws.
+ * The caller (PyTorch on the host side) owns all memory.
+ *
+ * Layout convention: activations are NHWC ("pixels x channels", channels contiguous); dtype
+ * codes are ST_F32 = 0 and ST_BF16 = 1.  All reductions accumulate in fp32.
+ *
+ * What each group replaces in the reference (file:line relative to the reference root):
+ *   st_upfirdn2d        op/upfirdn2d.cpp:12-19, op/upfirdn2d_kernel.cu:209-368
+ *   st_fused_bias_act   op/fused_bias_act.cpp:4-17, op/fused_bias_act_kernel.cu:18-98
+ *   st_gemm             F.conv2d / nn.Linear / NIN einsum / attention einsums
+ *                       (models/layers.py:100-124,546-555; models/layerspp.py:95-99) incl. their
+ *                       autograd backward (dgrad / wgrad)
+ *   st_gn_*             nn.GroupNorm + SiLU + Dropout (models/layerspp.py:232,244-245,258,275-278)
+ *   st_resample2x       naive_upsample_2d / naive_downsample_2d (models/up_or_down_sampling.py:59-69)
+ *   st_softmax_*        F.softmax in AttnBlockpp (models/layerspp.py:97)
+ *   st_timestep_embedding / st_fourier_embedding
+ *                       models/layers.py:515-529, models/layerspp.py:45-54
+ *   st_dsm_perturb / st_dsm_loss
+ *                       losses.py:116-132
+ *   st_sumsq / st_adam_ema
+ *                       losses.py:44-58 (clip_grad_norm_ + Adam) and models/ema.py:32-51
+ *   st_pc_update / st_batch_norms
+ *                       sampling.py:185-210, 263-292, 402-408
+ */
+#ifndef ST_B200_H_
+#define ST_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ST_F32 0
+#define ST_BF16 1
+
+/* ------------------------------------------------------------------ library */
+int st_version(void);
+const char* st_last_error(void);
+/* 1 when the tcgen05/TMA GEMM path can run on the current device (sm_100 + driver entry point). */
+int st_tc_available(void);
+
+/* ------------------------------------------------------------------ GEMM / implicit-GEMM conv
+ * C[b][m][n] = alpha * ( sum_k A(b,m,k) * B(b,n,k) + bias[n] + rowbias[m / rows_per_rb][n]
+ *                        + residual[b][m][n] )
+ * or, with accumulate != 0,  C[b][m][n] += alpha * sum_k ...   (C must be fp32).
+ *
+ * a_mode / b_mode select how operand elements are addressed:
+ *   ST_OP_STRIDED   X(b,i,k) = X[b*sXb + i*sXi + k*sXk]            (one of sXi, sXk must be 1)
+ *   ST_OP_GATHER    implicit im2col of an NHWC tensor: for A, i is the output pixel and
+ *                   k = tap*(C1+C2) + c;  for B (weight gradient), k is the pixel and
+ *                   i = tap*(C1+C2) + c.  Taps walk a kh x kw window with "same" zero padding.
+ *                   The channel axis may be the concatenation of two tensors (src, src2).
+ *   ST_OP_DGRADW    (B only) conv weights W[co][tap][ci] read as B(n=ci, k=tap'*Co+co) =
+ *                   W[co][ntaps-1-tap'][ci]: the data-gradient of a "same" convolution.
+ */
+#define ST_OP_STRIDED 0
+#define ST_OP_GATHER 1
+#define ST_OP_DGRADW 2
+
+#define ST_BACKEND_AUTO 0
+#define ST_BACKEND_SIMT 1
+#define ST_BACKEND_TCGEN05 2
+
+typedef struct st_gemm_args {
+  int32_t a_mode, b_mode;
+  int32_t in_dtype;       /* dtype of A, B and residual */
+  int32_t out_dtype;      /* dtype of C */
+  int32_t backend;
+  int32_t accumulate;
+  int32_t split_k;        /* >1 only with accumulate (fp32 atomics) */
+  int32_t M, N, K, batch;
+  int64_t sAm, sAk, sAb;
+  int64_t sBn, sBk, sBb;
+  int64_t sCm, sCb;       /* C row stride / batch stride (n stride is 1) */
+  const void* A;
+  const void* A2;         /* second gather source (channels C1..C1+C2) or NULL */
+  const void* B;
+  const void* B2;
+  void* C;
+  /* gather geometry */
+  int32_t n_img, H, W, C1, C2, kh, kw;
+  /* epilogue */
+  const float* bias;      /* [N] or NULL */
+  const float* rowbias;   /* [M / rows_per_rb][ld_rb] or NULL */
+  int32_t rows_per_rb;
+  int64_t ld_rb;
+  const void* residual;   /* in_dtype, [b][m][n] with strides sRb, sRm or NULL */
+  int64_t sRm, sRb;
+  float alpha;
+} st_gemm_args;
+
+int st_gemm(const st_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------ GroupNorm (+SiLU, +dropout)
+ * x is NHWC [n_img][hw][C1] (+ optional second tensor [n_img][hw][C2] concatenated on channels),
+ * G groups of (C1+C2)/G adjacent channels, statistics per (image, group).
+ */
+/* partial sums: part[n_img][splits][G][2] (sum, sum of squares) */
+int st_gn_stats(const void* x1, const void* x2, int dtype, int n_img, int hw, int C1, int C2, int G,
+                int splits, float* part, void* stream);
+/* mean/rstd [n_img][G] from the partials */
+int st_gn_finalize(const float* part, int n_img, int splits, int G, int64_t count, float eps,
+                   float* mean, float* rstd, void* stream);
+/* y = dropout( act( gamma*(x-mean)*rstd + beta ) );  act: 0 none, 1 SiLU.
+ * dropout: keep-mask multiplies by 1/(1-p); `mask` (same dtype/shape as y, already scaled) is used
+ * when non-NULL, else if p > 0 a counter-based RNG keyed by (seed, element index). */
+int st_gn_apply(const void* x1, const void* x2, int dtype, int n_img, int hw, int C1, int C2, int G,
+                const float* gamma, const float* beta, const float* mean, const float* rstd, int act,
+                float p_drop, uint64_t seed, const void* mask, void* y, void* stream);
+/* backward, pass 1: per (image, pixel split, channel) sums  red[n_img][splits][C][2] = (sum dz, sum dz*xhat) where
+ * dz = dy * dropout_mask * act'(.)  */
+int st_gn_bwd_reduce(const void* x1, const void* x2, const void* dy, int dtype, int n_img, int hw, int C1,
+                     int C2, int G, const float* gamma, const float* beta, const float* mean,
+                     const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
+                     int splits, float* red, void* stream);
+/* dgamma[c] += sum_r red[r][c][1], dbeta[c] += sum_r red[r][c][0], r over rows = n_img*splits */
+int st_gn_bwd_params(const float* red, int rows, int C, float* dgamma, float* dbeta, void* stream);
+/* backward, pass 2: dx = rstd*(gamma*dz - mean_g(gamma*dz) - xhat*mean_g(gamma*dz*xhat))
+ *                        + extra_scale*extra,  written split over dx1 [..][C1] and dx2 [..][C2];
+ * accum1/accum2 != 0 adds into the destination instead of overwriting. */
+int st_gn_bwd_apply(const void* x1, const void* x2, const void* dy, int dtype, int n_img, int hw, int C1,
+                    int C2, int G, const float* gamma, const float* beta, const float* mean,
+                    const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
+                    int splits, const float* red, const void* extra, float extra_scale, void* dx1, int accum1,
+                    void* dx2, int accum2, void* stream);
+
+/* ------------------------------------------------------------------ elementwise / small
+ * All take element counts; pointers must be 16-byte aligned. */
+int st_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* out = alpha*a + beta*b (b may be NULL) */
+int st_axpby(const void* a, const void* b, void* out, int dtype, float alpha, float beta, int64_t n,
+             void* stream);
+/* y = x*sigmoid(x);  dx = dy * silu'(x) */
+int st_silu(const void* x, void* y, int dtype, int64_t n, void* stream);
+int st_silu_bwd(const void* x, const void* dy, void* dx, int dtype, int64_t n, void* stream);
+/* 2x nearest replicate (dir=+1: [n][H][W][C] -> [n][2H][2W][C]) or 2x2 box sum (dir=-1), times scale.
+ * The input may be a channel concatenation of two tensors. */
+int st_resample2x(const void* x1, const void* x2, void* y, int dtype, int n_img, int H, int W, int C1,
+                  int C2, int dir, float scale, void* stream);
+/* out[g][c] = sum over rows r in group g of x[r][c];  x is [groups*rows_per_group][C] */
+int st_colsum(const void* x, int dtype, int64_t groups, int64_t rows_per_group, int C, float scale,
+              float* out, int accumulate, void* stream);
+/* row softmax of scale*logits: logits fp32 [rows][L] -> p (dtype) */
+int st_softmax_fwd(const float* logits, void* p, int dtype, int64_t rows, int L, float scale, void* stream);
+/* ds = scale * p * (dp - sum_j dp*p) ; dp fp32, ds dtype */
+int st_softmax_bwd(const void* p, const float* dp, void* ds, int dtype, int64_t rows, int L, float scale,
+                   void* stream);
+/* sinusoidal embedding of labels[B] -> out[B][dim] (fp32) */
+int st_timestep_embedding(const float* labels, float* out, int B, int dim, float max_positions, void* stream);
+/* [sin(2 pi W x), cos(2 pi W x)] with x = log(sigma): out[B][2*nW] */
+int st_fourier_embedding(const float* sigma, const float* W, float* out, int B, int nW, void* stream);
+/* NCHW fp32 [n][C][H][W] -> NHWC dtype [n][H][W][Cpad] (channels >= C zero-filled), y = alpha*x + beta;
+ * and back: the first C of Cpad channels, optionally times row_scale[n]. */
+int st_nchw_to_nhwc(const float* x, void* y, int dtype, int n_img, int C, int H, int W, int Cpad, float alpha,
+                    float beta, void* stream);
+int st_nhwc_to_nchw(const void* x, int dtype, float* y, int n_img, int C, int H, int W, int Cpad,
+                    const float* row_scale, void* stream);
+/* bf16 im2col of a small-channel NHWC tensor: out[pixel][Kpad] (zero padded), k = tap*C + c */
+int st_im2col_small(const void* x, int dtype, void* out, int n_img, int H, int W, int C, int kh, int kw,
+                    int Kpad, void* stream);
+
+/* ------------------------------------------------------------------ reference native ops */
+/* x [major][in_h][in_w][minor] -> y [major][out_h][out_w][minor]; k fp32 [kh][kw]
+ * (reference op/upfirdn2d.cpp:12-19; out_h = (in_h*up_y + pad_y0 + pad_y1 - kh + down_y)/down_y). */
+int st_upfirdn2d(const void* x, void* y, int dtype, const float* k, int major, int in_h, int in_w, int minor,
+                 int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1,
+                 int pad_y0, int pad_y1, void* stream);
+/* y = act(x + b[(i/step_b) % size_b]) * scale (reference op/fused_bias_act_kernel.cu:18-49);
+ * act 1 linear / 3 leaky-relu; grad 0/1/2; b and ref may be NULL. */
+int st_fused_bias_act(const void* x, const void* b, const void* ref, void* y, int dtype, int64_t n,
+                      int size_b, int step_b, int act, int grad, float alpha, float scale, void* stream);
+
+/* ------------------------------------------------------------------ loss head */
+/* x_t[n][i] = mean_coeff[n]*x0[n][i] + std[n]*z[n][i]   (all fp32 NCHW-flat [B][D]) */
+int st_dsm_perturb(const float* x0, const float* z, const float* mean_coeff, const float* std, float* xt,
+                   int B, int64_t D, void* stream);
+/* per-sample loss[n] = w[n] * red( (a[n]*out[n][i] + b[n]*z[n][i])^2 ), red = mean (reduce_mean=1) or
+ * 0.5*sum.  When dout != NULL also dout[n][i] = gvec[n] * w[n]*red'*2*(a out + b z)*a, i.e. the
+ * gradient w.r.t. `out` for upstream per-sample gradients gvec.  `out` is the raw network output,
+ * fp32 [B][D]. */
+int st_dsm_loss(const float* out, const float* z, const float* a, const float* b, const float* w, float* loss,
+                float* dout, const float* gvec, int B, int64_t D, int reduce_mean, void* stream);
+
+/* ------------------------------------------------------------------ optimizer */
+/* acc[0] += sum x^2 (double accumulation across blocks via fp32 partials + one atomic per block) */
+int st_sumsq(const float* x, int64_t n, float* acc, void* stream);
+/* Fused clip + Adam (+ weight decay) + EMA over flat fp32 buffers.
+ *   coef = min(1, clip / (sqrt(*gnorm_sq) + 1e-6)) if clip >= 0 and gnorm_sq != NULL else 1
+ *   g = coef*grad (+ wd*p); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2
+ *   p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps);  ema -= (1-decay)*(ema - p)   (ema_mask[i]==0 skips)
+ *   p16 (optional) receives bf16(p).  */
+int st_adam_ema(float* p, const float* grad, float* m, float* v, float* ema, const uint8_t* ema_mask,
+                void* p16, int64_t n, const float* gnorm_sq, float clip, float lr, float b1, float b2,
+                float eps, float wd, float bc1, float bc2, float ema_decay, void* stream);
+
+/* ------------------------------------------------------------------ sampler */
+/* x_mean = ca[n]*x + cb[n]*s ; x_new = x_mean + cc[n]*noise   (fp32 [B][D]); noise may be NULL.
+ * Covers Euler-Maruyama, reverse diffusion, Langevin and the denoise step with host/device-computed
+ * per-sample coefficients (sampling.py:190-196,205-210,283-290). */
+int st_pc_update(const float* x, const float* s, const float* noise, const float* ca, const float* cb,
+                 const float* cc, float* x_mean, float* x_new, int B, int64_t D, void* stream);
+/* out[0] = mean_n ||a[n]||_2 , out[1] = mean_n ||b[n]||_2  (b may be NULL) */
+int st_batch_norms(const float* a, const float* b, float* out, int B, int64_t D, void* stream);
+/* Langevin step size from the two norms, on device: step[n] = (snr*out[1]/out[0])^2 * 2 * alpha[n];
+ * writes cb[n] = step[n], cc[n] = sqrt(2*step[n]), ca[n] = 1. */
+int st_langevin_coeffs(const float* norms, const float* alpha, float snr, float* ca, float* cb, float* cc,
+                       int B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* ST_B200_H_ */

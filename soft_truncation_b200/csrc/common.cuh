@@ -1,0 +1,121 @@
+// Shared helpers for libst_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "st_b200.h"
+
+#define ST_ERR_ARG 1
+#define ST_ERR_CUDA 2
+#define ST_ERR_UNSUPPORTED 3
+
+void st_set_error(const char* fmt, ...);
+
+#define ST_CHECK_ARG(cond, ...)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      st_set_error(__VA_ARGS__);         \
+      return ST_ERR_ARG;                 \
+    }                                    \
+  } while (0)
+
+// Launch errors (bad configuration, missing image) surface here; execution errors surface at the
+// caller's next synchronisation, as with any CUDA stream work.
+#define ST_CHECK_LAUNCH(name)                                            \
+  do {                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                \
+    if (e__ != cudaSuccess) {                                            \
+      st_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return ST_ERR_CUDA;                                                \
+    }                                                                    \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4 consecutive elements <-> 4 floats (pointer must be aligned to 4 elements)
+__device__ __forceinline__ void load4(const float* p, float v[4]) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const bf16* p, float v[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+  v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+}
+__device__ __forceinline__ void store4(float* p, const float v[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(bf16* p, const float v[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a);
+  t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// d/dx [x*sigmoid(x)] = s*(1 + x*(1-s))
+__device__ __forceinline__ float silu_grad_f(float x) {
+  float s = 1.f / (1.f + __expf(-x));
+  return s * (1.f + x * (1.f - s));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Counter-based RNG (Philox-4x32-10): 4 uniform 32-bit words per (seed, counter).
+__device__ __forceinline__ uint4 philox4(uint64_t seed, uint64_t ctr) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x5eed5eedu, c3 = 0x0b200b20u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// keep-multiplier for 4 consecutive elements starting at element index e4*4
+__device__ __forceinline__ void dropout4(uint64_t seed, uint64_t e4, float p, float keep[4]) {
+  uint4 r = philox4(seed, e4);
+  float inv = 1.f / (1.f - p);
+  uint32_t thr = (uint32_t)(p * 4294967296.0);
+  keep[0] = r.x >= thr ? inv : 0.f;
+  keep[1] = r.y >= thr ? inv : 0.f;
+  keep[2] = r.z >= thr ? inv : 0.f;
+  keep[3] = r.w >= thr ? inv : 0.f;
+}
+
+static inline int st_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// dispatch on dtype code
+#define ST_DISPATCH_DTYPE(dtype, T, ...)                      \
+  do {                                                        \
+    if ((dtype) == ST_F32) { typedef float T; __VA_ARGS__; }  \
+    else if ((dtype) == ST_BF16) { typedef bf16 T; __VA_ARGS__; } \
+    else { st_set_error("bad dtype %d", (int)(dtype)); return ST_ERR_ARG; } \
+  } while (0)

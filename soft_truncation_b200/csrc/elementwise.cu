@@ -1,0 +1,546 @@
+// HBM-bound elementwise / small-reduction kernels of the score-network hot path.
+#include "common.cuh"
+
+namespace {
+
+inline int grid1d(long long items, int per_block) {
+  long long b = (items + per_block - 1) / per_block;
+  long long cap = (long long)st_num_sms() * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+#define GRID_STRIDE(i, n) \
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
+
+// ---------------------------------------------------------------- cast / axpby / silu
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, long long n4, long long n) {
+  GRID_STRIDE(i, n4) {
+    float v[4];
+    load4(s + i * 4, v);
+    store4(d + i * 4, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    long long j = (n & ~3LL) + threadIdx.x;
+    d[j] = from_f<TD>(to_f(s[j]));
+  }
+}
+
+template <typename T>
+__global__ void axpby_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, float alpha,
+                             float beta, long long n4, long long n) {
+  GRID_STRIDE(i, n4) {
+    float va[4], vb[4] = {0.f, 0.f, 0.f, 0.f}, r[4];
+    load4(a + i * 4, va);
+    if (b) load4(b + i * 4, vb);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = alpha * va[k] + beta * vb[k];
+    store4(o + i * 4, r);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    long long j = (n & ~3LL) + threadIdx.x;
+    o[j] = from_f<T>(alpha * to_f(a[j]) + (b ? beta * to_f(b[j]) : 0.f));
+  }
+}
+
+template <typename T>
+__global__ void silu_kernel(const T* __restrict__ x, T* __restrict__ y, long long n) {
+  GRID_STRIDE(i, n) y[i] = from_f<T>(silu_f(to_f(x[i])));
+}
+template <typename T>
+__global__ void silu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, long long n) {
+  GRID_STRIDE(i, n) dx[i] = from_f<T>(to_f(dy[i]) * silu_grad_f(to_f(x[i])));
+}
+
+// ---------------------------------------------------------------- 2x resampling
+// dir=+1: y[n][2i+a][2j+b][c] = scale*x[n][i][j][c];  dir=-1: y[n][i][j][c] = scale*sum_ab x[n][2i+a][2j+b][c]
+template <typename T>
+__global__ void up2_kernel(const T* x1, const T* x2, T* y, long long total_quads, int H, int W, int C1, int C2, float scale) {
+  const int Ct = C1 + C2, Q = Ct / 4;
+  GRID_STRIDE(gq, total_quads) {   // over OUTPUT quads
+    int quad = (int)(gq % Q);
+    long long row = gq / Q;
+    int ox = (int)(row % (2 * W));
+    long long t = row / (2 * W);
+    int oy = (int)(t % (2 * H));
+    long long n = t / (2 * H);
+    long long irow = (n * H + oy / 2) * W + ox / 2;
+    int c0 = quad * 4;
+    float v[4];
+    load4(c0 < C1 ? x1 + irow * C1 + c0 : x2 + irow * C2 + (c0 - C1), v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] *= scale;
+    store4(y + gq * 4, v);
+  }
+}
+template <typename T>
+__global__ void down2_kernel(const T* x1, const T* x2, T* y, long long total_quads, int H, int W, int C1, int C2, float scale) {
+  const int Ct = C1 + C2, Q = Ct / 4;     // H, W are INPUT sizes
+  const int Ho = H / 2, Wo = W / 2;
+  GRID_STRIDE(gq, total_quads) {   // over OUTPUT quads
+    int quad = (int)(gq % Q);
+    long long row = gq / Q;
+    int ox = (int)(row % Wo);
+    long long t = row / Wo;
+    int oy = (int)(t % Ho);
+    long long n = t / Ho;
+    int c0 = quad * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        long long irow = (n * H + 2 * oy + a) * W + 2 * ox + b;
+        float v[4];
+        load4(c0 < C1 ? x1 + irow * C1 + c0 : x2 + irow * C2 + (c0 - C1), v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += v[k];
+      }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] *= scale;
+    store4(y + gq * 4, acc);
+  }
+}
+
+// ---------------------------------------------------------------- column sums
+// grid (groups, ceil(C/128)), block 256 = 8 row-lanes x 32 quad-lanes
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long rows_per_group, int C, float scale,
+                                                     float* out, int accumulate) {
+  const long long g = blockIdx.x;
+  const int c0 = (blockIdx.y * 32 + threadIdx.x % 32) * 4;
+  const int rl = threadIdx.x / 32;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c0 < C) {
+    const T* base = x + g * rows_per_group * C + c0;
+    for (long long r = rl; r < rows_per_group; r += 8) {
+      float v[4];
+      load4(base + r * C, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] += v[k];
+    }
+  }
+  __shared__ float4 sm[256];
+  sm[threadIdx.x] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  __syncthreads();
+  if (rl == 0 && c0 < C) {
+    float4 t = sm[threadIdx.x];
+    for (int l = 1; l < 8; ++l) {
+      float4 u = sm[l * 32 + threadIdx.x];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    float* o = out + g * C + c0;
+    if (accumulate) { o[0] += scale * t.x; o[1] += scale * t.y; o[2] += scale * t.z; o[3] += scale * t.w; }
+    else { o[0] = scale * t.x; o[1] = scale * t.y; o[2] = scale * t.z; o[3] = scale * t.w; }
+  }
+}
+
+// ---------------------------------------------------------------- softmax (one warp per row)
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ logits, T* __restrict__ p, long long rows,
+                                                          int L, float scale) {
+  const int lane = threadIdx.x % 32;
+  for (long long row = (long long)blockIdx.x * 8 + threadIdx.x / 32; row < rows; row += (long long)gridDim.x * 8) {
+    const float* src = logits + row * L;
+    float mx = -INFINITY;
+    for (int j = lane; j < L; j += 32) mx = fmaxf(mx, src[j] * scale);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < L; j += 32) sum += __expf(src[j] * scale - mx);
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int j = lane; j < L; j += 32) p[row * L + j] = from_f<T>(__expf(src[j] * scale - mx) * inv);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ p, const float* __restrict__ dp,
+                                                          T* __restrict__ ds, long long rows, int L, float scale) {
+  const int lane = threadIdx.x % 32;
+  for (long long row = (long long)blockIdx.x * 8 + threadIdx.x / 32; row < rows; row += (long long)gridDim.x * 8) {
+    float dot = 0.f;
+    for (int j = lane; j < L; j += 32) dot = fmaf(to_f(p[row * L + j]), dp[row * L + j], dot);
+    dot = warp_sum(dot);
+    for (int j = lane; j < L; j += 32)
+      ds[row * L + j] = from_f<T>(scale * to_f(p[row * L + j]) * (dp[row * L + j] - dot));
+  }
+}
+
+// ---------------------------------------------------------------- embeddings
+__global__ void timestep_embedding_kernel(const float* labels, float* out, int B, int dim, float max_positions) {
+  // models/layers.py:515-529: emb = t * exp(-log(max_pos)/(half-1) * i); [sin | cos]
+  int half = dim / 2;
+  GRID_STRIDE(i, (long long)B * half) {
+    int b = (int)(i / half), j = (int)(i % half);
+    float freq = expf((float)j * -(logf(max_positions) / (float)(half - 1)));
+    float arg = labels[b] * freq;
+    out[(long long)b * dim + j] = sinf(arg);
+    out[(long long)b * dim + half + j] = cosf(arg);
+  }
+}
+__global__ void fourier_embedding_kernel(const float* sigma, const float* W, float* out, int B, int nW) {
+  // models/layerspp.py:52-54 on x = log(sigma): x[:,None]*W[None,:]*2*pi -> [sin | cos]
+  GRID_STRIDE(i, (long long)B * nW) {
+    int b = (int)(i / nW), j = (int)(i % nW);
+    float proj = logf(sigma[b]) * W[j] * 2.f * 3.14159265358979323846f;
+    out[(long long)b * 2 * nW + j] = sinf(proj);
+    out[(long long)b * 2 * nW + nW + j] = cosf(proj);
+  }
+}
+
+// ---------------------------------------------------------------- layout changes at the network boundary
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, long long total, int C, int HW,
+                                    int Cpad, float alpha, float beta) {
+  GRID_STRIDE(i, total) {           // i indexes the (channel-padded) NHWC output
+    int c = (int)(i % Cpad);
+    long long t = i / Cpad;
+    int p = (int)(t % HW);
+    long long n = t / HW;
+    y[i] = from_f<T>(c < C ? alpha * x[(n * C + c) * HW + p] + beta : 0.f);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, long long total, int C, int HW,
+                                    int Cpad, const float* row_scale) {
+  GRID_STRIDE(i, total) {           // i indexes NCHW output
+    int p = (int)(i % HW);
+    long long t = i / HW;
+    int c = (int)(t % C);
+    long long n = t / C;
+    float v = to_f(x[(n * HW + p) * Cpad + c]);
+    y[i] = row_scale ? v * row_scale[n] : v;
+  }
+}
+
+// out[pixel][Kpad] = im2col of x (NHWC, small C), zero padded; k = tap*C + c
+template <typename T>
+__global__ void im2col_small_kernel(const T* __restrict__ x, bf16* __restrict__ out, long long total, int H, int W, int C,
+                                    int kh, int kw, int Kpad) {
+  GRID_STRIDE(i, total) {
+    int k = (int)(i % Kpad);
+    long long pix = i / Kpad;
+    float v = 0.f;
+    if (k < kh * kw * C) {
+      int tap = k / C, c = k % C;
+      int xx = (int)(pix % W) + tap % kw - (kw - 1) / 2;
+      long long t = pix / W;
+      int yy = (int)(t % H) + tap / kw - (kh - 1) / 2;
+      long long n = t / H;
+      if (xx >= 0 && xx < W && yy >= 0 && yy < H) v = to_f(x[((n * H + yy) * W + xx) * C + c]);
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------- fused_bias_act (reference op)
+template <typename T>
+__global__ void fused_bias_act_kernel(const T* __restrict__ x, const T* __restrict__ b, const T* __restrict__ ref,
+                                      T* __restrict__ y, long long n, int size_b, int step_b, int act, int grad,
+                                      float alpha, float scale) {
+  GRID_STRIDE(i, n) {
+    float v = to_f(x[i]);
+    if (b) v += to_f(b[(i / step_b) % size_b]);
+    float r = ref ? to_f(ref[i]) : 0.f;
+    float o;
+    if (act == 3) {
+      if (grad == 0) o = v > 0.f ? v : v * alpha;
+      else if (grad == 1) o = r > 0.f ? v : v * alpha;
+      else o = 0.f;
+    } else {
+      o = grad < 2 ? v : 0.f;
+    }
+    y[i] = from_f<T>(o * scale);
+  }
+}
+
+// ---------------------------------------------------------------- loss head
+__global__ void dsm_perturb_kernel(const float* __restrict__ x0, const float* __restrict__ z,
+                                   const float* __restrict__ mc, const float* __restrict__ sd, float* __restrict__ xt,
+                                   long long total, long long D) {
+  GRID_STRIDE(i, total) {
+    long long n = i / D;
+    xt[i] = fmaf(sd[n], z[i], mc[n] * x0[i]);
+  }
+}
+// one block per sample
+__global__ void __launch_bounds__(256) dsm_loss_kernel(const float* __restrict__ out, const float* __restrict__ z,
+                                                       const float* __restrict__ a, const float* __restrict__ b,
+                                                       const float* __restrict__ w, float* loss, float* dout,
+                                                       const float* __restrict__ gvec, long long D, int reduce_mean) {
+  const long long n = blockIdx.x;
+  const float an = a[n], bn = b[n], wn = w[n];
+  const float gscale = (dout && gvec) ? gvec[n] : 1.f;
+  const float red = reduce_mean ? 1.f / (float)D : 0.5f;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < D; i += 256) {
+    float e = fmaf(an, out[n * D + i], bn * z[n * D + i]);
+    acc = fmaf(e, e, acc);
+    if (dout) dout[n * D + i] = gscale * wn * red * 2.f * e * an;
+  }
+  acc = warp_sum(acc);
+  __shared__ float sm[8];
+  if (threadIdx.x % 32 == 0) sm[threadIdx.x / 32] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.;
+    for (int i = 0; i < 8; ++i) t += (double)sm[i];
+    loss[n] = wn * red * (float)t;
+  }
+}
+
+// ---------------------------------------------------------------- optimizer
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n4, long long n, float* acc) {
+  float s = 0.f;
+  GRID_STRIDE(i, n4) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { float v = x[(n & ~3LL) + threadIdx.x]; s = fmaf(v, v, s); }
+  s = warp_sum(s);
+  __shared__ float sm[8];
+  if (threadIdx.x % 32 == 0) sm[threadIdx.x / 32] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sm[i];
+    atomicAdd(acc, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                       float* __restrict__ v, float* __restrict__ ema,
+                                                       const uint8_t* __restrict__ ema_mask, bf16* __restrict__ p16,
+                                                       long long n, const float* gnorm_sq, float clip, float lr, float b1,
+                                                       float b2, float eps, float wd, float bc1, float bc2, float decay) {
+  float coef = 1.f;
+  if (gnorm_sq && clip >= 0.f) coef = fminf(1.f, clip / (sqrtf(*gnorm_sq) + 1e-6f));
+  const float step_size = lr / bc1, sq_bc2 = sqrtf(bc2);
+  GRID_STRIDE(i, n) {
+    float pi = p[i];
+    float gi = g[i] * coef;
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / sq_bc2 + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi;
+    if (ema && (!ema_mask || ema_mask[i])) {
+      float e = ema[i];
+      ema[i] = e - (1.f - decay) * (e - pi);
+    }
+    if (p16) p16[i] = __float2bfloat16_rn(pi);
+  }
+}
+
+// ---------------------------------------------------------------- sampler
+__global__ void pc_update_kernel(const float* __restrict__ x, const float* __restrict__ s, const float* __restrict__ noise,
+                                 const float* __restrict__ ca, const float* __restrict__ cb, const float* __restrict__ cc,
+                                 float* __restrict__ x_mean, float* __restrict__ x_new, long long total, long long D) {
+  GRID_STRIDE(i, total) {
+    long long n = i / D;
+    float xm = fmaf(cb[n], s[i], ca[n] * x[i]);
+    if (x_mean) x_mean[i] = xm;
+    x_new[i] = noise ? fmaf(cc[n], noise[i], xm) : xm;
+  }
+}
+// grid B blocks: per-sample L2 norms, then atomically accumulate the batch mean
+__global__ void __launch_bounds__(256) batch_norms_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                          float* out, int B, long long D) {
+  const long long n = blockIdx.x;
+  float sa = 0.f, sb = 0.f;
+  for (long long i = threadIdx.x; i < D; i += 256) {
+    float u = a[n * D + i];
+    sa = fmaf(u, u, sa);
+    if (b) { float w = b[n * D + i]; sb = fmaf(w, w, sb); }
+  }
+  sa = warp_sum(sa);
+  sb = warp_sum(sb);
+  __shared__ float sm[16];
+  if (threadIdx.x % 32 == 0) { sm[threadIdx.x / 32] = sa; sm[8 + threadIdx.x / 32] = sb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ta = 0.f, tb = 0.f;
+    for (int i = 0; i < 8; ++i) { ta += sm[i]; tb += sm[8 + i]; }
+    atomicAdd(out + 0, sqrtf(ta) / (float)B);
+    if (b) atomicAdd(out + 1, sqrtf(tb) / (float)B);
+  }
+}
+__global__ void langevin_coeffs_kernel(const float* norms, const float* alpha, float snr, float* ca, float* cb, float* cc, int B) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= B) return;
+  float r = snr * norms[1] / norms[0];
+  float step = r * r * 2.f * alpha[n];
+  ca[n] = 1.f;
+  cb[n] = step;
+  cc[n] = sqrtf(step * 2.f);
+}
+
+}  // namespace
+
+#define S ((cudaStream_t)stream)
+
+extern "C" __attribute__((visibility("default"))) int st_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* stream) {
+  long long n4 = n / 4;
+  int g = grid1d(n4, 256 * 2);
+  if (sdt == ST_F32 && ddt == ST_BF16) cast_kernel<float, bf16><<<g, 256, 0, S>>>((const float*)src, (bf16*)dst, n4, n);
+  else if (sdt == ST_BF16 && ddt == ST_F32) cast_kernel<bf16, float><<<g, 256, 0, S>>>((const bf16*)src, (float*)dst, n4, n);
+  else if (sdt == ST_F32 && ddt == ST_F32) cast_kernel<float, float><<<g, 256, 0, S>>>((const float*)src, (float*)dst, n4, n);
+  else if (sdt == ST_BF16 && ddt == ST_BF16) cast_kernel<bf16, bf16><<<g, 256, 0, S>>>((const bf16*)src, (bf16*)dst, n4, n);
+  else { st_set_error("st_cast: bad dtypes"); return ST_ERR_ARG; }
+  ST_CHECK_LAUNCH("st_cast");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_axpby(const void* a, const void* b, void* out, int dtype, float alpha, float beta, int64_t n, void* stream) {
+  long long n4 = n / 4;
+  ST_DISPATCH_DTYPE(dtype, T, (axpby_kernel<T><<<grid1d(n4, 256 * 2), 256, 0, S>>>((const T*)a, (const T*)b, (T*)out, alpha, beta, n4, n)));
+  ST_CHECK_LAUNCH("st_axpby");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_silu(const void* x, void* y, int dtype, int64_t n, void* stream) {
+  ST_DISPATCH_DTYPE(dtype, T, (silu_kernel<T><<<grid1d(n, 256 * 4), 256, 0, S>>>((const T*)x, (T*)y, n)));
+  ST_CHECK_LAUNCH("st_silu");
+  return 0;
+}
+extern "C" __attribute__((visibility("default"))) int st_silu_bwd(const void* x, const void* dy, void* dx, int dtype, int64_t n, void* stream) {
+  ST_DISPATCH_DTYPE(dtype, T, (silu_bwd_kernel<T><<<grid1d(n, 256 * 4), 256, 0, S>>>((const T*)x, (const T*)dy, (T*)dx, n)));
+  ST_CHECK_LAUNCH("st_silu_bwd");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_resample2x(const void* x1, const void* x2, void* y, int dtype, int n_img, int H, int W, int C1, int C2,
+                             int dir, float scale, void* stream) {
+  ST_CHECK_ARG(C1 % 4 == 0 && C2 % 4 == 0, "st_resample2x: channels must be multiples of 4");
+  ST_CHECK_ARG(dir == 1 || (dir == -1 && H % 2 == 0 && W % 2 == 0), "st_resample2x: bad dir/size");
+  int Q = (C1 + C2) / 4;
+  if (dir == 1) {
+    long long total = (long long)n_img * (2 * H) * (2 * W) * Q;
+    ST_DISPATCH_DTYPE(dtype, T, (up2_kernel<T><<<grid1d(total, 256 * 2), 256, 0, S>>>((const T*)x1, (const T*)x2, (T*)y, total, H, W, C1, C2, scale)));
+  } else {
+    long long total = (long long)n_img * (H / 2) * (W / 2) * Q;
+    ST_DISPATCH_DTYPE(dtype, T, (down2_kernel<T><<<grid1d(total, 256 * 2), 256, 0, S>>>((const T*)x1, (const T*)x2, (T*)y, total, H, W, C1, C2, scale)));
+  }
+  ST_CHECK_LAUNCH("st_resample2x");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_colsum(const void* x, int dtype, int64_t groups, int64_t rows_per_group, int C, float scale, float* out,
+                         int accumulate, void* stream) {
+  ST_CHECK_ARG(C % 4 == 0, "st_colsum: C must be a multiple of 4");
+  ST_CHECK_ARG(groups >= 1 && groups < (1LL << 31), "st_colsum: bad groups");
+  dim3 grid((unsigned)groups, (C + 127) / 128);
+  ST_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<grid, 256, 0, S>>>((const T*)x, rows_per_group, C, scale, out, accumulate)));
+  ST_CHECK_LAUNCH("st_colsum");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_softmax_fwd(const float* logits, void* p, int dtype, int64_t rows, int L, float scale, void* stream) {
+  ST_DISPATCH_DTYPE(dtype, T, (softmax_fwd_kernel<T><<<grid1d(rows, 8), 256, 0, S>>>(logits, (T*)p, rows, L, scale)));
+  ST_CHECK_LAUNCH("st_softmax_fwd");
+  return 0;
+}
+extern "C" __attribute__((visibility("default"))) int st_softmax_bwd(const void* p, const float* dp, void* ds, int dtype, int64_t rows, int L, float scale, void* stream) {
+  ST_DISPATCH_DTYPE(dtype, T, (softmax_bwd_kernel<T><<<grid1d(rows, 8), 256, 0, S>>>((const T*)p, dp, (T*)ds, rows, L, scale)));
+  ST_CHECK_LAUNCH("st_softmax_bwd");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_timestep_embedding(const float* labels, float* out, int B, int dim, float max_positions, void* stream) {
+  ST_CHECK_ARG(dim % 2 == 0 && dim >= 4, "st_timestep_embedding: dim must be even");
+  timestep_embedding_kernel<<<grid1d((long long)B * dim / 2, 256), 256, 0, S>>>(labels, out, B, dim, max_positions);
+  ST_CHECK_LAUNCH("st_timestep_embedding");
+  return 0;
+}
+extern "C" __attribute__((visibility("default"))) int st_fourier_embedding(const float* sigma, const float* W, float* out, int B, int nW, void* stream) {
+  fourier_embedding_kernel<<<grid1d((long long)B * nW, 256), 256, 0, S>>>(sigma, W, out, B, nW);
+  ST_CHECK_LAUNCH("st_fourier_embedding");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_nchw_to_nhwc(const float* x, void* y, int dtype, int n_img, int C, int H, int W, int Cpad, float alpha,
+                               float beta, void* stream) {
+  ST_CHECK_ARG(Cpad >= C, "st_nchw_to_nhwc: Cpad < C");
+  long long total = (long long)n_img * Cpad * H * W;
+  ST_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid1d(total, 256 * 4), 256, 0, S>>>(x, (T*)y, total, C, H * W, Cpad, alpha, beta)));
+  ST_CHECK_LAUNCH("st_nchw_to_nhwc");
+  return 0;
+}
+extern "C" __attribute__((visibility("default"))) int st_nhwc_to_nchw(const void* x, int dtype, float* y, int n_img, int C, int H, int W, int Cpad,
+                               const float* row_scale, void* stream) {
+  ST_CHECK_ARG(Cpad >= C, "st_nhwc_to_nchw: Cpad < C");
+  long long total = (long long)n_img * C * H * W;
+  ST_DISPATCH_DTYPE(dtype, T, (nhwc_to_nchw_kernel<T><<<grid1d(total, 256 * 4), 256, 0, S>>>((const T*)x, y, total, C, H * W, Cpad, row_scale)));
+  ST_CHECK_LAUNCH("st_nhwc_to_nchw");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_im2col_small(const void* x, int dtype, void* out, int n_img, int H, int W, int C, int kh, int kw, int Kpad,
+                               void* stream) {
+  ST_CHECK_ARG(Kpad >= kh * kw * C, "st_im2col_small: Kpad too small");
+  long long total = (long long)n_img * H * W * Kpad;
+  ST_DISPATCH_DTYPE(dtype, T, (im2col_small_kernel<T><<<grid1d(total, 256 * 4), 256, 0, S>>>((const T*)x, (bf16*)out, total, H, W, C, kh, kw, Kpad)));
+  ST_CHECK_LAUNCH("st_im2col_small");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_fused_bias_act(const void* x, const void* b, const void* ref, void* y, int dtype, int64_t n, int size_b,
+                                 int step_b, int act, int grad, float alpha, float scale, void* stream) {
+  ST_CHECK_ARG(!b || (size_b > 0 && step_b > 0), "st_fused_bias_act: bad bias geometry");
+  ST_DISPATCH_DTYPE(dtype, T, (fused_bias_act_kernel<T><<<grid1d(n, 256 * 4), 256, 0, S>>>((const T*)x, (const T*)b, (const T*)ref, (T*)y, n, size_b, step_b, act, grad, alpha, scale)));
+  ST_CHECK_LAUNCH("st_fused_bias_act");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_dsm_perturb(const float* x0, const float* z, const float* mean_coeff, const float* std, float* xt, int B,
+                              int64_t D, void* stream) {
+  long long total = (long long)B * D;
+  dsm_perturb_kernel<<<grid1d(total, 256 * 4), 256, 0, S>>>(x0, z, mean_coeff, std, xt, total, D);
+  ST_CHECK_LAUNCH("st_dsm_perturb");
+  return 0;
+}
+extern "C" __attribute__((visibility("default"))) int st_dsm_loss(const float* out, const float* z, const float* a, const float* b, const float* w, float* loss,
+                           float* dout, const float* gvec, int B, int64_t D, int reduce_mean, void* stream) {
+  dsm_loss_kernel<<<B, 256, 0, S>>>(out, z, a, b, w, loss, dout, gvec, D, reduce_mean);
+  ST_CHECK_LAUNCH("st_dsm_loss");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_sumsq(const float* x, int64_t n, float* acc, void* stream) {
+  long long n4 = n / 4;
+  int g = grid1d(n4, 256 * 8);
+  sumsq_kernel<<<g, 256, 0, S>>>(x, n4, n, acc);
+  ST_CHECK_LAUNCH("st_sumsq");
+  return 0;
+}
+extern "C" __attribute__((visibility("default"))) int st_adam_ema(float* p, const float* grad, float* m, float* v, float* ema, const uint8_t* ema_mask, void* p16,
+                           int64_t n, const float* gnorm_sq, float clip, float lr, float b1, float b2, float eps, float wd,
+                           float bc1, float bc2, float ema_decay, void* stream) {
+  adam_ema_kernel<<<grid1d(n, 256 * 4), 256, 0, S>>>(p, grad, m, v, ema, ema_mask, (bf16*)p16, n, gnorm_sq, clip, lr, b1, b2,
+                                                     eps, wd, bc1, bc2, ema_decay);
+  ST_CHECK_LAUNCH("st_adam_ema");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_pc_update(const float* x, const float* s, const float* noise, const float* ca, const float* cb,
+                            const float* cc, float* x_mean, float* x_new, int B, int64_t D, void* stream) {
+  long long total = (long long)B * D;
+  pc_update_kernel<<<grid1d(total, 256 * 4), 256, 0, S>>>(x, s, noise, ca, cb, cc, x_mean, x_new, total, D);
+  ST_CHECK_LAUNCH("st_pc_update");
+  return 0;
+}
+extern "C" __attribute__((visibility("default"))) int st_batch_norms(const float* a, const float* b, float* out, int B, int64_t D, void* stream) {
+  cudaMemsetAsync(out, 0, 2 * sizeof(float), S);
+  batch_norms_kernel<<<B, 256, 0, S>>>(a, b, out, B, D);
+  ST_CHECK_LAUNCH("st_batch_norms");
+  return 0;
+}
+extern "C" __attribute__((visibility("default"))) int st_langevin_coeffs(const float* norms, const float* alpha, float snr, float* ca, float* cb, float* cc, int B,
+                                  void* stream) {
+  langevin_coeffs_kernel<<<(B + 127) / 128, 128, 0, S>>>(norms, alpha, snr, ca, cb, cc, B);
+  ST_CHECK_LAUNCH("st_langevin_coeffs");
+  return 0;
+}

@@ -1,0 +1,793 @@
+"""NCSN++ / DDPM++ score network on the B200 kernels.
+
+Same constructor, call signature, parameter names and shapes as the reference
+`models.ncsnpp.NCSNpp(config, sde)` (reference models/ncsnpp.py:34-432), but the network is executed by
+hand-written CUDA (libst_b200) on NHWC activations, and its backward pass is written out explicitly
+(one autograd node for the whole network) instead of being recorded op by op:
+
+  * ResnetBlockBigGANpp  (reference models/layerspp.py:225-287)   -> ResBlock.fwd / .bwd
+  * AttnBlockpp + NIN    (models/layerspp.py:75-104, layers.py:546-555) -> AttnBlock.fwd / .bwd
+  * time embedding MLP   (models/ncsnpp.py:262-292)                -> TimeEmbedding.fwd / .bwd
+  * torch.cat skip connections (models/ncsnpp.py:368) are never materialised: GroupNorm, the 1x1
+    shortcut and the 3x3 convolutions read the two tensors as one channel axis.
+
+Numeric modes: `compute_dtype=torch.bfloat16` (tensor-core path, fp32 accumulation) or
+`torch.float32` (parity path).  Parameters, gradients, optimizer state and all statistics stay fp32.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from . import utils
+from .params import (ParamStore, _logical_view, _phys_view, init_conv, init_ones, init_zeros, register_owner)
+
+SQRT2 = math.sqrt(2.)
+CPAD = 64     # physical channel count of the 3-channel image-side tensors
+
+
+class _Holder(nn.Module):
+  """Parameter container that reproduces the reference's module/parameter names."""
+
+
+def _attach(root, dotted, param):
+  parts = dotted.split('.')
+  mod = root
+  for p in parts[:-1]:
+    if not hasattr(mod, p):
+      mod.add_module(p, _Holder())
+    mod = getattr(mod, p)
+  mod.register_parameter(parts[-1], param)
+
+
+def _fir_kernel(taps, gain, device):
+  k = np.asarray(taps, dtype=np.float32)
+  k = np.outer(k, k)
+  k = k / k.sum() * gain
+  return torch.tensor(k, dtype=torch.float32, device=device)
+
+
+# ===================================================================================== blocks
+class Tape:
+  """Minimal reverse-mode tape over activation ids (one entry per block)."""
+
+  def __init__(self, enabled):
+    self.enabled = enabled
+    self.ops = []
+    self.next_id = 0
+
+  def new_id(self):
+    self.next_id += 1
+    return self.next_id
+
+  def record(self, bwd, in_ids, out_id):
+    if self.enabled:
+      self.ops.append((bwd, in_ids, out_id))
+
+
+class Act:
+  """An activation tensor plus its tape id."""
+  __slots__ = ('t', 'id')
+
+  def __init__(self, t, tape):
+    self.t, self.id = t, tape.new_id()
+
+
+class NetCtx:
+  """Per-call state shared by all blocks."""
+
+  def __init__(self, model, train, tape):
+    self.m, self.train, self.tape = model, train, tape
+    self.dense = None          # fp32 [B][sum Cout]: Dense_0(act(temb)) of every res-block
+    self.d_dense = None        # its gradient, filled slice by slice during backward
+    self.taps = model._taps
+    self.drop_calls = 0
+
+
+class ResBlock:
+  """ResnetBlockBigGANpp (reference models/layerspp.py:225-287)."""
+
+  def __init__(self, model, idx, cin, cout, up=False, down=False):
+    self.idx, self.cin, self.cout, self.up, self.down = idx, cin, cout, up, down
+    m = model.config.model
+    add = model._add_param
+    pre = f'all_modules.{idx}.'
+    add(pre + 'GroupNorm_0.weight', (cin,), init=init_ones)
+    add(pre + 'GroupNorm_0.bias', (cin,), init=init_zeros)
+    add(pre + 'Conv_0.weight', (cout, cin, 3, 3), 'conv', init=init_conv(1.))
+    add(pre + 'Conv_0.bias', (cout,), init=init_zeros)
+    self.dense_off = model._dense_cols
+    model._dense_cols += cout
+    add(pre + 'Dense_0.weight', (cout, model.temb_dim), 'linear', region='dense_w', init=init_conv(1.))
+    add(pre + 'Dense_0.bias', (cout,), region='dense_b', init=init_zeros)
+    add(pre + 'GroupNorm_1.weight', (cout,), init=init_ones)
+    add(pre + 'GroupNorm_1.bias', (cout,), init=init_zeros)
+    add(pre + 'Conv_1.weight', (cout, cout, 3, 3), 'conv', init=init_conv(m.init_scale))
+    add(pre + 'Conv_1.bias', (cout,), init=init_zeros)
+    self.shortcut = cin != cout or up or down
+    if self.shortcut:
+      add(pre + 'Conv_2.weight', (cout, cin, 1, 1), 'conv', init=init_conv(1.))
+      add(pre + 'Conv_2.bias', (cout,), init=init_zeros)
+    self.pre = pre
+    self.scale = 1. / SQRT2 if m.skip_rescale else 1.
+    self.G0, self.G1 = min(cin // 4, 32), min(cout // 4, 32)
+    self.fir = m.fir
+
+  # ---- resampling of (h, x): nearest / box when fir=False, FIR [1,3,3,1] otherwise
+  def _resample(self, net, t, t2):
+    m = net.m
+    if not self.fir:
+      return ops.resample2x(t, t2, +1, 1.0) if self.up else ops.resample2x(t, t2, -1, 0.25)
+    assert t2 is None
+    if self.up:      # upsample_2d: up=2, pad=((p+1)//2+1, p//2) with p = 4-2 (up_or_down_sampling.py:195-224)
+      return ops.upfirdn2d_nhwc(t, m._fir_up, up=2, pad=(2, 1))
+    return ops.upfirdn2d_nhwc(t, m._fir_down, down=2, pad=(1, 1))
+
+  def _resample_adj(self, net, g):
+    m = net.m
+    if not self.fir:
+      return ops.resample2x(g, None, -1, 1.0) if self.up else ops.resample2x(g, None, +1, 0.25)
+    # adjoint of upfirdn2d = upfirdn2d with the flipped FIR and up/down swapped (op/upfirdn2d.py:101-116);
+    # [1,3,3,1] (x) [1,3,3,1] is symmetric, so the flip is the identity.
+    if self.up:      # forward up=2,pad=(2,1): g_pad0 = kw-pad0-1 = 1, g_pad1 = in*2 - out + pad0 - 2 + 1 = 1
+      return ops.upfirdn2d_nhwc(g, m._fir_up, down=2, pad=(1, 1))
+    return ops.upfirdn2d_nhwc(g, m._fir_down, up=2, pad=(2, 1))   # forward down=2,pad=(1,1)
+
+  def fwd(self, net, xa, xb=None):
+    """xa: Act (B,H,W,C1); xb: optional skip Act (B,H,W,C2) concatenated on channels."""
+    P, m = net.m.P, net.m
+    pre = self.pre
+    x1, x2 = xa.t, (xb.t if xb is not None else None)
+    if x2 is not None and (self.up or self.down) and self.fir:
+      raise NotImplementedError('FIR resampling of a concatenated input')
+    st0 = ops.gn_stats(x1, x2, self.G0)
+    a0 = ops.gn_apply(x1, x2, self.G0, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st0, act=1)
+    xr = None
+    if self.up or self.down:
+      a0 = self._resample(net, a0, None)
+      xr = self._resample(net, x1, x2)
+    B, H, W, _ = a0.shape
+    h1 = ops.conv_fwd(a0, P.c(pre + 'Conv_0.weight'), self.cout, bias=P.f(pre + 'Conv_0.bias'),
+                      rowbias=net.dense[:, self.dense_off:], rowbias_ld=net.dense.shape[1])
+    st1 = ops.gn_stats(h1, None, self.G1)
+    p_drop, seed, mask = 0., 0, None
+    if net.train and m.dropout > 0:
+      mask = m._mask_for(self.idx, h1)
+      if mask is None:
+        p_drop, seed = m.dropout, m._next_seed(self.idx)
+    a1 = ops.gn_apply(h1, None, self.G1, P.f(pre + 'GroupNorm_1.weight'), P.f(pre + 'GroupNorm_1.bias'), st1, act=1,
+                      p_drop=p_drop, seed=seed, mask=mask)
+    if self.shortcut:
+      if xr is not None:
+        sc = ops.conv_fwd(xr, P.c(pre + 'Conv_2.weight'), self.cout, 1, 1, bias=P.f(pre + 'Conv_2.bias'))
+      else:
+        sc = ops.conv_fwd(x1, P.c(pre + 'Conv_2.weight'), self.cout, 1, 1, x2=x2, bias=P.f(pre + 'Conv_2.bias'))
+    else:
+      sc = x1
+    out = ops.conv_fwd(a1, P.c(pre + 'Conv_1.weight'), self.cout, bias=P.f(pre + 'Conv_1.bias'), residual=sc,
+                       alpha=self.scale)
+    y = Act(out, net.tape)
+    if net.tape.enabled:
+      saved = (x1, x2, st0, a0, xr, h1, st1, a1, p_drop, seed, mask)
+      net.tape.record(lambda g, acc: self.bwd(net, saved, g, acc), (xa.id,) + ((xb.id,) if xb is not None else ()), y.id)
+    if net.taps is not None:
+      net.taps[self.idx] = out
+    return y
+
+  def bwd(self, net, saved, g, acc):
+    """g: d(out); acc: existing gradient tensors of (xa[, xb]) to accumulate into, or None."""
+    P = net.m.P
+    pre, s = self.pre, self.scale
+    x1, x2, st0, a0, xr, h1, st1, a1, p_drop, seed, mask = saved
+    B, H, W, Co = g.shape
+    npix = B * H * W
+    g2 = g.view(npix, Co)
+    # ---- Conv_1 (and the 1/sqrt2 output scale)
+    ops.colsum(g2, 1, npix, Co, P.g(pre + 'Conv_1.bias'), scale=s, accumulate=True)
+    ops.conv_wgrad(g, a1, P.g(pre + 'Conv_1.weight'), alpha=s)
+    da1 = ops.conv_dgrad(g, P.c(pre + 'Conv_1.weight'), Co, alpha=s)
+    # ---- GroupNorm_1 + SiLU + dropout
+    dh1, _ = ops.gn_backward(h1, None, da1, self.G1, P.f(pre + 'GroupNorm_1.weight'), P.f(pre + 'GroupNorm_1.bias'),
+                             st1, 1, P.g(pre + 'GroupNorm_1.weight'), P.g(pre + 'GroupNorm_1.bias'), p_drop=p_drop,
+                             seed=seed, mask=mask)
+    del da1
+    # ---- Conv_0 bias, temb projection (per-image column sums), weights, data
+    dd = torch.empty((B, Co), dtype=torch.float32, device=g.device)
+    ops.colsum(dh1.view(npix, Co), B, H * W, Co, dd)
+    net.d_dense[:, self.dense_off:self.dense_off + Co].copy_(dd)
+    ops.colsum(dd, 1, B, Co, P.g(pre + 'Conv_0.bias'), accumulate=True)
+    ops.conv_wgrad(dh1, a0, P.g(pre + 'Conv_0.weight'))
+    da0 = ops.conv_dgrad(dh1, P.c(pre + 'Conv_0.weight'), self.cin)
+    del dh1
+    # ---- shortcut
+    extra, extra_scale = None, 1.0
+    if self.shortcut:
+      ops.colsum(g2, 1, npix, Co, P.g(pre + 'Conv_2.bias'), scale=s, accumulate=True)
+      if xr is not None:
+        ops.conv_wgrad(g, xr, P.g(pre + 'Conv_2.weight'), 1, 1, alpha=s)
+      else:
+        ops.conv_wgrad(g, x1, P.g(pre + 'Conv_2.weight'), 1, 1, x2=x2, alpha=s)
+      extra = ops.conv_dgrad(g, P.c(pre + 'Conv_2.weight'), self.cin, 1, 1, alpha=s)
+    else:
+      extra, extra_scale = g, s
+    if self.up or self.down:
+      da0 = self._resample_adj(net, da0)
+      extra = self._resample_adj(net, extra)
+    # ---- GroupNorm_0 + SiLU, plus the shortcut gradient, split over the two inputs
+    a1_acc = acc[0]
+    a2_acc = acc[1] if x2 is not None else None
+    dx1, dx2 = ops.gn_backward(x1, x2, da0, self.G0, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'),
+                               st0, 1, P.g(pre + 'GroupNorm_0.weight'), P.g(pre + 'GroupNorm_0.bias'), extra=extra,
+                               extra_scale=extra_scale, dx1=a1_acc, accum1=a1_acc is not None, dx2=a2_acc,
+                               accum2=a2_acc is not None)
+    return (dx1,) if x2 is None else (dx1, dx2)
+
+
+class AttnBlock:
+  """AttnBlockpp with its four NIN projections (reference models/layerspp.py:75-104)."""
+
+  def __init__(self, model, idx, c):
+    self.idx, self.c = idx, c
+    m = model.config.model
+    add = model._add_param
+    pre = f'all_modules.{idx}.'
+    add(pre + 'GroupNorm_0.weight', (c,), init=init_ones)
+    add(pre + 'GroupNorm_0.bias', (c,), init=init_zeros)
+    # NIN_0..2 W / b are laid out back to back so that q,k,v come from ONE (3C x C) GEMM
+    self.names_w = [pre + f'NIN_{j}.W' for j in range(3)]
+    self.names_b = [pre + f'NIN_{j}.b' for j in range(3)]
+    for j in range(3):
+      add(pre + f'NIN_{j}.W', (c, c), 'nin', init=init_conv(0.1), pack=pre + 'qkv.W')
+      add(pre + f'NIN_{j}.b', (c,), init=init_zeros, pack=pre + 'qkv.b')
+    add(pre + 'NIN_3.W', (c, c), 'nin', init=init_conv(m.init_scale))
+    add(pre + 'NIN_3.b', (c,), init=init_zeros)
+    self.pre = pre
+    self.scale = 1. / SQRT2 if m.skip_rescale else 1.
+    self.G = min(c // 4, 32)
+
+  def fwd(self, net, xa):
+    P = net.m.P
+    pre, C = self.pre, self.c
+    x = xa.t
+    B, H, W, _ = x.shape
+    L, npix = H * W, B * H * W
+    st = ops.gn_stats(x, None, self.G)
+    h = ops.gn_apply(x, None, self.G, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st, act=0)
+    wqkv, bqkv = P.c_group(self.names_w), P.f_group(self.names_b)        # (3C, C), (3C,)
+    qkv = ops.gemm_nt(h.view(npix, C), wqkv, bias=bqkv)                 # (npix, 3C)
+    # logits[b][i][j] = sum_c q[b,i,c] k[b,j,c]   (einsum 'bchw,bcij->bhwij')
+    logits = ops.gemm_nt(qkv, qkv[:, C:], out_dtype=torch.float32, M=L, N=L, K=C, lda=3 * C, ldb=3 * C, batch=B,
+                         sAb=L * 3 * C, sBb=L * 3 * C, sCb=L * L)
+    p = ops.softmax_fwd(logits, L, float(C) ** -0.5, x.dtype)           # (B, L, L)
+    del logits
+    o = ops.gemm_nn(p, qkv[:, 2 * C:], C, M=L, K=L, lda=L, ldb=3 * C, batch=B, sAb=L * L, sBb=L * 3 * C,
+                    sCb=L * C)                                          # (B, L, C)
+    out = ops.gemm_nt(o.view(npix, C), P.c(pre + 'NIN_3.W'), bias=P.f(pre + 'NIN_3.b'), residual=x.view(npix, C),
+                      alpha=self.scale).view(B, H, W, C)
+    y = Act(out, net.tape)
+    if net.tape.enabled:
+      saved = (x, st, h, qkv, p, o)
+      net.tape.record(lambda g, acc: self.bwd(net, saved, g, acc), (xa.id,), y.id)
+    if net.taps is not None:
+      net.taps[self.idx] = out
+    return y
+
+  def bwd(self, net, saved, g, acc):
+    P = net.m.P
+    pre, C, s = self.pre, self.c, self.scale
+    x, st, h, qkv, p, o = saved
+    B, H, W, _ = x.shape
+    L, npix = H * W, B * H * W
+    g2 = g.view(npix, C)
+    # ---- NIN_3
+    ops.colsum(g2, 1, npix, C, P.g(pre + 'NIN_3.b'), scale=s, accumulate=True)
+    ops.gemm_tn(g2, o.view(npix, C), C, C, npix, out=P.g(pre + 'NIN_3.W'), alpha=s, accumulate=True)
+    do = ops.gemm_nn(g2, P.c(pre + 'NIN_3.W'), C, alpha=s)              # (npix, C): g W3 (W3 is [out][in])
+    # ---- attention core
+    dqkv = torch.empty_like(qkv)
+    bs = dict(batch=B)
+    # dV[j][c] = sum_i p[i][j] do[i][c]
+    ops.gemm_tn(p, do, L, C, L, out=dqkv[:, 2 * C:], lda=L, ldb=C, ldc=3 * C, sAb=L * L, sBb=L * C, sCb=L * 3 * C, **bs)
+    # dP[i][j] = sum_c do[i][c] v[j][c]
+    dp = ops.gemm_nt(do, qkv[:, 2 * C:], out_dtype=torch.float32, M=L, N=L, K=C, lda=C, ldb=3 * C, sAb=L * C,
+                     sBb=L * 3 * C, sCb=L * L, **bs)
+    ds = ops.softmax_bwd(p, dp, L, float(C) ** -0.5)
+    del dp
+    # dQ[i][c] = sum_j ds[i][j] k[j][c];  dK[j][c] = sum_i ds[i][j] q[i][c]
+    ops.gemm_nn(ds, qkv[:, C:], C, out=dqkv, M=L, K=L, lda=L, ldb=3 * C, ldc=3 * C, sAb=L * L, sBb=L * 3 * C,
+                sCb=L * 3 * C, **bs)
+    ops.gemm_tn(ds, qkv, L, C, L, out=dqkv[:, C:], lda=L, ldb=3 * C, ldc=3 * C, sAb=L * L, sBb=L * 3 * C,
+                sCb=L * 3 * C, **bs)
+    del ds
+    # ---- q,k,v projections
+    ops.colsum(dqkv, 1, npix, 3 * C, P.g_group(self.names_b), accumulate=True)
+    ops.gemm_tn(dqkv, h.view(npix, C), 3 * C, C, npix, out=P.g_group(self.names_w), accumulate=True)
+    dh = ops.gemm_nn(dqkv, P.c_group(self.names_w), C).view(B, H, W, C)
+    # ---- GroupNorm (no activation) + residual
+    dx, _ = ops.gn_backward(x, None, dh, self.G, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st, 0,
+                            P.g(pre + 'GroupNorm_0.weight'), P.g(pre + 'GroupNorm_0.bias'), extra=g, extra_scale=s,
+                            dx1=acc[0], accum1=acc[0] is not None)
+    return (dx,)
+
+
+class ConvBlock:
+  """Plain 3x3 / 1x1 convolution (ddpm_conv3x3 / conv1x1, reference models/layers.py:100-124)."""
+
+  def __init__(self, model, idx, cin, cout, k=3, init_scale=1., name='', is_input=False):
+    """cin / cout are the LOGICAL channel counts; image-side (3-channel) axes are stored padded to
+    CPAD so that the convolution runs on the common 64-wide K/N blocks."""
+    self.idx, self.k, self.is_input = idx, k, is_input
+    self.cin_l, self.cout_l = cin, cout
+    self.cin = cin if cin % 64 == 0 else CPAD
+    self.cout = cout if cout % 64 == 0 else CPAD
+    pre = f'all_modules.{idx}.' + (name + '.' if name else '')
+    model._add_param(pre + 'weight', (cout, cin, k, k), 'conv', init=init_conv(init_scale), pad=(self.cout, self.cin))
+    model._add_param(pre + 'bias', (cout,), init=init_zeros, pad=(self.cout,))
+    self.pre = pre
+
+  def fwd(self, net, xa, record_tap=True):
+    P = net.m.P
+    out = ops.conv_fwd(xa.t, P.c(self.pre + 'weight'), self.cout, self.k, self.k, bias=P.f(self.pre + 'bias'))
+    y = Act(out, net.tape)
+    if net.tape.enabled:
+      x = xa.t
+      net.tape.record(lambda g, acc: self.bwd(net, x, g, acc, need_dx=net.need_dx or not self.is_input), (xa.id,),
+                      y.id)
+    if net.taps is not None and record_tap:
+      net.taps[self.idx] = out
+    return y
+
+  def bwd(self, net, x, g, acc, need_dx=True):
+    P = net.m.P
+    B, H, W, Co = g.shape
+    ops.colsum(g.view(-1, Co), 1, B * H * W, Co, P.g(self.pre + 'bias'), accumulate=True)
+    ops.conv_wgrad(g, x, P.g(self.pre + 'weight'), self.k, self.k)
+    if not need_dx:
+      return (None,)
+    dx = ops.conv_dgrad(g, P.c(self.pre + 'weight'), self.cin, self.k, self.k)
+    if acc[0] is not None:
+      ops.axpby(acc[0], dx, out=acc[0])
+      dx = acc[0]
+    return (dx,)
+
+
+class NormActConv:
+  """Output head: GroupNorm -> SiLU -> conv3x3 (reference models/ncsnpp.py:250-254, 422-425)."""
+
+  def __init__(self, model, idx_gn, idx_conv, cin, cout, init_scale):
+    self.idx_gn, self.idx_conv, self.cin, self.cout = idx_gn, idx_conv, cin, cout
+    self.pg = f'all_modules.{idx_gn}.'
+    model._add_param(self.pg + 'weight', (cin,), init=init_ones)
+    model._add_param(self.pg + 'bias', (cin,), init=init_zeros)
+    self.conv = ConvBlock(model, idx_conv, cin, cout, 3, init_scale)
+    self.G = min(cin // 4, 32)
+
+  def fwd(self, net, xa):
+    P = net.m.P
+    x = xa.t
+    st = ops.gn_stats(x, None, self.G)
+    a = ops.gn_apply(x, None, self.G, P.f(self.pg + 'weight'), P.f(self.pg + 'bias'), st, act=1)
+    out = ops.conv_fwd(a, P.c(self.conv.pre + 'weight'), self.conv.cout, bias=P.f(self.conv.pre + 'bias'))
+    y = Act(out, net.tape)
+    if net.tape.enabled:
+      net.tape.record(lambda g, acc: self.bwd(net, (x, st, a), g, acc), (xa.id,), y.id)
+    if net.taps is not None:
+      net.taps[self.idx_conv] = out
+    return y
+
+  def bwd(self, net, saved, g, acc):
+    P = net.m.P
+    x, st, a = saved
+    (da,) = self.conv.bwd(net, a, g, (None,))
+    dx, _ = ops.gn_backward(x, None, da, self.G, P.f(self.pg + 'weight'), P.f(self.pg + 'bias'), st, 1,
+                            P.g(self.pg + 'weight'), P.g(self.pg + 'bias'), dx1=acc[0], accum1=acc[0] is not None)
+    return (dx,)
+
+
+class TimeEmbedding:
+  """Embedding -> Linear -> SiLU -> Linear, then SiLU -> all Dense_0 projections at once
+  (reference models/ncsnpp.py:262-292 and layerspp.py:272-274)."""
+
+  def __init__(self, model, first_idx):
+    m = model.config.model
+    nf = m.nf
+    self.fourier = m.embedding_type.lower() == 'fourier'
+    i = first_idx
+    if self.fourier:
+      model._add_param(f'all_modules.{i}.W', (nf,), trainable=False,
+                       init=lambda shape, gen: torch.randn(*shape, generator=gen) * m.fourier_scale)
+      self.w_name = f'all_modules.{i}.W'
+      i += 1
+      self.embed_dim = 2 * nf
+    else:
+      self.embed_dim = nf
+    self.l0, self.l1 = f'all_modules.{i}.', f'all_modules.{i + 1}.'
+    model._add_param(self.l0 + 'weight', (4 * nf, self.embed_dim), 'linear', init=init_conv(1.))
+    model._add_param(self.l0 + 'bias', (4 * nf,), init=init_zeros)
+    model._add_param(self.l1 + 'weight', (4 * nf, 4 * nf), 'linear', init=init_conv(1.))
+    model._add_param(self.l1 + 'bias', (4 * nf,), init=init_zeros)
+    self.next_idx = i + 2
+
+  def fwd(self, net, time_cond):
+    m, P = net.m, net.m.P
+    cd = m.compute_dtype
+    if self.fourier:
+      emb = ops.fourier_embedding(time_cond, P.f(self.w_name))
+    else:
+      emb = ops.timestep_embedding(time_cond, self.embed_dim)
+    emb_c = ops.cast(emb, cd) if cd != torch.float32 else emb
+    e0 = ops.gemm_nt(emb_c, P.c(self.l0 + 'weight'), out_dtype=torch.float32, bias=P.f(self.l0 + 'bias'))
+    a0 = ops.silu(e0)
+    a0_c = ops.cast(a0, cd) if cd != torch.float32 else a0
+    temb = ops.gemm_nt(a0_c, P.c(self.l1 + 'weight'), out_dtype=torch.float32, bias=P.f(self.l1 + 'bias'))
+    at = ops.silu(temb)
+    at_c = ops.cast(at, cd) if cd != torch.float32 else at
+    wd, bd = P.c_region('dense_w').view(-1, 4 * m.config.model.nf), P.f_region('dense_b')
+    net.dense = ops.gemm_nt(at_c, wd, out_dtype=torch.float32, bias=bd)      # (B, sum Cout)
+    if net.tape.enabled:
+      net.d_dense = torch.zeros_like(net.dense)
+      net.temb_saved = (emb_c, e0, a0_c, temb, at_c)
+
+  def bwd(self, net):
+    m, P = net.m, net.m.P
+    cd = m.compute_dtype
+    emb_c, e0, a0_c, temb, at_c = net.temb_saved
+    B = emb_c.shape[0]
+    nd = net.d_dense.shape[1]
+    td = 4 * m.config.model.nf
+    dd = net.d_dense
+    # Dense_0 biases were accumulated per block (Conv_0.bias shares the column sums); weights here
+    ops.colsum(dd, 1, B, nd, P.g_region('dense_b'), accumulate=True)
+    dd_c = ops.cast(dd, cd) if cd != torch.float32 else dd
+    ops.gemm_tn(dd_c, at_c, nd, td, B, out=P.g_region('dense_w').view(nd, td), accumulate=True, split_k=1)
+    d_at = ops.gemm_nn(dd_c, P.c_region('dense_w').view(nd, td), td, out_dtype=torch.float32)
+    d_temb = ops.silu_bwd(temb, d_at)
+    ops.colsum(d_temb, 1, B, td, P.g(self.l1 + 'bias'), accumulate=True)
+    d_temb_c = ops.cast(d_temb, cd) if cd != torch.float32 else d_temb
+    ops.gemm_tn(d_temb_c, a0_c, td, td, B, out=P.g(self.l1 + 'weight'), accumulate=True, split_k=1)
+    d_a0 = ops.gemm_nn(d_temb_c, P.c(self.l1 + 'weight'), td, out_dtype=torch.float32)
+    d_e0 = ops.silu_bwd(e0, d_a0)
+    ops.colsum(d_e0, 1, B, td, P.g(self.l0 + 'bias'), accumulate=True)
+    d_e0_c = ops.cast(d_e0, cd) if cd != torch.float32 else d_e0
+    ops.gemm_tn(d_e0_c, emb_c, td, self.embed_dim, B, out=P.g(self.l0 + 'weight'), accumulate=True, split_k=1)
+
+
+# ===================================================================================== parameter access
+class _ParamAccess:
+  """Physical-layout views of parameters (compute dtype / fp32 master / fp32 gradient)."""
+
+  def __init__(self, model):
+    self.model = model
+    self._cache = {}
+
+  def reset(self):
+    self._cache.clear()
+
+  def _view(self, buf_name, name):
+    key = (buf_name, name)
+    v = self._cache.get(key)
+    if v is None:
+      v = _phys_view(getattr(self.model, buf_name), self.model.store.by_name[name])
+      self._cache[key] = v
+    return v
+
+  def c(self, name):
+    return self._view('_comp', name)
+
+  def f(self, name):
+    return self._view('_flat', name)
+
+  def g(self, name):
+    return self._view('_grad', name)
+
+  def _group(self, buf_name, names):
+    key = (buf_name, tuple(names))
+    v = self._cache.get(key)
+    if v is None:
+      es = [self.model.store.by_name[n] for n in names]
+      off, n = es[0].offset, sum(e.numel for e in es)
+      for a, b in zip(es[:-1], es[1:]):
+        assert b.offset == a.offset + a.numel, 'grouped parameters must be contiguous'
+      v = getattr(self.model, buf_name)[off:off + n]
+      if es[0].kind == 'nin':
+        v = v.view(-1, es[0].shape[0])
+      self._cache[key] = v
+    return v
+
+  def c_group(self, names):
+    return self._group('_comp', names)
+
+  def f_group(self, names):
+    return self._group('_flat', names)
+
+  def g_group(self, names):
+    return self._group('_grad', names)
+
+  def _region(self, buf_name, region):
+    off, n = self.model.store.region_span(region)
+    return getattr(self.model, buf_name)[off:off + n]
+
+  def c_region(self, region):
+    return self._region('_comp', region)
+
+  def f_region(self, region):
+    return self._region('_flat', region)
+
+  def g_region(self, region):
+    return self._region('_grad', region)
+
+
+# ===================================================================================== the network
+class _UNetFn(torch.autograd.Function):
+  """One autograd node for the whole network.  Parameter gradients are accumulated directly into the
+  model's flat gradient buffer (which `param.grad` views), so backward returns only d(input)."""
+
+  @staticmethod
+  def forward(ctx, x, time_cond, anchor, model):
+    out, net = model._execute(x, time_cond, record=True)
+    ctx.net = net
+    ctx.model = model
+    return out
+
+  @staticmethod
+  def backward(ctx, dout):
+    dx = ctx.model._backward(ctx.net, dout, need_dx=ctx.needs_input_grad[0])
+    ctx.net = None
+    return dx, None, None, None
+
+
+@utils.register_model(name='ncsnpp')
+class NCSNpp(nn.Module):
+  """NCSN++ model (same surface as reference models/ncsnpp.py:34-432)."""
+
+  def __init__(self, config, sde=None, compute_dtype=None, seed=None):
+    super().__init__()
+    self.config = config
+    self.sde = config.training.sde
+    m = config.model
+    if m.resblock_type.lower() != 'biggan':
+      raise NotImplementedError("only resblock_type='biggan' (every BASELINE config) is built")
+    if m.nonlinearity.lower() != 'swish':
+      raise NotImplementedError("only the 'swish' nonlinearity (every shipped NCSN++ config) is built")
+    if m.progressive != 'none' or m.progressive_input != 'none':
+      raise NotImplementedError('progressive growing heads are not built yet')
+    cd = compute_dtype or getattr(m, 'compute_dtype', None) or torch.bfloat16
+    self.compute_dtype = {'bf16': torch.bfloat16, 'fp32': torch.float32}.get(cd, cd) if isinstance(cd, str) else cd
+    self.nf = nf = m.nf
+    self.temb_dim = nf * 4
+    self.dropout = m.dropout
+    self.scale_by_sigma = m.scale_by_sigma
+    self.conditional = m.conditional
+    if not m.conditional:
+      raise NotImplementedError('unconditional NCSN++ is not built')
+    self.centered = config.data.centered
+    self.num_scales = m.num_scales
+    self.store = ParamStore()
+    self._dense_cols = 0
+    self._taps = None
+    self.drop_masks = None
+    self._seed_base = 0x5eed
+    self._calls = 0
+
+    ch = config.data.num_channels
+    n_res = len(m.ch_mult)
+    res = [config.data.image_size // 2 ** i for i in range(n_res)]
+    aux = m.auxiliary_resblock
+    attn_on = m.attention
+
+    # ---- build the block list in the reference's module order (models/ncsnpp.py:74-256)
+    self.temb = TimeEmbedding(self, 0)
+    i = self.temb.next_idx
+    self.conv_in = ConvBlock(self, i, ch, nf, 3, is_input=True)
+    i += 1
+    self.down = []          # list of levels; each level = list of (ResBlock, AttnBlock|None), then optional down block
+    hs_c = [nf]
+    cin = nf
+    for lvl in range(n_res):
+      blocks = []
+      for _ in range(m.num_res_blocks):
+        cout = nf * m.ch_mult[lvl]
+        rb = ResBlock(self, i, cin, cout)
+        i += 1
+        cin = cout
+        ab = None
+        if res[lvl] in m.attn_resolutions and attn_on:
+          ab = AttnBlock(self, i, cin)
+          i += 1
+        blocks.append((rb, ab))
+        hs_c.append(cin)
+      dn = None
+      if lvl != n_res - 1:
+        if not aux:
+          raise NotImplementedError('auxiliary_resblock=False is not built')
+        dn = ResBlock(self, i, cin, cin, down=True)
+        i += 1
+        hs_c.append(cin)
+      self.down.append((blocks, dn))
+    self.mid = (ResBlock(self, i, cin, cin), AttnBlock(self, i + 1, cin), ResBlock(self, i + 2, cin, cin))
+    i += 3
+    self.up = []
+    for lvl in reversed(range(n_res)):
+      blocks = []
+      for _ in range(m.num_res_blocks + 1):
+        cout = nf * m.ch_mult[lvl]
+        skip_c = hs_c.pop()
+        blocks.append((ResBlock(self, i, cin + skip_c, cout), cin, skip_c))
+        i += 1
+        cin = cout
+      ab = None
+      if res[lvl] in m.attn_resolutions and attn_on:
+        ab = AttnBlock(self, i, cin)
+        i += 1
+      upb = None
+      if lvl != 0:
+        upb = ResBlock(self, i, cin, cin, up=True)
+        i += 1
+      self.up.append((blocks, ab, upb))
+    assert not hs_c
+    self.head = NormActConv(self, i, i + 1, cin, ch, m.init_scale)
+    self.n_modules = i + 2
+
+    # ---- storage
+    self.store.layout()
+    gen = torch.Generator().manual_seed(int(seed if seed is not None else torch.initial_seed() % (2 ** 31)))
+    flat = torch.zeros(self.store.total, dtype=torch.float32)
+    for e in self.store.entries:
+      _logical_view(flat, e).copy_(e.init(e.shape, gen))
+    self._flat = flat
+    self._grad = torch.zeros_like(flat)
+    self._comp = flat
+    self.P = _ParamAccess(self)
+    self.all_modules = nn.ModuleList([_Holder() for _ in range(self.n_modules)])
+    self._params = {}
+    for e in self.store.entries:
+      p = nn.Parameter(_logical_view(self._flat, e), requires_grad=e.trainable)
+      self._params[e.name] = p
+      _attach(self, e.name, p)
+    self.register_buffer('sigmas', torch.tensor(utils.get_sigmas(config)))
+    self._fir_up = self._fir_down = None
+    self._rebind()
+
+  # ---------------------------------------------------------------- construction helpers
+  def _add_param(self, name, shape, kind='vec', region='main', trainable=True, init=None, pad=None, pack=None):
+    return self.store.add(name, shape, kind, region, trainable, init, pad, pack)
+
+  def _rebind(self):
+    """Re-point every Parameter (and its .grad) at the flat buffers after they moved."""
+    for e in self.store.entries:
+      p = self._params[e.name]
+      p.data = _logical_view(self._flat, e)
+      p.grad = _logical_view(self._grad, e) if e.trainable else None
+    if self.compute_dtype == torch.float32:
+      self._comp = self._flat
+    else:
+      self._comp = torch.empty(self._flat.shape, dtype=self.compute_dtype, device=self._flat.device)
+    taps = self.config.model.fir_kernel
+    self._fir_up = _fir_kernel(taps, 4., self._flat.device)
+    self._fir_down = _fir_kernel(taps, 1., self._flat.device)
+    self.P.reset()
+    register_owner(self)
+
+  def _apply(self, fn, recurse=True):
+    # Move the flat buffers as a whole and rebuild the views (nn.Module._apply would break the sharing).
+    new_flat = fn(self._flat)
+    if new_flat.dtype != torch.float32:
+      raise TypeError('NCSNpp master parameters are fp32; pick the compute dtype with compute_dtype=')
+    self._flat = new_flat.contiguous()
+    self._grad = fn(self._grad).contiguous()
+    for k, b in list(self._buffers.items()):
+      if b is not None:
+        self._buffers[k] = fn(b)
+    self._rebind()
+    return self
+
+  def flat_parameters(self):
+    """(flat fp32 params, flat fp32 grads, bool mask of trainable elements)."""
+    return self._flat, self._grad
+
+  def trainable_mask(self):
+    mask = torch.zeros(self.store.total, dtype=torch.uint8)
+    for e in self.store.entries:
+      if e.trainable:
+        mask[e.offset:e.offset + e.numel] = 1
+    return mask.to(self._flat.device)
+
+  def zero_grad(self, set_to_none=False):
+    self._grad.zero_()
+    for e in self.store.entries:        # restore views if someone set them to None
+      p = self._params[e.name]
+      if e.trainable and p.grad is None:
+        p.grad = _logical_view(self._grad, e)
+
+  def sync_compute_weights(self):
+    """Refresh the compute-dtype copy of the parameters (one cast kernel over the flat buffer)."""
+    if self._comp is not self._flat:
+      ops.cast(self._flat, self.compute_dtype, out=self._comp)
+
+  def _mask_for(self, idx, like):
+    if self.drop_masks is None or idx not in self.drop_masks:
+      return None
+    mk = self.drop_masks[idx]            # NCHW fp32 keep-mask already scaled by 1/(1-p)
+    return ops.nchw_to_nhwc(mk.to(like.device).float().contiguous(), like.dtype)
+
+  def _next_seed(self, idx):
+    return (self._seed_base * 1000003 + self._calls * 7919 + idx) & 0xFFFFFFFFFFFF
+
+  def seed_dropout(self, seed):
+    self._seed_base, self._calls = int(seed), 0
+
+  # ---------------------------------------------------------------- execution
+  def forward(self, x, time_cond):
+    if not x.is_cuda:
+      raise RuntimeError('NCSNpp (B200 build) runs on CUDA tensors only; there is no CPU fallback')
+    x = x.float().contiguous()
+    time_cond = time_cond.float().contiguous()
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self._params.values())):
+      return _UNetFn.apply(x, time_cond, self._params[self.head.conv.pre + 'weight'], self)
+    out, _ = self._execute(x, time_cond, record=False)
+    return out
+
+  def _execute(self, x, time_cond, record):
+    m = self.config.model
+    self._calls += 1
+    self.sync_compute_weights()
+    tape = Tape(record)
+    net = NetCtx(self, self.training, tape)
+    self.temb.fwd(net, time_cond)
+    if m.embedding_type.lower() == 'fourier':
+      used_sigmas = time_cond
+    else:
+      used_sigmas = self.sigmas[time_cond.long()].float()
+    # data in [0,1] is re-centred to [-1,1] here when the loader has not done it (ncsnpp.py:303-305)
+    h_in = Act(ops.nchw_to_nhwc(x, self.compute_dtype, CPAD, *((1., 0.) if self.centered else (2., -1.))), tape)
+    net.x_id = h_in.id
+    h = self.conv_in.fwd(net, h_in)
+    hs = [h]
+    for blocks, dn in self.down:
+      for rb, ab in blocks:
+        h = rb.fwd(net, hs[-1])
+        if ab is not None:
+          h = ab.fwd(net, h)
+        hs.append(h)
+      if dn is not None:
+        hs.append(dn.fwd(net, hs[-1]))
+    h = hs[-1]
+    h = self.mid[0].fwd(net, h)
+    h = self.mid[1].fwd(net, h)
+    h = self.mid[2].fwd(net, h)
+    for blocks, ab, upb in self.up:
+      for rb, _, _ in blocks:
+        h = rb.fwd(net, h, hs.pop())
+      if ab is not None:
+        h = ab.fwd(net, h)
+      if upb is not None:
+        h = upb.fwd(net, h)
+    assert not hs
+    h = self.head.fwd(net, h)
+    net.out_id = h.id
+    net.out_scale = (1. / used_sigmas).contiguous() if m.scale_by_sigma else None
+    out = ops.nhwc_to_nchw(h.t, x.shape[1], net.out_scale)
+    return out, net
+
+  def _backward(self, net, dout, need_dx=False):
+    dout = dout.float().contiguous()
+    if net.out_scale is not None:
+      dout = dout * net.out_scale[:, None, None, None]
+    net.need_dx = need_dx
+    grads = {net.out_id: ops.nchw_to_nhwc(dout, self.compute_dtype, CPAD)}
+    for bwd, in_ids, out_id in reversed(net.tape.ops):
+      g = grads.pop(out_id, None)
+      if g is None:
+        continue
+      res = bwd(g, tuple(grads.get(i) for i in in_ids))
+      for i, r in zip(in_ids, res):
+        if r is not None:
+          grads[i] = r
+    self.temb.bwd(net)
+    net.tape.ops = []
+    if need_dx:
+      dx = ops.nhwc_to_nchw(grads[net.x_id], dout.shape[1])
+      return dx if self.centered else dx * 2.
+    return None

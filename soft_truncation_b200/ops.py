@@ -1,0 +1,297 @@
+"""Tensor-level wrappers over the C ABI (no autograd here; the blocks in models/ncsnpp.py write
+their own backward).  Activations are NHWC torch tensors (B, H, W, C), fp32 or bf16, contiguous.
+Every wrapper enqueues on torch's current CUDA stream and never synchronises.
+"""
+import ctypes
+
+import torch
+
+from ._lib import GemmArgs, check, lib
+
+F32, BF16 = 0, 1
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+OP_STRIDED, OP_GATHER, OP_DGRADW = 0, 1, 2
+BACKEND = {'auto': 0, 'simt': 1, 'tcgen05': 2}
+
+# default backend for st_gemm; tests flip this to pin a path
+gemm_backend = 'auto'
+
+
+def dt(t):
+  return _DT[t.dtype]
+
+
+def ptr(t):
+  if t is None:
+    return None
+  assert t.is_cuda, 'libst_b200 works on CUDA tensors only'
+  return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+  return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def tc_available():
+  return bool(lib.st_tc_available())
+
+
+# ------------------------------------------------------------------------------------ GEMM
+def _gemm(**kw):
+  a = GemmArgs()
+  a.backend = BACKEND[gemm_backend]
+  a.alpha = 1.0
+  a.batch = 1
+  a.split_k = 1
+  keep = []
+  for k, v in kw.items():
+    if isinstance(v, torch.Tensor):
+      keep.append(v)
+      v = v.data_ptr()
+    setattr(a, k, v)
+  check(lib.st_gemm(ctypes.byref(a), stream()))
+
+
+def _split_k(M, N, K):
+  """Split the reduction so that a weight-gradient GEMM (few output tiles, huge K) fills the GPU."""
+  tiles = ((M + 127) // 128) * ((N + 127) // 128)
+  want = max(1, (148 * 2) // max(tiles, 1))
+  return int(max(1, min(want, K // 2048 if K >= 4096 else 1, 64)))
+
+
+def conv_fwd(x, w, cout, kh=3, kw=3, x2=None, bias=None, rowbias=None, rowbias_ld=0, residual=None, alpha=1.0,
+             out_dtype=None, out=None):
+  """'same' convolution of NHWC x (optionally channel-concatenated with x2) with packed weights
+  w[cout][kh*kw][cin] (contiguous, same dtype as x).  rowbias: fp32 [B][rowbias_ld] slice added per image."""
+  B, H, W, C1 = x.shape
+  C2 = 0 if x2 is None else x2.shape[3]
+  K = kh * kw * (C1 + C2)
+  od = out_dtype or x.dtype
+  if out is None:
+    out = torch.empty((B, H, W, cout), dtype=od, device=x.device)
+  _gemm(a_mode=OP_GATHER, b_mode=OP_STRIDED, in_dtype=dt(x), out_dtype=_DT[od], M=B * H * W, N=cout, K=K,
+        A=x, A2=x2, B=w, C=out, sBn=K, sBk=1, sCm=cout, n_img=B, H=H, W=W, C1=C1, C2=C2, kh=kh, kw=kw,
+        bias=bias, rowbias=rowbias, rows_per_rb=H * W, ld_rb=rowbias_ld, residual=residual, sRm=cout,
+        alpha=alpha)
+  return out
+
+
+def conv_dgrad(dy, w, cin, kh=3, kw=3, alpha=1.0, out=None):
+  """Data gradient of conv_fwd: dy (B,H,W,cout) x w[cout][taps][cin] -> (B,H,W,cin)."""
+  B, H, W, Co = dy.shape
+  if out is None:
+    out = torch.empty((B, H, W, cin), dtype=dy.dtype, device=dy.device)
+  _gemm(a_mode=OP_GATHER, b_mode=OP_DGRADW, in_dtype=dt(dy), out_dtype=dt(out), M=B * H * W, N=cin,
+        K=kh * kw * Co, A=dy, B=w, C=out, sCm=cin, n_img=B, H=H, W=W, C1=Co, C2=0, kh=kh, kw=kw, alpha=alpha)
+  return out
+
+
+def conv_wgrad(dy, x, dw, kh=3, kw=3, x2=None, alpha=1.0):
+  """dw[cout][taps][cin] (fp32, contiguous view into the flat gradient buffer) += alpha * dy^T * im2col(x)."""
+  B, H, W, Co = dy.shape
+  C1 = x.shape[3]
+  C2 = 0 if x2 is None else x2.shape[3]
+  N = kh * kw * (C1 + C2)
+  K = B * H * W
+  _gemm(a_mode=OP_STRIDED, b_mode=OP_GATHER, in_dtype=dt(dy), out_dtype=F32, M=Co, N=N, K=K, A=dy, B=x, B2=x2,
+        C=dw, sAm=1, sAk=Co, sCm=N, n_img=B, H=H, W=W, C1=C1, C2=C2, kh=kh, kw=kw, accumulate=1,
+        split_k=_split_k(Co, N, K), alpha=alpha)
+
+
+def gemm_nt(a, b, out=None, out_dtype=None, bias=None, residual=None, alpha=1.0, lda=None, ldb=None, ldc=None,
+            M=None, N=None, K=None, batch=1, sAb=0, sBb=0, sCb=0, sRb=0, ldr=None):
+  """C[m][n] = alpha*(sum_k a[m][k] b[n][k] + bias[n] + residual[m][n]); a, b row-major with leading
+  dimensions lda/ldb (K contiguous)."""
+  M = M if M is not None else a.shape[-2]
+  K = K if K is not None else a.shape[-1]
+  N = N if N is not None else b.shape[-2]
+  od = out_dtype or a.dtype
+  if out is None:
+    out = torch.empty((M, N) if batch == 1 else (batch, M, N), dtype=od, device=a.device)
+  ldc = ldc or N
+  _gemm(a_mode=OP_STRIDED, b_mode=OP_STRIDED, in_dtype=dt(a), out_dtype=dt(out), M=M, N=N, K=K, batch=batch, A=a,
+        B=b, C=out, sAm=lda or K, sAk=1, sAb=sAb, sBn=ldb or K, sBk=1, sBb=sBb, sCm=ldc, sCb=sCb, bias=bias,
+        residual=residual, sRm=ldr or ldc, sRb=sRb, alpha=alpha)
+  return out
+
+
+def gemm_nn(a, b, N, out=None, out_dtype=None, alpha=1.0, lda=None, ldb=None, ldc=None, M=None, K=None, batch=1,
+            sAb=0, sBb=0, sCb=0):
+  """C[m][n] = alpha * sum_k a[m][k] b[k][n]; b row-major [K][ldb] (N contiguous)."""
+  M = M if M is not None else a.shape[-2]
+  K = K if K is not None else a.shape[-1]
+  od = out_dtype or a.dtype
+  if out is None:
+    out = torch.empty((M, N) if batch == 1 else (batch, M, N), dtype=od, device=a.device)
+  _gemm(a_mode=OP_STRIDED, b_mode=OP_STRIDED, in_dtype=dt(a), out_dtype=dt(out), M=M, N=N, K=K, batch=batch, A=a,
+        B=b, C=out, sAm=lda or K, sAk=1, sAb=sAb, sBn=1, sBk=ldb or N, sBb=sBb, sCm=ldc or N, sCb=sCb, alpha=alpha)
+  return out
+
+
+def gemm_tn(a, b, M, N, K, out=None, out_dtype=None, alpha=1.0, lda=None, ldb=None, ldc=None, batch=1, sAb=0,
+            sBb=0, sCb=0, accumulate=False, split_k=None):
+  """C[m][n] (+)= alpha * sum_k a[k][m] b[k][n]; a row-major [K][lda], b row-major [K][ldb]."""
+  od = out_dtype or a.dtype
+  if out is None:
+    out = torch.empty((M, N) if batch == 1 else (batch, M, N), dtype=od, device=a.device)
+  if split_k is None:
+    split_k = _split_k(M, N, K) if accumulate else 1
+  _gemm(a_mode=OP_STRIDED, b_mode=OP_STRIDED, in_dtype=dt(a), out_dtype=dt(out), M=M, N=N, K=K, batch=batch, A=a,
+        B=b, C=out, sAm=1, sAk=lda or M, sAb=sAb, sBn=1, sBk=ldb or N, sBb=sBb, sCm=ldc or N, sCb=sCb,
+        accumulate=int(accumulate), split_k=split_k, alpha=alpha)
+  return out
+
+
+# ------------------------------------------------------------------------------------ GroupNorm
+def _gn_splits(n_img, hw):
+  s = max(1, min((148 * 4 + n_img - 1) // n_img, hw // 64, 64))
+  return int(s)
+
+
+def gn_stats(x, x2, G, eps=1e-6):
+  B, H, W, C1 = x.shape
+  C2 = 0 if x2 is None else x2.shape[3]
+  hw = H * W
+  splits = _gn_splits(B, hw)
+  part = torch.empty((B, splits, G, 2), dtype=torch.float32, device=x.device)
+  stats = torch.empty((2, B, G), dtype=torch.float32, device=x.device)
+  check(lib.st_gn_stats(ptr(x), ptr(x2), dt(x), B, hw, C1, C2, G, splits, ptr(part), stream()))
+  check(lib.st_gn_finalize(ptr(part), B, splits, G, hw * ((C1 + C2) // G), eps, ptr(stats[0]), ptr(stats[1]), stream()))
+  return stats
+
+
+def gn_apply(x, x2, G, gamma, beta, stats, act, p_drop=0., seed=0, mask=None):
+  B, H, W, C1 = x.shape
+  C2 = 0 if x2 is None else x2.shape[3]
+  y = torch.empty((B, H, W, C1 + C2), dtype=x.dtype, device=x.device)
+  check(lib.st_gn_apply(ptr(x), ptr(x2), dt(x), B, H * W, C1, C2, G, ptr(gamma), ptr(beta), ptr(stats[0]),
+                        ptr(stats[1]), int(act), float(p_drop), int(seed), ptr(mask), ptr(y), stream()))
+  return y
+
+
+def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0., seed=0, mask=None, extra=None,
+                extra_scale=1.0, dx1=None, accum1=False, dx2=None, accum2=False):
+  """Returns (dx1, dx2); accumulates dgamma/dbeta (fp32 views into the flat gradient buffer)."""
+  B, H, W, C1 = x.shape
+  C2 = 0 if x2 is None else x2.shape[3]
+  hw, Ct = H * W, C1 + C2
+  splits = _gn_splits(B, hw)
+  red = torch.empty((B, splits, Ct, 2), dtype=torch.float32, device=x.device)
+  common = (ptr(x), ptr(x2), ptr(dy), dt(x), B, hw, C1, C2, G, ptr(gamma), ptr(beta), ptr(stats[0]), ptr(stats[1]),
+            int(act), float(p_drop), int(seed), ptr(mask), splits, ptr(red))
+  check(lib.st_gn_bwd_reduce(*common, stream()))
+  check(lib.st_gn_bwd_params(ptr(red), B * splits, Ct, ptr(dgamma), ptr(dbeta), stream()))
+  if dx1 is None:
+    dx1 = torch.empty_like(x)
+    accum1 = False
+  if x2 is not None and dx2 is None:
+    dx2 = torch.empty_like(x2)
+    accum2 = False
+  check(lib.st_gn_bwd_apply(*common, ptr(extra), float(extra_scale), ptr(dx1), int(accum1), ptr(dx2), int(accum2),
+                            stream()))
+  return dx1, dx2
+
+
+# ------------------------------------------------------------------------------------ elementwise
+def cast(src, dtype, out=None):
+  if out is None:
+    out = torch.empty(src.shape, dtype=dtype, device=src.device)
+  check(lib.st_cast(ptr(src), dt(src), ptr(out), dt(out), src.numel(), stream()))
+  return out
+
+
+def axpby(a, b=None, alpha=1.0, beta=1.0, out=None):
+  if out is None:
+    out = torch.empty_like(a)
+  check(lib.st_axpby(ptr(a), ptr(b), ptr(out), dt(a), float(alpha), float(beta), a.numel(), stream()))
+  return out
+
+
+def silu(x):
+  y = torch.empty_like(x)
+  check(lib.st_silu(ptr(x), ptr(y), dt(x), x.numel(), stream()))
+  return y
+
+
+def silu_bwd(x, dy):
+  dx = torch.empty_like(x)
+  check(lib.st_silu_bwd(ptr(x), ptr(dy), ptr(dx), dt(x), x.numel(), stream()))
+  return dx
+
+
+def resample2x(x, x2, direction, scale):
+  """direction=+1: nearest replicate x2 (times scale); -1: 2x2 box sum (times scale)."""
+  B, H, W, C1 = x.shape
+  C2 = 0 if x2 is None else x2.shape[3]
+  oh, ow = (2 * H, 2 * W) if direction > 0 else (H // 2, W // 2)
+  y = torch.empty((B, oh, ow, C1 + C2), dtype=x.dtype, device=x.device)
+  check(lib.st_resample2x(ptr(x), ptr(x2), ptr(y), dt(x), B, H, W, C1, C2, int(direction), float(scale), stream()))
+  return y
+
+
+def colsum(x, groups, rows_per_group, C, out, scale=1.0, accumulate=False):
+  check(lib.st_colsum(ptr(x), dt(x), groups, rows_per_group, C, float(scale), ptr(out), int(accumulate), stream()))
+  return out
+
+
+def softmax_fwd(logits, L, scale, dtype):
+  rows = logits.numel() // L
+  p = torch.empty(logits.shape, dtype=dtype, device=logits.device)
+  check(lib.st_softmax_fwd(ptr(logits), ptr(p), dt(p), rows, L, float(scale), stream()))
+  return p
+
+
+def softmax_bwd(p, dp, L, scale):
+  rows = p.numel() // L
+  ds = torch.empty_like(p)
+  check(lib.st_softmax_bwd(ptr(p), ptr(dp), ptr(ds), dt(p), rows, L, float(scale), stream()))
+  return ds
+
+
+def timestep_embedding(labels, dim, max_positions=10000.):
+  out = torch.empty((labels.shape[0], dim), dtype=torch.float32, device=labels.device)
+  check(lib.st_timestep_embedding(ptr(labels), ptr(out), labels.shape[0], dim, float(max_positions), stream()))
+  return out
+
+
+def fourier_embedding(sigma, W):
+  out = torch.empty((sigma.shape[0], 2 * W.numel()), dtype=torch.float32, device=sigma.device)
+  check(lib.st_fourier_embedding(ptr(sigma), ptr(W), ptr(out), sigma.shape[0], W.numel(), stream()))
+  return out
+
+
+def nchw_to_nhwc(x, dtype, cpad=None, alpha=1.0, beta=0.0):
+  """NCHW fp32 -> NHWC `dtype` with the channel axis zero-padded to `cpad`; y = alpha*x + beta."""
+  B, C, H, W = x.shape
+  cpad = cpad or C
+  y = torch.empty((B, H, W, cpad), dtype=dtype, device=x.device)
+  check(lib.st_nchw_to_nhwc(ptr(x), ptr(y), dt(y), B, C, H, W, cpad, float(alpha), float(beta), stream()))
+  return y
+
+
+def nhwc_to_nchw(x, C=None, row_scale=None):
+  """First C channels of NHWC x -> NCHW fp32 (optionally times row_scale[n])."""
+  B, H, W, cpad = x.shape
+  C = C or cpad
+  y = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+  check(lib.st_nhwc_to_nchw(ptr(x), dt(x), ptr(y), B, C, H, W, cpad, ptr(row_scale), stream()))
+  return y
+
+
+def im2col_small(x, kh, kw, kpad):
+  B, H, W, C = x.shape
+  out = torch.empty((B * H * W, kpad), dtype=torch.bfloat16, device=x.device)
+  check(lib.st_im2col_small(ptr(x), dt(x), ptr(out), B, H, W, C, kh, kw, kpad, stream()))
+  return out
+
+
+def upfirdn2d_nhwc(x, k, up=1, down=1, pad=(0, 0)):
+  """x (major, H, W, minor) -> FIR-resampled tensor; k fp32 (kh, kw) on the device."""
+  mj, H, W, mn = x.shape
+  kh, kw = k.shape
+  oh = (H * up + pad[0] + pad[1] - kh + down) // down
+  ow = (W * up + pad[0] + pad[1] - kw + down) // down
+  y = torch.empty((mj, oh, ow, mn), dtype=x.dtype, device=x.device)
+  check(lib.st_upfirdn2d(ptr(x), ptr(y), dt(x), ptr(k), mj, H, W, mn, kh, kw, up, up, down, down, pad[0], pad[1],
+                         pad[0], pad[1], stream()))
+  return y

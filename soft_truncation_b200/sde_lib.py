@@ -182,11 +182,14 @@ class VPSDE(_LinearBeta, SDE):
                                    torch.log(1. + torch.exp(Z * u + self.antiderivative(t_min))))) / db
     return t, Z.detach()
 
-  def get_diffusion_time(self, config, batch_size, batch_device, t_min, importance_sampling=True):
-    u = torch.rand(batch_size, device=batch_device)
+  def time_from_uniform(self, u, t_min, importance_sampling=True):
+    """Diffusion times for given uniforms `u` (the deterministic part of get_diffusion_time)."""
     if importance_sampling:
       return self.importance_time_from_uniform(u, t_min)
     return u * (self.T - t_min) + t_min, 1
+
+  def get_diffusion_time(self, config, batch_size, batch_device, t_min, importance_sampling=True):
+    return self.time_from_uniform(torch.rand(batch_size, device=batch_device), t_min, importance_sampling)
 
   def get_t_min(self, config):
     if config.training.st:
@@ -274,7 +277,9 @@ class VESDE(SDE):
   def get_diffusion_time(self, config, batch_size, batch_device, t_min, importance_sampling=None):
     if importance_sampling is None:
       importance_sampling = config.training.importance_sampling
-    u = torch.rand(batch_size, device=batch_device)
+    return self.time_from_uniform(torch.rand(batch_size, device=batch_device), t_min, importance_sampling)
+
+  def time_from_uniform(self, u, t_min, importance_sampling=False):
     if importance_sampling:
       Z = self.normalizing_constant(t_min)
       return t_min + ((Z * u) / (2. * (np.log(self.sigma_max) - np.log(self.sigma_min)))), Z.detach()
@@ -350,7 +355,10 @@ class reciprocal_VESDE(SDE):
             + (sigmas < 0.01) * (-self.c_1_ / (sigmas + 1e-4) + self.c_2__))
 
   def get_diffusion_time(self, config, batch_size, batch_device, t_min, importance_sampling=False):
-    inv_t = torch.rand(batch_size, device=batch_device) * (1. / t_min - 1. / self.T) + 1. / self.T
+    return self.time_from_uniform(torch.rand(batch_size, device=batch_device), t_min)
+
+  def time_from_uniform(self, u, t_min, importance_sampling=False):
+    inv_t = u * (1. / t_min - 1. / self.T) + 1. / self.T
     return 1. / inv_t, 1
 
   def get_t_min(self, config, st=False):
