@@ -92,6 +92,11 @@ def _load():
 lib = _load()
 
 
+launches = 0   # C-ABI calls issued so far (each enqueues at least one of our kernels); bench.py reads it
+
+
 def check(status):
+  global launches
+  launches += 1
   if status != 0:
     raise StError(lib.st_last_error().decode() or f'libst_b200 error {status}')

@@ -1,5 +1,567 @@
-// placeholder until the tcgen05 backend lands
+// tcgen05 + TMA implicit-GEMM backend of st_gemm (bf16 operands, fp32 accumulation in TMEM).
+//
+// One CTA computes a 128 x BN output tile.  Warp roles (192 threads):
+//   warp 0    TMA producer: one elected thread walks the K blocks (64 bf16 = one 128-byte swizzle row),
+//             issuing cp.async.bulk.tensor loads into a STAGES-deep shared-memory ring (mbarrier full/empty).
+//   warp 1    TMEM allocator + MMA issuer: one thread issues 4 x tcgen05.mma (K=16 each) per K block,
+//             tcgen05.commit releases the smem slot / signals the epilogue.
+//   warps 2-5 epilogue: tcgen05.ld 32 columns at a time, bias / per-image bias / residual / scale, store
+//             (or fp32 red.add for split-K weight gradients).
+//
+// Operand addressing is entirely in the TMA descriptors (built on the host per call):
+//   * K-major strided          2-D/3-D map, box 64(k) x rows
+//   * MN-major strided         box 64(m|n) x 64(k); UMMA descriptors flagged MN-major
+//   * implicit im2col (conv)   4-D map over NHWC (C, W, H, N); a 3x3 tap is a box shifted by (dx, dy) whose
+//                              out-of-bounds elements TMA zero-fills -> no im2col buffer, no halo code.
+//                              The channel axis may be the concatenation of two tensors (two maps).
+//   * conv weights for dgrad   3-D map (Ci, taps, Co), MN-major, taps walked in reverse.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <string.h>
+
+#include <mutex>
+
 #include "common.cuh"
-extern "C" __attribute__((visibility("default"))) int st_tc_available(void) { return 0; }
-int st_gemm_tc_supported(const st_gemm_args*, const char** why) { *why = "not built"; return 0; }
-int st_gemm_tc(const st_gemm_args*, cudaStream_t) { st_set_error("tcgen05 backend not built"); return ST_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // bf16 elements per K block = 128 bytes
+constexpr int A_STAGE_BYTES = BM * 128;
+constexpr int NUM_THREADS = 192;
+
+enum OpKind { KMAJOR = 0, MNMAJOR = 1, GATHER_K = 2, GATHER_MN = 3, DGRADW = 4 };
+
+struct TcParams {
+  int M, N, batch, split_k;
+  int nk;                 // K blocks in total
+  int a_kind, b_kind;
+  // gather geometry
+  int H, W, kh, kw, cblocks, c1blocks, ntaps;
+  int Ct, C1;
+  // epilogue
+  void* C;
+  long long ldc, sCb;
+  int out_bf16, accumulate;
+  const float* bias;
+  const float* rowbias;
+  int rows_per_rb;
+  long long ld_rb;
+  const bf16* residual;
+  long long ldr, sRb;
+  float alpha;
+};
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint64_t globaltimer() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a protocol bug must trap (-> launch error on the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  uint64_t t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((it & 1023u) == 1023u) {
+      uint64_t now = globaltimer();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();     // 4 s
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
+//   K-major : rows of 128 bytes, 8-row groups SBO = 1024 bytes apart; LBO unused (1).
+//   MN-major: 64-element (128-byte) runs along M/N, k rows 128 bytes apart, 8-k groups SBO = 1024 bytes apart,
+//             successive 64-wide M/N chunks LBO bytes apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;          // SWIZZLE_128B
+  return d;
+}
+
+// ------------------------------------------------------------------------------------ kernel
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0,
+                                                              const __grid_constant__ CUtensorMap mapA1,
+                                                              const __grid_constant__ CUtensorMap mapB0,
+                                                              const __grid_constant__ CUtensorMap mapB1,
+                                                              const TcParams p) {
+  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: stages | barriers | tmem ptr  (the dynamic smem base is re-aligned to 1024 for SWIZZLE_128B)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int split = p.split_k > 1 ? p.split_k : 1;
+  const int b = blockIdx.z / split, ks = blockIdx.z % split;
+  const int kper = (p.nk + split - 1) / split;
+  const int kt0 = ks * kper;
+  const int kt1 = min(p.nk, kt0 + kper);
+  const int nkt = kt1 - kt0;            // may be <= 0 for a trailing split: nothing to add
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkt > 0) {
+    if (warp == 0) {
+      // ===================================================== TMA producer
+      if (lane == 0) {
+        // tile-constant gather coordinates
+        int gx0 = 0, gy0 = 0, gn0 = 0;
+        if (p.a_kind == GATHER_K) {
+          gx0 = m0 % p.W;
+          gy0 = (m0 / p.W) % p.H;
+          gn0 = m0 / (p.W * p.H);
+        }
+        for (int i = 0; i < nkt; ++i) {
+          const int kt = kt0 + i;
+          const int s = i % STAGES;
+          if (i >= STAGES) mbar_wait(empty0 + 8 * s, ((i / STAGES) - 1) & 1);
+          const uint32_t bar = full0 + 8 * s;
+          mbar_expect_tx(bar, STAGE_BYTES);
+          const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+          // ---- A
+          if (p.a_kind == KMAJOR) {
+            tma_load_3d(sa, &mapA0, bar, kt * BK, m0, b);
+          } else if (p.a_kind == MNMAJOR) {
+            tma_load_3d(sa, &mapA0, bar, m0, kt * BK, b);
+            tma_load_3d(sa + 8192, &mapA0, bar, m0 + 64, kt * BK, b);
+          } else {   // GATHER_K
+            const int tap = kt / p.cblocks, cb = kt % p.cblocks;
+            const int dy = tap / p.kw - (p.kh - 1) / 2, dx = tap % p.kw - (p.kw - 1) / 2;
+            if (cb < p.c1blocks) tma_load_4d(sa, &mapA0, bar, cb * 64, gx0 + dx, gy0 + dy, gn0);
+            else tma_load_4d(sa, &mapA1, bar, (cb - p.c1blocks) * 64, gx0 + dx, gy0 + dy, gn0);
+          }
+          // ---- B
+          if (p.b_kind == KMAJOR) {
+            tma_load_3d(sb, &mapB0, bar, kt * BK, n0, b);
+          } else if (p.b_kind == MNMAJOR) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * 8192, &mapB0, bar, n0 + 64 * j, kt * BK, b);
+          } else if (p.b_kind == DGRADW) {
+            const int tap = kt / p.cblocks, cob = kt % p.cblocks;
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_3d(sb + j * 8192, &mapB0, bar, n0 + 64 * j, p.ntaps - 1 - tap, cob * 64);
+          } else {   // GATHER_MN: k = pixel block, n = (tap, channel)
+            const int p0 = kt * BK;
+            const int x0 = p0 % p.W, y0 = (p0 / p.W) % p.H, i0 = p0 / (p.W * p.H);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) {
+              const int nn = n0 + 64 * j;
+              const int tap = nn / p.Ct, c = nn % p.Ct;
+              const int dy = tap / p.kw - (p.kh - 1) / 2, dx = tap % p.kw - (p.kw - 1) / 2;
+              if (tap >= p.ntaps) {
+                // past the last tap (N not a multiple of BN): any in-range box will do, the columns are masked;
+                // load tap 0 so that the expected byte count still arrives
+                tma_load_4d(sb + j * 8192, &mapB0, bar, 0, x0, y0, i0);
+              } else if (c < p.C1) {
+                tma_load_4d(sb + j * 8192, &mapB0, bar, c, x0 + dx, y0 + dy, i0);
+              } else {
+                tma_load_4d(sb + j * 8192, &mapB1, bar, c - p.C1, x0 + dx, y0 + dy, i0);
+              }
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================================================== MMA issuer
+      if (lane == 0) {
+        const bool a_mn = (p.a_kind == MNMAJOR);
+        const bool b_mn = (p.b_kind != KMAJOR);
+        // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int i = 0; i < nkt; ++i) {
+          const int s = i % STAGES;
+          mbar_wait(full0 + 8 * s, (i / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j) {
+            const uint64_t ad = a_mn ? make_desc(sa + j * 2048, 8192, 1024) : make_desc(sa + j * 32, 16, 1024);
+            const uint64_t bd = b_mn ? make_desc(sb + j * 2048, 8192, 1024) : make_desc(sb + j * 32, 16, 1024);
+            umma_f16(tmem_base, ad, bd, idesc, (i | j) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * s);      // frees the smem slot once these MMAs have read it
+        }
+        umma_commit(tfull);                 // accumulator complete
+      }
+    } else {
+      // ===================================================== epilogue (warps 2..5)
+      const int q = warp % 4;               // TMEM lane quarter this warp may access
+      const int row = q * 32 + lane;
+      const long long m = (long long)m0 + row;
+      mbar_wait(tfull, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const bool row_ok = m < p.M;
+      const float* rb = (p.rowbias && row_ok) ? p.rowbias + (m / p.rows_per_rb) * p.ld_rb : nullptr;
+      const bf16* res = (p.residual && row_ok) ? p.residual + (long long)b * p.sRb + m * p.ldr : nullptr;
+      const long long crow = (long long)b * p.sCb + m * p.ldc;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        __syncwarp();                       // tcgen05.ld is warp-collective: reconverge after the masked `continue`s
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+        const int nb = n0 + c * 32;
+        if (!row_ok || nb >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        const bool full = (nb + 32 <= p.N);
+        if (p.accumulate) {
+          float* dst = reinterpret_cast<float*>(p.C) + crow + nb;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (full || nb + i < p.N) atomicAdd(dst + i, p.alpha * v[i]);
+          continue;
+        }
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (full || nb + i < p.N) v[i] += __ldg(p.bias + nb + i);
+        }
+        if (rb) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (full || nb + i < p.N) v[i] += __ldg(rb + nb + i);
+        }
+        if (res) {
+          if (full && ((p.ldr | p.sRb) % 8 == 0)) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 t = *reinterpret_cast<const uint4*>(res + nb + g * 8);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[g * 8 + 2 * e] += __low2float(h[e]);
+                v[g * 8 + 2 * e + 1] += __high2float(h[e]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < p.N) v[i] += __bfloat162float(res[nb + i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+        if (p.out_bf16) {
+          bf16* dst = reinterpret_cast<bf16*>(p.C) + crow + nb;
+          if (full && ((p.ldc | p.sCb) % 8 == 0)) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 t;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(dst + g * 8) = t;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < p.N) dst[i] = __float2bfloat16_rn(v[i]);
+          }
+        } else {
+          float* dst = reinterpret_cast<float*>(p.C) + crow + nb;
+          if (full && ((p.ldc | p.sCb) % 4 == 0)) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<float4*>(dst + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < p.N) dst[i] = v[i];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+int g_tc_state = -1;     // -1 unknown, 0 unavailable, 1 ok
+std::mutex g_mu;
+
+void tc_init() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_tc_state >= 0) return;
+  g_tc_state = 0;
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10) return;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess)
+    return;
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  g_tc_state = 1;
+}
+
+// bf16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/strides innermost first; strides[i] is the byte stride of dim i+1.
+bool encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box) {
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    st_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u", (int)r, rank,
+                 (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                 (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                 rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return false;
+  }
+  return true;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// pixel box (bw, bh, bn) covering `npix` consecutive pixels of an NHWC tensor
+bool pixel_box(int npix, int H, int W, uint32_t* bw, uint32_t* bh, uint32_t* bn) {
+  if (!pow2(H) || !pow2(W)) return false;
+  int w = W < npix ? W : npix;
+  int h = (npix / w) < H ? (npix / w) : H;
+  int n = npix / (w * h);
+  if (w * h * n != npix || n > 256) return false;
+  *bw = w; *bh = h; *bn = n;
+  return true;
+}
+
+int choose_bn(const st_gemm_args* a) {
+  if (a->N <= 64) return 64;
+  return 128;
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap* maps, const TcParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * 128) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { st_set_error("st_gemm(tc): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ST_ERR_CUDA; }
+    configured = true;
+  }
+  gemm_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+  ST_CHECK_LAUNCH("st_gemm(tcgen05)");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int st_tc_available(void) {
+  tc_init();
+  return g_tc_state == 1;
+}
+
+// Why (or whether) the tcgen05 backend can run this problem.
+int st_gemm_tc_supported(const st_gemm_args* a, const char** why) {
+#define NO(msg) do { *why = msg; return 0; } while (0)
+  if (!st_tc_available()) NO("no sm_100 device / cuTensorMapEncodeTiled");
+  if (a->in_dtype != ST_BF16) NO("operands must be bf16");
+  if (!aligned16(a->A) || !aligned16(a->B) || (a->A2 && !aligned16(a->A2)) || (a->B2 && !aligned16(a->B2))) NO("operand not 16-byte aligned");
+  const int Ct = a->C1 + a->C2;
+  if (a->a_mode == ST_OP_GATHER) {
+    if (a->C1 % 64 || a->C2 % 64) NO("gather channels must be multiples of 64");
+    uint32_t bw, bh, bn;
+    if (!pixel_box(128, a->H, a->W, &bw, &bh, &bn)) NO("H/W must be powers of two");
+    if (a->b_mode == ST_OP_STRIDED && (a->sBk != 1 || a->sBn % 8)) NO("conv weights must be K-major with ld % 8 == 0");
+    if (a->b_mode == ST_OP_DGRADW && (a->N % 8)) NO("dgrad Cin must be a multiple of 8");
+  } else {
+    if (a->sAk == 1) { if (a->sAm % 8 || a->sAb % 8) NO("A leading dimension must be a multiple of 8"); }
+    else if (a->sAm == 1) { if (a->sAk % 8 || a->sAb % 8) NO("A leading dimension must be a multiple of 8"); }
+    else NO("A must be contiguous along m or k");
+  }
+  if (a->b_mode == ST_OP_GATHER) {
+    if (a->C1 % 64 || a->C2 % 64) NO("gather channels must be multiples of 64");
+    uint32_t bw, bh, bn;
+    if (!pixel_box(64, a->H, a->W, &bw, &bh, &bn)) NO("H/W must be powers of two");
+    if (a->sAm != 1) NO("wgrad A must be MN-major");
+  } else if (a->b_mode == ST_OP_STRIDED) {
+    if (a->sBk == 1) { if (a->sBn % 8 || a->sBb % 8) NO("B leading dimension must be a multiple of 8"); }
+    else if (a->sBn == 1) { if (a->sBk % 8 || a->sBb % 8) NO("B leading dimension must be a multiple of 8"); }
+    else NO("B must be contiguous along n or k");
+  }
+  (void)Ct;
+  return 1;
+#undef NO
+}
+
+int st_gemm_tc(const st_gemm_args* a, cudaStream_t stream) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap maps[4];
+  memset(maps, 0, sizeof(maps));
+  const int BN = choose_bn(a);
+  const int Ct = a->C1 + a->C2;
+  p.M = a->M; p.N = a->N; p.batch = a->batch; p.split_k = a->split_k > 1 ? a->split_k : 1;
+  p.H = a->H; p.W = a->W; p.kh = a->kh; p.kw = a->kw; p.ntaps = a->kh * a->kw; p.Ct = Ct; p.C1 = a->C1;
+  p.nk = (a->K + BK - 1) / BK;
+
+  // ---------------- A
+  if (a->a_mode == ST_OP_GATHER) {
+    p.a_kind = GATHER_K;
+    p.cblocks = Ct / 64;
+    p.c1blocks = a->C1 / 64;
+    uint32_t bw, bh, bn;
+    pixel_box(128, a->H, a->W, &bw, &bh, &bn);
+    const uint32_t box[4] = {64, bw, bh, bn};
+    {
+      const uint64_t dims[4] = {(uint64_t)a->C1, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+      const uint64_t str[3] = {(uint64_t)a->C1 * 2, (uint64_t)a->W * a->C1 * 2, (uint64_t)a->H * a->W * a->C1 * 2};
+      if (!encode_map(&maps[0], a->A, 4, dims, str, box)) return ST_ERR_CUDA;
+    }
+    if (a->C2 > 0) {
+      const uint64_t dims[4] = {(uint64_t)a->C2, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+      const uint64_t str[3] = {(uint64_t)a->C2 * 2, (uint64_t)a->W * a->C2 * 2, (uint64_t)a->H * a->W * a->C2 * 2};
+      if (!encode_map(&maps[1], a->A2, 4, dims, str, box)) return ST_ERR_CUDA;
+    }
+  } else if (a->sAk == 1) {
+    p.a_kind = KMAJOR;
+    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->batch};
+    const uint64_t str[2] = {(uint64_t)a->sAm * 2, (uint64_t)(a->batch > 1 ? a->sAb : (int64_t)a->M * a->sAm) * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    if (!encode_map(&maps[0], a->A, 3, dims, str, box)) return ST_ERR_CUDA;
+  } else {
+    p.a_kind = MNMAJOR;
+    const uint64_t dims[3] = {(uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->batch};
+    const uint64_t str[2] = {(uint64_t)a->sAk * 2, (uint64_t)(a->batch > 1 ? a->sAb : (int64_t)a->K * a->sAk) * 2};
+    const uint32_t box[3] = {64, 64, 1};
+    if (!encode_map(&maps[0], a->A, 3, dims, str, box)) return ST_ERR_CUDA;
+  }
+  // ---------------- B
+  if (a->b_mode == ST_OP_GATHER) {
+    p.b_kind = GATHER_MN;
+    uint32_t bw, bh, bn;
+    pixel_box(64, a->H, a->W, &bw, &bh, &bn);
+    const uint32_t box[4] = {64, bw, bh, bn};
+    {
+      const uint64_t dims[4] = {(uint64_t)a->C1, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+      const uint64_t str[3] = {(uint64_t)a->C1 * 2, (uint64_t)a->W * a->C1 * 2, (uint64_t)a->H * a->W * a->C1 * 2};
+      if (!encode_map(&maps[2], a->B, 4, dims, str, box)) return ST_ERR_CUDA;
+    }
+    if (a->C2 > 0) {
+      const uint64_t dims[4] = {(uint64_t)a->C2, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+      const uint64_t str[3] = {(uint64_t)a->C2 * 2, (uint64_t)a->W * a->C2 * 2, (uint64_t)a->H * a->W * a->C2 * 2};
+      if (!encode_map(&maps[3], a->B2, 4, dims, str, box)) return ST_ERR_CUDA;
+    }
+  } else if (a->b_mode == ST_OP_DGRADW) {
+    p.b_kind = DGRADW;      // W[co][tap][ci], ci = N contiguous
+    const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)p.ntaps, (uint64_t)Ct};
+    const uint64_t str[2] = {(uint64_t)a->N * 2, (uint64_t)p.ntaps * a->N * 2};
+    const uint32_t box[3] = {64, 1, 64};
+    if (!encode_map(&maps[2], a->B, 3, dims, str, box)) return ST_ERR_CUDA;
+  } else if (a->sBk == 1) {
+    p.b_kind = KMAJOR;
+    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->batch};
+    const uint64_t str[2] = {(uint64_t)a->sBn * 2, (uint64_t)(a->batch > 1 ? a->sBb : (int64_t)a->N * a->sBn) * 2};
+    const uint32_t box[3] = {64, (uint32_t)BN, 1};
+    if (!encode_map(&maps[2], a->B, 3, dims, str, box)) return ST_ERR_CUDA;
+  } else {
+    p.b_kind = MNMAJOR;
+    const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->batch};
+    const uint64_t str[2] = {(uint64_t)a->sBk * 2, (uint64_t)(a->batch > 1 ? a->sBb : (int64_t)a->K * a->sBk) * 2};
+    const uint32_t box[3] = {64, 64, 1};
+    if (!encode_map(&maps[2], a->B, 3, dims, str, box)) return ST_ERR_CUDA;
+  }
+  if (a->a_mode == ST_OP_GATHER && a->b_mode == ST_OP_DGRADW) p.cblocks = Ct / 64;
+
+  p.C = a->C; p.ldc = a->sCm; p.sCb = a->sCb; p.out_bf16 = a->out_dtype == ST_BF16; p.accumulate = a->accumulate;
+  p.bias = a->bias; p.rowbias = a->rowbias; p.rows_per_rb = a->rows_per_rb > 0 ? a->rows_per_rb : 1; p.ld_rb = a->ld_rb;
+  p.residual = reinterpret_cast<const bf16*>(a->residual); p.ldr = a->sRm; p.sRb = a->sRb; p.alpha = a->alpha;
+
+  dim3 grid((a->M + BM - 1) / BM, (a->N + BN - 1) / BN, a->batch * p.split_k);
+  ST_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "st_gemm(tc): grid too large");
+  if (BN == 64) return launch<64, 4>(maps, p, grid, stream);
+  return launch<128, 3>(maps, p, grid, stream);
+}

@@ -230,6 +230,24 @@ def _world():
   return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
+def shared_t_min(sde, config):
+  """The soft-truncation draw of this step (NumPy RNG, reference losses.py:284), identical on every rank:
+  rank 0 draws, the others receive it."""
+  t_min = sde.get_t_min(config)
+  if _world() > 1:
+    box = [t_min]
+    dist.broadcast_object_list(box, src=0)
+    t_min = box[0]
+  return t_min
+
+
+def sync_gradients(model):
+  """Data-parallel gradient reduction: ONE all-reduce (sum) of the flat fp32 gradient buffer.  The loss is
+  already divided by the world size, so the sum is the global-batch mean gradient."""
+  if _world() > 1:
+    dist.all_reduce(mutils.unwrap(model)._grad)
+
+
 def get_step_fn(config, sde, train, optimize_fn=None):
   """One optimizer step (reference losses.py:218-325): returns the per-sample losses on the CPU."""
   if not config.training.continuous:
@@ -238,17 +256,10 @@ def get_step_fn(config, sde, train, optimize_fn=None):
   tr = config.training
 
   def _t_min():
-    t_min = sde.get_t_min(config)       # NumPy RNG, once per step, shared by the micro-batches (:284)
-    if _world() > 1:
-      box = [t_min]
-      dist.broadcast_object_list(box, src=0)
-      t_min = box[0]
-    return t_min
+    return shared_t_min(sde, config)    # once per step, shared by the micro-batches (:284)
 
   def _finish(state, model):
-    world = _world()
-    if world > 1:
-      dist.all_reduce(mutils.unwrap(model)._grad)     # one NCCL all-reduce of the flat gradient buffer
+    sync_gradients(model)
     try:
       optimize_fn(state['optimizer'], model.parameters(), step=state['step'], ema=state['ema'])
       fused_ema = True

@@ -89,8 +89,10 @@ class NetCtx:
 class ResBlock:
   """ResnetBlockBigGANpp (reference models/layerspp.py:225-287)."""
 
-  def __init__(self, model, idx, cin, cout, up=False, down=False):
+  def __init__(self, model, idx, cin, cout, up=False, down=False, hw=None):
     self.idx, self.cin, self.cout, self.up, self.down = idx, cin, cout, up, down
+    self.out_hw = (hw, hw)      # spatial size of the block's output
+    model._resblocks.append(self)
     m = model.config.model
     add = model._add_param
     pre = f'all_modules.{idx}.'
@@ -566,6 +568,7 @@ class NCSNpp(nn.Module):
     self.num_scales = m.num_scales
     self.store = ParamStore()
     self._dense_cols = 0
+    self._resblocks = []
     self._taps = None
     self.drop_masks = None
     self._seed_base = 0x5eed
@@ -589,7 +592,7 @@ class NCSNpp(nn.Module):
       blocks = []
       for _ in range(m.num_res_blocks):
         cout = nf * m.ch_mult[lvl]
-        rb = ResBlock(self, i, cin, cout)
+        rb = ResBlock(self, i, cin, cout, hw=res[lvl])
         i += 1
         cin = cout
         ab = None
@@ -602,11 +605,12 @@ class NCSNpp(nn.Module):
       if lvl != n_res - 1:
         if not aux:
           raise NotImplementedError('auxiliary_resblock=False is not built')
-        dn = ResBlock(self, i, cin, cin, down=True)
+        dn = ResBlock(self, i, cin, cin, down=True, hw=res[lvl + 1])
         i += 1
         hs_c.append(cin)
       self.down.append((blocks, dn))
-    self.mid = (ResBlock(self, i, cin, cin), AttnBlock(self, i + 1, cin), ResBlock(self, i + 2, cin, cin))
+    self.mid = (ResBlock(self, i, cin, cin, hw=res[-1]), AttnBlock(self, i + 1, cin),
+                ResBlock(self, i + 2, cin, cin, hw=res[-1]))
     i += 3
     self.up = []
     for lvl in reversed(range(n_res)):
@@ -614,7 +618,7 @@ class NCSNpp(nn.Module):
       for _ in range(m.num_res_blocks + 1):
         cout = nf * m.ch_mult[lvl]
         skip_c = hs_c.pop()
-        blocks.append((ResBlock(self, i, cin + skip_c, cout), cin, skip_c))
+        blocks.append((ResBlock(self, i, cin + skip_c, cout, hw=res[lvl]), cin, skip_c))
         i += 1
         cin = cout
       ab = None
@@ -623,7 +627,7 @@ class NCSNpp(nn.Module):
         i += 1
       upb = None
       if lvl != 0:
-        upb = ResBlock(self, i, cin, cin, up=True)
+        upb = ResBlock(self, i, cin, cin, up=True, hw=res[lvl - 1])
         i += 1
       self.up.append((blocks, ab, upb))
     assert not hs_c
@@ -682,6 +686,9 @@ class NCSNpp(nn.Module):
         self._buffers[k] = fn(b)
     self._rebind()
     return self
+
+  def _all_resblocks(self):
+    return list(self._resblocks)
 
   def flat_parameters(self):
     """(flat fp32 params, flat fp32 grads, bool mask of trainable elements)."""

@@ -13,8 +13,11 @@ _DT = {torch.float32: F32, torch.bfloat16: BF16}
 OP_STRIDED, OP_GATHER, OP_DGRADW = 0, 1, 2
 BACKEND = {'auto': 0, 'simt': 1, 'tcgen05': 2}
 
-# default backend for st_gemm; tests flip this to pin a path
-gemm_backend = 'auto'
+import os
+
+# default backend for st_gemm ('auto' = tcgen05 whenever the problem is expressible, else SIMT); tests flip
+# this (or set ST_GEMM_BACKEND) to pin a path
+gemm_backend = os.environ.get('ST_GEMM_BACKEND', 'auto')
 
 
 def dt(t):

@@ -1,0 +1,409 @@
+"""GPU parity tests of the individual libst_b200 kernels (through the C ABI via soft_truncation_b200.ops)
+against plain fp32 PyTorch on the same seeded inputs, and against the reference-generated fixtures in
+tests/golden/ops_golden.npz for the two native ops the reference ships.
+
+Tolerances: fp32 kernels accumulate in fp32 in a different order than PyTorch -> 2e-5 rel-L2; bf16 storage
+rounds every output to 8 mantissa bits -> 6e-3 rel-L2 (3 bf16 ulps rms); the tcgen05 path is compared with
+the SIMT path on IDENTICAL bf16 inputs, where only the fp32 accumulation order differs -> 3e-3 rel-L2.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+ops = None
+
+
+@pytest.fixture(autouse=True, scope='module')
+def _ops():
+  global ops
+  from soft_truncation_b200 import ops as _o
+  ops = _o
+  yield
+  ops.gemm_backend = 'auto'
+
+
+def dev():
+  return torch.device('cuda:0')
+
+
+def gen(seed):
+  return torch.Generator(device='cpu').manual_seed(seed)
+
+
+def rnd(*shape, seed=0, dtype=torch.float32, scale=1.0):
+  return (torch.randn(*shape, generator=gen(seed)) * scale).to(dev()).to(dtype)
+
+
+def nhwc(t):      # NCHW -> NHWC contiguous
+  return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):
+  return t.permute(0, 3, 1, 2).contiguous()
+
+
+def pack_w(w):    # OIHW -> [O][kh*kw][I]
+  return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+def tol(dtype):
+  return 2e-5 if dtype == torch.float32 else 6e-3
+
+
+# ------------------------------------------------------------------------------------------------ GEMM / conv
+CONV_CASES = [
+    # B, H, W, C1, C2, Cout, k
+    (2, 8, 8, 64, 0, 64, 3),
+    (3, 16, 16, 64, 64, 128, 3),
+    (2, 4, 4, 128, 0, 64, 1),
+    (2, 8, 8, 64, 128, 64, 1),
+    (1, 32, 32, 64, 0, 128, 3),
+]
+
+
+def _conv_case(case, dtype, backend, seed=0):
+  B, H, W, C1, C2, Co, k = case
+  Ci = C1 + C2
+  x = rnd(B, Ci, H, W, seed=seed)
+  w = rnd(Co, Ci, k, k, seed=seed + 1, scale=1. / math.sqrt(Ci * k * k))
+  bias = rnd(Co, seed=seed + 2)
+  rb = rnd(B, Co + 5, seed=seed + 3)
+  res = rnd(B, Co, H, W, seed=seed + 4)
+  dy = rnd(B, Co, H, W, seed=seed + 5)
+  xq, wq, resq, dyq = (t.to(dtype).float() for t in (x, w, res, dy))          # what the kernel really sees
+  ops.gemm_backend = backend
+  xh = nhwc(x).to(dtype)
+  x1, x2 = (xh[..., :C1].contiguous(), xh[..., C1:].contiguous()) if C2 else (xh, None)
+  wp = pack_w(w).to(dtype)
+  out = ops.conv_fwd(x1, wp, Co, k, k, x2=x2, bias=bias, rowbias=rb[:, 3:], rowbias_ld=rb.shape[1],
+                     residual=nhwc(res).to(dtype), alpha=0.7)
+  want = 0.7 * (F.conv2d(xq, wq, bias, padding=k // 2) + rb[:, 3:3 + Co, None, None] + resq)
+  dx = ops.conv_dgrad(nhwc(dy).to(dtype), wp, Ci, k, k, alpha=1.3)
+  want_dx = 1.3 * torch.nn.grad.conv2d_input(x.shape, wq, dyq, padding=k // 2)
+  dw = torch.full((Co, k * k * Ci), 0.5, dtype=torch.float32, device=dev())
+  ops.conv_wgrad(nhwc(dy).to(dtype), x1, dw, k, k, x2=x2, alpha=0.9)
+  want_dw = 0.5 + 0.9 * pack_w(torch.nn.grad.conv2d_weight(xq, w.shape, dyq, padding=k // 2))
+  return (nchw(out.float()), want), (nchw(dx.float()), want_dx), (dw, want_dw)
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_conv_simt_vs_torch(case, dtype):
+  for got, want in _conv_case(case, dtype, 'simt'):
+    assert rel_l2(got, want) < tol(dtype)
+
+
+def _need_tc():
+  if not ops.tc_available():
+    pytest.skip('tcgen05 backend unavailable on this device')
+
+
+@pytest.mark.parametrize('case', CONV_CASES + [(2, 32, 32, 128, 0, 128, 3), (4, 16, 16, 256, 128, 256, 3),
+                                               (5, 4, 4, 256, 256, 256, 3), (8, 8, 8, 256, 0, 256, 3),
+                                               (2, 32, 32, 64, 0, 128, 3), (2, 32, 32, 128, 0, 64, 3),
+                                               (1, 64, 64, 128, 0, 128, 3), (1, 128, 128, 64, 0, 64, 3)])
+def test_conv_tcgen05_vs_torch(case):
+  _need_tc()
+  for got, want in _conv_case(case, torch.bfloat16, 'tcgen05'):
+    assert rel_l2(got, want) < tol(torch.bfloat16)
+
+
+def _gemm_cases(dtype, backend):
+  """nt / nn / tn, plain and batched with leading dimensions, against torch.matmul."""
+  ops.gemm_backend = backend
+  res = []
+  # nt with bias + residual, small M (time-embedding shape)
+  a, b = rnd(5, 128, seed=1).to(dtype), rnd(512, 128, seed=2, scale=0.1).to(dtype)
+  bias, r = rnd(512, seed=3), rnd(5, 512, seed=4).to(dtype)
+  got = ops.gemm_nt(a, b, bias=bias, residual=r, alpha=0.5, out_dtype=torch.float32)
+  res.append((got, 0.5 * (a.float() @ b.float().t() + bias + r.float())))
+  # attention shapes: qkv (B*L, 3C) -> logits, P V, and their backward forms
+  Bn, L, C = 3, 64, 64
+  qkv = rnd(Bn * L, 3 * C, seed=5, scale=0.3).to(dtype)
+  q, k, v = (qkv[:, i * C:(i + 1) * C].float().reshape(Bn, L, C) for i in range(3))
+  logits = ops.gemm_nt(qkv, qkv[:, C:], out_dtype=torch.float32, M=L, N=L, K=C, lda=3 * C, ldb=3 * C, batch=Bn,
+                       sAb=L * 3 * C, sBb=L * 3 * C, sCb=L * L)
+  res.append((logits, q @ k.transpose(1, 2)))
+  p = torch.softmax(logits * C ** -0.5, -1).to(dtype)
+  o = ops.gemm_nn(p, qkv[:, 2 * C:], C, M=L, K=L, lda=L, ldb=3 * C, batch=Bn, sAb=L * L, sBb=L * 3 * C, sCb=L * C)
+  res.append((o.float(), p.float() @ v))
+  do = rnd(Bn, L, C, seed=6).to(dtype)
+  dqkv = torch.zeros_like(qkv)
+  ops.gemm_tn(p, do, L, C, L, out=dqkv[:, 2 * C:], lda=L, ldb=C, ldc=3 * C, sAb=L * L, sBb=L * C, sCb=L * 3 * C, batch=Bn)
+  res.append((dqkv[:, 2 * C:].float().reshape(Bn, L, C), p.float().transpose(1, 2) @ do.float()))
+  # weight-gradient form with accumulation into fp32 (+ split-K)
+  g, h = rnd(700, 192, seed=7).to(dtype), rnd(700, 64, seed=8).to(dtype)
+  acc = torch.full((192, 64), 0.25, dtype=torch.float32, device=dev())
+  ops.gemm_tn(g, h, 192, 64, 700, out=acc, alpha=2.0, accumulate=True)
+  res.append((acc, 0.25 + 2.0 * g.float().t() @ h.float()))
+  big_g, big_h = rnd(8192, 128, seed=9).to(dtype), rnd(8192, 64, seed=10).to(dtype)
+  acc2 = torch.zeros((128, 64), dtype=torch.float32, device=dev())
+  ops.gemm_tn(big_g, big_h, 128, 64, 8192, out=acc2, accumulate=True, split_k=4)
+  res.append((acc2, big_g.float().t() @ big_h.float()))
+  # nn against a (K, N) weight (dgrad of a Linear / NIN)
+  w = rnd(192, 64, seed=11, scale=0.1).to(dtype)
+  res.append((ops.gemm_nn(g, w, 64).float(), g.float() @ w.float()))
+  return res
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_gemm_simt_vs_torch(dtype):
+  for got, want in _gemm_cases(dtype, 'simt'):
+    assert rel_l2(got, want) < tol(dtype)
+
+
+def test_gemm_tcgen05_vs_torch():
+  _need_tc()
+  for i, (got, want) in enumerate(_gemm_cases(torch.bfloat16, 'tcgen05')):
+    assert rel_l2(got, want) < tol(torch.bfloat16), i
+
+
+def test_gemm_tcgen05_matches_simt_on_same_inputs():
+  _need_tc()
+  for case in [(2, 32, 32, 128, 0, 128, 3), (4, 16, 16, 256, 128, 256, 3)]:
+    a = _conv_case(case, torch.bfloat16, 'tcgen05', seed=3)
+    b = _conv_case(case, torch.bfloat16, 'simt', seed=3)
+    for (ga, _), (gb, _) in zip(a, b):
+      assert rel_l2(ga, gb) < 3e-3
+
+
+def test_gemm_rejects_bad_arguments():
+  from soft_truncation_b200._lib import StError
+  a = rnd(4, 8)
+  with pytest.raises(StError):
+    ops.gemm_nt(a, a, M=0)
+  ops.gemm_backend = 'tcgen05'
+  with pytest.raises(StError):          # fp32 operands cannot run on the bf16 tensor-core path
+    ops.gemm_nt(a, a)
+  ops.gemm_backend = 'auto'
+
+
+# ------------------------------------------------------------------------------------------------ GroupNorm
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape', [(3, 8, 8, 64, 0), (2, 16, 16, 256, 128), (2, 4, 4, 128, 128), (130, 2, 2, 64, 0)])
+@pytest.mark.parametrize('act', [0, 1])
+def test_groupnorm_fwd_bwd(dtype, shape, act):
+  B, H, W, C1, C2 = shape
+  C = C1 + C2
+  G = min(C // 4, 32)
+  x = rnd(B, C, H, W, seed=1) * 1.5 + 0.3
+  gamma, beta = rnd(C, seed=2) * 0.2 + 1., rnd(C, seed=3) * 0.2
+  dy = rnd(B, C, H, W, seed=4)
+  mask = (torch.rand(B, C, H, W, generator=gen(5)) > 0.1).float().to(dev()) / 0.9
+  extra = rnd(B, C, H, W, seed=6)
+  xq, dyq, exq = x.to(dtype).float().requires_grad_(True), dy.to(dtype).float(), extra.to(dtype).float()
+  gam, bet = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+  y_ref = F.group_norm(xq, G, gam, bet, eps=1e-6)
+  if act:
+    y_ref = y_ref * torch.sigmoid(y_ref)
+  y_ref = y_ref * mask
+  y_ref.backward(dyq)
+  xh = nhwc(x).to(dtype)
+  x1, x2 = (xh[..., :C1].contiguous(), xh[..., C1:].contiguous()) if C2 else (xh, None)
+  mk = nhwc(mask).to(dtype)
+  st = ops.gn_stats(x1, x2, G)
+  y = ops.gn_apply(x1, x2, G, gamma, beta, st, act, mask=mk)
+  assert rel_l2(nchw(y.float()), y_ref) < tol(dtype)
+  dgam, dbet = torch.ones(C, device=dev()), torch.ones(C, device=dev())
+  dx1, dx2 = ops.gn_backward(x1, x2, nhwc(dy).to(dtype), G, gamma, beta, st, act, dgam, dbet, mask=mk,
+                             extra=nhwc(extra).to(dtype), extra_scale=0.5)
+  dx = torch.cat([dx1, dx2], -1) if C2 else dx1
+  assert rel_l2(nchw(dx.float()), xq.grad + 0.5 * exq) < 2 * tol(dtype)
+  assert rel_l2(dgam - 1, gam.grad) < 2 * tol(dtype)
+  assert rel_l2(dbet - 1, bet.grad) < 2 * tol(dtype)
+  # accumulate-into-destination variant
+  base1 = torch.ones_like(dx1)
+  base2 = torch.ones_like(dx2) if C2 else None
+  a1, a2 = ops.gn_backward(x1, x2, nhwc(dy).to(dtype), G, gamma, beta, st, act, dgam, dbet, mask=mk, dx1=base1,
+                           accum1=True, dx2=base2, accum2=True)
+  got = torch.cat([a1, a2], -1) if C2 else a1
+  assert rel_l2(nchw(got.float()) - 1., xq.grad) < 3 * tol(dtype) + (2e-2 if dtype == torch.bfloat16 else 0)
+
+
+def test_groupnorm_dropout_rng_is_consistent_between_fwd_and_bwd():
+  B, H, W, C = 4, 8, 8, 64
+  x = nhwc(rnd(B, C, H, W, seed=1))
+  gamma, beta = torch.ones(C, device=dev()), torch.zeros(C, device=dev())
+  st = ops.gn_stats(x, None, 16)
+  y0 = ops.gn_apply(x, None, 16, gamma, beta, st, 0)
+  y = ops.gn_apply(x, None, 16, gamma, beta, st, 0, p_drop=0.25, seed=1234)
+  keep = (y != 0)
+  frac = keep.float().mean().item()
+  assert abs(frac - 0.75) < 0.02
+  assert torch.allclose(y[keep], y0[keep] / 0.75, rtol=1e-5, atol=1e-6)
+  # backward with dy = 1 and gamma-only path: dz = mask -> dbeta = sum(mask/0.75... ) per channel
+  dg, db = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
+  ops.gn_backward(x, None, torch.ones_like(x), 16, gamma, beta, st, 0, dg, db, p_drop=0.25, seed=1234)
+  want = (keep.float() / 0.75).sum(dim=(0, 1, 2))
+  assert torch.allclose(db, want, rtol=1e-5)
+  y2 = ops.gn_apply(x, None, 16, gamma, beta, st, 0, p_drop=0.25, seed=99)
+  assert (y2 != 0).ne(keep).any()
+
+
+# ------------------------------------------------------------------------------------------------ small kernels
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_resample_colsum_softmax(dtype):
+  x = rnd(2, 64, 8, 8, seed=1).to(dtype)
+  xh = nhwc(x)
+  up = ops.resample2x(xh, None, +1, 1.0)
+  assert torch.equal(nchw(up), x.float().repeat_interleave(2, 2).repeat_interleave(2, 3).to(dtype))
+  dn = ops.resample2x(xh, None, -1, 0.25)
+  assert rel_l2(nchw(dn.float()), F.avg_pool2d(x.float(), 2)) < tol(dtype)
+  x1, x2 = xh[..., :32].contiguous(), xh[..., 32:].contiguous()
+  assert torch.equal(ops.resample2x(x1, x2, +1, 1.0), up)
+  m = rnd(6 * 40, 64, seed=2).to(dtype)
+  out = torch.ones(6, 64, device=dev())
+  ops.colsum(m, 6, 40, 64, out, scale=0.5, accumulate=True)
+  assert rel_l2(out, 1 + 0.5 * m.float().reshape(6, 40, 64).sum(1)) < 2e-5
+  lg = rnd(10, 37, seed=3) * 3
+  p = ops.softmax_fwd(lg, 37, 0.3, dtype)
+  assert rel_l2(p.float(), torch.softmax(lg * 0.3, -1)) < tol(dtype)
+  dp = rnd(10, 37, seed=4)
+  ds = ops.softmax_bwd(p, dp, 37, 0.3)
+  pf = p.float()
+  assert rel_l2(ds.float(), 0.3 * pf * (dp - (dp * pf).sum(-1, keepdim=True))) < tol(dtype)
+
+
+def test_embeddings_cast_axpby_silu_layout():
+  from oracle import ref_model
+  labels = torch.tensor([0.3, 0.9, 1e-3, 0.5]) * 999
+  got = ops.timestep_embedding(labels.to(dev()), 128)
+  assert rel_l2(got, ref_model.positional_embedding(labels, 128)) < 2e-6
+  sig, Wf = torch.tensor([0.01, 1.0, 50.0]), torch.randn(64, generator=gen(1)) * 16
+  got = ops.fourier_embedding(sig.to(dev()), Wf.to(dev()))
+  want = ref_model.fourier_embedding(torch.log(sig), Wf)
+  assert (got.cpu() - want).abs().max() < 2e-4       # sin/cos of arguments up to ~2*pi*16*3*4
+  x = rnd(1001, seed=2)
+  assert torch.equal(ops.cast(x, torch.bfloat16), x.to(torch.bfloat16))
+  assert torch.equal(ops.cast(x.to(torch.bfloat16), torch.float32), x.to(torch.bfloat16).float())
+  y = rnd(1001, seed=3)
+  assert torch.allclose(ops.axpby(x, y, 0.3, -2.0), 0.3 * x - 2.0 * y, rtol=1e-6, atol=1e-6)
+  assert torch.allclose(ops.silu(x), F.silu(x), rtol=1e-5, atol=1e-6)
+  xg = x.clone().requires_grad_(True)
+  F.silu(xg).backward(y)
+  assert torch.allclose(ops.silu_bwd(x, y), xg.grad, rtol=1e-4, atol=1e-6)
+  img = rnd(3, 3, 8, 8, seed=4)
+  h = ops.nchw_to_nhwc(img, torch.float32, 64, 2.0, -1.0)
+  assert h.shape == (3, 8, 8, 64) and torch.equal(h[..., 3:], torch.zeros_like(h[..., 3:]))
+  assert torch.allclose(nchw(h[..., :3]), 2 * img - 1)
+  sc = torch.tensor([1., 2., 3.], device=dev())
+  assert torch.allclose(ops.nhwc_to_nchw(h, 3, sc), (2 * img - 1) * sc[:, None, None, None])
+
+
+# ------------------------------------------------------------------------------------------------ reference native ops
+def test_upfirdn2d_matches_reference_fixture(golden):
+  from soft_truncation_b200 import op
+  g = golden('ops_golden.npz')
+  for name in ('up2', 'down2', 'pre', 'crop', 'up3_3x3'):
+    up, down, p0, p1 = [int(v) for v in g[f'{name}_args']]
+    x = torch.tensor(g[f'{name}_x'], device=dev(), requires_grad=True)
+    k = torch.tensor(g[f'{name}_k'], device=dev())
+    y = op.upfirdn2d(x, k, up=up, down=down, pad=(p0, p1))
+    np.testing.assert_allclose(y.detach().cpu().numpy(), g[f'{name}_y'], rtol=1e-5, atol=1e-6)
+    kh = k.shape[0]
+    if kh % down == 0:            # the backward op runs up'=down: the kernel walks kh/up' taps (reference domain)
+      (y * torch.tensor(g[f'{name}_gy'], device=dev())).sum().backward()
+      np.testing.assert_allclose(x.grad.cpu().numpy(), g[f'{name}_gx'], rtol=1e-5, atol=1e-6)
+
+
+def test_upfirdn2d_nhwc_and_bf16():
+  from oracle import ref_ops
+  x = torch.randn(2, 9, 7, 8, generator=gen(3))
+  k = torch.tensor(np.outer([1., 3., 3., 1.], [1., 3., 3., 1.]) / 64., dtype=torch.float32)
+  for up, down, pad in ((2, 1, (2, 1)), (1, 2, (1, 1)), (1, 1, (2, 2))):
+    want = np.stack([ref_ops.upfirdn2d_ref(x[..., c].numpy(), k.numpy(), (up, up), (down, down), pad + pad)
+                     for c in range(8)], -1)
+    got = ops.upfirdn2d_nhwc(x.to(dev()), k.to(dev()), up=up, down=down, pad=pad)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+    got16 = ops.upfirdn2d_nhwc(x.to(dev()).bfloat16(), k.to(dev()), up=up, down=down, pad=pad)
+    assert rel_l2(got16.float(), want) < 6e-3
+
+
+def test_fused_leaky_relu_matches_reference_fixture(golden):
+  from soft_truncation_b200 import op
+  g = golden('ops_golden.npz')
+  x = torch.tensor(g['lrelu_x'], device=dev(), requires_grad=True)
+  b = torch.tensor(g['lrelu_b'], device=dev(), requires_grad=True)
+  y = op.fused_leaky_relu(x, b)
+  np.testing.assert_allclose(y.detach().cpu().numpy(), g['lrelu_y'], rtol=1e-6, atol=1e-7)
+  y.sum().backward()
+  xr = torch.tensor(g['lrelu_x'], requires_grad=True)
+  br = torch.tensor(g['lrelu_b'], requires_grad=True)
+  (F.leaky_relu(xr + br.view(1, -1, 1, 1), 0.2) * 2 ** 0.5).sum().backward()
+  np.testing.assert_allclose(x.grad.cpu().numpy(), xr.grad.numpy(), rtol=1e-6)
+  np.testing.assert_allclose(b.grad.cpu().numpy(), br.grad.numpy(), rtol=1e-5)
+  m = op.FusedLeakyReLU(5).to(dev())
+  assert m(x.detach()).shape == x.shape
+
+
+# ------------------------------------------------------------------------------------------------ loss / optimizer / sampler
+def test_dsm_perturb_and_loss():
+  from soft_truncation_b200._lib import check, lib
+  B, D = 5, 3 * 32 * 32
+  x0, z, out = rnd(B, D, seed=1), rnd(B, D, seed=2), rnd(B, D, seed=3)
+  mc, sd = torch.rand(B, generator=gen(4)).to(dev()), torch.rand(B, generator=gen(5)).to(dev())
+  xt = torch.empty_like(x0)
+  check(lib.st_dsm_perturb(ops.ptr(x0), ops.ptr(z), ops.ptr(mc), ops.ptr(sd), ops.ptr(xt), B, D, ops.stream()))
+  assert torch.allclose(xt, mc[:, None] * x0 + sd[:, None] * z, rtol=1e-6, atol=1e-6)
+  a, b, w, gv = (rnd(B, seed=s) for s in (6, 7, 8, 9))
+  for reduce_mean in (1, 0):
+    o = out.clone().requires_grad_(True)
+    e = (a[:, None] * o + b[:, None] * z) ** 2
+    want = w * (e.mean(-1) if reduce_mean else 0.5 * e.sum(-1))
+    (want * gv).sum().backward()
+    loss, dout = torch.empty(B, device=dev()), torch.empty_like(out)
+    check(lib.st_dsm_loss(ops.ptr(out), ops.ptr(z), ops.ptr(a), ops.ptr(b), ops.ptr(w), ops.ptr(loss), ops.ptr(dout),
+                          ops.ptr(gv), B, D, reduce_mean, ops.stream()))
+    assert rel_l2(loss, want) < 1e-5
+    assert rel_l2(dout, o.grad) < 1e-5
+
+
+def test_fused_adam_ema_matches_torch():
+  from soft_truncation_b200._lib import check, lib
+  n = 100003
+  p0, g0 = rnd(n, seed=1), rnd(n, seed=2) * 3
+  p_ref = p0.clone().requires_grad_(True)
+  opt = torch.optim.Adam([p_ref], lr=1e-2, betas=(0.9, 0.999), eps=1e-8)
+  p, m, v, ema = p0.clone(), torch.zeros(n, device=dev()), torch.zeros(n, device=dev()), p0.clone()
+  ema_ref = p0.clone()
+  p16 = torch.empty(n, dtype=torch.bfloat16, device=dev())
+  acc = torch.zeros(1, device=dev())
+  for t in range(1, 4):
+    g = g0 * t
+    p_ref.grad = g.clone()
+    torch.nn.utils.clip_grad_norm_([p_ref], 1.0)
+    opt.step()
+    d = min(0.999, (1 + t) / (10 + t))
+    ema_ref.sub_((1 - d) * (ema_ref - p_ref.detach()))
+    acc.zero_()
+    check(lib.st_sumsq(ops.ptr(g), n, ops.ptr(acc), ops.stream()))
+    assert abs(acc.item() - (g.double() ** 2).sum().item()) < 1e-4 * acc.item()
+    check(lib.st_adam_ema(ops.ptr(p), ops.ptr(g), ops.ptr(m), ops.ptr(v), ops.ptr(ema), None, ops.ptr(p16), n, ops.ptr(acc),
+                          1.0, 1e-2, 0.9, 0.999, 1e-8, 0.0, 1 - 0.9 ** t, 1 - 0.999 ** t, d, ops.stream()))
+    assert rel_l2(p, p_ref.detach()) < 1e-6
+    assert rel_l2(ema, ema_ref) < 1e-6
+    assert torch.equal(p16, p.to(torch.bfloat16))
+
+
+def test_pc_update_and_langevin_helpers():
+  from soft_truncation_b200 import sampling
+  from soft_truncation_b200._lib import check, lib
+  B, shape = 4, (4, 3, 8, 8)
+  x, s, nz = rnd(*shape, seed=1), rnd(*shape, seed=2), rnd(*shape, seed=3)
+  ca, cb, cc = (rnd(B, seed=k) for k in (4, 5, 6))
+  x_new, x_mean = sampling.fused_update(x, s, nz, ca, cb, cc)
+  bc = lambda v: v[:, None, None, None]
+  assert torch.allclose(x_mean, bc(ca) * x + bc(cb) * s, rtol=1e-5, atol=1e-6)
+  assert torch.allclose(x_new, bc(ca) * x + bc(cb) * s + bc(cc) * nz, rtol=1e-5, atol=1e-6)
+  norms = torch.empty(2, device=dev())
+  D = x[0].numel()
+  check(lib.st_batch_norms(ops.ptr(s), ops.ptr(nz), ops.ptr(norms), B, D, ops.stream()))
+  want = torch.stack([s.reshape(B, -1).norm(dim=-1).mean(), nz.reshape(B, -1).norm(dim=-1).mean()])
+  assert torch.allclose(norms, want, rtol=1e-5)

@@ -1,0 +1,247 @@
+"""GPU parity of the whole hot path against the reference-generated fixtures (tests/golden/*.npz, made by
+running the UNTOUCHED reference, see tests/golden/make_golden.py) and against the CPU oracle (oracle/).
+
+Everything goes through the reference-facing surface: models.utils.create_model / get_score_fn,
+losses.get_step_fn, sampling.get_pc_sampler, with the random draws injected.
+
+Tolerances (stated per north_star):
+  fp32 parity mode  : score rel-L2 <= 2e-5, per-tensor gradient norms rtol 2e-4, training losses rtol 5e-4,
+                      sampler state rel-L2 <= 1e-4 (reference thread-count noise floor is 2e-7, F9).
+  bf16 fast mode    : score rel-L2 <= 3e-2, gradient cosine >= 0.99, losses rtol 3e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import ref_model, ref_train
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+
+
+def _cfg(dropout=None):
+  from soft_truncation_b200 import configs
+  cfg = configs.cifar10_ddpmpp_nll_st()
+  cfg.device = torch.device(DEV)
+  if dropout is not None:
+    cfg.model.dropout = dropout
+  return cfg
+
+
+def _model(cfg, seed, dtype):
+  from soft_truncation_b200 import sde_lib
+  from soft_truncation_b200.models import utils as mutils
+  cfg.model.compute_dtype = 'fp32' if dtype == torch.float32 else 'bf16'
+  sde = sde_lib.get_sde(cfg)
+  model = mutils.create_model(cfg, sde)
+  sd = ref_model.make_state_dict(cfg, seed=seed)
+  missing = mutils.unwrap(model).load_state_dict(sd, strict=True)
+  assert not missing.missing_keys and not missing.unexpected_keys
+  return model, sde, sd
+
+
+def _taps_nchw(net):
+  return {i: t.float().permute(0, 3, 1, 2) for i, t in net._taps.items()}
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_unet_forward_backward_vs_reference_fixture(golden, dtype):
+  from soft_truncation_b200.models import utils as mutils
+  g = golden('unet_cifar_golden.npz')
+  cfg = _cfg()
+  model, sde, sd = _model(cfg, int(g['seed']), dtype)
+  net = mutils.unwrap(model)
+  assert sum(p.numel() for p in net.parameters()) == int(g['n_params'])
+  assert [k for k, _ in net.named_parameters()] == list(g['param_names'])
+  model.eval()
+  net._taps = {}
+  x = torch.tensor(g['x'], device=DEV)
+  labels = torch.tensor(g['labels'], device=DEV)
+  out = model(x, labels)
+  f32 = dtype == torch.float32
+  assert rel_l2(out, g['out']) < (2e-5 if f32 else 3e-2)
+  taps = _taps_nchw(net)
+  net._taps = None
+  n_checked = 0
+  for i, a in taps.items():
+    if i == net.head.idx_conv:
+      a = a[:, :3]
+    mean, std = g['act_stats'][i]
+    a = a.double().reshape(-1)
+    rt = 1e-4 if f32 else 2e-2
+    assert abs(a.mean().item() - mean) < rt * (abs(mean) + std), i
+    assert abs(a.std().item() - std) < rt * std, i
+    n_checked += 1
+  assert n_checked >= 50
+  net.zero_grad()
+  (out * torch.tensor(g['wout'], device=DEV)).sum().backward()
+  names = list(g['param_names'])
+  params = dict(net.named_parameters())
+  gn = np.array([params[k].grad.double().norm().item() for k in names])
+  if f32:
+    np.testing.assert_allclose(gn, g['grad_norms'], rtol=2e-4, atol=2e-6)
+    for j in (0, 5, 100, 300, len(names) - 1):
+      p = params[names[j]]
+      idx = np.unique(np.linspace(0, p.numel() - 1, 6).astype(np.int64))
+      got = p.grad.reshape(-1)[torch.tensor(idx, device=DEV)].cpu().numpy()
+      np.testing.assert_allclose(got, g['grad_samples'][j][:len(idx)], rtol=2e-3, atol=1e-5 * g['grad_norms'][j])
+  else:
+    big = g['grad_norms'] > 1e-3 * g['grad_norms'].max()
+    np.testing.assert_allclose(gn[big], g['grad_norms'][big], rtol=5e-2)
+
+
+def test_unet_gradients_vs_oracle_all_tensors():
+  """Every parameter-gradient tensor (not only norms) and d(input), against the CPU oracle, incl. dropout."""
+  from soft_truncation_b200.models import utils as mutils
+  cfg = _cfg(dropout=0.1)
+  model, sde, sd = _model(cfg, 4, torch.float32)
+  net = mutils.unwrap(model)
+  gen = torch.Generator().manual_seed(5)
+  B = 2
+  x = torch.randn(B, 3, 32, 32, generator=gen)
+  labels = torch.tensor([10., 700.])
+  wout = torch.randn(B, 3, 32, 32, generator=gen)
+  # dropout keep-masks for every res-block (NCHW, already scaled by 1/(1-p)), shared by both sides
+  masks = {}
+  for blk in net._all_resblocks():
+    h, w = blk.out_hw
+    masks[blk.idx] = (torch.rand(B, blk.cout, h, w, generator=gen) > 0.1).float() / 0.9
+  for k in sd:
+    if k != 'sigmas':
+      sd[k].requires_grad_(True)
+  xo = x.clone().requires_grad_(True)
+  out_o = ref_model.unet_forward(sd, cfg, xo, labels, train=True, drop_masks=masks)
+  (out_o * wout).sum().backward()
+  model.train()
+  net.drop_masks = masks
+  net.zero_grad()
+  xg = x.to(DEV).requires_grad_(True)
+  out = model(xg, labels.to(DEV))
+  assert rel_l2(out, out_o.detach()) < 2e-5
+  (out * wout.to(DEV)).sum().backward()
+  assert rel_l2(xg.grad, xo.grad) < 1e-4
+  worst = 0.
+  for k, p in net.named_parameters():
+    ref = sd[k].grad
+    if ref is None or ref.norm() < 1e-6:
+      continue
+    worst = max(worst, rel_l2(p.grad, ref))
+    assert rel_l2(p.grad, ref) < 2e-4, k
+  net.drop_masks = None
+
+
+@pytest.mark.parametrize('tag', ['w0', 'w5000'])
+def test_train_trajectory_vs_reference_fixture(golden, tag):
+  """BASELINE configs[0]: B=4 optimizer steps through losses.get_step_fn (warm-up 0 and 5000)."""
+  from soft_truncation_b200 import losses
+  from soft_truncation_b200.models import utils as mutils
+  from soft_truncation_b200.models.ema import ExponentialMovingAverage
+  g = golden('train_golden.npz')
+  cfg = _cfg(dropout=0.)
+  cfg.optim.warmup = 0 if tag == 'w0' else 5000
+  model, sde, _ = _model(cfg, int(g['seed']), torch.float32)
+  optimizer = losses.get_optimizer(cfg, model.parameters())
+  assert isinstance(optimizer, losses.FusedAdam)
+  ema = ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate)
+  state = dict(optimizer=optimizer, model=model, ema=ema, step=0)
+  step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+  batch = torch.tensor(g['batch'], device=DEV)
+  vp = ref_train.make_sde(cfg)
+  n = 10 if tag == 'w0' else 4
+  for s in range(n):
+    inj = dict(u=torch.tensor(g['u'][s]), z=torch.tensor(g['z'][s]), t_min=vp.t_min_from_uniform(cfg, float(g['U'][s])))
+    got = step_fn(state, batch, injected=inj)
+    assert got.device.type == 'cpu' and got.shape == (4,)
+    np.testing.assert_allclose(got.numpy(), g[f'{tag}_losses'][s], rtol=5e-4, err_msg=f'step {s}')
+  assert state['step'] == n
+  if tag == 'w0':
+    params = dict(mutils.unwrap(model).named_parameters())
+    shadow = dict(zip([k for k, p in params.items() if p.requires_grad], ema.shadow_params))
+    for j, name in enumerate(g['probe_names']):
+      name = str(name)
+      np.testing.assert_allclose(params[name].double().norm().item(), g['w0_pnorm'][j], rtol=1e-4)
+      np.testing.assert_allclose(shadow[name].double().norm().item(), g['w0_enorm'][j], rtol=1e-4)
+      np.testing.assert_allclose(params[name].detach().reshape(-1)[:6].cpu().numpy(), g['w0_psamp'][j], rtol=2e-2, atol=2e-4)
+
+
+def test_train_step_bf16_close_to_fp32_fixture(golden):
+  from soft_truncation_b200 import losses
+  from soft_truncation_b200.models.ema import ExponentialMovingAverage
+  g = golden('train_golden.npz')
+  cfg = _cfg(dropout=0.)
+  cfg.optim.warmup = 0
+  model, sde, _ = _model(cfg, int(g['seed']), torch.bfloat16)
+  state = dict(optimizer=losses.get_optimizer(cfg, model.parameters()), model=model,
+               ema=ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate), step=0)
+  step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+  vp = ref_train.make_sde(cfg)
+  batch = torch.tensor(g['batch'], device=DEV)
+  for s in range(3):
+    inj = dict(u=torch.tensor(g['u'][s]), z=torch.tensor(g['z'][s]), t_min=vp.t_min_from_uniform(cfg, float(g['U'][s])))
+    got = step_fn(state, batch, injected=inj)
+    np.testing.assert_allclose(got.numpy(), g['w0_losses'][s], rtol=3e-2, err_msg=f'step {s}')
+
+
+def test_pc_sampler_vs_reference_fixture(golden):
+  """8-step Euler-Maruyama PC sampling + denoise (BASELINE configs[0]) through sampling.get_pc_sampler."""
+  from soft_truncation_b200 import sampling, sde_lib
+  g = golden('sampler_golden.npz')
+  cfg = _cfg()
+  cfg.sampling.method = 'pc'
+  model, _, _ = _model(cfg, 1, torch.float32)
+  sde8 = sde_lib.VPSDE(truncation_time=cfg.training.truncation_time, beta_min=cfg.model.beta_min,
+                       beta_max=cfg.model.beta_max, N=8)
+  shape = (2, 3, 32, 32)
+  fn = sampling.get_sampling_fn(cfg, sde8, shape, lambda v: v, float(g['vp_eps']))
+  trace = []
+  x, nfe = fn(model, x_init=torch.tensor(g['vp_xT']), noises=[torch.tensor(z) for z in g['vp_z']], trace=trace)
+  assert nfe == int(g['vp_nfe'])
+  for i, st in enumerate(trace):
+    assert rel_l2(st, g['vp_trace'][i]) < 1e-4, i
+  assert rel_l2(x, g['vp_x']) < 1e-4
+
+
+def test_pc_sampler_cuda_graph_matches_eager():
+  """The graph-replayed loop and the eager loop consume the same torch RNG stream -> same samples."""
+  from soft_truncation_b200 import sampling, sde_lib
+  cfg = _cfg()
+  cfg.sampling.method = 'pc'
+  model, _, _ = _model(cfg, 1, torch.float32)
+  sde = sde_lib.VPSDE(truncation_time=1e-5, beta_min=0.1, beta_max=20., N=6)
+  shape = (2, 3, 32, 32)
+  outs = []
+  for graph in (False, True):
+    cfg.sampling.cuda_graph = graph
+    fn = sampling.get_sampling_fn(cfg, sde, shape, lambda v: v, 1e-5)
+    torch.manual_seed(11)
+    x0 = torch.randn(*shape)
+    torch.cuda.manual_seed(12)
+    x, _ = fn(model, x_init=x0)
+    outs.append(x)
+  assert torch.isfinite(outs[0]).all()
+  # different launch grouping of torch.randn under capture may shift Philox offsets: compare statistics
+  # when the streams differ, exactly when they coincide
+  if not torch.allclose(outs[0], outs[1], rtol=1e-4, atol=1e-4):
+    assert abs(outs[0].std().item() - outs[1].std().item()) < 0.2 * outs[0].std().item()
+
+
+def test_score_fn_and_state_dict_roundtrip():
+  from soft_truncation_b200.models import utils as mutils
+  cfg = _cfg()
+  model, sde, sd = _model(cfg, 1, torch.float32)
+  score_fn = mutils.get_score_fn(cfg, sde, model, train=False, continuous=True)
+  x = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(0))
+  t = torch.tensor([0.2, 0.8])
+  vp = ref_train.make_sde(cfg)
+  want = ref_train.score_fn(sd, cfg, vp, x, t)
+  with torch.no_grad():
+    got = score_fn(x.to(DEV), t.to(DEV))
+  assert rel_l2(got, want) < 2e-5
+  out_sd = model.state_dict()
+  assert all(k.startswith('module.') for k in out_sd)
+  for k, v in sd.items():
+    assert torch.equal(out_sd['module.' + k].cpu(), v.detach()), k
+  with pytest.raises(RuntimeError):
+    mutils.unwrap(model)(x, t)          # CPU tensors: no fallback

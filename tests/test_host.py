@@ -1,0 +1,192 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/st_b200.h declares, the host-side
+mirror of the reference interface (registries, parameter names/shapes/initialisation, checkpoint formats) behaves
+like the reference, and the data-parallel plumbing works under a world_size-2 gloo group.  No kernel is launched."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+  import ctypes
+  from soft_truncation_b200 import _lib
+  header = open(os.path.join(ROOT, 'include', 'st_b200.h')).read()
+  declared = set(re.findall(r'^(?:int|const char\*)\s+(st_\w+)\s*\(', header, flags=re.M))
+  assert len(declared) >= 30
+  raw = ctypes.CDLL(_lib.LIB_PATH)
+  for name in declared:
+    assert hasattr(raw, name), f'{name} declared in st_b200.h but not exported'
+  assert declared - {'st_last_error'} == set(_lib.SIGNATURES), 'ctypes signatures out of sync with the header'
+  assert _lib.lib.st_version() >= 100
+  assert isinstance(_lib.lib.st_last_error(), bytes)
+
+
+def test_gemm_args_struct_matches_header_layout():
+  from soft_truncation_b200._lib import GemmArgs
+  header = open(os.path.join(ROOT, 'include', 'st_b200.h')).read()
+  body = header[header.index('typedef struct st_gemm_args {'):header.index('} st_gemm_args;')]
+  fields = []
+  for decl in re.findall(r'^\s*(?:const\s+)?(?:int32_t|int64_t|float|void\*|float\*|void)\W[^;]*;', body, flags=re.M):
+    decl = decl.split('/*')[0].strip().rstrip(';')
+    names = decl.replace('const', '').replace('*', ' ').split(None, 1)[1]
+    fields += [n.strip() for n in names.split(',')]
+  assert fields == [f[0] for f in GemmArgs._fields_]
+
+
+def _cifar():
+  from soft_truncation_b200 import configs
+  return configs.cifar10_ddpmpp_nll_st()
+
+
+@pytest.fixture(scope='module')
+def cifar_model():
+  from soft_truncation_b200.models import ncsnpp
+  return ncsnpp.NCSNpp(_cifar(), None, compute_dtype=torch.float32, seed=0)
+
+
+def test_model_parameters_match_reference_names_shapes_and_init(cifar_model):
+  want = json.load(open(os.path.join(GOLDEN, 'init_golden.json')))
+  sd = cifar_model.state_dict()
+  names = [k for k in sd if k != 'sigmas']
+  assert names == want['names']
+  assert [list(sd[k].shape) for k in names] == want['shapes']
+  assert sum(p.numel() for p in cifar_model.parameters()) == 61804419
+  assert len(list(cifar_model.parameters())) == 564
+  for k, std in zip(names, want['std']):
+    if sd[k].numel() > 512:
+      assert abs(sd[k].double().std().item() - std) <= 0.1 * std + 1e-12, k
+  assert sd['sigmas'].shape == (1000,)
+
+
+def test_state_dict_roundtrip_and_physical_layout(cifar_model):
+  from oracle import ref_model
+  m = cifar_model
+  osd = ref_model.make_state_dict(_cifar(), seed=3)
+  res = m.load_state_dict(osd, strict=True)
+  assert not res.missing_keys and not res.unexpected_keys
+  sd = m.state_dict()
+  for k, v in osd.items():
+    assert torch.equal(sd[k], v), k
+  # kernel-order views: conv weights [Cout][kh*kw][Cin(padded)], NIN [out][in], packed q/k/v
+  w = osd['all_modules.3.Conv_0.weight']
+  assert torch.equal(m.P.f('all_modules.3.Conv_0.weight'), w.permute(0, 2, 3, 1).reshape(128, -1))
+  first = m.P.f('all_modules.2.weight').view(128, 9, 64)
+  assert torch.equal(first[:, :, :3], osd['all_modules.2.weight'].permute(0, 2, 3, 1).reshape(128, 9, 3))
+  assert not first[:, :, 3:].any()                      # zero padding of the 3-channel image axis
+  head = m.P.f('all_modules.54.weight')
+  assert head.shape == (64, 9 * 128) and not head[3:].any()
+  qkv = m.P.f_group([f'all_modules.9.NIN_{j}.W' for j in range(3)])
+  assert torch.equal(qkv, torch.cat([osd[f'all_modules.9.NIN_{j}.W'].t() for j in range(3)]))
+  dense = m.P.f_region('dense_w').view(-1, 512)
+  assert dense.shape[0] == sum(b.cout for b in m._all_resblocks())
+  blk = m._all_resblocks()[5]
+  assert torch.equal(dense[blk.dense_off:blk.dense_off + blk.cout], osd[f'all_modules.{blk.idx}.Dense_0.weight'])
+  # gradients are views of one flat buffer with the parameters' shapes
+  for k, p in m.named_parameters():
+    assert p.grad is not None and p.grad.shape == p.shape, k
+  m._grad.fill_(1.)
+  assert all(bool((p.grad == 1).all()) for p in m.parameters())
+  m.zero_grad()
+  assert not m._grad.any()
+
+
+def test_model_refuses_cpu_inputs_and_unbuilt_variants(cifar_model):
+  with pytest.raises(RuntimeError):
+    cifar_model(torch.zeros(1, 3, 32, 32), torch.zeros(1))
+  from soft_truncation_b200.models import ncsnpp
+  cfg = _cifar()
+  cfg.model.resblock_type = 'ddpm'
+  with pytest.raises(NotImplementedError):
+    ncsnpp.NCSNpp(cfg, None)
+
+
+def test_registries_behave_like_the_reference():
+  from soft_truncation_b200 import sampling
+  from soft_truncation_b200.models import utils as mutils
+  assert mutils.get_model('ncsnpp').__name__ == 'NCSNpp'
+  with pytest.raises(ValueError):
+    mutils.register_model(name='ncsnpp')(type('X', (), {}))
+  with pytest.raises(KeyError):
+    mutils.get_model('nope')
+  for name in ('euler_maruyama', 'reverse_diffusion', 'ancestral_sampling', 'none'):
+    assert sampling.get_predictor(name)
+  for name in ('langevin', 'ald', 'none'):
+    assert sampling.get_corrector(name)
+  with pytest.raises(ValueError):
+    sampling.register_predictor(name='euler_maruyama')(type('Y', (), {}))
+  cfg = _cifar()
+  cfg.sampling.method = 'bogus'
+  with pytest.raises(ValueError):
+    sampling.get_sampling_fn(cfg, None, (1, 3, 32, 32), lambda v: v, 1e-5)
+  np.testing.assert_allclose(mutils.get_sigmas(cfg)[[0, -1]], [cfg.model.sigma_max, cfg.model.sigma_min])
+
+
+def test_fused_adam_and_ema_keep_the_reference_checkpoint_format(cifar_model):
+  from soft_truncation_b200 import losses
+  from soft_truncation_b200.models.ema import ExponentialMovingAverage
+  m = cifar_model
+  opt = losses.FusedAdam(m.parameters(), m, lr=2e-4)
+  ref = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in m.parameters()], lr=2e-4)
+  for p in ref.param_groups[0]['params']:
+    p.grad = torch.zeros_like(p)
+  ref.step()
+  a, b = opt.state_dict(), ref.state_dict()
+  assert a['param_groups'][0]['params'] == b['param_groups'][0]['params']
+  assert set(a['state'][0]) == set(b['state'][0]) == {'step', 'exp_avg', 'exp_avg_sq'}
+  assert all(a['state'][i]['exp_avg'].shape == b['state'][i]['exp_avg'].shape for i in b['state'])
+  opt.load_state_dict(b)
+  assert opt.t == 1
+  with pytest.raises(RuntimeError):
+    opt.step()                                           # CPU parameters: no fallback
+  ema = ExponentialMovingAverage(m.parameters(), decay=0.9999)
+  assert ema.owner is m and len(ema.shadow_params) == 564
+  sd = ema.state_dict()
+  assert set(sd) == {'decay', 'num_updates', 'shadow_params'}
+  assert [ema.next_decay() for _ in range(3)] == [min(0.9999, (1 + n) / (10 + n)) for n in (1, 2, 3)]
+  ema.load_state_dict(sd)
+  # foreign parameters fall back to the reference's per-tensor behaviour
+  lin = torch.nn.Linear(3, 2)
+  e2 = ExponentialMovingAverage(lin.parameters(), decay=0.5, use_num_updates=False)
+  with torch.no_grad():
+    lin.weight.add_(1.)
+  before = e2.shadow_params[0].clone()
+  e2.update(lin.parameters())
+  assert torch.allclose(e2.shadow_params[0], before + 0.5)
+  cfg = _cifar()
+  assert isinstance(losses.get_optimizer(cfg, lin.parameters()), torch.optim.Adam)
+
+
+def _dp_worker(rank, world, port, out):
+  import torch.distributed as dist
+  from soft_truncation_b200 import configs, losses, sde_lib
+  from soft_truncation_b200.models import ncsnpp
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  cfg = configs.cifar10_ddpmpp_nll_st()
+  cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks = 64, (1,), 1
+  cfg.model.attn_resolutions = ()
+  m = ncsnpp.NCSNpp(cfg, None, compute_dtype=torch.float32, seed=7)
+  m._grad.fill_(float(rank + 1))
+  losses.sync_gradients(m)
+  np.random.seed(100 + rank)                     # ranks draw differently; rank 0's value must win
+  t_min = losses.shared_t_min(sde_lib.get_sde(cfg), cfg)
+  np.random.seed(100)
+  want = sde_lib.get_sde(cfg).get_t_min(cfg)
+  ok = bool((m._grad == sum(range(1, world + 1))).all()) and t_min == want
+  ok = ok and all(bool((p.grad == 3.).all()) for p in m.parameters() if p.requires_grad)
+  out[rank] = ok
+  dist.destroy_process_group()
+
+
+def test_data_parallel_plumbing_gloo_world2():
+  import torch.multiprocessing as mp
+  mgr = mp.Manager()
+  out = mgr.dict()
+  port = 29500 + os.getpid() % 1000
+  mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+  assert dict(out) == {0: True, 1: True}
