@@ -35,6 +35,6 @@ def golden():
 
 def rel_l2(a, b):
   import torch
-  a = torch.as_tensor(a).double().reshape(-1)
-  b = torch.as_tensor(b).double().reshape(-1)
+  a = torch.as_tensor(a).detach().cpu().double().reshape(-1)
+  b = torch.as_tensor(b).detach().cpu().double().reshape(-1)
   return float((a - b).norm() / (b.norm() + 1e-30))

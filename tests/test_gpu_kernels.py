@@ -25,6 +25,9 @@ def _ops():
   global ops
   from soft_truncation_b200 import ops as _o
   ops = _o
+  # the PyTorch side of every comparison must be true fp32 (cuDNN/cuBLAS default to TF32 on this GPU)
+  torch.backends.cudnn.allow_tf32 = False
+  torch.backends.cuda.matmul.allow_tf32 = False
   yield
   ops.gemm_backend = 'auto'
 
