@@ -150,8 +150,8 @@ int st_softmax_fwd(const float* logits, void* p, int dtype, int64_t rows, int L,
 /* ds = scale * p * (dp - sum_j dp*p) ; dp fp32, ds dtype */
 int st_softmax_bwd(const void* p, const float* dp, void* ds, int dtype, int64_t rows, int L, float scale,
                    void* stream);
-/* sinusoidal embedding of labels[B] -> out[B][dim] (fp32) */
-int st_timestep_embedding(const float* labels, float* out, int B, int dim, float max_positions, void* stream);
+/* sinusoidal embedding: out[b] = [sin(labels[b]*freqs), cos(labels[b]*freqs)], freqs[dim/2], out[B][dim] (fp32) */
+int st_timestep_embedding(const float* labels, const float* freqs, float* out, int B, int dim, void* stream);
 /* [sin(2 pi W x), cos(2 pi W x)] with x = log(sigma): out[B][2*nW] */
 int st_fourier_embedding(const float* sigma, const float* W, float* out, int B, int nW, void* stream);
 /* NCHW fp32 [n][C][H][W] -> NHWC dtype [n][H][W][Cpad] (channels >= C zero-filled), y = alpha*x + beta;
@@ -163,6 +163,14 @@ int st_nhwc_to_nchw(const void* x, int dtype, float* y, int n_img, int C, int H,
 /* bf16 im2col of a small-channel NHWC tensor: out[pixel][Kpad] (zero padded), k = tap*C + c */
 int st_im2col_small(const void* x, int dtype, void* out, int n_img, int H, int W, int C, int kh, int kw,
                     int Kpad, void* stream);
+
+/* Strided im2col of an NHWC tensor and its adjoint (the stride-2 convolutions of the input pyramid,
+ * models/up_or_down_sampling.py:144-178, models/layerspp.py:142-176):
+ * cols[(n,oy,ox)][kh*kw][C], element = x[n][oy*stride + r - pad][ox*stride + q - pad][c] or 0. */
+int st_im2col(const void* x, void* cols, int dtype, int n_img, int H, int W, int C, int kh, int kw, int stride,
+              int pad, int OH, int OW, void* stream);
+int st_col2im(const void* dcols, void* dx, int dtype, int n_img, int H, int W, int C, int kh, int kw, int stride,
+              int pad, int OH, int OW, void* stream);
 
 /* ------------------------------------------------------------------ reference native ops */
 /* x [major][in_h][in_w][minor] -> y [major][out_h][out_w][minor]; k fp32 [kh][kw]

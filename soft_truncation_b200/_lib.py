@@ -52,11 +52,13 @@ SIGNATURES = {
     'st_colsum': [c_p, c_int, c_i64, c_i64, c_int, c_f, c_p, c_int, c_p],
     'st_softmax_fwd': [c_p, c_p, c_int, c_i64, c_int, c_f, c_p],
     'st_softmax_bwd': [c_p, c_p, c_p, c_int, c_i64, c_int, c_f, c_p],
-    'st_timestep_embedding': [c_p, c_p, c_int, c_int, c_f, c_p],
+    'st_timestep_embedding': [c_p, c_p, c_p, c_int, c_int, c_p],
     'st_fourier_embedding': [c_p, c_p, c_p, c_int, c_int, c_p],
     'st_nchw_to_nhwc': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_f, c_f, c_p],
     'st_nhwc_to_nchw': [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p],
     'st_im2col_small': [c_p, c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p],
+    'st_im2col': [c_p, c_p] + [c_int] * 11 + [c_p],
+    'st_col2im': [c_p, c_p] + [c_int] * 11 + [c_p],
     'st_upfirdn2d': [c_p, c_p, c_int, c_p] + [c_int] * 14 + [c_p],
     'st_fused_bias_act': [c_p, c_p, c_p, c_p, c_int, c_i64, c_int, c_int, c_int, c_int, c_f, c_f, c_p],
     'st_dsm_perturb': [c_p, c_p, c_p, c_p, c_p, c_int, c_i64, c_p],

@@ -167,13 +167,13 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ 
 }
 
 // ---------------------------------------------------------------- embeddings
-__global__ void timestep_embedding_kernel(const float* labels, float* out, int B, int dim, float max_positions) {
-  // models/layers.py:515-529: emb = t * exp(-log(max_pos)/(half-1) * i); [sin | cos]
+__global__ void timestep_embedding_kernel(const float* labels, const float* freqs, float* out, int B, int dim) {
+  // models/layers.py:515-529: emb = t[:,None] * freqs[None,:]; [sin | cos].  freqs = exp(-log(max_pos)/(half-1) * i)
+  // is computed once on the host with the reference's own expression so that the arguments are bit-identical.
   int half = dim / 2;
   GRID_STRIDE(i, (long long)B * half) {
     int b = (int)(i / half), j = (int)(i % half);
-    float freq = expf((float)j * -(logf(max_positions) / (float)(half - 1)));
-    float arg = labels[b] * freq;
+    float arg = labels[b] * freqs[j];
     out[(long long)b * dim + j] = sinf(arg);
     out[(long long)b * dim + half + j] = cosf(arg);
   }
@@ -230,6 +230,61 @@ __global__ void im2col_small_kernel(const T* __restrict__ x, bf16* __restrict__ 
       if (xx >= 0 && xx < W && yy >= 0 && yy < H) v = to_f(x[((n * H + yy) * W + xx) * C + c]);
     }
     out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+
+// ---------------------------------------------------------------- strided im2col / col2im (pyramid down-convs)
+// cols[(n,oy,ox)][tap][c] = x[n][oy*s + r - pad][ox*s + q - pad][c]  (0 outside), vectorised over channel quads
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ x, T* __restrict__ cols, long long total_quads, int H, int W, int C,
+                              int kh, int kw, int stride, int pad, int OH, int OW) {
+  const int Q = C / 4, taps = kh * kw;
+  GRID_STRIDE(gq, total_quads) {
+    int quad = (int)(gq % Q);
+    long long t = gq / Q;
+    int tap = (int)(t % taps);
+    t /= taps;
+    int ox = (int)(t % OW);
+    t /= OW;
+    int oy = (int)(t % OH);
+    long long n = t / OH;
+    int y = oy * stride + tap / kw - pad, xx = ox * stride + tap % kw - pad;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (y >= 0 && y < H && xx >= 0 && xx < W) load4(x + ((n * H + y) * W + xx) * C + quad * 4, v);
+    store4(cols + gq * 4, v);
+  }
+}
+// dx[n][y][x][c] = sum over (oy,ox,tap) that read (y,x): dcols[(n,oy,ox)][tap][c]
+template <typename T>
+__global__ void col2im_kernel(const T* __restrict__ dcols, T* __restrict__ dx, long long total_quads, int H, int W, int C,
+                              int kh, int kw, int stride, int pad, int OH, int OW) {
+  const int Q = C / 4, taps = kh * kw;
+  GRID_STRIDE(gq, total_quads) {
+    int quad = (int)(gq % Q);
+    long long t = gq / Q;
+    int xx = (int)(t % W);
+    t /= W;
+    int y = (int)(t % H);
+    long long n = t / H;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < kh; ++r) {
+      int ty = y + pad - r;
+      if (ty < 0 || ty % stride) continue;
+      int oy = ty / stride;
+      if (oy >= OH) continue;
+      for (int q = 0; q < kw; ++q) {
+        int tx = xx + pad - q;
+        if (tx < 0 || tx % stride) continue;
+        int ox = tx / stride;
+        if (ox >= OW) continue;
+        float v[4];
+        load4(dcols + ((((n * OH + oy) * OW + ox) * taps + r * kw + q) * (long long)C) + quad * 4, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += v[k];
+      }
+    }
+    store4(dx + gq * 4, acc);
   }
 }
 
@@ -449,9 +504,9 @@ extern "C" __attribute__((visibility("default"))) int st_softmax_bwd(const void*
   return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) int st_timestep_embedding(const float* labels, float* out, int B, int dim, float max_positions, void* stream) {
+extern "C" __attribute__((visibility("default"))) int st_timestep_embedding(const float* labels, const float* freqs, float* out, int B, int dim, void* stream) {
   ST_CHECK_ARG(dim % 2 == 0 && dim >= 4, "st_timestep_embedding: dim must be even");
-  timestep_embedding_kernel<<<grid1d((long long)B * dim / 2, 256), 256, 0, S>>>(labels, out, B, dim, max_positions);
+  timestep_embedding_kernel<<<grid1d((long long)B * dim / 2, 256), 256, 0, S>>>(labels, freqs, out, B, dim);
   ST_CHECK_LAUNCH("st_timestep_embedding");
   return 0;
 }
@@ -542,5 +597,22 @@ extern "C" __attribute__((visibility("default"))) int st_langevin_coeffs(const f
                                   void* stream) {
   langevin_coeffs_kernel<<<(B + 127) / 128, 128, 0, S>>>(norms, alpha, snr, ca, cb, cc, B);
   ST_CHECK_LAUNCH("st_langevin_coeffs");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_im2col(const void* x, void* cols, int dtype, int n_img, int H, int W, int C, int kh, int kw, int stride,
+                             int pad, int OH, int OW, void* stream) {
+  ST_CHECK_ARG(C % 4 == 0 && stride > 0 && OH > 0 && OW > 0, "st_im2col: bad geometry");
+  long long total = (long long)n_img * OH * OW * kh * kw * (C / 4);
+  ST_DISPATCH_DTYPE(dtype, T, (im2col_kernel<T><<<grid1d(total, 256 * 2), 256, 0, S>>>((const T*)x, (T*)cols, total, H, W, C, kh, kw, stride, pad, OH, OW)));
+  ST_CHECK_LAUNCH("st_im2col");
+  return 0;
+}
+extern "C" __attribute__((visibility("default"))) int st_col2im(const void* dcols, void* dx, int dtype, int n_img, int H, int W, int C, int kh, int kw, int stride,
+                             int pad, int OH, int OW, void* stream) {
+  ST_CHECK_ARG(C % 4 == 0 && stride > 0 && OH > 0 && OW > 0, "st_col2im: bad geometry");
+  long long total = (long long)n_img * H * W * (C / 4);
+  ST_DISPATCH_DTYPE(dtype, T, (col2im_kernel<T><<<grid1d(total, 256 * 2), 256, 0, S>>>((const T*)dcols, (T*)dx, total, H, W, C, kh, kw, stride, pad, OH, OW)));
+  ST_CHECK_LAUNCH("st_col2im");
   return 0;
 }

@@ -177,16 +177,29 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> s, const T* 
 }
 
 // dgamma[c] += sum_rows red[row][c][1]; dbeta[c] += sum_rows red[row][c][0]
-__global__ void gn_bwd_params_kernel(const float* red, int rows, int C, float* dgamma, float* dbeta) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double a = 0., b = 0.;
-  for (int r = 0; r < rows; ++r) {
-    a += (double)red[((long long)r * C + c) * 2 + 0];
-    b += (double)red[((long long)r * C + c) * 2 + 1];
+// block = 32 channels x 8 row lanes (coalesced float2 reads), fixed-order reduction
+__global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restrict__ red, int rows, int C, float* dgamma,
+                                                            float* dbeta) {
+  const int c = blockIdx.x * 32 + threadIdx.x % 32;
+  const int rl = threadIdx.x / 32;
+  float a = 0.f, b = 0.f;
+  if (c < C) {
+    for (int r = rl; r < rows; r += 8) {
+      float2 v = *reinterpret_cast<const float2*>(red + ((long long)r * C + c) * 2);
+      a += v.x;
+      b += v.y;
+    }
   }
-  dbeta[c] += (float)a;
-  dgamma[c] += (float)b;
+  __shared__ float sa[256], sb[256];
+  sa[threadIdx.x] = a;
+  sb[threadIdx.x] = b;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    double ta = 0., tb = 0.;
+    for (int l = 0; l < 8; ++l) { ta += (double)sa[l * 32 + threadIdx.x]; tb += (double)sb[l * 32 + threadIdx.x]; }
+    dbeta[c] += (float)ta;
+    dgamma[c] += (float)tb;
+  }
 }
 
 // ---------------------------------------------------------------- backward pass 2
@@ -318,7 +331,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_reduce(const voi
 }
 
 extern "C" __attribute__((visibility("default"))) int st_gn_bwd_params(const float* red, int rows, int C, float* dgamma, float* dbeta, void* stream) {
-  gn_bwd_params_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(red, rows, C, dgamma, dbeta);
+  gn_bwd_params_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(red, rows, C, dgamma, dbeta);
   ST_CHECK_LAUNCH("st_gn_bwd_params");
   return 0;
 }

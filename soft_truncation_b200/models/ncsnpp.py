@@ -366,15 +366,18 @@ class NormActConv:
     self.conv = ConvBlock(model, idx_conv, cin, cout, 3, init_scale)
     self.G = min(cin // 4, 32)
 
-  def fwd(self, net, xa):
+  def fwd(self, net, xa, res=None):
+    """`res`: optional Act added to the output (the up-sampled output pyramid, ncsnpp.py:391-396)."""
     P = net.m.P
     x = xa.t
     st = ops.gn_stats(x, None, self.G)
     a = ops.gn_apply(x, None, self.G, P.f(self.pg + 'weight'), P.f(self.pg + 'bias'), st, act=1)
-    out = ops.conv_fwd(a, P.c(self.conv.pre + 'weight'), self.conv.cout, bias=P.f(self.conv.pre + 'bias'))
+    out = ops.conv_fwd(a, P.c(self.conv.pre + 'weight'), self.conv.cout, bias=P.f(self.conv.pre + 'bias'),
+                       residual=res.t if res is not None else None)
     y = Act(out, net.tape)
     if net.tape.enabled:
-      net.tape.record(lambda g, acc: self.bwd(net, (x, st, a), g, acc), (xa.id,), y.id)
+      ids = (xa.id,) + ((res.id,) if res is not None else ())
+      net.tape.record(lambda g, acc: self.bwd(net, (x, st, a), g, acc), ids, y.id)
     if net.taps is not None:
       net.taps[self.idx_conv] = out
     return y
@@ -385,7 +388,127 @@ class NormActConv:
     (da,) = self.conv.bwd(net, a, g, (None,))
     dx, _ = ops.gn_backward(x, None, da, self.G, P.f(self.pg + 'weight'), P.f(self.pg + 'bias'), st, 1,
                             P.g(self.pg + 'weight'), P.g(self.pg + 'bias'), dx1=acc[0], accum1=acc[0] is not None)
-    return (dx,)
+    if len(acc) == 1:
+      return (dx,)
+    if acc[1] is not None:
+      ops.axpby(acc[1], g, out=acc[1])
+      return (dx, acc[1])
+    return (dx, g)
+
+
+class ImageResample:
+  """2x FIR / nearest-box resampling of an image-side tensor (pyramid_upsample / pyramid_downsample without
+  convolution, reference models/ncsnpp.py:112-124, layerspp.py:107-176 with with_conv=False)."""
+
+  def __init__(self, model, up):
+    self.up, self.fir = up, model.config.model.fir
+
+  def _run(self, net, t, up):
+    m = net.m
+    if up:
+      return ops.upfirdn2d_nhwc(t, m._fir_up, up=2, pad=(2, 1)) if self.fir else ops.resample2x(t, None, +1, 1.0)
+    return ops.upfirdn2d_nhwc(t, m._fir_down, down=2, pad=(1, 1)) if self.fir else ops.resample2x(t, None, -1, 0.25)
+
+  def _adj(self, net, g, up):
+    m = net.m
+    if up:
+      return ops.upfirdn2d_nhwc(g, m._fir_up, down=2, pad=(1, 1)) if self.fir else ops.resample2x(g, None, -1, 1.0)
+    return ops.upfirdn2d_nhwc(g, m._fir_down, up=2, pad=(2, 1)) if self.fir else ops.resample2x(g, None, +1, 0.25)
+
+  def fwd(self, net, xa, image_side_input=False):
+    y = Act(self._run(net, xa.t, self.up), net.tape)
+    if net.tape.enabled:
+      def bwd(g, acc):
+        if image_side_input and not net.need_dx:
+          return (None,)
+        d = self._adj(net, g, self.up)
+        if acc[0] is not None:
+          ops.axpby(acc[0], d, out=acc[0])
+          d = acc[0]
+        return (d,)
+      net.tape.record(bwd, (xa.id,), y.id)
+    return y
+
+
+class CombineBlock:
+  """Combine(method='sum'): h + conv1x1(image pyramid) (reference models/layerspp.py:57-72)."""
+
+  def __init__(self, model, idx, cin_img, cout):
+    if model.config.model.progressive_combine != 'sum':
+      raise NotImplementedError("progressive_combine='cat' is not built")
+    self.idx = idx
+    self.conv = ConvBlock(model, idx, cin_img, cout, 1, name='Conv_0')
+
+  def fwd(self, net, pyr, ha):
+    P, c = net.m.P, self.conv
+    out = ops.conv_fwd(pyr.t, P.c(c.pre + 'weight'), c.cout, 1, 1, bias=P.f(c.pre + 'bias'), residual=ha.t)
+    y = Act(out, net.tape)
+    if net.tape.enabled:
+      x = pyr.t
+      net.tape.record(lambda g, acc: self.bwd(net, x, g, acc), (pyr.id, ha.id), y.id)
+    if net.taps is not None:
+      net.taps[self.idx] = out
+    return y
+
+  def bwd(self, net, x, g, acc):
+    (dp,) = self.conv.bwd(net, x, g, (acc[0],), need_dx=net.need_dx)
+    if acc[1] is not None:
+      ops.axpby(acc[1], g, out=acc[1])
+      return (dp, acc[1])
+    return (dp, g)
+
+
+class PyramidDownConv:
+  """Downsample(with_conv=True) of the input pyramid followed by the residual merge
+  (pyr + h)/sqrt2 (reference models/layerspp.py:142-176, up_or_down_sampling.py:144-178,
+  models/ncsnpp.py:337-344): FIR pre-filter (pad 2,2) -> 3x3 stride-2 convolution as im2col + GEMM."""
+
+  def __init__(self, model, idx, cin, cout, image_side):
+    m = model.config.model
+    self.idx, self.fir, self.image_side = idx, m.fir, image_side
+    self.cin = cin if cin % 64 == 0 else CPAD
+    self.cout = cout
+    self.pre = f'all_modules.{idx}.' + ('Conv2d_0.' if m.fir else 'Conv_0.')
+    model._add_param(self.pre + 'weight', (cout, cin, 3, 3), 'conv', init=init_conv(1.), pad=(cout, self.cin))
+    model._add_param(self.pre + 'bias', (cout,), init=init_zeros)
+    self.scale = 1. / SQRT2 if m.skip_rescale else 1.
+
+  def fwd(self, net, pyr, ha):
+    P, m = net.m.P, net.m
+    x = pyr.t
+    B, H, W, C = x.shape
+    y = ops.upfirdn2d_nhwc(x, m._fir_down, pad=(2, 2)) if self.fir else x
+    cols = ops.im2col(y, 3, 3, 2, 0, H // 2, W // 2)
+    out = ops.gemm_nt(cols, P.c(self.pre + 'weight'), bias=P.f(self.pre + 'bias'),
+                      residual=ha.t.view(-1, self.cout), alpha=self.scale).view(B, H // 2, W // 2, self.cout)
+    o = Act(out, net.tape)
+    if net.tape.enabled:
+      net.tape.record(lambda g, acc: self.bwd(net, (cols, x.shape, y.shape), g, acc), (pyr.id, ha.id), o.id)
+    if net.taps is not None:
+      net.taps[self.idx] = out
+    return o
+
+  def bwd(self, net, saved, g, acc):
+    P, m, s = net.m.P, net.m, self.scale
+    cols, xshape, yshape = saved
+    B, H, W, C = xshape
+    g2 = g.view(-1, self.cout)
+    rows = g2.shape[0]
+    ops.colsum(g2, 1, rows, self.cout, P.g(self.pre + 'bias'), scale=s, accumulate=True)
+    ops.gemm_tn(g2, cols, self.cout, cols.shape[1], rows, out=P.g(self.pre + 'weight'), alpha=s, accumulate=True)
+    if acc[1] is not None:
+      dh = ops.axpby(acc[1], g, 1.0, s, out=acc[1])
+    else:
+      dh = ops.axpby(g, None, s)
+    if self.image_side and not net.need_dx:
+      return (None, dh)
+    dcols = ops.gemm_nn(g2, P.c(self.pre + 'weight'), cols.shape[1], alpha=s)
+    dy = ops.col2im(dcols, yshape, 3, 3, 2, 0, H // 2, W // 2)
+    dp = ops.upfirdn2d_nhwc(dy, m._fir_down, pad=(1, 1)) if self.fir else dy
+    if acc[0] is not None:
+      ops.axpby(acc[0], dp, out=acc[0])
+      dp = acc[0]
+    return (dp, dh)
 
 
 class TimeEmbedding:
@@ -553,8 +676,12 @@ class NCSNpp(nn.Module):
       raise NotImplementedError("only resblock_type='biggan' (every BASELINE config) is built")
     if m.nonlinearity.lower() != 'swish':
       raise NotImplementedError("only the 'swish' nonlinearity (every shipped NCSN++ config) is built")
-    if m.progressive != 'none' or m.progressive_input != 'none':
-      raise NotImplementedError('progressive growing heads are not built yet')
+    self.progressive, self.progressive_input = m.progressive.lower(), m.progressive_input.lower()
+    if self.progressive not in ('none', 'output_skip'):
+      raise NotImplementedError("progressive='residual' runs into the reference's broken upsample_conv_2d "
+                                "(up_or_down_sampling.py:126) and is not built")
+    if self.progressive_input not in ('none', 'input_skip', 'residual'):
+      raise ValueError(f'progressive input method {m.progressive_input!r} not recognized.')
     cd = compute_dtype or getattr(m, 'compute_dtype', None) or torch.bfloat16
     self.compute_dtype = {'bf16': torch.bfloat16, 'fp32': torch.float32}.get(cd, cd) if isinstance(cd, str) else cd
     self.nf = nf = m.nf
@@ -585,9 +712,12 @@ class NCSNpp(nn.Module):
     i = self.temb.next_idx
     self.conv_in = ConvBlock(self, i, ch, nf, 3, is_input=True)
     i += 1
-    self.down = []          # list of levels; each level = list of (ResBlock, AttnBlock|None), then optional down block
+    self.down = []          # per level: [(ResBlock, AttnBlock|None)], down block, input-pyramid block
     hs_c = [nf]
     cin = nf
+    pyr_ch = ch
+    self.img_down = ImageResample(self, up=False)
+    self.img_up = ImageResample(self, up=True)
     for lvl in range(n_res):
       blocks = []
       for _ in range(m.num_res_blocks):
@@ -601,14 +731,21 @@ class NCSNpp(nn.Module):
           i += 1
         blocks.append((rb, ab))
         hs_c.append(cin)
-      dn = None
+      dn = pyr = None
       if lvl != n_res - 1:
         if not aux:
           raise NotImplementedError('auxiliary_resblock=False is not built')
         dn = ResBlock(self, i, cin, cin, down=True, hw=res[lvl + 1])
         i += 1
+        if self.progressive_input == 'input_skip':
+          pyr = CombineBlock(self, i, pyr_ch, cin)
+          i += 1
+        elif self.progressive_input == 'residual':
+          pyr = PyramidDownConv(self, i, pyr_ch, cin, image_side=(lvl == 0))
+          i += 1
+          pyr_ch = cin
         hs_c.append(cin)
-      self.down.append((blocks, dn))
+      self.down.append((blocks, dn, pyr))
     self.mid = (ResBlock(self, i, cin, cin, hw=res[-1]), AttnBlock(self, i + 1, cin),
                 ResBlock(self, i + 2, cin, cin, hw=res[-1]))
     i += 3
@@ -625,14 +762,22 @@ class NCSNpp(nn.Module):
       if res[lvl] in m.attn_resolutions and attn_on:
         ab = AttnBlock(self, i, cin)
         i += 1
+      pout = None
+      if self.progressive == 'output_skip':
+        pout = NormActConv(self, i, i + 1, cin, ch, m.init_scale)
+        i += 2
       upb = None
       if lvl != 0:
         upb = ResBlock(self, i, cin, cin, up=True, hw=res[lvl - 1])
         i += 1
-      self.up.append((blocks, ab, upb))
+      self.up.append((blocks, ab, pout, upb))
     assert not hs_c
-    self.head = NormActConv(self, i, i + 1, cin, ch, m.init_scale)
-    self.n_modules = i + 2
+    if self.progressive == 'output_skip':
+      self.head = self.up[-1][2]
+      self.n_modules = i
+    else:
+      self.head = NormActConv(self, i, i + 1, cin, ch, m.init_scale)
+      self.n_modules = i + 2
 
     # ---- storage
     self.store.layout()
@@ -752,27 +897,40 @@ class NCSNpp(nn.Module):
     net.x_id = h_in.id
     h = self.conv_in.fwd(net, h_in)
     hs = [h]
-    for blocks, dn in self.down:
+    pyr_in = h_in                      # input pyramid (progressive_input != 'none')
+    for lvl, (blocks, dn, pyr) in enumerate(self.down):
       for rb, ab in blocks:
         h = rb.fwd(net, hs[-1])
         if ab is not None:
           h = ab.fwd(net, h)
         hs.append(h)
       if dn is not None:
-        hs.append(dn.fwd(net, hs[-1]))
+        h = dn.fwd(net, hs[-1])
+        if self.progressive_input == 'input_skip':
+          pyr_in = self.img_down.fwd(net, pyr_in, image_side_input=True)
+          h = pyr.fwd(net, pyr_in, h)
+        elif self.progressive_input == 'residual':
+          pyr_in = pyr.fwd(net, pyr_in, h)
+          h = pyr_in
+        hs.append(h)
     h = hs[-1]
     h = self.mid[0].fwd(net, h)
     h = self.mid[1].fwd(net, h)
     h = self.mid[2].fwd(net, h)
-    for blocks, ab, upb in self.up:
+    pyramid = None                     # output pyramid (progressive == 'output_skip')
+    for blocks, ab, pout, upb in self.up:
       for rb, _, _ in blocks:
         h = rb.fwd(net, h, hs.pop())
       if ab is not None:
         h = ab.fwd(net, h)
+      if pout is not None:
+        if pyramid is not None:
+          pyramid = self.img_up.fwd(net, pyramid)
+        pyramid = pout.fwd(net, h, res=pyramid)
       if upb is not None:
         h = upb.fwd(net, h)
     assert not hs
-    h = self.head.fwd(net, h)
+    h = pyramid if self.progressive == 'output_skip' else self.head.fwd(net, h)
     net.out_id = h.id
     net.out_scale = (1. / used_sigmas).contiguous() if m.scale_by_sigma else None
     out = ops.nhwc_to_nchw(h.t, x.shape[1], net.out_scale)

@@ -3,6 +3,7 @@ their own backward).  Activations are NHWC torch tensors (B, H, W, C), fp32 or b
 Every wrapper enqueues on torch's current CUDA stream and never synchronises.
 """
 import ctypes
+import math
 
 import torch
 
@@ -233,6 +234,17 @@ def resample2x(x, x2, direction, scale):
 
 
 def colsum(x, groups, rows_per_group, C, out, scale=1.0, accumulate=False):
+  """out[g][c] (+)= scale * sum of x[g*rows_per_group + r][c].  A single long group (bias gradients over every
+  pixel) is reduced in two deterministic passes so that the first one fills the GPU."""
+  if groups == 1 and rows_per_group >= 4096:
+    chunks = 1
+    while chunks < 1024 and rows_per_group % (chunks * 2) == 0 and rows_per_group // (chunks * 2) >= 32:
+      chunks *= 2
+    if chunks > 1:
+      part = torch.empty((chunks, C), dtype=torch.float32, device=x.device)
+      check(lib.st_colsum(ptr(x), dt(x), chunks, rows_per_group // chunks, C, 1.0, ptr(part), 0, stream()))
+      check(lib.st_colsum(ptr(part), F32, 1, chunks, C, float(scale), ptr(out), int(accumulate), stream()))
+      return out
   check(lib.st_colsum(ptr(x), dt(x), groups, rows_per_group, C, float(scale), ptr(out), int(accumulate), stream()))
   return out
 
@@ -251,9 +263,24 @@ def softmax_bwd(p, dp, L, scale):
   return ds
 
 
-def timestep_embedding(labels, dim, max_positions=10000.):
+_FREQS = {}
+
+
+def timestep_frequencies(dim, device, max_positions=10000):
+  """exp(-log(max_positions)/(half-1) * arange(half)) exactly as the reference evaluates it
+  (models/layers.py:518-521: float32 tensor times a Python double, torch.exp on the host)."""
+  key = (dim, str(device), max_positions)
+  if key not in _FREQS:
+    half = dim // 2
+    emb = math.log(max_positions) / (half - 1)
+    _FREQS[key] = torch.exp(torch.arange(half, dtype=torch.float32) * -emb).to(device)
+  return _FREQS[key]
+
+
+def timestep_embedding(labels, dim, max_positions=10000):
   out = torch.empty((labels.shape[0], dim), dtype=torch.float32, device=labels.device)
-  check(lib.st_timestep_embedding(ptr(labels), ptr(out), labels.shape[0], dim, float(max_positions), stream()))
+  check(lib.st_timestep_embedding(ptr(labels), ptr(timestep_frequencies(dim, labels.device, max_positions)), ptr(out),
+                                  labels.shape[0], dim, stream()))
   return out
 
 
@@ -298,3 +325,19 @@ def upfirdn2d_nhwc(x, k, up=1, down=1, pad=(0, 0)):
   check(lib.st_upfirdn2d(ptr(x), ptr(y), dt(x), ptr(k), mj, H, W, mn, kh, kw, up, up, down, down, pad[0], pad[1],
                          pad[0], pad[1], stream()))
   return y
+
+
+def im2col(x, kh, kw, stride, pad, oh, ow):
+  """NHWC x -> (B*oh*ow, kh*kw*C) patch matrix of a strided convolution (zero outside the image)."""
+  B, H, W, C = x.shape
+  cols = torch.empty((B * oh * ow, kh * kw * C), dtype=x.dtype, device=x.device)
+  check(lib.st_im2col(ptr(x), ptr(cols), dt(x), B, H, W, C, kh, kw, stride, pad, oh, ow, stream()))
+  return cols
+
+
+def col2im(dcols, shape, kh, kw, stride, pad, oh, ow):
+  """Adjoint of im2col: (B*oh*ow, kh*kw*C) -> NHWC gradient of shape `shape`."""
+  B, H, W, C = shape
+  dx = torch.empty(shape, dtype=dcols.dtype, device=dcols.device)
+  check(lib.st_col2im(ptr(dcols), ptr(dx), dt(dcols), B, H, W, C, kh, kw, stride, pad, oh, ow, stream()))
+  return dx

@@ -198,9 +198,23 @@ def test_pc_sampler_vs_reference_fixture(golden):
   trace = []
   x, nfe = fn(model, x_init=torch.tensor(g['vp_xT']), noises=[torch.tensor(z) for z in g['vp_z']], trace=trace)
   assert nfe == int(g['vp_nfe'])
-  for i, st in enumerate(trace):
+  for i, st in enumerate(trace[:-1]):
     assert rel_l2(st, g['vp_trace'][i]) < 1e-4, i
-  assert rel_l2(x, g['vp_x']) < 1e-4
+  # The last reverse step and the denoise step run at t = eps = 1e-5, where the reference evaluates
+  # std = sqrt(1 - exp(2*log_mean_coeff)) in fp32 (sde_lib.py:151-155): 1 - exp(-1e-6) keeps ~4 significant
+  # bits, so one ulp of difference between the host's and the device's expf moves std (and the score = -out/std
+  # that dominates the update) by up to a few per cent.  The bound below is that measured schedule difference.
+  t_eps = torch.full((2,), float(g['vp_eps']))
+  unit = torch.ones(2, 1, 1, 1)
+  std_cpu = sde8.marginal_prob(unit, t_eps)[1]
+  std_gpu = sde8.marginal_prob(unit.to(DEV), t_eps.to(DEV))[1].cpu()
+  sched = float((std_gpu / std_cpu - 1).abs().max())
+  assert rel_l2(trace[-1], g['vp_trace'][-1]) < 1e-4 + 2 * sched, sched
+  t0 = torch.zeros(2)
+  fd_c, G_c = sde8.discretize(unit, t_eps, t0)
+  fd_g, G_g = sde8.discretize(unit.to(DEV), t_eps.to(DEV), t0.to(DEV))
+  sched2 = sched + float((G_g.cpu() ** 2 / G_c ** 2 - 1).abs().max())
+  assert rel_l2(x, g['vp_x']) < 1e-4 + 4 * sched2, sched2
 
 
 def test_pc_sampler_cuda_graph_matches_eager():
@@ -245,3 +259,44 @@ def test_score_fn_and_state_dict_roundtrip():
     assert torch.equal(out_sd['module.' + k].cpu(), v.detach()), k
   with pytest.raises(RuntimeError):
     mutils.unwrap(model)(x, t)          # CPU tensors: no fallback
+
+
+def _reduced(tag):
+  from soft_truncation_b200 import configs
+  if tag == 'c3':       # RVE, FIR res-blocks, 'residual' input pyramid (configs/ve/CELEBA/uncsnpp_st.py, reduced width)
+    cfg = configs.celeba_uncsnpp_st()
+    cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks = 32, (1, 2, 2), 1
+    cfg.model.dropout = 0.
+  else:                 # VE, FIR, input_skip + output_skip pyramids (configs/ve/celebahq/uncsnpp_st.py, reduced)
+    cfg = configs.celebahq_uncsnpp_st()
+    cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks = 32, (1, 1, 2, 2), 1
+  cfg.data.image_size = 32
+  cfg.device = torch.device(DEV)
+  return cfg
+
+
+@pytest.mark.parametrize('tag', ['c3', 'c5'])
+def test_fir_and_pyramid_variants_vs_reference_fixture(golden, tag):
+  """BASELINE configs[2]/[4] block types (FIR resampling, input/output pyramids, Fourier embedding, VE/RVE loss)."""
+  from soft_truncation_b200 import losses
+  from soft_truncation_b200.models import utils as mutils
+  g = golden('variants_golden.npz')
+  cfg = _reduced(tag)
+  model, sde, _ = _model(cfg, int(g[f'{tag}_seed']), torch.float32)
+  net = mutils.unwrap(model)
+  names = [k for k, _ in net.named_parameters()]
+  assert names == list(g[f'{tag}_names'])
+  x = torch.tensor(g[f'{tag}_x'], device=DEV)
+  model.eval()
+  with torch.no_grad():
+    score = model(x, torch.tensor(g[f'{tag}_sig'], device=DEV))
+  assert rel_l2(score, g[f'{tag}_score']) < 2e-5
+  loss_fn = losses.get_sde_loss_fn(cfg, sde, train=True)
+  net.zero_grad()
+  ls = loss_fn(model, x, importance_sampling=cfg.training.importance_sampling, t_min=float(g[f'{tag}_tmin']),
+               injected=dict(u=torch.tensor(g[f'{tag}_u']), z=torch.tensor(g[f'{tag}_z'])))
+  np.testing.assert_allclose(ls.detach().cpu().numpy(), g[f'{tag}_losses'], rtol=2e-4)
+  torch.mean(ls).backward()
+  params = dict(net.named_parameters())
+  gn = np.array([params[k].grad.double().norm().item() if params[k].requires_grad else 0. for k in names])
+  np.testing.assert_allclose(gn, g[f'{tag}_gnorm'], rtol=2e-3, atol=1e-6 * g[f'{tag}_gnorm'].max())
