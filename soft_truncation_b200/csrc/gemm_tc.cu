@@ -32,6 +32,8 @@ constexpr int A_STAGE_BYTES = BM * 128;
 constexpr int NUM_THREADS = 192;
 
 enum OpKind { KMAJOR = 0, MNMAJOR = 1, GATHER_K = 2, GATHER_MN = 3, DGRADW = 4 };
+// GATHER_MN is valid for either operand: as B it is the v1 weight-gradient form, as A it is the transposed
+// weight-gradient form of the persistent kernel (M = taps*Cin, N = Cout, output stored transposed).
 
 struct TcParams {
   int M, N, batch, split_k;
@@ -51,6 +53,10 @@ struct TcParams {
   const bf16* residual;
   long long ldr, sRb;
   float alpha;
+  // persistent kernel only
+  int cluster;            // CTAs per cluster along M (B tiles are multicast across them)
+  int trans_out;          // store C[n][m] instead of C[m][n] (accumulate mode)
+  int m_tiles, n_tiles;
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -99,6 +105,30 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -360,6 +390,293 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+  }
+}
+
+
+// ------------------------------------------------------------------------------------ persistent kernel (v2)
+// Same warp roles as gemm_tc_kernel, but
+//   * one CTA per SM loops over output tiles (static round-robin over clusters), the smem ring keeps streaming
+//     across tile boundaries,
+//   * the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the MMAs of
+//     tile i+1,
+//   * `cluster` CTAs that work on M-adjacent tiles share the B tile: each loads 1/cluster of it and TMA-multicasts
+//     its slice into every CTA of the cluster (L2 -> SM traffic for B drops by `cluster`),
+//   * weight gradients run transposed (A = shifted NHWC boxes MN-major, B = dY MN-major, C stored transposed) so
+//     that the big dimension taps*Cin is M and the dY tile is the multicast operand.
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0,
+                                                                  const __grid_constant__ CUtensorMap mapA1,
+                                                                  const __grid_constant__ CUtensorMap mapB0,
+                                                                  const __grid_constant__ CUtensorMap mapB1,
+                                                                  const TcParams p) {
+  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int TMEM_COLS = 2 * BN;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+  const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int cs = p.cluster;
+  const int rank = cs > 1 ? (int)cluster_ctarank() : 0;
+  const uint16_t mc_mask = (uint16_t)((1u << cs) - 1u);
+  const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
+  const int split = p.split_k > 1 ? p.split_k : 1;
+  const int m_groups = (p.m_tiles + cs - 1) / cs;
+  const int total = p.batch * split * p.n_tiles * m_groups;
+  const int kper = (p.nk + split - 1) / split;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, cs);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull0 + 8 * b, 1);
+      mbar_init(tempty0 + 8 * b, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (cs > 1) cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // decode a work item
+  auto decode = [&](int st, int& m0, int& n0, int& b, int& kt0, int& nkt) {
+    const int mg = st % m_groups;
+    const int nt = (st / m_groups) % p.n_tiles;
+    const int z = st / (m_groups * p.n_tiles);
+    b = z / split;
+    const int ks = z % split;
+    m0 = (mg * cs + rank) * BM;
+    n0 = nt * BN;
+    kt0 = ks * kper;
+    nkt = min(p.nk, kt0 + kper) - kt0;
+  };
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int st = cluster_id; st < total; st += n_clusters) {
+        int m0, n0, b, kt0, nkt;
+        decode(st, m0, n0, b, kt0, nkt);
+        if (nkt <= 0) continue;
+        int gx0 = 0, gy0 = 0, gn0 = 0;
+        if (p.a_kind == GATHER_K) {
+          gx0 = m0 % p.W;
+          gy0 = (m0 / p.W) % p.H;
+          gn0 = m0 / (p.W * p.H);
+        }
+        for (int i = 0; i < nkt; ++i, ++it) {
+          const int kt = kt0 + i;
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+          const uint32_t bar = full0 + 8 * s;
+          mbar_expect_tx(bar, STAGE_BYTES);
+          const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+          // ---- A (private to this CTA)
+          if (p.a_kind == KMAJOR) {
+            tma_load_3d(sa, &mapA0, bar, kt * BK, m0, b);
+          } else if (p.a_kind == MNMAJOR) {
+            tma_load_3d(sa, &mapA0, bar, m0, kt * BK, b);
+            tma_load_3d(sa + 8192, &mapA0, bar, m0 + 64, kt * BK, b);
+          } else if (p.a_kind == GATHER_K) {
+            const int tap = kt / p.cblocks, cb = kt % p.cblocks;
+            const int dy = tap / p.kw - (p.kh - 1) / 2, dx = tap % p.kw - (p.kw - 1) / 2;
+            if (cb < p.c1blocks) tma_load_4d(sa, &mapA0, bar, cb * 64, gx0 + dx, gy0 + dy, gn0);
+            else tma_load_4d(sa, &mapA1, bar, (cb - p.c1blocks) * 64, gx0 + dx, gy0 + dy, gn0);
+          } else {   // GATHER_MN as A: m = (tap, channel), k = pixel block
+            const int p0 = kt * BK;
+            const int x0 = p0 % p.W, y0 = (p0 / p.W) % p.H, i0 = p0 / (p.W * p.H);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int mm = m0 + 64 * j;
+              const int tap = mm / p.Ct, c = mm % p.Ct;
+              const int dy = tap / p.kw - (p.kh - 1) / 2, dx = tap % p.kw - (p.kw - 1) / 2;
+              if (tap >= p.ntaps) tma_load_4d(sa + j * 8192, &mapA0, bar, 0, x0, y0, i0);      // masked rows
+              else if (c < p.C1) tma_load_4d(sa + j * 8192, &mapA0, bar, c, x0 + dx, y0 + dy, i0);
+              else tma_load_4d(sa + j * 8192, &mapA1, bar, c - p.C1, x0 + dx, y0 + dy, i0);
+            }
+          }
+          // ---- B: this CTA's slice, multicast to the whole cluster
+          if (p.b_kind == KMAJOR) {
+            const int rows = BN / cs;
+            if (cs > 1) tma_load_3d_mc(sb + rank * rows * 128, &mapB0, bar, kt * BK, n0 + rank * rows, b, mc_mask);
+            else tma_load_3d(sb, &mapB0, bar, kt * BK, n0, b);
+          } else {
+            const int nb = BN / 64, per = nb / cs;       // host guarantees cs <= nb
+            for (int jj = 0; jj < per; ++jj) {
+              const int j = rank * per + jj;
+              int c0, c1, c2;
+              if (p.b_kind == MNMAJOR) { c0 = n0 + 64 * j; c1 = kt * BK; c2 = b; }
+              else { const int tap = kt / p.cblocks, cob = kt % p.cblocks; c0 = n0 + 64 * j; c1 = p.ntaps - 1 - tap; c2 = cob * 64; }
+              if (cs > 1) tma_load_3d_mc(sb + j * 8192, &mapB0, bar, c0, c1, c2, mc_mask);
+              else tma_load_3d(sb + j * 8192, &mapB0, bar, c0, c1, c2);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      const bool a_mn = (p.a_kind == MNMAJOR || p.a_kind == GATHER_MN);
+      const bool b_mn = (p.b_kind != KMAJOR);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int it = 0, tl = 0;
+      for (int st = cluster_id; st < total; st += n_clusters) {
+        int m0, n0, b, kt0, nkt;
+        decode(st, m0, n0, b, kt0, nkt);
+        if (nkt <= 0) continue;
+        const int buf = tl & 1;
+        if (tl >= 2) mbar_wait(tempty0 + 8 * buf, ((tl >> 1) - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+        for (int i = 0; i < nkt; ++i, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j) {
+            const uint64_t ad = a_mn ? make_desc(sa + j * 2048, 8192, 1024) : make_desc(sa + j * 32, 16, 1024);
+            const uint64_t bd = b_mn ? make_desc(sb + j * 2048, 8192, 1024) : make_desc(sb + j * 32, 16, 1024);
+            umma_f16(tacc, ad, bd, idesc, (i | j) != 0 ? 1u : 0u);
+          }
+          if (cs > 1) umma_commit_mc(empty0 + 8 * s, mc_mask);
+          else umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull0 + 8 * buf);
+        ++tl;
+      }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5)
+    const int q = warp % 4;
+    const int row = q * 32 + lane;
+    int tl = 0;
+    for (int st = cluster_id; st < total; st += n_clusters) {
+      int m0, n0, b, kt0, nkt;
+      decode(st, m0, n0, b, kt0, nkt);
+      if (nkt <= 0) continue;
+      const int buf = tl & 1;
+      const long long m = (long long)m0 + row;
+      mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const bool row_ok = m < p.M;
+      const float* rb = (p.rowbias && row_ok) ? p.rowbias + (m / p.rows_per_rb) * p.ld_rb : nullptr;
+      const bf16* res = (p.residual && row_ok) ? p.residual + (long long)b * p.sRb + m * p.ldr : nullptr;
+      const long long crow = (long long)b * p.sCb + m * p.ldc;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
+        const int nb = n0 + c * 32;
+        if (!row_ok || nb >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        const bool full = (nb + 32 <= p.N);
+        if (p.accumulate) {
+          if (p.trans_out) {
+            float* dst = reinterpret_cast<float*>(p.C) + (long long)b * p.sCb + m;     // C[n][m]: lanes are contiguous
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (full || nb + i < p.N) atomicAdd(dst + (long long)(nb + i) * p.ldc, p.alpha * v[i]);
+          } else {
+            float* dst = reinterpret_cast<float*>(p.C) + crow + nb;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (full || nb + i < p.N) atomicAdd(dst + i, p.alpha * v[i]);
+          }
+          continue;
+        }
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (full || nb + i < p.N) v[i] += __ldg(p.bias + nb + i);
+        }
+        if (rb) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (full || nb + i < p.N) v[i] += __ldg(rb + nb + i);
+        }
+        if (res) {
+          if (full && ((p.ldr | p.sRb) % 8 == 0)) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 t = *reinterpret_cast<const uint4*>(res + nb + g * 8);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[g * 8 + 2 * e] += __low2float(h[e]);
+                v[g * 8 + 2 * e + 1] += __high2float(h[e]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < p.N) v[i] += __bfloat162float(res[nb + i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+        if (p.out_bf16) {
+          bf16* dst = reinterpret_cast<bf16*>(p.C) + crow + nb;
+          if (full && ((p.ldc | p.sCb) % 8 == 0)) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 t;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+              *reinterpret_cast<uint4*>(dst + g * 8) = t;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < p.N) dst[i] = __float2bfloat16_rn(v[i]);
+          }
+        } else {
+          float* dst = reinterpret_cast<float*>(p.C) + crow + nb;
+          if (full && ((p.ldc | p.sCb) % 4 == 0)) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<float4*>(dst + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < p.N) dst[i] = v[i];
+          }
+        }
+      }
+      // this warp has drained its quarter of the accumulator buffer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+      ++tl;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (cs > 1) cluster_sync_all();     // no CTA may exit while peers can still multicast into it
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
 
