@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -794,7 +795,165 @@ int st_gemm_tc_supported(const st_gemm_args* a, const char** why) {
 #undef NO
 }
 
+// ---------------------------------------------------------------- persistent kernel: plan + launch
+namespace {
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int BN, int STAGES>
+int launch2(const CUtensorMap* maps, TcParams& p, int total_super, cudaStream_t stream) {
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static bool configured = false;
+  static int max_clusters[5] = {0, 0, 0, 0, 0};
+  auto kern = gemm_tc2_kernel<BN, STAGES>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { st_set_error("st_gemm(tc2): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ST_ERR_CUDA; }
+    configured = true;
+  }
+  const int cs = p.cluster;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters[cs] == 0) {
+    int n = 0;
+    cfg.gridDim = dim3(cs * 64);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = st_num_sms() / cs; }
+    max_clusters[cs] = n;
+  }
+  int clusters = total_super < max_clusters[cs] ? total_super : max_clusters[cs];
+  cfg.gridDim = dim3(clusters * cs);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], p);
+  if (e != cudaSuccess) { st_set_error("st_gemm(tc2): launch failed: %s", cudaGetErrorString(e)); return ST_ERR_CUDA; }
+  return 0;
+}
+
+bool gather_maps(CUtensorMap* m0, CUtensorMap* m1, const void* p1, const void* p2, int C1, int C2, int W, int H, int n_img,
+                 int npix) {
+  uint32_t bw, bh, bn;
+  pixel_box(npix, H, W, &bw, &bh, &bn);
+  const uint32_t box[4] = {64, bw, bh, bn};
+  {
+    const uint64_t dims[4] = {(uint64_t)C1, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
+    const uint64_t str[3] = {(uint64_t)C1 * 2, (uint64_t)W * C1 * 2, (uint64_t)H * W * C1 * 2};
+    if (!encode_map(m0, p1, 4, dims, str, box)) return false;
+  }
+  if (C2 > 0) {
+    const uint64_t dims[4] = {(uint64_t)C2, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
+    const uint64_t str[3] = {(uint64_t)C2 * 2, (uint64_t)W * C2 * 2, (uint64_t)H * W * C2 * 2};
+    if (!encode_map(m1, p2, 4, dims, str, box)) return false;
+  }
+  return true;
+}
+
+int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap maps[4];
+  memset(maps, 0, sizeof(maps));
+  const int Ct = a->C1 + a->C2;
+  const bool wgrad = (a->b_mode == ST_OP_GATHER);     // runs transposed: M' = taps*Cin, N' = Cout
+  const int M = wgrad ? a->N : a->M, N = wgrad ? a->M : a->N;
+  p.M = M; p.N = N; p.batch = a->batch; p.split_k = a->split_k > 1 ? a->split_k : 1;
+  p.H = a->H; p.W = a->W; p.kh = a->kh; p.kw = a->kw; p.ntaps = a->kh * a->kw; p.Ct = Ct; p.C1 = a->C1;
+  p.nk = (a->K + BK - 1) / BK;
+  p.cblocks = Ct > 0 ? Ct / 64 : 0;
+  p.c1blocks = a->C1 / 64;
+  const int BN = (N >= 256 && N % 256 == 0) ? 256 : (N > 64 ? 128 : 64);
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = (N + BN - 1) / BN;
+
+  // B kind first (it bounds the cluster size)
+  const bool b_kmajor = !wgrad && a->b_mode == ST_OP_STRIDED && a->sBk == 1;
+  int cs = env_int("ST_TC_CLUSTER", 2);
+  if (cs != 1 && cs != 2 && cs != 4) cs = 2;
+  while (cs > 1 && cs > p.m_tiles) cs >>= 1;
+  if (!b_kmajor) while (cs > 1 && cs > BN / 64) cs >>= 1;
+  p.cluster = cs;
+
+  // ---------------- A
+  if (wgrad) {
+    p.a_kind = GATHER_MN;
+    if (!gather_maps(&maps[0], &maps[1], a->B, a->B2, a->C1, a->C2, a->W, a->H, a->n_img, 64)) return ST_ERR_CUDA;
+  } else if (a->a_mode == ST_OP_GATHER) {
+    p.a_kind = GATHER_K;
+    if (!gather_maps(&maps[0], &maps[1], a->A, a->A2, a->C1, a->C2, a->W, a->H, a->n_img, 128)) return ST_ERR_CUDA;
+  } else if (a->sAk == 1) {
+    p.a_kind = KMAJOR;
+    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->batch};
+    const uint64_t str[2] = {(uint64_t)a->sAm * 2, (uint64_t)(a->batch > 1 ? a->sAb : (int64_t)a->M * a->sAm) * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    if (!encode_map(&maps[0], a->A, 3, dims, str, box)) return ST_ERR_CUDA;
+  } else {
+    p.a_kind = MNMAJOR;
+    const uint64_t dims[3] = {(uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->batch};
+    const uint64_t str[2] = {(uint64_t)a->sAk * 2, (uint64_t)(a->batch > 1 ? a->sAb : (int64_t)a->K * a->sAk) * 2};
+    const uint32_t box[3] = {64, 64, 1};
+    if (!encode_map(&maps[0], a->A, 3, dims, str, box)) return ST_ERR_CUDA;
+  }
+  // ---------------- B
+  if (wgrad) {
+    p.b_kind = MNMAJOR;        // dY[pixel][co]: n' = co contiguous, k = pixel
+    const uint64_t dims[3] = {(uint64_t)a->M, (uint64_t)a->K, 1};
+    const uint64_t str[2] = {(uint64_t)a->sAk * 2, (uint64_t)a->K * a->sAk * 2};
+    const uint32_t box[3] = {64, 64, 1};
+    if (!encode_map(&maps[2], a->A, 3, dims, str, box)) return ST_ERR_CUDA;
+  } else if (a->b_mode == ST_OP_DGRADW) {
+    p.b_kind = DGRADW;
+    const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)p.ntaps, (uint64_t)Ct};
+    const uint64_t str[2] = {(uint64_t)a->N * 2, (uint64_t)p.ntaps * a->N * 2};
+    const uint32_t box[3] = {64, 1, 64};
+    if (!encode_map(&maps[2], a->B, 3, dims, str, box)) return ST_ERR_CUDA;
+  } else if (a->sBk == 1) {
+    p.b_kind = KMAJOR;
+    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->batch};
+    const uint64_t str[2] = {(uint64_t)a->sBn * 2, (uint64_t)(a->batch > 1 ? a->sBb : (int64_t)a->N * a->sBn) * 2};
+    const uint32_t box[3] = {64, (uint32_t)(BN / cs), 1};
+    if (!encode_map(&maps[2], a->B, 3, dims, str, box)) return ST_ERR_CUDA;
+  } else {
+    p.b_kind = MNMAJOR;
+    const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->batch};
+    const uint64_t str[2] = {(uint64_t)a->sBk * 2, (uint64_t)(a->batch > 1 ? a->sBb : (int64_t)a->K * a->sBk) * 2};
+    const uint32_t box[3] = {64, 64, 1};
+    if (!encode_map(&maps[2], a->B, 3, dims, str, box)) return ST_ERR_CUDA;
+  }
+
+  p.C = a->C; p.ldc = a->sCm; p.sCb = a->sCb; p.out_bf16 = a->out_dtype == ST_BF16; p.accumulate = a->accumulate;
+  p.trans_out = wgrad ? 1 : 0;
+  p.bias = a->bias; p.rowbias = a->rowbias; p.rows_per_rb = a->rows_per_rb > 0 ? a->rows_per_rb : 1; p.ld_rb = a->ld_rb;
+  p.residual = reinterpret_cast<const bf16*>(a->residual); p.ldr = a->sRm; p.sRb = a->sRb; p.alpha = a->alpha;
+
+  const int m_groups = (p.m_tiles + cs - 1) / cs;
+  const long long total = (long long)p.batch * p.split_k * p.n_tiles * m_groups;
+  ST_CHECK_ARG(total < (1LL << 30), "st_gemm(tc2): too many tiles");
+  if (BN == 256) return launch2<256, 4>(maps, p, (int)total, stream);
+  if (BN == 128) return launch2<128, 6>(maps, p, (int)total, stream);
+  return launch2<64, 8>(maps, p, (int)total, stream);
+}
+
+}  // namespace
+
+int st_gemm_tc1(const st_gemm_args* a, cudaStream_t stream);
+
 int st_gemm_tc(const st_gemm_args* a, cudaStream_t stream) {
+  static const int variant = env_int("ST_TC_VARIANT", 2);
+  return variant == 1 ? st_gemm_tc1(a, stream) : st_gemm_tc2(a, stream);
+}
+
+int st_gemm_tc1(const st_gemm_args* a, cudaStream_t stream) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   CUtensorMap maps[4];

@@ -28,6 +28,11 @@ SQRT2 = math.sqrt(2.)
 CPAD = 64     # physical channel count of the 3-channel image-side tensors
 
 
+def _phys_channels(c):
+  """Image-side channel counts (3) are stored padded to CPAD; feature channel counts are kept."""
+  return c if (c >= 16 and c % 4 == 0) else CPAD
+
+
 class _Holder(nn.Module):
   """Parameter container that reproduces the reference's module/parameter names."""
 
@@ -322,8 +327,7 @@ class ConvBlock:
     CPAD so that the convolution runs on the common 64-wide K/N blocks."""
     self.idx, self.k, self.is_input = idx, k, is_input
     self.cin_l, self.cout_l = cin, cout
-    self.cin = cin if cin % 64 == 0 else CPAD
-    self.cout = cout if cout % 64 == 0 else CPAD
+    self.cin, self.cout = _phys_channels(cin), _phys_channels(cout)
     pre = f'all_modules.{idx}.' + (name + '.' if name else '')
     model._add_param(pre + 'weight', (cout, cin, k, k), 'conv', init=init_conv(init_scale), pad=(self.cout, self.cin))
     model._add_param(pre + 'bias', (cout,), init=init_zeros, pad=(self.cout,))
@@ -466,7 +470,7 @@ class PyramidDownConv:
   def __init__(self, model, idx, cin, cout, image_side):
     m = model.config.model
     self.idx, self.fir, self.image_side = idx, m.fir, image_side
-    self.cin = cin if cin % 64 == 0 else CPAD
+    self.cin = _phys_channels(cin)
     self.cout = cout
     self.pre = f'all_modules.{idx}.' + ('Conv2d_0.' if m.fir else 'Conv_0.')
     model._add_param(self.pre + 'weight', (cout, cin, 3, 3), 'conv', init=init_conv(1.), pad=(cout, self.cin))
