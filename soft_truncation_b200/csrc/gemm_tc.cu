@@ -396,27 +396,34 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
 
 
 // ------------------------------------------------------------------------------------ persistent kernel (v2)
-// Same warp roles as gemm_tc_kernel, but
+// Same producer / MMA roles as gemm_tc_kernel, but
 //   * one CTA per SM loops over output tiles (static round-robin over clusters), the smem ring keeps streaming
 //     across tile boundaries,
 //   * the accumulator is double-buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the MMAs of
-//     tile i+1,
+//     tile i+1; EIGHT epilogue warps (two per TMEM lane quarter, each taking half of the columns),
+//   * the residual tile of the epilogue is prefetched with cp.async into thread-private shared-memory slots
+//     while the tile's MMAs are still running, so no global-load latency sits between tcgen05.ld and the store,
 //   * `cluster` CTAs that work on M-adjacent tiles share the B tile: each loads 1/cluster of it and TMA-multicasts
 //     its slice into every CTA of the cluster (L2 -> SM traffic for B drops by `cluster`),
 //   * weight gradients run transposed (A = shifted NHWC boxes MN-major, B = dY MN-major, C stored transposed) so
 //     that the big dimension taps*Cin is M and the dY tile is the multicast operand.
+constexpr int NUM_THREADS2 = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0,
-                                                                  const __grid_constant__ CUtensorMap mapA1,
-                                                                  const __grid_constant__ CUtensorMap mapB0,
-                                                                  const __grid_constant__ CUtensorMap mapB1,
-                                                                  const TcParams p) {
+__global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0,
+                                                                   const __grid_constant__ CUtensorMap mapA1,
+                                                                   const __grid_constant__ CUtensorMap mapB0,
+                                                                   const __grid_constant__ CUtensorMap mapB1,
+                                                                   const TcParams p) {
   constexpr int B_STAGE_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr int TMEM_COLS = 2 * BN;
+  constexpr int CH = BN / 64;                 // 32-column chunks per epilogue warp
+  constexpr int RES_BYTES = BN * 256;         // 256 epilogue threads x CH chunks x 64 bytes
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* res_stage = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(res_stage + RES_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
@@ -439,7 +446,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, 1);
-      mbar_init(tempty0 + 8 * b, 4);
+      mbar_init(tempty0 + 8 * b, 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -565,9 +572,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..5)
-    const int q = warp % 4;
+    // ===================================================== epilogue (warps 2..9)
+    const int q = warp % 4;                   // TMEM lane quarter of this warp
+    const int half = (warp - 2) / 4;          // which half of the tile's columns
+    const int et = (warp - 2) * 32 + lane;    // epilogue thread index (0..255): its private staging slots
     const int row = q * 32 + lane;
+    const bool vec_res = p.residual && ((p.ldr | p.sRb) % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+    const bool vec_bias = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+    uint8_t* my_stage = res_stage + (size_t)et * 16;
     int tl = 0;
     for (int st = cluster_id; st < total; st += n_clusters) {
       int m0, n0, b, kt0, nkt;
@@ -575,18 +587,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
       if (nkt <= 0) continue;
       const int buf = tl & 1;
       const long long m = (long long)m0 + row;
-      mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const bool row_ok = m < p.M;
+      const int ncol0 = n0 + half * (BN / 2);
       const float* rb = (p.rowbias && row_ok) ? p.rowbias + (m / p.rows_per_rb) * p.ld_rb : nullptr;
       const bf16* res = (p.residual && row_ok) ? p.residual + (long long)b * p.sRb + m * p.ldr : nullptr;
       const long long crow = (long long)b * p.sCb + m * p.ldc;
+      // ---- prefetch this tile's residual slice (overlaps the MMAs that are still filling the accumulator)
+      bool staged = false;
+      if (res && vec_res && ncol0 + BN / 2 <= p.N) {
+        staged = true;
+#pragma unroll
+        for (int j = 0; j < CH * 4; ++j) {
+          const uint32_t dst = smem_u32(my_stage + (size_t)j * 256 * 16);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(res + ncol0 + j * 8) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < CH; ++c) {
         uint32_t r[32];
         __syncwarp();
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
-        const int nb = n0 + c * 32;
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * (BN / 2) + c * 32), r);
+        const int nb = ncol0 + c * 32;
         if (!row_ok || nb >= p.N) continue;
         float v[32];
 #pragma unroll
@@ -607,20 +632,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
           continue;
         }
         if (p.bias) {
+          if (full && vec_bias) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (full || nb + i < p.N) v[i] += __ldg(p.bias + nb + i);
+            for (int g = 0; g < 8; ++g) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + g);
+              v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < p.N) v[i] += __ldg(p.bias + nb + i);
+          }
         }
         if (rb) {
+          if (full && ((reinterpret_cast<uintptr_t>(rb + nb) & 15) == 0)) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (full || nb + i < p.N) v[i] += __ldg(rb + nb + i);
+            for (int g = 0; g < 8; ++g) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(rb + nb) + g);
+              v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < p.N) v[i] += __ldg(rb + nb + i);
+          }
         }
         if (res) {
-          if (full && ((p.ldr | p.sRb) % 8 == 0)) {
+          if (staged) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              uint4 t = *reinterpret_cast<const uint4*>(res + nb + g * 8);
+              const uint4 t = *reinterpret_cast<const uint4*>(my_stage + (size_t)(c * 4 + g) * 256 * 16);
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -665,7 +706,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc2_kernel(const __grid_c
           }
         }
       }
-      // this warp has drained its quarter of the accumulator buffer
+      // this warp has drained its part of the accumulator buffer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
@@ -805,7 +846,8 @@ int env_int(const char* name, int dflt) {
 
 template <int BN, int STAGES>
 int launch2(const CUtensorMap* maps, TcParams& p, int total_super, cudaStream_t stream) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * 128) + BN * 256 + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   static int max_clusters[5] = {0, 0, 0, 0, 0};
   auto kern = gemm_tc2_kernel<BN, STAGES>;
@@ -817,7 +859,7 @@ int launch2(const CUtensorMap* maps, TcParams& p, int total_super, cudaStream_t 
   const int cs = p.cluster;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(NUM_THREADS2);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -939,7 +981,7 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   const int m_groups = (p.m_tiles + cs - 1) / cs;
   const long long total = (long long)p.batch * p.split_k * p.n_tiles * m_groups;
   ST_CHECK_ARG(total < (1LL << 30), "st_gemm(tc2): too many tiles");
-  if (BN == 256) return launch2<256, 4>(maps, p, (int)total, stream);
+  if (BN == 256) return launch2<256, 3>(maps, p, (int)total, stream);
   if (BN == 128) return launch2<128, 6>(maps, p, (int)total, stream);
   return launch2<64, 8>(maps, p, (int)total, stream);
 }
@@ -949,7 +991,7 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
 int st_gemm_tc1(const st_gemm_args* a, cudaStream_t stream);
 
 int st_gemm_tc(const st_gemm_args* a, cudaStream_t stream) {
-  static const int variant = env_int("ST_TC_VARIANT", 2);
+  const int variant = env_int("ST_TC_VARIANT", 2);
   return variant == 1 ? st_gemm_tc1(a, stream) : st_gemm_tc2(a, stream);
 }
 

@@ -2,49 +2,116 @@
 // concatenation of two tensors (the U-Net skip concatenation is never materialised).
 // Reference: nn.GroupNorm(min(C//4,32), C, eps=1e-6) -> act -> Dropout, models/layerspp.py:232,244-245,
 // 258,275-278; models/ncsnpp.py:219-253.
-// All kernels are HBM-bound: 8/16-byte vector loads, fp32 math, deterministic reductions.
+//
+// All kernels are HBM-bound streaming passes.  Thread mapping: one thread owns a fixed run of 8 channels
+// (16-byte bf16 / 32-byte fp32 vectors) of one image and walks that image's pixels, so per-channel constants
+// (gamma, beta, mean, rstd) sit in registers and the inner loop has no integer division; two pixels are in
+// flight per iteration.  Reductions are deterministic (fixed-order shared-memory trees, no float atomics).
 #include "common.cuh"
 
 namespace {
+
+__device__ __forceinline__ void load8(const float* p, float v[8]) {
+  float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float v[8]) {
+  uint4 t = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+__device__ __forceinline__ void store8(float* p, const float v[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float v[8]) {
+  uint4 t;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+
+// keep-multipliers (0 or 1/(1-p)) of 8 consecutive elements: one Philox call, 16 random bits per element
+__device__ __forceinline__ void dropout8(uint64_t seed, uint64_t oct, float p, float keep[8]) {
+  uint4 r = philox4(seed, oct);
+  const float inv = 1.f / (1.f - p);
+  const uint32_t thr = (uint32_t)(p * 65536.f);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    keep[2 * i] = (w[i] & 0xFFFFu) >= thr ? inv : 0.f;
+    keep[2 * i + 1] = (w[i] >> 16) >= thr ? inv : 0.f;
+  }
+}
 
 template <typename T>
 struct Src2 {
   const T* x1;
   const T* x2;
   int C1, C2;
-  // pointer to channel c0 (multiple of 4) of pixel row `row`
+  // pointer to channel c0 (multiple of 8) of pixel row `row`
   __device__ __forceinline__ const T* at(long long row, int c0) const {
     return c0 < C1 ? x1 + row * C1 + c0 : x2 + row * C2 + (c0 - C1);
   }
 };
 
+// per-thread constants of the 8 channels it owns
+struct ChanConst {
+  float gam[8], bet[8], mu[2], r[2];
+  int g[2];
+};
+__device__ __forceinline__ void load_consts(ChanConst& k, int n, int c0, int G, int cpg, const float* gamma, const float* beta,
+                                            const float* mean, const float* rstd) {
+  load8(gamma + c0, k.gam);
+  load8(beta + c0, k.bet);
+  k.g[0] = c0 / cpg;
+  k.g[1] = (c0 + 4) / cpg;
+  k.mu[0] = mean[n * G + k.g[0]]; k.r[0] = rstd[n * G + k.g[0]];
+  k.mu[1] = mean[n * G + k.g[1]]; k.r[1] = rstd[n * G + k.g[1]];
+}
+
 // ---------------------------------------------------------------- stats
-// grid (n_img, splits), block 256.  Thread -> fixed channel quad, strided over pixels.
+// grid (n_img, splits): part[n][split][G][2] = (sum, sum of squares) over the split's pixels
 template <typename T>
 __global__ void __launch_bounds__(256) gn_stats_kernel(Src2<T> s, int hw, int G, int splits, float* part) {
-  const int Ct = s.C1 + s.C2, Q = Ct / 4, cpg = Ct / G;
+  const int Ct = s.C1 + s.C2, V = Ct / 8, cpg = Ct / G;
   const int n = blockIdx.x, sp = blockIdx.y;
-  const int ppb = 256 / Q;                 // pixels processed in parallel
-  const int quad = threadIdx.x % Q, lane = threadIdx.x / Q;
+  const int lanes = 256 / V;
+  const int v = threadIdx.x % V, lane = threadIdx.x / V;
   const int per = (hw + splits - 1) / splits;
   const int p0 = sp * per, p1 = min(hw, p0 + per);
-  float sum = 0.f, sq = 0.f;
-  if (lane < ppb) {
-    for (int p = p0 + lane; p < p1; p += ppb) {
-      float v[4];
-      load4(s.at((long long)n * hw + p, quad * 4), v);
+  float sum[2] = {0.f, 0.f}, sq[2] = {0.f, 0.f};
+  if (lane < lanes) {
+    const int c0 = v * 8;
+    int p = p0 + lane;
+    for (; p + lanes < p1; p += 2 * lanes) {
+      float a[8], b[8];
+      load8(s.at((long long)n * hw + p, c0), a);
+      load8(s.at((long long)n * hw + p + lanes, c0), b);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { sum += v[i]; sq = fmaf(v[i], v[i], sq); }
+      for (int i = 0; i < 8; ++i) {
+        sum[i >> 2] += a[i] + b[i];
+        sq[i >> 2] = fmaf(a[i], a[i], fmaf(b[i], b[i], sq[i >> 2]));
+      }
+    }
+    if (p < p1) {
+      float a[8];
+      load8(s.at((long long)n * hw + p, c0), a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sum[i >> 2] += a[i]; sq[i >> 2] = fmaf(a[i], a[i], sq[i >> 2]); }
     }
   }
-  __shared__ float s_sum[256], s_sq[256];
-  s_sum[threadIdx.x] = sum;
-  s_sq[threadIdx.x] = sq;
+  // quad q = 2*v + half holds channels [4q, 4q+4): whole quads never straddle a group (cpg % 4 == 0)
+  __shared__ float s_sum[512], s_sq[512];
+  s_sum[2 * threadIdx.x] = sum[0]; s_sum[2 * threadIdx.x + 1] = sum[1];
+  s_sq[2 * threadIdx.x] = sq[0]; s_sq[2 * threadIdx.x + 1] = sq[1];
   __syncthreads();
   if (threadIdx.x < G) {
-    const int g = threadIdx.x, qpg = cpg / 4;
+    const int g = threadIdx.x, qpg = cpg / 4, Q = 2 * V;
     double a = 0., b = 0.;
-    for (int l = 0; l < ppb; ++l)
+    for (int l = 0; l < lanes; ++l)
       for (int q = 0; q < qpg; ++q) {
         a += (double)s_sum[l * Q + g * qpg + q];
         b += (double)s_sq[l * Q + g * qpg + q];
@@ -75,56 +142,77 @@ __global__ void gn_finalize_kernel(const float* part, int n_img, int splits, int
 
 // ---------------------------------------------------------------- apply
 template <typename T>
-__global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> s, long long total_quads, int hw, int G,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                       int act, float p_drop, uint64_t seed, const T* mask, T* y) {
-  const int Ct = s.C1 + s.C2, Q = Ct / 4, cpg = Ct / G;
-  for (long long gq = (long long)blockIdx.x * blockDim.x + threadIdx.x; gq < total_quads;
-       gq += (long long)gridDim.x * blockDim.x) {
-    const int quad = (int)(gq % Q);
-    const long long row = gq / Q;          // n*hw + pixel
-    const int n = (int)(row / hw);
-    const int c0 = quad * 4, g = c0 / cpg;
-    float v[4], o[4];
-    load4(s.at(row, c0), v);
-    const float mu = mean[n * G + g], r = rstd[n * G + g];
-    float4 ga = *reinterpret_cast<const float4*>(gamma + c0);
-    float4 be = *reinterpret_cast<const float4*>(beta + c0);
-    const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
+__device__ __forceinline__ void apply8(const float x[8], const ChanConst& k, int act, float p_drop, uint64_t seed,
+                                       const T* mask, long long oct, T* y) {
+  float o[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float u = fmaf((v[i] - mu) * r, gam[i], bet[i]);
-      o[i] = act ? silu_f(u) : u;
-    }
-    if (mask) {
-      float mk[4];
-      load4(mask + gq * 4, mk);
+  for (int i = 0; i < 8; ++i) {
+    float u = fmaf((x[i] - k.mu[i >> 2]) * k.r[i >> 2], k.gam[i], k.bet[i]);
+    o[i] = act ? silu_f(u) : u;
+  }
+  if (mask) {
+    float mk[8];
+    load8(mask + oct * 8, mk);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] *= mk[i];
-    } else if (p_drop > 0.f) {
-      float keep[4];
-      dropout4(seed, (uint64_t)gq, p_drop, keep);
+    for (int i = 0; i < 8; ++i) o[i] *= mk[i];
+  } else if (p_drop > 0.f) {
+    float keep[8];
+    dropout8(seed, (uint64_t)oct, p_drop, keep);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] *= keep[i];
-    }
-    store4(y + gq * 4, o);
+    for (int i = 0; i < 8; ++i) o[i] *= keep[i];
+  }
+  store8(y + oct * 8, o);
+}
+
+// grid (chunks, n_img)
+template <typename T>
+__global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> s, int hw, int G, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, int act, float p_drop, uint64_t seed,
+                                                       const T* mask, T* y) {
+  const int Ct = s.C1 + s.C2, V = Ct / 8, cpg = Ct / G;
+  const int n = blockIdx.y;
+  const int lanes = 256 / V;
+  const int v = threadIdx.x % V, lane = threadIdx.x / V;
+  if (lane >= lanes) return;
+  const int c0 = v * 8;
+  ChanConst k;
+  load_consts(k, n, c0, G, cpg, gamma, beta, mean, rstd);
+  const int per = (hw + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
+  int p = p0 + lane;
+  for (; p + lanes < p1; p += 2 * lanes) {
+    const long long ra = (long long)n * hw + p, rb = ra + lanes;
+    float a[8], b[8];
+    load8(s.at(ra, c0), a);
+    load8(s.at(rb, c0), b);
+    apply8<T>(a, k, act, p_drop, seed, mask, ra * V + v, y);
+    apply8<T>(b, k, act, p_drop, seed, mask, rb * V + v, y);
+  }
+  if (p < p1) {
+    const long long ra = (long long)n * hw + p;
+    float a[8];
+    load8(s.at(ra, c0), a);
+    apply8<T>(a, k, act, p_drop, seed, mask, ra * V + v, y);
   }
 }
 
-// dz for one quad (shared by both backward passes)
+// dz and xhat of one 8-vector (shared by both backward passes)
 template <typename T>
-__device__ __forceinline__ void gn_dz(const float v[4], const float dyv[4], float mu, float r, const float gam[4],
-                                      const float bet[4], int act, float p_drop, uint64_t seed, const T* mask,
-                                      long long gq, float xhat[4], float dz[4]) {
-  float mk[4] = {1.f, 1.f, 1.f, 1.f};
-  if (mask) load4(mask + gq * 4, mk);
-  else if (p_drop > 0.f) dropout4(seed, (uint64_t)gq, p_drop, mk);
+__device__ __forceinline__ void gn_dz8(const float x[8], const float dyv[8], const ChanConst& k, int act, float p_drop,
+                                       uint64_t seed, const T* mask, long long oct, float xhat[8], float dz[8]) {
+  float mk[8];
+  if (mask) load8(mask + oct * 8, mk);
+  else if (p_drop > 0.f) dropout8(seed, (uint64_t)oct, p_drop, mk);
+  else {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    xhat[i] = (v[i] - mu) * r;
+    for (int i = 0; i < 8; ++i) mk[i] = 1.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    xhat[i] = (x[i] - k.mu[i >> 2]) * k.r[i >> 2];
     float d = dyv[i] * mk[i];
-    if (act) d *= silu_grad_f(fmaf(xhat[i], gam[i], bet[i]));
+    if (act) d *= silu_grad_f(fmaf(xhat[i], k.gam[i], k.bet[i]));
     dz[i] = d;
   }
 }
@@ -136,43 +224,57 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> s, const T* 
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             int act, float p_drop, uint64_t seed, const T* mask, float* red) {
-  const int Ct = s.C1 + s.C2, Q = Ct / 4, cpg = Ct / G;
+  const int Ct = s.C1 + s.C2, V = Ct / 8, cpg = Ct / G;
   const int n = blockIdx.x, sp = blockIdx.y;
-  const int ppb = 256 / Q;
-  const int quad = threadIdx.x % Q, lane = threadIdx.x / Q;
+  const int lanes = 256 / V;
+  const int v = threadIdx.x % V, lane = threadIdx.x / V;
   const int per = (hw + splits - 1) / splits;
   const int p0 = sp * per, p1 = min(hw, p0 + per);
-  const int c0 = quad * 4, g = c0 / cpg;
-  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
-  if (lane < ppb) {
-    const float mu = mean[n * G + g], r = rstd[n * G + g];
-    float4 ga = *reinterpret_cast<const float4*>(gamma + c0);
-    float4 be = *reinterpret_cast<const float4*>(beta + c0);
-    const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
-    for (int p = p0 + lane; p < p1; p += ppb) {
-      const long long row = (long long)n * hw + p;
-      const long long gq = row * Q + quad;
-      float v[4], dyv[4], xhat[4], dz[4];
-      load4(s.at(row, c0), v);
-      load4(dy + gq * 4, dyv);
-      gn_dz<T>(v, dyv, mu, r, gam, bet, act, p_drop, seed, mask, gq, xhat, dz);
+  const int c0 = v * 8;
+  float a[8], b[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xhat[i], b[i]); }
+  for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.f;
+  if (lane < lanes) {
+    ChanConst k;
+    load_consts(k, n, c0, G, cpg, gamma, beta, mean, rstd);
+    int p = p0 + lane;
+    for (; p + lanes < p1; p += 2 * lanes) {
+      const long long r0 = (long long)n * hw + p, r1 = r0 + lanes;
+      float x0[8], x1[8], d0[8], d1[8], xh[8], dz[8];
+      load8(s.at(r0, c0), x0);
+      load8(s.at(r1, c0), x1);
+      load8(dy + (r0 * V + v) * 8, d0);
+      load8(dy + (r1 * V + v) * 8, d1);
+      gn_dz8<T>(x0, d0, k, act, p_drop, seed, mask, r0 * V + v, xh, dz);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
+      gn_dz8<T>(x1, d1, k, act, p_drop, seed, mask, r1 * V + v, xh, dz);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
+    }
+    if (p < p1) {
+      const long long r0 = (long long)n * hw + p;
+      float x0[8], d0[8], xh[8], dz[8];
+      load8(s.at(r0, c0), x0);
+      load8(dy + (r0 * V + v) * 8, d0);
+      gn_dz8<T>(x0, d0, k, act, p_drop, seed, mask, r0 * V + v, xh, dz);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
     }
   }
-  __shared__ float4 s_a[256], s_b[256];
-  s_a[threadIdx.x] = make_float4(a[0], a[1], a[2], a[3]);
-  s_b[threadIdx.x] = make_float4(b[0], b[1], b[2], b[3]);
+  // reduce over pixel lanes: smem [lane][V][16]
+  extern __shared__ float s_red[];
+  if (lane < lanes) {
+    float* o = s_red + ((size_t)lane * V + v) * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[2 * i] = a[i]; o[2 * i + 1] = b[i]; }
+  }
   __syncthreads();
-  if (threadIdx.x < Q) {
-    float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta;
-    for (int l = 0; l < ppb; ++l) {
-      float4 u = s_a[l * Q + threadIdx.x], w = s_b[l * Q + threadIdx.x];
-      ta.x += u.x; ta.y += u.y; ta.z += u.z; ta.w += u.w;
-      tb.x += w.x; tb.y += w.y; tb.z += w.z; tb.w += w.w;
-    }
-    float* o = red + (((long long)n * splits + sp) * Ct + threadIdx.x * 4) * 2;
-    o[0] = ta.x; o[1] = tb.x; o[2] = ta.y; o[3] = tb.y; o[4] = ta.z; o[5] = tb.z; o[6] = ta.w; o[7] = tb.w;
+  // thread t sums one (channel, component) column: 16*V columns
+  for (int col = threadIdx.x; col < 16 * V; col += 256) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += s_red[(size_t)l * V * 16 + col];
+    red[((long long)n * splits + sp) * Ct * 2 + col] = t;     // col = (v*8 + i)*2 + comp = c*2 + comp
   }
 }
 
@@ -203,7 +305,35 @@ __global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------- backward pass 2
-// grid (n_img, chunks)
+template <typename T>
+__device__ __forceinline__ void bwd8(const Src2<T>& s, const float x[8], const float dyv[8], const ChanConst& k,
+                                     const float s1[2], const float s2[2], int act, float p_drop, uint64_t seed,
+                                     const T* mask, const T* extra, float extra_scale, long long row, int c0, long long oct,
+                                     T* dx1, int accum1, T* dx2, int accum2) {
+  float xh[8], dz[8], o[8];
+  gn_dz8<T>(x, dyv, k, act, p_drop, seed, mask, oct, xh, dz);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = k.r[i >> 2] * (k.gam[i] * dz[i] - s1[i >> 2] - xh[i] * s2[i >> 2]);
+  if (extra) {
+    float ex[8];
+    load8(extra + oct * 8, ex);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(extra_scale, ex[i], o[i]);
+  }
+  T* dst;
+  int acc;
+  if (c0 < s.C1) { dst = dx1 + row * s.C1 + c0; acc = accum1; }
+  else { dst = dx2 + row * s.C2 + (c0 - s.C1); acc = accum2; }
+  if (acc) {
+    float old[8];
+    load8(dst, old);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] += old[i];
+  }
+  store8(dst, o);
+}
+
+// grid (chunks, n_img)
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -211,9 +341,9 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> s, const T* d
                                                            int act, float p_drop, uint64_t seed, const T* mask,
                                                            const float* __restrict__ red, const T* extra, float extra_scale,
                                                            T* dx1, int accum1, T* dx2, int accum2) {
-  const int Ct = s.C1 + s.C2, Q = Ct / 4, cpg = Ct / G;
-  const int n = blockIdx.x;
-  __shared__ float s1[64], s2[64];
+  const int Ct = s.C1 + s.C2, V = Ct / 8, cpg = Ct / G;
+  const int n = blockIdx.y;
+  __shared__ float sh1[64], sh2[64];
   if (threadIdx.x < G) {
     const int g = threadIdx.x;
     double a = 0., b = 0.;
@@ -224,59 +354,55 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> s, const T* d
         b += (double)gamma[c] * (double)o[1];
       }
     const double inv = 1.0 / ((double)hw * cpg);
-    s1[g] = (float)(a * inv);
-    s2[g] = (float)(b * inv);
+    sh1[g] = (float)(a * inv);
+    sh2[g] = (float)(b * inv);
   }
   __syncthreads();
-  const long long quads_img = (long long)hw * Q;
-  for (long long lq = (long long)blockIdx.y * blockDim.x + threadIdx.x; lq < quads_img;
-       lq += (long long)gridDim.y * blockDim.x) {
-    const int quad = (int)(lq % Q);
-    const long long row = (long long)n * hw + lq / Q;
-    const long long gq = row * Q + quad;
-    const int c0 = quad * 4, g = c0 / cpg;
-    const float mu = mean[n * G + g], r = rstd[n * G + g];
-    float4 ga = *reinterpret_cast<const float4*>(gamma + c0);
-    float4 be = *reinterpret_cast<const float4*>(beta + c0);
-    const float gam[4] = {ga.x, ga.y, ga.z, ga.w}, bet[4] = {be.x, be.y, be.z, be.w};
-    float v[4], dyv[4], xhat[4], dz[4], o[4];
-    load4(s.at(row, c0), v);
-    load4(dy + gq * 4, dyv);
-    gn_dz<T>(v, dyv, mu, r, gam, bet, act, p_drop, seed, mask, gq, xhat, dz);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = r * (gam[i] * dz[i] - s1[g] - xhat[i] * s2[g]);
-    if (extra) {
-      float ex[4];
-      load4(extra + gq * 4, ex);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = fmaf(extra_scale, ex[i], o[i]);
-    }
-    T* dst;
-    int acc;
-    if (c0 < s.C1) { dst = dx1 + row * s.C1 + c0; acc = accum1; }
-    else { dst = dx2 + row * s.C2 + (c0 - s.C1); acc = accum2; }
-    if (acc) {
-      float old[4];
-      load4(dst, old);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] += old[i];
-    }
-    store4(dst, o);
+  const int lanes = 256 / V;
+  const int v = threadIdx.x % V, lane = threadIdx.x / V;
+  if (lane >= lanes) return;
+  const int c0 = v * 8;
+  ChanConst k;
+  load_consts(k, n, c0, G, cpg, gamma, beta, mean, rstd);
+  const float s1[2] = {sh1[k.g[0]], sh1[k.g[1]]}, s2[2] = {sh2[k.g[0]], sh2[k.g[1]]};
+  const int per = (hw + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
+  int p = p0 + lane;
+  for (; p + lanes < p1; p += 2 * lanes) {
+    const long long r0 = (long long)n * hw + p, r1 = r0 + lanes;
+    float x0[8], x1[8], d0[8], d1[8];
+    load8(s.at(r0, c0), x0);
+    load8(s.at(r1, c0), x1);
+    load8(dy + (r0 * V + v) * 8, d0);
+    load8(dy + (r1 * V + v) * 8, d1);
+    bwd8<T>(s, x0, d0, k, s1, s2, act, p_drop, seed, mask, extra, extra_scale, r0, c0, r0 * V + v, dx1, accum1, dx2, accum2);
+    bwd8<T>(s, x1, d1, k, s1, s2, act, p_drop, seed, mask, extra, extra_scale, r1, c0, r1 * V + v, dx1, accum1, dx2, accum2);
+  }
+  if (p < p1) {
+    const long long r0 = (long long)n * hw + p;
+    float x0[8], d0[8];
+    load8(s.at(r0, c0), x0);
+    load8(dy + (r0 * V + v) * 8, d0);
+    bwd8<T>(s, x0, d0, k, s1, s2, act, p_drop, seed, mask, extra, extra_scale, r0, c0, r0 * V + v, dx1, accum1, dx2, accum2);
   }
 }
 
 int check_geom(int C1, int C2, int G) {
   int Ct = C1 + C2;
-  ST_CHECK_ARG(C1 > 0 && C2 >= 0 && C1 % 4 == 0 && C2 % 4 == 0, "groupnorm: channel counts must be multiples of 4 (got %d,%d)", C1, C2);
+  ST_CHECK_ARG(C1 > 0 && C2 >= 0 && C1 % 8 == 0 && C2 % 8 == 0, "groupnorm: channel counts must be multiples of 8 (got %d,%d)", C1, C2);
   ST_CHECK_ARG(G > 0 && G <= 64 && Ct % G == 0 && (Ct / G) % 4 == 0, "groupnorm: group size must be a multiple of 4 (C=%d,G=%d)", Ct, G);
-  ST_CHECK_ARG(Ct <= 1024, "groupnorm: C > 1024 unsupported");
+  ST_CHECK_ARG(Ct <= 2048, "groupnorm: C > 2048 unsupported");
   return 0;
 }
 
-int grid_for(long long work_items, int per_block) {
-  long long b = (work_items + per_block - 1) / per_block;
-  long long cap = (long long)st_num_sms() * 16;
-  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+// pixel chunks per image so that the grid is a few waves of 148 SMs x 8 resident blocks
+int chunks_for(int n_img, int hw, int V) {
+  int lanes = 256 / V;
+  int max_chunks = (hw + 2 * lanes - 1) / (2 * lanes);       // at least one double iteration per block
+  int want = (st_num_sms() * 8 + n_img - 1) / n_img;
+  int c = want < max_chunks ? want : max_chunks;
+  if (c > 65535) c = 65535;
+  return c < 1 ? 1 : c;
 }
 
 }  // namespace
@@ -306,11 +432,12 @@ extern "C" __attribute__((visibility("default"))) int st_gn_apply(const void* x1
                            const float* gamma, const float* beta, const float* mean, const float* rstd, int act,
                            float p_drop, uint64_t seed, const void* mask, void* y, void* stream) {
   if (int e = check_geom(C1, C2, G)) return e;
-  long long total = (long long)n_img * hw * ((C1 + C2) / 4);
+  ST_CHECK_ARG(n_img <= 65535, "st_gn_apply: more than 65535 images");
+  const int V = (C1 + C2) / 8;
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
-    gn_apply_kernel<T><<<grid_for(total, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
-        s, total, hw, G, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, (T*)y);
+    gn_apply_kernel<T><<<dim3(chunks_for(n_img, hw, V), n_img), 256, 0, (cudaStream_t)stream>>>(
+        s, hw, G, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, (T*)y);
   });
   ST_CHECK_LAUNCH("st_gn_apply");
   return 0;
@@ -321,9 +448,12 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_reduce(const voi
                                 const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
                                 int splits, float* red, void* stream) {
   if (int e = check_geom(C1, C2, G)) return e;
+  const int V = (C1 + C2) / 8;
+  const int lanes = 256 / V;
+  const size_t smem = (size_t)lanes * V * 16 * sizeof(float);     // <= 16 KB
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
-    gn_bwd_reduce_kernel<T><<<dim3(n_img, splits), 256, 0, (cudaStream_t)stream>>>(
+    gn_bwd_reduce_kernel<T><<<dim3(n_img, splits), 256, smem, (cudaStream_t)stream>>>(
         s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, red);
   });
   ST_CHECK_LAUNCH("st_gn_bwd_reduce");
@@ -342,14 +472,11 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_apply(const void
                                int splits, const float* red, const void* extra, float extra_scale, void* dx1,
                                int accum1, void* dx2, int accum2, void* stream) {
   if (int e = check_geom(C1, C2, G)) return e;
-  long long quads_img = (long long)hw * ((C1 + C2) / 4);
-  int chunks = (int)((quads_img + 256 * 4 - 1) / (256 * 4));
-  int cap = (st_num_sms() * 16 + n_img - 1) / n_img;
-  if (chunks > cap) chunks = cap;
-  if (chunks < 1) chunks = 1;
+  ST_CHECK_ARG(n_img <= 65535, "st_gn_bwd_apply: more than 65535 images");
+  const int V = (C1 + C2) / 8;
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
-    gn_bwd_apply_kernel<T><<<dim3(n_img, chunks), 256, 0, (cudaStream_t)stream>>>(
+    gn_bwd_apply_kernel<T><<<dim3(chunks_for(n_img, hw, V), n_img), 256, 0, (cudaStream_t)stream>>>(
         s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, red,
         (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2);
   });
