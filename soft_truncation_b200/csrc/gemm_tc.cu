@@ -914,13 +914,14 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   p.nk = (a->K + BK - 1) / BK;
   p.cblocks = Ct > 0 ? Ct / 64 : 0;
   p.c1blocks = a->C1 / 64;
-  const int BN = (N >= 256 && N % 256 == 0) ? 256 : (N > 64 ? 128 : 64);
+  int BN = (N >= 256 && N % 256 == 0) ? 256 : (N > 64 ? 128 : 64);
+  if (BN == 256 && env_int("ST_TC_BN", 256) == 128) BN = 128;
   p.m_tiles = (M + BM - 1) / BM;
   p.n_tiles = (N + BN - 1) / BN;
 
   // B kind first (it bounds the cluster size)
   const bool b_kmajor = !wgrad && a->b_mode == ST_OP_STRIDED && a->sBk == 1;
-  int cs = env_int("ST_TC_CLUSTER", 2);
+  int cs = env_int("ST_TC_CLUSTER", 1);
   if (cs != 1 && cs != 2 && cs != 4) cs = 2;
   while (cs > 1 && cs > p.m_tiles) cs >>= 1;
   if (!b_kmajor) while (cs > 1 && cs > BN / 64) cs >>= 1;
@@ -991,8 +992,14 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
 int st_gemm_tc1(const st_gemm_args* a, cudaStream_t stream);
 
 int st_gemm_tc(const st_gemm_args* a, cudaStream_t stream) {
-  const int variant = env_int("ST_TC_VARIANT", 2);
-  return variant == 1 ? st_gemm_tc1(a, stream) : st_gemm_tc2(a, stream);
+  // ST_TC_VARIANT: 1 = one tile per CTA, two CTAs per SM; 2 = persistent double-buffered kernel; 0 (default) =
+  // measured best per operand form on B200 (tools/gemm_bench.py): the persistent kernel when B is K-major
+  // (forward convolutions, Linear/NIN, QK^T), the two-CTAs-per-SM kernel when B is read MN-major (dgrad, wgrad).
+  const int variant = env_int("ST_TC_VARIANT", 0);
+  if (variant == 1) return st_gemm_tc1(a, stream);
+  if (variant == 2) return st_gemm_tc2(a, stream);
+  const bool b_kmajor = a->b_mode == ST_OP_STRIDED && a->sBk == 1;
+  return b_kmajor ? st_gemm_tc2(a, stream) : st_gemm_tc1(a, stream);
 }
 
 int st_gemm_tc1(const st_gemm_args* a, cudaStream_t stream) {

@@ -33,6 +33,26 @@ __device__ __forceinline__ void store8(bf16* p, const float v[8]) {
   *reinterpret_cast<uint4*>(p) = t;
 }
 
+// Raw 8-element vectors: loads are issued back to back (4 pixels in flight per thread) and only converted to
+// fp32 when consumed, which keeps the number of live registers per pending load at 4 (bf16) / 8 (fp32).
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> { uint4 a; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ void ldraw(const bf16* p, Raw8<bf16>& r) { r.a = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void ldraw(const float* p, Raw8<float>& r) {
+  r.a = reinterpret_cast<const float4*>(p)[0];
+  r.b = reinterpret_cast<const float4*>(p)[1];
+}
+__device__ __forceinline__ void cvt(const Raw8<bf16>& r, float v[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.a);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+__device__ __forceinline__ void cvt(const Raw8<float>& r, float v[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+constexpr int UNR = 4;   // pixels in flight per thread
+
 // keep-multipliers (0 or 1/(1-p)) of 8 consecutive elements: one Philox call, 16 random bits per element
 __device__ __forceinline__ void dropout8(uint64_t seed, uint64_t oct, float p, float keep[8]) {
   uint4 r = philox4(seed, oct);
@@ -85,22 +105,19 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(Src2<T> s, int hw, int G,
   float sum[2] = {0.f, 0.f}, sq[2] = {0.f, 0.f};
   if (lane < lanes) {
     const int c0 = v * 8;
-    int p = p0 + lane;
-    for (; p + lanes < p1; p += 2 * lanes) {
-      float a[8], b[8];
-      load8(s.at((long long)n * hw + p, c0), a);
-      load8(s.at((long long)n * hw + p + lanes, c0), b);
+    for (int p = p0 + lane; p < p1; p += UNR * lanes) {
+      Raw8<T> raw[UNR];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        sum[i >> 2] += a[i] + b[i];
-        sq[i >> 2] = fmaf(a[i], a[i], fmaf(b[i], b[i], sq[i >> 2]));
-      }
-    }
-    if (p < p1) {
-      float a[8];
-      load8(s.at((long long)n * hw + p, c0), a);
+      for (int u = 0; u < UNR; ++u)
+        if (p + u * lanes < p1) ldraw(s.at((long long)n * hw + p + u * lanes, c0), raw[u]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { sum[i >> 2] += a[i]; sq[i >> 2] = fmaf(a[i], a[i], sq[i >> 2]); }
+      for (int u = 0; u < UNR; ++u)
+        if (p + u * lanes < p1) {
+          float a[8];
+          cvt(raw[u], a);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { sum[i >> 2] += a[i]; sq[i >> 2] = fmaf(a[i], a[i], sq[i >> 2]); }
+        }
     }
   }
   // quad q = 2*v + half holds channels [4q, 4q+4): whole quads never straddle a group (cpg % 4 == 0)
@@ -180,20 +197,19 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> s, int hw, int G,
   load_consts(k, n, c0, G, cpg, gamma, beta, mean, rstd);
   const int per = (hw + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
-  int p = p0 + lane;
-  for (; p + lanes < p1; p += 2 * lanes) {
-    const long long ra = (long long)n * hw + p, rb = ra + lanes;
-    float a[8], b[8];
-    load8(s.at(ra, c0), a);
-    load8(s.at(rb, c0), b);
-    apply8<T>(a, k, act, p_drop, seed, mask, ra * V + v, y);
-    apply8<T>(b, k, act, p_drop, seed, mask, rb * V + v, y);
-  }
-  if (p < p1) {
-    const long long ra = (long long)n * hw + p;
-    float a[8];
-    load8(s.at(ra, c0), a);
-    apply8<T>(a, k, act, p_drop, seed, mask, ra * V + v, y);
+  for (int p = p0 + lane; p < p1; p += UNR * lanes) {
+    Raw8<T> raw[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (p + u * lanes < p1) ldraw(s.at((long long)n * hw + p + u * lanes, c0), raw[u]);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (p + u * lanes < p1) {
+        const long long row = (long long)n * hw + p + u * lanes;
+        float a[8];
+        cvt(raw[u], a);
+        apply8<T>(a, k, act, p_drop, seed, mask, row * V + v, y);
+      }
   }
 }
 
@@ -237,29 +253,26 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> s, const T* 
   if (lane < lanes) {
     ChanConst k;
     load_consts(k, n, c0, G, cpg, gamma, beta, mean, rstd);
-    int p = p0 + lane;
-    for (; p + lanes < p1; p += 2 * lanes) {
-      const long long r0 = (long long)n * hw + p, r1 = r0 + lanes;
-      float x0[8], x1[8], d0[8], d1[8], xh[8], dz[8];
-      load8(s.at(r0, c0), x0);
-      load8(s.at(r1, c0), x1);
-      load8(dy + (r0 * V + v) * 8, d0);
-      load8(dy + (r1 * V + v) * 8, d1);
-      gn_dz8<T>(x0, d0, k, act, p_drop, seed, mask, r0 * V + v, xh, dz);
+    for (int p = p0 + lane; p < p1; p += UNR * lanes) {
+      Raw8<T> rx[UNR], rd[UNR];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
-      gn_dz8<T>(x1, d1, k, act, p_drop, seed, mask, r1 * V + v, xh, dz);
+      for (int u = 0; u < UNR; ++u)
+        if (p + u * lanes < p1) {
+          const long long row = (long long)n * hw + p + u * lanes;
+          ldraw(s.at(row, c0), rx[u]);
+          ldraw(dy + (row * V + v) * 8, rd[u]);
+        }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
-    }
-    if (p < p1) {
-      const long long r0 = (long long)n * hw + p;
-      float x0[8], d0[8], xh[8], dz[8];
-      load8(s.at(r0, c0), x0);
-      load8(dy + (r0 * V + v) * 8, d0);
-      gn_dz8<T>(x0, d0, k, act, p_drop, seed, mask, r0 * V + v, xh, dz);
+      for (int u = 0; u < UNR; ++u)
+        if (p + u * lanes < p1) {
+          const long long row = (long long)n * hw + p + u * lanes;
+          float x0[8], d0[8], xh[8], dz[8];
+          cvt(rx[u], x0);
+          cvt(rd[u], d0);
+          gn_dz8<T>(x0, d0, k, act, p_drop, seed, mask, row * V + v, xh, dz);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
+          for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
+        }
     }
   }
   // reduce over pixel lanes: smem [lane][V][16]
@@ -305,34 +318,6 @@ __global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------- backward pass 2
-template <typename T>
-__device__ __forceinline__ void bwd8(const Src2<T>& s, const float x[8], const float dyv[8], const ChanConst& k,
-                                     const float s1[2], const float s2[2], int act, float p_drop, uint64_t seed,
-                                     const T* mask, const T* extra, float extra_scale, long long row, int c0, long long oct,
-                                     T* dx1, int accum1, T* dx2, int accum2) {
-  float xh[8], dz[8], o[8];
-  gn_dz8<T>(x, dyv, k, act, p_drop, seed, mask, oct, xh, dz);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = k.r[i >> 2] * (k.gam[i] * dz[i] - s1[i >> 2] - xh[i] * s2[i >> 2]);
-  if (extra) {
-    float ex[8];
-    load8(extra + oct * 8, ex);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = fmaf(extra_scale, ex[i], o[i]);
-  }
-  T* dst;
-  int acc;
-  if (c0 < s.C1) { dst = dx1 + row * s.C1 + c0; acc = accum1; }
-  else { dst = dx2 + row * s.C2 + (c0 - s.C1); acc = accum2; }
-  if (acc) {
-    float old[8];
-    load8(dst, old);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] += old[i];
-  }
-  store8(dst, o);
-}
-
 // grid (chunks, n_img)
 template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
@@ -365,25 +350,48 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> s, const T* d
   ChanConst k;
   load_consts(k, n, c0, G, cpg, gamma, beta, mean, rstd);
   const float s1[2] = {sh1[k.g[0]], sh1[k.g[1]]}, s2[2] = {sh2[k.g[0]], sh2[k.g[1]]};
+  // destination of this thread's channels (first or second tensor of the concatenation)
+  T* const dbase = c0 < s.C1 ? dx1 + c0 : dx2 + (c0 - s.C1);
+  const int dld = c0 < s.C1 ? s.C1 : s.C2;
+  const int acc = c0 < s.C1 ? accum1 : accum2;
   const int per = (hw + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
-  int p = p0 + lane;
-  for (; p + lanes < p1; p += 2 * lanes) {
-    const long long r0 = (long long)n * hw + p, r1 = r0 + lanes;
-    float x0[8], x1[8], d0[8], d1[8];
-    load8(s.at(r0, c0), x0);
-    load8(s.at(r1, c0), x1);
-    load8(dy + (r0 * V + v) * 8, d0);
-    load8(dy + (r1 * V + v) * 8, d1);
-    bwd8<T>(s, x0, d0, k, s1, s2, act, p_drop, seed, mask, extra, extra_scale, r0, c0, r0 * V + v, dx1, accum1, dx2, accum2);
-    bwd8<T>(s, x1, d1, k, s1, s2, act, p_drop, seed, mask, extra, extra_scale, r1, c0, r1 * V + v, dx1, accum1, dx2, accum2);
-  }
-  if (p < p1) {
-    const long long r0 = (long long)n * hw + p;
-    float x0[8], d0[8];
-    load8(s.at(r0, c0), x0);
-    load8(dy + (r0 * V + v) * 8, d0);
-    bwd8<T>(s, x0, d0, k, s1, s2, act, p_drop, seed, mask, extra, extra_scale, r0, c0, r0 * V + v, dx1, accum1, dx2, accum2);
+  for (int p = p0 + lane; p < p1; p += UNR * lanes) {
+    Raw8<T> rx[UNR], rd[UNR], re[UNR], ro[UNR];
+    // all global loads of the iteration first: x, dy, (extra), (old destination)
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (p + u * lanes < p1) {
+        const long long row = (long long)n * hw + p + u * lanes;
+        ldraw(s.at(row, c0), rx[u]);
+        ldraw(dy + (row * V + v) * 8, rd[u]);
+        if (extra) ldraw(extra + (row * V + v) * 8, re[u]);
+        if (acc) ldraw(dbase + row * dld, ro[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (p + u * lanes < p1) {
+        const long long row = (long long)n * hw + p + u * lanes;
+        float x0[8], d0[8], xh[8], dz[8], o[8];
+        cvt(rx[u], x0);
+        cvt(rd[u], d0);
+        gn_dz8<T>(x0, d0, k, act, p_drop, seed, mask, row * V + v, xh, dz);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = k.r[i >> 2] * (k.gam[i] * dz[i] - s1[i >> 2] - xh[i] * s2[i >> 2]);
+        if (extra) {
+          float ex[8];
+          cvt(re[u], ex);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = fmaf(extra_scale, ex[i], o[i]);
+        }
+        if (acc) {
+          float old[8];
+          cvt(ro[u], old);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += old[i];
+        }
+        store8(dbase + row * dld, o);
+      }
   }
 }
 
@@ -398,7 +406,7 @@ int check_geom(int C1, int C2, int G) {
 // pixel chunks per image so that the grid is a few waves of 148 SMs x 8 resident blocks
 int chunks_for(int n_img, int hw, int V) {
   int lanes = 256 / V;
-  int max_chunks = (hw + 2 * lanes - 1) / (2 * lanes);       // at least one double iteration per block
+  int max_chunks = (hw + UNR * lanes - 1) / (UNR * lanes);   // at least one full iteration per block
   int want = (st_num_sms() * 8 + n_img - 1) / n_img;
   int c = want < max_chunks ? want : max_chunks;
   if (c > 65535) c = 65535;

@@ -238,7 +238,7 @@ def colsum(x, groups, rows_per_group, C, out, scale=1.0, accumulate=False):
   pixel) is reduced in two deterministic passes so that the first one fills the GPU."""
   if groups == 1 and rows_per_group >= 4096:
     chunks = 1
-    while chunks < 1024 and rows_per_group % (chunks * 2) == 0 and rows_per_group // (chunks * 2) >= 32:
+    while chunks < 256 and rows_per_group % (chunks * 2) == 0 and rows_per_group // (chunks * 2) >= 32:
       chunks *= 2
     if chunks > 1:
       part = torch.empty((chunks, C), dtype=torch.float32, device=x.device)
