@@ -43,6 +43,7 @@ struct TcParams {
   // gather geometry
   int H, W, kh, kw, cblocks, c1blocks, ntaps;
   int Ct, C1;
+  int logW, logH;         // H, W are powers of two (checked on the host)
   // epilogue
   void* C;
   long long ldc, sCb;
@@ -473,67 +474,88 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
     nkt = min(p.nk, kt0 + kper) - kt0;
   };
 
+  // Both single-thread loops below are latency-bound chains of dependent scalar instructions, so they are written
+  // with incremental state only: no integer division, no modulo, descriptors advanced by adding constants.
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      int it = 0;
+      int s = 0;
+      uint32_t par = 1;                 // parity to wait on empty[s]: a fresh barrier passes parity 1 immediately
+      const int pw = (p.kw - 1) / 2, ph = (p.kh - 1) / 2;
+      const int lw = p.logW, lhw = p.logW + p.logH;
+      const int Wm = p.W - 1, Hm = p.H - 1;
       for (int st = cluster_id; st < total; st += n_clusters) {
         int m0, n0, b, kt0, nkt;
         decode(st, m0, n0, b, kt0, nkt);
         if (nkt <= 0) continue;
+        // ---- per-tile constants
         int gx0 = 0, gy0 = 0, gn0 = 0;
+        if (p.a_kind == GATHER_K) { gx0 = m0 & Wm; gy0 = (m0 >> lw) & Hm; gn0 = m0 >> lhw; }
+        int tap = 0, cb = 0, dy = -ph, dx = -pw;         // (tap, channel block) walk of conv-shaped K axes
         if (p.a_kind == GATHER_K) {
-          gx0 = m0 % p.W;
-          gy0 = (m0 / p.W) % p.H;
-          gn0 = m0 / (p.W * p.H);
+          tap = kt0 / p.cblocks; cb = kt0 - tap * p.cblocks;
+          dy = tap / p.kw - ph; dx = tap - (tap / p.kw) * p.kw - pw;
         }
-        for (int i = 0; i < nkt; ++i, ++it) {
-          const int kt = kt0 + i;
-          const int s = it % STAGES;
-          if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+        int a_c[2] = {0, 0}, a_dx[2] = {0, 0}, a_dy[2] = {0, 0}, a_src[2] = {0, 0};
+        if (p.a_kind == GATHER_MN) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int mm = m0 + 64 * j;
+            const int t = mm / p.Ct, c = mm - t * p.Ct;
+            if (t >= p.ntaps) { a_src[j] = 2; }            // masked rows: any in-range box
+            else {
+              a_dy[j] = t / p.kw - ph; a_dx[j] = t - (t / p.kw) * p.kw - pw;
+              a_src[j] = c < p.C1 ? 0 : 1; a_c[j] = c < p.C1 ? c : c - p.C1;
+            }
+          }
+        }
+        int kk = kt0 * BK;
+        for (int i = 0; i < nkt; ++i) {
+          mbar_wait(empty0 + 8 * s, par);
           const uint32_t bar = full0 + 8 * s;
           mbar_expect_tx(bar, STAGE_BYTES);
           const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
           // ---- A (private to this CTA)
           if (p.a_kind == KMAJOR) {
-            tma_load_3d(sa, &mapA0, bar, kt * BK, m0, b);
+            tma_load_3d(sa, &mapA0, bar, kk, m0, b);
           } else if (p.a_kind == MNMAJOR) {
-            tma_load_3d(sa, &mapA0, bar, m0, kt * BK, b);
-            tma_load_3d(sa + 8192, &mapA0, bar, m0 + 64, kt * BK, b);
+            tma_load_3d(sa, &mapA0, bar, m0, kk, b);
+            tma_load_3d(sa + 8192, &mapA0, bar, m0 + 64, kk, b);
           } else if (p.a_kind == GATHER_K) {
-            const int tap = kt / p.cblocks, cb = kt % p.cblocks;
-            const int dy = tap / p.kw - (p.kh - 1) / 2, dx = tap % p.kw - (p.kw - 1) / 2;
             if (cb < p.c1blocks) tma_load_4d(sa, &mapA0, bar, cb * 64, gx0 + dx, gy0 + dy, gn0);
             else tma_load_4d(sa, &mapA1, bar, (cb - p.c1blocks) * 64, gx0 + dx, gy0 + dy, gn0);
           } else {   // GATHER_MN as A: m = (tap, channel), k = pixel block
-            const int p0 = kt * BK;
-            const int x0 = p0 % p.W, y0 = (p0 / p.W) % p.H, i0 = p0 / (p.W * p.H);
+            const int x0 = kk & Wm, y0 = (kk >> lw) & Hm, i0 = kk >> lhw;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              const int mm = m0 + 64 * j;
-              const int tap = mm / p.Ct, c = mm % p.Ct;
-              const int dy = tap / p.kw - (p.kh - 1) / 2, dx = tap % p.kw - (p.kw - 1) / 2;
-              if (tap >= p.ntaps) tma_load_4d(sa + j * 8192, &mapA0, bar, 0, x0, y0, i0);      // masked rows
-              else if (c < p.C1) tma_load_4d(sa + j * 8192, &mapA0, bar, c, x0 + dx, y0 + dy, i0);
-              else tma_load_4d(sa + j * 8192, &mapA1, bar, c - p.C1, x0 + dx, y0 + dy, i0);
+              if (a_src[j] == 2) tma_load_4d(sa + j * 8192, &mapA0, bar, 0, x0, y0, i0);
+              else if (a_src[j] == 0) tma_load_4d(sa + j * 8192, &mapA0, bar, a_c[j], x0 + a_dx[j], y0 + a_dy[j], i0);
+              else tma_load_4d(sa + j * 8192, &mapA1, bar, a_c[j], x0 + a_dx[j], y0 + a_dy[j], i0);
             }
           }
           // ---- B: this CTA's slice, multicast to the whole cluster
           if (p.b_kind == KMAJOR) {
-            const int rows = BN / cs;
-            if (cs > 1) tma_load_3d_mc(sb + rank * rows * 128, &mapB0, bar, kt * BK, n0 + rank * rows, b, mc_mask);
-            else tma_load_3d(sb, &mapB0, bar, kt * BK, n0, b);
+            if (cs > 1) {
+              const int rows = BN / cs;
+              tma_load_3d_mc(sb + rank * rows * 128, &mapB0, bar, kk, n0 + rank * rows, b, mc_mask);
+            } else {
+              tma_load_3d(sb, &mapB0, bar, kk, n0, b);
+            }
           } else {
-            const int nb = BN / 64, per = nb / cs;       // host guarantees cs <= nb
+            const int per = (BN / 64) / cs;       // host guarantees cs <= BN/64
             for (int jj = 0; jj < per; ++jj) {
               const int j = rank * per + jj;
               int c0, c1, c2;
-              if (p.b_kind == MNMAJOR) { c0 = n0 + 64 * j; c1 = kt * BK; c2 = b; }
-              else { const int tap = kt / p.cblocks, cob = kt % p.cblocks; c0 = n0 + 64 * j; c1 = p.ntaps - 1 - tap; c2 = cob * 64; }
+              if (p.b_kind == MNMAJOR) { c0 = n0 + 64 * j; c1 = kk; c2 = b; }
+              else { c0 = n0 + 64 * j; c1 = p.ntaps - 1 - tap; c2 = cb * 64; }
               if (cs > 1) tma_load_3d_mc(sb + j * 8192, &mapB0, bar, c0, c1, c2, mc_mask);
               else tma_load_3d(sb + j * 8192, &mapB0, bar, c0, c1, c2);
             }
           }
+          // ---- advance
+          kk += BK;
+          if (++cb == p.cblocks) { cb = 0; ++tap; if (++dx > pw) { dx = -pw; ++dy; } }
+          if (++s == STAGES) { s = 0; par ^= 1; }
         }
       }
     }
@@ -544,7 +566,14 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
       const bool b_mn = (p.b_kind != KMAJOR);
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int it = 0, tl = 0;
+      // descriptor = hi32 (SBO=1024, version 1, SWIZZLE_128B) : lo32 (start>>4 | LBO>>4 << 16)
+      const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo0 = (smem_base >> 4) | ((a_mn ? (8192u >> 4) : 1u) << 16);
+      const uint32_t b_lo0 = ((smem_base + A_STAGE_BYTES) >> 4) | ((b_mn ? (8192u >> 4) : 1u) << 16);
+      const uint32_t a_step = a_mn ? (2048u >> 4) : (32u >> 4), b_step = b_mn ? (2048u >> 4) : (32u >> 4);
+      int s = 0, tl = 0;
+      uint32_t par = 0;
+      uint32_t a_lo = a_lo0, b_lo = b_lo0;
       for (int st = cluster_id; st < total; st += n_clusters) {
         int m0, n0, b, kt0, nkt;
         decode(st, m0, n0, b, kt0, nkt);
@@ -553,19 +582,22 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
         if (tl >= 2) mbar_wait(tempty0 + 8 * buf, ((tl >> 1) - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
-        for (int i = 0; i < nkt; ++i, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+        uint32_t accum = 0;
+        for (int i = 0; i < nkt; ++i) {
+          mbar_wait(full0 + 8 * s, par);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
 #pragma unroll
           for (int j = 0; j < BK / 16; ++j) {
-            const uint64_t ad = a_mn ? make_desc(sa + j * 2048, 8192, 1024) : make_desc(sa + j * 32, 16, 1024);
-            const uint64_t bd = b_mn ? make_desc(sb + j * 2048, 8192, 1024) : make_desc(sb + j * 32, 16, 1024);
-            umma_f16(tacc, ad, bd, idesc, (i | j) != 0 ? 1u : 0u);
+            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + j * a_step);
+            const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + j * b_step);
+            umma_f16(tacc, ad, bd, idesc, accum);
+            accum = 1;
           }
           if (cs > 1) umma_commit_mc(empty0 + 8 * s, mc_mask);
           else umma_commit(empty0 + 8 * s);
+          a_lo += STAGE_BYTES >> 4;
+          b_lo += STAGE_BYTES >> 4;
+          if (++s == STAGES) { s = 0; par ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
         }
         umma_commit(tfull0 + 8 * buf);
         ++tl;
@@ -912,8 +944,10 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   p.M = M; p.N = N; p.batch = a->batch; p.split_k = a->split_k > 1 ? a->split_k : 1;
   p.H = a->H; p.W = a->W; p.kh = a->kh; p.kw = a->kw; p.ntaps = a->kh * a->kw; p.Ct = Ct; p.C1 = a->C1;
   p.nk = (a->K + BK - 1) / BK;
-  p.cblocks = Ct > 0 ? Ct / 64 : 0;
+  p.cblocks = Ct > 0 ? Ct / 64 : 1;
   p.c1blocks = a->C1 / 64;
+  for (p.logW = 0; (1 << p.logW) < a->W; ++p.logW) {}
+  for (p.logH = 0; (1 << p.logH) < a->H; ++p.logH) {}
   int BN = (N >= 256 && N % 256 == 0) ? 256 : (N > 64 ? 128 : 64);
   if (BN == 256 && env_int("ST_TC_BN", 256) == 128) BN = 128;
   p.m_tiles = (M + BM - 1) / BM;

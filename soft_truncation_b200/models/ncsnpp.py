@@ -104,7 +104,7 @@ class ResBlock:
     add(pre + 'GroupNorm_0.weight', (cin,), init=init_ones)
     add(pre + 'GroupNorm_0.bias', (cin,), init=init_zeros)
     add(pre + 'Conv_0.weight', (cout, cin, 3, 3), 'conv', init=init_conv(1.))
-    add(pre + 'Conv_0.bias', (cout,), init=init_zeros)
+    add(pre + 'Conv_0.bias', (cout,), region='conv0_b', init=init_zeros)    # same order as the Dense_0 columns
     self.dense_off = model._dense_cols
     model._dense_cols += cout
     add(pre + 'Dense_0.weight', (cout, model.temb_dim), 'linear', region='dense_w', init=init_conv(1.))
@@ -203,8 +203,7 @@ class ResBlock:
     # ---- Conv_0 bias, temb projection (per-image column sums), weights, data
     dd = torch.empty((B, Co), dtype=torch.float32, device=g.device)
     ops.colsum(dh1.view(npix, Co), B, H * W, Co, dd)
-    net.d_dense[:, self.dense_off:self.dense_off + Co].copy_(dd)
-    ops.colsum(dd, 1, B, Co, P.g(pre + 'Conv_0.bias'), accumulate=True)
+    net.d_dense[:, self.dense_off:self.dense_off + Co].copy_(dd)     # Conv_0.bias gradient = its column sums (temb.bwd)
     ops.conv_wgrad(dh1, a0, P.g(pre + 'Conv_0.weight'))
     da0 = ops.conv_dgrad(dh1, P.c(pre + 'Conv_0.weight'), self.cin)
     del dh1
@@ -567,8 +566,12 @@ class TimeEmbedding:
     nd = net.d_dense.shape[1]
     td = 4 * m.config.model.nf
     dd = net.d_dense
-    # Dense_0 biases were accumulated per block (Conv_0.bias shares the column sums); weights here
-    ops.colsum(dd, 1, B, nd, P.g_region('dense_b'), accumulate=True)
+    # column sums of d_dense are the gradient of every Dense_0.bias AND of every Conv_0.bias (both are added to
+    # the same pre-GroupNorm_1 activation); the two bias regions are laid out in the same block order
+    colsum = torch.empty(nd, dtype=torch.float32, device=dd.device)
+    ops.colsum(dd, 1, B, nd, colsum)
+    ops.axpby(P.g_region('dense_b'), colsum, out=P.g_region('dense_b'))
+    ops.axpby(P.g_region('conv0_b'), colsum, out=P.g_region('conv0_b'))
     dd_c = ops.cast(dd, cd) if cd != torch.float32 else dd
     ops.gemm_tn(dd_c, at_c, nd, td, B, out=P.g_region('dense_w').view(nd, td), accumulate=True, split_k=1)
     d_at = ops.gemm_nn(dd_c, P.c_region('dense_w').view(nd, td), td, out_dtype=torch.float32)

@@ -71,7 +71,7 @@ def _logical_view(buf, e):
 
 
 class ParamStore:
-  REGIONS = ('dense_w', 'dense_b', 'main')
+  REGIONS = ('dense_w', 'dense_b', 'conv0_b', 'main')
 
   def __init__(self):
     self.entries = []
