@@ -123,6 +123,15 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -477,8 +486,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
   // Both single-thread loops below are latency-bound chains of dependent scalar instructions, so they are written
   // with incremental state only: no integer division, no modulo, descriptors advanced by adding constants.
   if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================== TMA producer (whole warp walks the loop, one elected lane issues)
+    {
       int s = 0;
       uint32_t par = 1;                 // parity to wait on empty[s]: a fresh barrier passes parity 1 immediately
       const int pw = (p.kw - 1) / 2, ph = (p.kh - 1) / 2;
@@ -513,8 +522,9 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
         for (int i = 0; i < nkt; ++i) {
           mbar_wait(empty0 + 8 * s, par);
           const uint32_t bar = full0 + 8 * s;
-          mbar_expect_tx(bar, STAGE_BYTES);
           const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+          if (elect_one()) {
+          mbar_expect_tx(bar, STAGE_BYTES);
           // ---- A (private to this CTA)
           if (p.a_kind == KMAJOR) {
             tma_load_3d(sa, &mapA0, bar, kk, m0, b);
@@ -552,6 +562,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
               else tma_load_3d(sb + j * 8192, &mapB0, bar, c0, c1, c2);
             }
           }
+          }
+          __syncwarp();
           // ---- advance
           kk += BK;
           if (++cb == p.cblocks) { cb = 0; ++tap; if (++dx > pw) { dx = -pw; ++dy; } }
@@ -560,8 +572,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================== MMA issuer (whole warp walks the loop, one elected lane issues)
+    {
       const bool a_mn = (p.a_kind == MNMAJOR || p.a_kind == GATHER_MN);
       const bool b_mn = (p.b_kind != KMAJOR);
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
@@ -586,6 +598,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
         for (int i = 0; i < nkt; ++i) {
           mbar_wait(full0 + 8 * s, par);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
 #pragma unroll
           for (int j = 0; j < BK / 16; ++j) {
             const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + j * a_step);
@@ -595,11 +608,15 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
           }
           if (cs > 1) umma_commit_mc(empty0 + 8 * s, mc_mask);
           else umma_commit(empty0 + 8 * s);
+          }
+          __syncwarp();
+          accum = 1;
           a_lo += STAGE_BYTES >> 4;
           b_lo += STAGE_BYTES >> 4;
           if (++s == STAGES) { s = 0; par ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
         }
-        umma_commit(tfull0 + 8 * buf);
+        if (elect_one()) umma_commit(tfull0 + 8 * buf);
+        __syncwarp();
         ++tl;
       }
     }
