@@ -419,17 +419,24 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
 //     that the big dimension taps*Cin is M and the dY tile is the multicast operand.
 constexpr int NUM_THREADS2 = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
-template <int BN, int STAGES>
+// MH = number of 128-row accumulators per CTA tile: the tile is (128*MH) x BN with MH*BN <= 256 TMEM columns per
+// buffer.  MH = 2 (256 x 128) is the N <= 128 counterpart of the 128 x 256 tile: both stream 48 KB per K block
+// for 4.2 MFLOP, i.e. the single TMA / MMA issuing threads have 512 tensor-core cycles per K block to hide behind.
+template <int BN, int MH, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                    const __grid_constant__ CUtensorMap mapA1,
                                                                    const __grid_constant__ CUtensorMap mapB0,
                                                                    const __grid_constant__ CUtensorMap mapB1,
                                                                    const TcParams p) {
+  static_assert(BN * MH <= 256, "accumulator buffer exceeds half of TMEM");
+  constexpr int BMT = BM * MH;                // tile rows
+  constexpr int A_BYTES = A_STAGE_BYTES * MH;
   constexpr int B_STAGE_BYTES = BN * 128;
-  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  constexpr int TMEM_COLS = 2 * BN;
-  constexpr int CH = BN / 64;                 // 32-column chunks per epilogue warp
-  constexpr int RES_BYTES = BN * 256;         // 256 epilogue threads x CH chunks x 64 bytes
+  constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
+  constexpr int TC = BN * MH;                 // TMEM columns per accumulator buffer
+  constexpr int TMEM_COLS = 2 * TC;
+  constexpr int CH = TC / 64;                 // 32-column chunks per epilogue warp
+  constexpr int RES_BYTES = TC * 256;         // 256 epilogue threads x CH chunks x 64 bytes
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* res_stage = smem + STAGES * STAGE_BYTES;
@@ -477,7 +484,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
     const int z = st / (m_groups * p.n_tiles);
     b = z / split;
     const int ks = z % split;
-    m0 = (mg * cs + rank) * BM;
+    m0 = (mg * cs + rank) * BMT;
     n0 = nt * BN;
     kt0 = ks * kper;
     nkt = min(p.nk, kt0 + kper) - kt0;
@@ -498,17 +505,23 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
         decode(st, m0, n0, b, kt0, nkt);
         if (nkt <= 0) continue;
         // ---- per-tile constants
-        int gx0 = 0, gy0 = 0, gn0 = 0;
-        if (p.a_kind == GATHER_K) { gx0 = m0 & Wm; gy0 = (m0 >> lw) & Hm; gn0 = m0 >> lhw; }
+        int gx0[MH], gy0[MH], gn0[MH];
+#pragma unroll
+        for (int h = 0; h < MH; ++h) {
+          const int mh = m0 + h * BM;
+          gx0[h] = mh & Wm; gy0[h] = (mh >> lw) & Hm; gn0[h] = mh >> lhw;
+        }
         int tap = 0, cb = 0, dy = -ph, dx = -pw;         // (tap, channel block) walk of conv-shaped K axes
         if (p.a_kind == GATHER_K) {
           tap = kt0 / p.cblocks; cb = kt0 - tap * p.cblocks;
           dy = tap / p.kw - ph; dx = tap - (tap / p.kw) * p.kw - pw;
         }
-        int a_c[2] = {0, 0}, a_dx[2] = {0, 0}, a_dy[2] = {0, 0}, a_src[2] = {0, 0};
+        int a_c[2 * MH], a_dx[2 * MH], a_dy[2 * MH], a_src[2 * MH];
+#pragma unroll
+        for (int j = 0; j < 2 * MH; ++j) { a_c[j] = 0; a_dx[j] = 0; a_dy[j] = 0; a_src[j] = 2; }
         if (p.a_kind == GATHER_MN) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < 2 * MH; ++j) {
             const int mm = m0 + 64 * j;
             const int t = mm / p.Ct, c = mm - t * p.Ct;
             if (t >= p.ntaps) { a_src[j] = 2; }            // masked rows: any in-range box
@@ -522,22 +535,26 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
         for (int i = 0; i < nkt; ++i) {
           mbar_wait(empty0 + 8 * s, par);
           const uint32_t bar = full0 + 8 * s;
-          const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+          const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
           if (elect_one()) {
           mbar_expect_tx(bar, STAGE_BYTES);
-          // ---- A (private to this CTA)
+          // ---- A (private to this CTA): MH blocks of 128 rows, 16 KB each
           if (p.a_kind == KMAJOR) {
-            tma_load_3d(sa, &mapA0, bar, kk, m0, b);
+#pragma unroll
+            for (int h = 0; h < MH; ++h) tma_load_3d(sa + h * A_STAGE_BYTES, &mapA0, bar, kk, m0 + h * BM, b);
           } else if (p.a_kind == MNMAJOR) {
-            tma_load_3d(sa, &mapA0, bar, m0, kk, b);
-            tma_load_3d(sa + 8192, &mapA0, bar, m0 + 64, kk, b);
+#pragma unroll
+            for (int j = 0; j < 2 * MH; ++j) tma_load_3d(sa + j * 8192, &mapA0, bar, m0 + 64 * j, kk, b);
           } else if (p.a_kind == GATHER_K) {
-            if (cb < p.c1blocks) tma_load_4d(sa, &mapA0, bar, cb * 64, gx0 + dx, gy0 + dy, gn0);
-            else tma_load_4d(sa, &mapA1, bar, (cb - p.c1blocks) * 64, gx0 + dx, gy0 + dy, gn0);
+#pragma unroll
+            for (int h = 0; h < MH; ++h) {
+              if (cb < p.c1blocks) tma_load_4d(sa + h * A_STAGE_BYTES, &mapA0, bar, cb * 64, gx0[h] + dx, gy0[h] + dy, gn0[h]);
+              else tma_load_4d(sa + h * A_STAGE_BYTES, &mapA1, bar, (cb - p.c1blocks) * 64, gx0[h] + dx, gy0[h] + dy, gn0[h]);
+            }
           } else {   // GATHER_MN as A: m = (tap, channel), k = pixel block
             const int x0 = kk & Wm, y0 = (kk >> lw) & Hm, i0 = kk >> lhw;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < 2 * MH; ++j) {
               if (a_src[j] == 2) tma_load_4d(sa + j * 8192, &mapA0, bar, 0, x0, y0, i0);
               else if (a_src[j] == 0) tma_load_4d(sa + j * 8192, &mapA0, bar, a_c[j], x0 + a_dx[j], y0 + a_dy[j], i0);
               else tma_load_4d(sa + j * 8192, &mapA1, bar, a_c[j], x0 + a_dx[j], y0 + a_dy[j], i0);
@@ -581,7 +598,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
       // descriptor = hi32 (SBO=1024, version 1, SWIZZLE_128B) : lo32 (start>>4 | LBO>>4 << 16)
       const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t a_lo0 = (smem_base >> 4) | ((a_mn ? (8192u >> 4) : 1u) << 16);
-      const uint32_t b_lo0 = ((smem_base + A_STAGE_BYTES) >> 4) | ((b_mn ? (8192u >> 4) : 1u) << 16);
+      const uint32_t b_lo0 = ((smem_base + A_BYTES) >> 4) | ((b_mn ? (8192u >> 4) : 1u) << 16);
       const uint32_t a_step = a_mn ? (2048u >> 4) : (32u >> 4), b_step = b_mn ? (2048u >> 4) : (32u >> 4);
       int s = 0, tl = 0;
       uint32_t par = 0;
@@ -593,7 +610,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
         const int buf = tl & 1;
         if (tl >= 2) mbar_wait(tempty0 + 8 * buf, ((tl >> 1) - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * TC);
         uint32_t accum = 0;
         for (int i = 0; i < nkt; ++i) {
           mbar_wait(full0 + 8 * s, par);
@@ -601,9 +618,12 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
           if (elect_one()) {
 #pragma unroll
           for (int j = 0; j < BK / 16; ++j) {
-            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + j * a_step);
             const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + j * b_step);
-            umma_f16(tacc, ad, bd, idesc, accum);
+#pragma unroll
+            for (int h = 0; h < MH; ++h) {
+              const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + h * (A_STAGE_BYTES >> 4) + j * a_step);
+              umma_f16(tacc + (uint32_t)(h * BN), ad, bd, idesc, accum);
+            }
             accum = 1;
           }
           if (cs > 1) umma_commit_mc(empty0 + 8 * s, mc_mask);
@@ -623,9 +643,9 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
   } else {
     // ===================================================== epilogue (warps 2..9)
     const int q = warp % 4;                   // TMEM lane quarter of this warp
-    const int half = (warp - 2) / 4;          // which half of the tile's columns
+    const int half = (warp - 2) / 4;          // MH == 1: which half of the tile's columns; MH == 2: which 128 rows
     const int et = (warp - 2) * 32 + lane;    // epilogue thread index (0..255): its private staging slots
-    const int row = q * 32 + lane;
+    const int row = (MH == 2 ? half * BM : 0) + q * 32 + lane;
     const bool vec_res = p.residual && ((p.ldr | p.sRb) % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
     const bool vec_bias = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     uint8_t* my_stage = res_stage + (size_t)et * 16;
@@ -637,13 +657,14 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
       const int buf = tl & 1;
       const long long m = (long long)m0 + row;
       const bool row_ok = m < p.M;
-      const int ncol0 = n0 + half * (BN / 2);
+      const int ncol0 = n0 + (MH == 2 ? 0 : half * (BN / 2));
+      constexpr int NCOLS = TC / 2;             // columns handled by this warp
       const float* rb = (p.rowbias && row_ok) ? p.rowbias + (m / p.rows_per_rb) * p.ld_rb : nullptr;
       const bf16* res = (p.residual && row_ok) ? p.residual + (long long)b * p.sRb + m * p.ldr : nullptr;
       const long long crow = (long long)b * p.sCb + m * p.ldc;
       // ---- prefetch this tile's residual slice (overlaps the MMAs that are still filling the accumulator)
       bool staged = false;
-      if (res && vec_res && ncol0 + BN / 2 <= p.N) {
+      if (res && vec_res && ncol0 + NCOLS <= p.N) {
         staged = true;
 #pragma unroll
         for (int j = 0; j < CH * 4; ++j) {
@@ -659,7 +680,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
       for (int c = 0; c < CH; ++c) {
         uint32_t r[32];
         __syncwarp();
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * (BN / 2) + c * 32), r);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC + half * (TC / 2) + c * 32), r);
         const int nb = ncol0 + c * 32;
         if (!row_ok || nb >= p.N) continue;
         float v[32];
@@ -893,13 +914,13 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-template <int BN, int STAGES>
+template <int BN, int MH, int STAGES>
 int launch2(const CUtensorMap* maps, TcParams& p, int total_super, cudaStream_t stream) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + BN * 128) + BN * 256 + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * (A_STAGE_BYTES * MH + BN * 128) + BN * MH * 256 + (2 * STAGES + 4) * 8 + 16 + 1024;
   static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   static int max_clusters[5] = {0, 0, 0, 0, 0};
-  auto kern = gemm_tc2_kernel<BN, STAGES>;
+  auto kern = gemm_tc2_kernel<BN, MH, STAGES>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { st_set_error("st_gemm(tc2): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ST_ERR_CUDA; }
@@ -967,7 +988,13 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   for (p.logH = 0; (1 << p.logH) < a->H; ++p.logH) {}
   int BN = (N >= 256 && N % 256 == 0) ? 256 : (N > 64 ? 128 : 64);
   if (BN == 256 && env_int("ST_TC_BN", 256) == 128) BN = 128;
-  p.m_tiles = (M + BM - 1) / BM;
+  // 256 x 128 tiles (two accumulators sharing the B tile) when N fits 128-wide tiles and M is large
+  int MH = 1;
+  if (BN == 128 && env_int("ST_TC_MH", 2) == 2) {
+    const long long tiles2 = (long long)((M + 255) / 256) * ((N + BN - 1) / BN) * p.batch * p.split_k;
+    if (tiles2 >= 120) MH = 2;
+  }
+  p.m_tiles = (M + BM * MH - 1) / (BM * MH);
   p.n_tiles = (N + BN - 1) / BN;
 
   // B kind first (it bounds the cluster size)
@@ -1033,9 +1060,10 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   const int m_groups = (p.m_tiles + cs - 1) / cs;
   const long long total = (long long)p.batch * p.split_k * p.n_tiles * m_groups;
   ST_CHECK_ARG(total < (1LL << 30), "st_gemm(tc2): too many tiles");
-  if (BN == 256) return launch2<256, 3>(maps, p, (int)total, stream);
-  if (BN == 128) return launch2<128, 6>(maps, p, (int)total, stream);
-  return launch2<64, 8>(maps, p, (int)total, stream);
+  if (BN == 256) return launch2<256, 1, 3>(maps, p, (int)total, stream);
+  if (BN == 128 && MH == 2) return launch2<128, 2, 3>(maps, p, (int)total, stream);
+  if (BN == 128) return launch2<128, 1, 6>(maps, p, (int)total, stream);
+  return launch2<64, 1, 8>(maps, p, (int)total, stream);
 }
 
 }  // namespace

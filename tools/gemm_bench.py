@@ -36,8 +36,8 @@ def conv_shapes(B):
 
 def main():
   B = int(os.environ.get('GB_BATCH', '512'))
-  configs = [('v1', dict(ST_TC_VARIANT='1')), ('v2 cs1', dict(ST_TC_VARIANT='2', ST_TC_CLUSTER='1')), ('v2 bn128', dict(ST_TC_VARIANT='2', ST_TC_CLUSTER='1', ST_TC_BN='128')),
-             ('hybrid', dict(ST_TC_VARIANT='0', ST_TC_CLUSTER='1', ST_TC_BN='256'))]
+  configs = [('v1', dict(ST_TC_VARIANT='1')), ('v2', dict(ST_TC_VARIANT='2', ST_TC_CLUSTER='1', ST_TC_MH='2')), ('v2 mh1', dict(ST_TC_VARIANT='2', ST_TC_CLUSTER='1', ST_TC_MH='1')),
+             ('hybrid', dict(ST_TC_VARIANT='0', ST_TC_CLUSTER='1', ST_TC_MH='2'))]
   rows = []
   for name, H, C1, C2, Co, k in conv_shapes(B):
     Ci = C1 + C2
