@@ -1072,13 +1072,14 @@ int st_gemm_tc1(const st_gemm_args* a, cudaStream_t stream);
 
 int st_gemm_tc(const st_gemm_args* a, cudaStream_t stream) {
   // ST_TC_VARIANT: 1 = one tile per CTA, two CTAs per SM; 2 = persistent double-buffered kernel; 0 (default) =
-  // measured best per operand form on B200 (tools/gemm_bench.py): the persistent kernel when B is K-major
-  // (forward convolutions, Linear/NIN, QK^T), the two-CTAs-per-SM kernel when B is read MN-major (dgrad, wgrad).
+  // measured best per operand form on B200 (tools/gemm_bench.py, profiles/): the persistent kernel everywhere except
+  // 3x3 weight gradients with fewer than 256 output channels, where the transposed form needs 6 TMA boxes per K block
+  // and the two-CTAs-per-SM kernel is faster.
   const int variant = env_int("ST_TC_VARIANT", 0);
   if (variant == 1) return st_gemm_tc1(a, stream);
   if (variant == 2) return st_gemm_tc2(a, stream);
-  const bool b_kmajor = a->b_mode == ST_OP_STRIDED && a->sBk == 1;
-  return b_kmajor ? st_gemm_tc2(a, stream) : st_gemm_tc1(a, stream);
+  const bool small_wgrad = a->b_mode == ST_OP_GATHER && a->M < 256 && a->kh * a->kw > 1;
+  return small_wgrad ? st_gemm_tc1(a, stream) : st_gemm_tc2(a, stream);
 }
 
 int st_gemm_tc1(const st_gemm_args* a, cudaStream_t stream) {
