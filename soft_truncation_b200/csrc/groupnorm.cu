@@ -33,25 +33,47 @@ __device__ __forceinline__ void store8(bf16* p, const float v[8]) {
   *reinterpret_cast<uint4*>(p) = t;
 }
 
-// Raw 8-element vectors: loads are issued back to back (4 pixels in flight per thread) and only converted to
-// fp32 when consumed, which keeps the number of live registers per pending load at 4 (bf16) / 8 (fp32).
-template <typename T> struct Raw8;
-template <> struct Raw8<bf16> { uint4 a; };
-template <> struct Raw8<float> { float4 a, b; };
-__device__ __forceinline__ void ldraw(const bf16* p, Raw8<bf16>& r) { r.a = *reinterpret_cast<const uint4*>(p); }
-__device__ __forceinline__ void ldraw(const float* p, Raw8<float>& r) {
-  r.a = reinterpret_cast<const float4*>(p)[0];
-  r.b = reinterpret_cast<const float4*>(p)[1];
-}
-__device__ __forceinline__ void cvt(const Raw8<bf16>& r, float v[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.a);
+// Thread-private cp.async software pipeline.  Every thread streams its own sequence of 8-element vectors (one per
+// pixel and input stream) through DEPTH shared-memory slots: the bytes in flight per SM are set by the shared-memory
+// ring (DEPTH x streams x 16 B x 256 threads x resident blocks), not by registers, which is what an HBM-bound pass
+// needs to cover ~1-2 us of loaded-memory latency.  Slots are private to a thread (it only reads what it copied),
+// so no block barrier is involved; slot addresses are strided by the block size -> conflict-free.
+template <typename T, int NS, int DEPTH>
+struct Pipe {
+  static constexpr int PARTS = (int)sizeof(T) * 8 / 16;              // 16-byte pieces per vector (1 bf16, 2 fp32)
+  static constexpr int BYTES = DEPTH * NS * PARTS * 256 * 16;        // shared memory of one block
+  uint32_t base;                                                     // shared address of this thread's first slot
+  __device__ __forceinline__ explicit Pipe(uint8_t* smem) { base = (uint32_t)__cvta_generic_to_shared(smem) + threadIdx.x * 16; }
+  __device__ __forceinline__ uint32_t slot(int stage, int stream, int part) const {
+    return base + (uint32_t)(((stage * NS + stream) * PARTS + part) * 256 * 16);
+  }
+  __device__ __forceinline__ void issue(int stage, int stream, const T* g) const {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
-}
-__device__ __forceinline__ void cvt(const Raw8<float>& r, float v[8]) {
-  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
-}
-constexpr int UNR = 4;   // pixels in flight per thread
+    for (int part = 0; part < PARTS; ++part)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot(stage, stream, part)),
+                   "l"(reinterpret_cast<const uint8_t*>(g) + part * 16)
+                   : "memory");
+  }
+  __device__ __forceinline__ void read(int stage, int stream, float v[8]) const {
+    if constexpr (sizeof(T) == 2) {
+      uint4 t;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(slot(stage, stream, 0)));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+    } else {
+#pragma unroll
+      for (int part = 0; part < 2; ++part)
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v[4 * part]), "=f"(v[4 * part + 1]), "=f"(v[4 * part + 2]), "=f"(v[4 * part + 3])
+                     : "r"(slot(stage, stream, part)));
+    }
+  }
+  static __device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  static __device__ __forceinline__ void wait() { asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory"); }
+};
+constexpr int GN_DEPTH = 8;       // slots per thread (forward passes, backward reduction)
+constexpr int GN_BWD_DEPTH = 4;   // backward apply streams up to 5 inputs per pixel
 
 // keep-multipliers (0 or 1/(1-p)) of 8 consecutive elements: one Philox call, 16 random bits per element
 __device__ __forceinline__ void dropout8(uint64_t seed, uint64_t oct, float p, float keep[8]) {
@@ -96,6 +118,9 @@ __device__ __forceinline__ void load_consts(ChanConst& k, int n, int c0, int G, 
 // grid (n_img, splits): part[n][split][G][2] = (sum, sum of squares) over the split's pixels
 template <typename T>
 __global__ void __launch_bounds__(256) gn_stats_kernel(Src2<T> s, int hw, int G, int splits, float* part) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  using P = Pipe<T, 1, GN_DEPTH>;
+  const P pipe(gsm);
   const int Ct = s.C1 + s.C2, V = Ct / 8, cpg = Ct / G;
   const int n = blockIdx.x, sp = blockIdx.y;
   const int lanes = 256 / V;
@@ -103,22 +128,23 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(Src2<T> s, int hw, int G,
   const int per = (hw + splits - 1) / splits;
   const int p0 = sp * per, p1 = min(hw, p0 + per);
   float sum[2] = {0.f, 0.f}, sq[2] = {0.f, 0.f};
-  if (lane < lanes) {
-    const int c0 = v * 8;
-    for (int p = p0 + lane; p < p1; p += UNR * lanes) {
-      Raw8<T> raw[UNR];
+  const int c0 = v * 8;
+  const int n_it = (lane < lanes && p1 > p0 + lane) ? (p1 - p0 - lane + lanes - 1) / lanes : 0;
+  const long long row0 = (long long)n * hw + p0 + lane;
+  for (int d = 0; d < GN_DEPTH; ++d) {
+    if (d < n_it) pipe.issue(d, 0, s.at(row0 + (long long)d * lanes, c0));
+    P::commit();
+  }
+  int stage = 0;
+  for (int it = 0; it < n_it; ++it) {
+    P::wait();
+    float a[8];
+    pipe.read(stage, 0, a);
 #pragma unroll
-      for (int u = 0; u < UNR; ++u)
-        if (p + u * lanes < p1) ldraw(s.at((long long)n * hw + p + u * lanes, c0), raw[u]);
-#pragma unroll
-      for (int u = 0; u < UNR; ++u)
-        if (p + u * lanes < p1) {
-          float a[8];
-          cvt(raw[u], a);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { sum[i >> 2] += a[i]; sq[i >> 2] = fmaf(a[i], a[i], sq[i >> 2]); }
-        }
-    }
+    for (int i = 0; i < 8; ++i) { sum[i >> 2] += a[i]; sq[i >> 2] = fmaf(a[i], a[i], sq[i >> 2]); }
+    if (it + GN_DEPTH < n_it) pipe.issue(stage, 0, s.at(row0 + (long long)(it + GN_DEPTH) * lanes, c0));
+    P::commit();
+    stage = stage + 1 == GN_DEPTH ? 0 : stage + 1;
   }
   // quad q = 2*v + half holds channels [4q, 4q+4): whole quads never straddle a group (cpg % 4 == 0)
   __shared__ float s_sum[512], s_sq[512];
@@ -158,35 +184,15 @@ __global__ void gn_finalize_kernel(const float* part, int n_img, int splits, int
 }
 
 // ---------------------------------------------------------------- apply
-template <typename T>
-__device__ __forceinline__ void apply8(const float x[8], const ChanConst& k, int act, float p_drop, uint64_t seed,
-                                       const T* mask, long long oct, T* y) {
-  float o[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float u = fmaf((x[i] - k.mu[i >> 2]) * k.r[i >> 2], k.gam[i], k.bet[i]);
-    o[i] = act ? silu_f(u) : u;
-  }
-  if (mask) {
-    float mk[8];
-    load8(mask + oct * 8, mk);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] *= mk[i];
-  } else if (p_drop > 0.f) {
-    float keep[8];
-    dropout8(seed, (uint64_t)oct, p_drop, keep);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] *= keep[i];
-  }
-  store8(y + oct * 8, o);
-}
-
-// grid (chunks, n_img)
+// grid (chunks, n_img); streams: 0 = x, 1 = injected dropout mask (parity tests)
 template <typename T>
 __global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> s, int hw, int G, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float* __restrict__ mean,
                                                        const float* __restrict__ rstd, int act, float p_drop, uint64_t seed,
                                                        const T* mask, T* y) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  using P = Pipe<T, 2, GN_DEPTH>;
+  const P pipe(gsm);
   const int Ct = s.C1 + s.C2, V = Ct / 8, cpg = Ct / G;
   const int n = blockIdx.y;
   const int lanes = 256 / V;
@@ -197,32 +203,56 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> s, int hw, int G,
   load_consts(k, n, c0, G, cpg, gamma, beta, mean, rstd);
   const int per = (hw + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
-  for (int p = p0 + lane; p < p1; p += UNR * lanes) {
-    Raw8<T> raw[UNR];
+  const int n_it = p1 > p0 + lane ? (p1 - p0 - lane + lanes - 1) / lanes : 0;
+  const long long row0 = (long long)n * hw + p0 + lane;
+  auto issue = [&](int stage, int j) {
+    const long long row = row0 + (long long)j * lanes;
+    pipe.issue(stage, 0, s.at(row, c0));
+    if (mask) pipe.issue(stage, 1, mask + (row * V + v) * 8);
+  };
+  for (int d = 0; d < GN_DEPTH; ++d) {
+    if (d < n_it) issue(d, d);
+    P::commit();
+  }
+  int stage = 0;
+  for (int it = 0; it < n_it; ++it) {
+    P::wait();
+    const long long oct = (row0 + (long long)it * lanes) * V + v;
+    float x[8], o[8];
+    pipe.read(stage, 0, x);
 #pragma unroll
-    for (int u = 0; u < UNR; ++u)
-      if (p + u * lanes < p1) ldraw(s.at((long long)n * hw + p + u * lanes, c0), raw[u]);
+    for (int i = 0; i < 8; ++i) {
+      float u = fmaf((x[i] - k.mu[i >> 2]) * k.r[i >> 2], k.gam[i], k.bet[i]);
+      o[i] = act ? silu_f(u) : u;
+    }
+    if (mask) {
+      float mk[8];
+      pipe.read(stage, 1, mk);
 #pragma unroll
-    for (int u = 0; u < UNR; ++u)
-      if (p + u * lanes < p1) {
-        const long long row = (long long)n * hw + p + u * lanes;
-        float a[8];
-        cvt(raw[u], a);
-        apply8<T>(a, k, act, p_drop, seed, mask, row * V + v, y);
-      }
+      for (int i = 0; i < 8; ++i) o[i] *= mk[i];
+    } else if (p_drop > 0.f) {
+      float keep[8];
+      dropout8(seed, (uint64_t)oct, p_drop, keep);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] *= keep[i];
+    }
+    store8(y + oct * 8, o);
+    if (it + GN_DEPTH < n_it) issue(stage, it + GN_DEPTH);
+    P::commit();
+    stage = stage + 1 == GN_DEPTH ? 0 : stage + 1;
   }
 }
 
 // dz and xhat of one 8-vector (shared by both backward passes)
-template <typename T>
+// `mk` holds the injected mask values when has_mask, else it is filled here (in-kernel RNG or ones)
 __device__ __forceinline__ void gn_dz8(const float x[8], const float dyv[8], const ChanConst& k, int act, float p_drop,
-                                       uint64_t seed, const T* mask, long long oct, float xhat[8], float dz[8]) {
-  float mk[8];
-  if (mask) load8(mask + oct * 8, mk);
-  else if (p_drop > 0.f) dropout8(seed, (uint64_t)oct, p_drop, mk);
-  else {
+                                       uint64_t seed, bool has_mask, float mk[8], long long oct, float xhat[8], float dz[8]) {
+  if (!has_mask) {
+    if (p_drop > 0.f) dropout8(seed, (uint64_t)oct, p_drop, mk);
+    else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) mk[i] = 1.f;
+      for (int i = 0; i < 8; ++i) mk[i] = 1.f;
+    }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -244,39 +274,47 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> s, const T* 
   const int n = blockIdx.x, sp = blockIdx.y;
   const int lanes = 256 / V;
   const int v = threadIdx.x % V, lane = threadIdx.x / V;
+  extern __shared__ __align__(16) uint8_t gsm[];
   const int per = (hw + splits - 1) / splits;
   const int p0 = sp * per, p1 = min(hw, p0 + per);
   const int c0 = v * 8;
   float a[8], b[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.f;
-  if (lane < lanes) {
-    ChanConst k;
-    load_consts(k, n, c0, G, cpg, gamma, beta, mean, rstd);
-    for (int p = p0 + lane; p < p1; p += UNR * lanes) {
-      Raw8<T> rx[UNR], rd[UNR];
-#pragma unroll
-      for (int u = 0; u < UNR; ++u)
-        if (p + u * lanes < p1) {
-          const long long row = (long long)n * hw + p + u * lanes;
-          ldraw(s.at(row, c0), rx[u]);
-          ldraw(dy + (row * V + v) * 8, rd[u]);
-        }
-#pragma unroll
-      for (int u = 0; u < UNR; ++u)
-        if (p + u * lanes < p1) {
-          const long long row = (long long)n * hw + p + u * lanes;
-          float x0[8], d0[8], xh[8], dz[8];
-          cvt(rx[u], x0);
-          cvt(rd[u], d0);
-          gn_dz8<T>(x0, d0, k, act, p_drop, seed, mask, row * V + v, xh, dz);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
-        }
-    }
+  using P = Pipe<T, 3, GN_DEPTH>;            // streams: x, dy, injected mask
+  const P pipe(gsm);
+  const int n_it = (lane < lanes && p1 > p0 + lane) ? (p1 - p0 - lane + lanes - 1) / lanes : 0;
+  const long long row0 = (long long)n * hw + p0 + lane;
+  ChanConst k;
+  if (lane < lanes) load_consts(k, n, c0, G, cpg, gamma, beta, mean, rstd);
+  auto issue = [&](int stage, int j) {
+    const long long row = row0 + (long long)j * lanes;
+    pipe.issue(stage, 0, s.at(row, c0));
+    pipe.issue(stage, 1, dy + (row * V + v) * 8);
+    if (mask) pipe.issue(stage, 2, mask + (row * V + v) * 8);
+  };
+  for (int d = 0; d < GN_DEPTH; ++d) {
+    if (d < n_it) issue(d, d);
+    P::commit();
   }
-  // reduce over pixel lanes: smem [lane][V][16]
-  extern __shared__ float s_red[];
+  int stage = 0;
+  for (int it = 0; it < n_it; ++it) {
+    P::wait();
+    const long long oct = (row0 + (long long)it * lanes) * V + v;
+    float x0[8], d0[8], mk[8], xh[8], dz[8];
+    pipe.read(stage, 0, x0);
+    pipe.read(stage, 1, d0);
+    if (mask) pipe.read(stage, 2, mk);
+    gn_dz8(x0, d0, k, act, p_drop, seed, mask != nullptr, mk, oct, xh, dz);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
+    if (it + GN_DEPTH < n_it) issue(stage, it + GN_DEPTH);
+    P::commit();
+    stage = stage + 1 == GN_DEPTH ? 0 : stage + 1;
+  }
+  // reduce over pixel lanes: smem [lane][V][16] (reuses the pipeline's shared memory once it has drained)
+  __syncthreads();
+  float* s_red = reinterpret_cast<float*>(gsm);
   if (lane < lanes) {
     float* o = s_red + ((size_t)lane * V + v) * 16;
 #pragma unroll
@@ -326,6 +364,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> s, const T* d
                                                            int act, float p_drop, uint64_t seed, const T* mask,
                                                            const float* __restrict__ red, const T* extra, float extra_scale,
                                                            T* dx1, int accum1, T* dx2, int accum2) {
+  extern __shared__ __align__(16) uint8_t gsm[];
   const int Ct = s.C1 + s.C2, V = Ct / 8, cpg = Ct / G;
   const int n = blockIdx.y;
   __shared__ float sh1[64], sh2[64];
@@ -356,43 +395,59 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> s, const T* d
   const int acc = c0 < s.C1 ? accum1 : accum2;
   const int per = (hw + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
-  for (int p = p0 + lane; p < p1; p += UNR * lanes) {
-    Raw8<T> rx[UNR], rd[UNR], re[UNR], ro[UNR];
-    // all global loads of the iteration first: x, dy, (extra), (old destination)
-#pragma unroll
-    for (int u = 0; u < UNR; ++u)
-      if (p + u * lanes < p1) {
-        const long long row = (long long)n * hw + p + u * lanes;
-        ldraw(s.at(row, c0), rx[u]);
-        ldraw(dy + (row * V + v) * 8, rd[u]);
-        if (extra) ldraw(extra + (row * V + v) * 8, re[u]);
-        if (acc) ldraw(dbase + row * dld, ro[u]);
-      }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u)
-      if (p + u * lanes < p1) {
-        const long long row = (long long)n * hw + p + u * lanes;
-        float x0[8], d0[8], xh[8], dz[8], o[8];
-        cvt(rx[u], x0);
-        cvt(rd[u], d0);
-        gn_dz8<T>(x0, d0, k, act, p_drop, seed, mask, row * V + v, xh, dz);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = k.r[i >> 2] * (k.gam[i] * dz[i] - s1[i >> 2] - xh[i] * s2[i >> 2]);
-        if (extra) {
-          float ex[8];
-          cvt(re[u], ex);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = fmaf(extra_scale, ex[i], o[i]);
-        }
-        if (acc) {
-          float old[8];
-          cvt(ro[u], old);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] += old[i];
-        }
-        store8(dbase + row * dld, o);
-      }
+  using P = Pipe<T, 5, GN_BWD_DEPTH>;        // streams: x, dy, extra, old destination, injected mask
+  const P pipe(gsm);
+  const int n_it = p1 > p0 + lane ? (p1 - p0 - lane + lanes - 1) / lanes : 0;
+  const long long row0 = (long long)n * hw + p0 + lane;
+  auto issue = [&](int stage, int j) {
+    const long long row = row0 + (long long)j * lanes;
+    pipe.issue(stage, 0, s.at(row, c0));
+    pipe.issue(stage, 1, dy + (row * V + v) * 8);
+    if (extra) pipe.issue(stage, 2, extra + (row * V + v) * 8);
+    if (acc) pipe.issue(stage, 3, dbase + row * dld);
+    if (mask) pipe.issue(stage, 4, mask + (row * V + v) * 8);
+  };
+  for (int d = 0; d < GN_BWD_DEPTH; ++d) {
+    if (d < n_it) issue(d, d);
+    P::commit();
   }
+  int stage = 0;
+  for (int it = 0; it < n_it; ++it) {
+    P::wait();
+    const long long row = row0 + (long long)it * lanes;
+    float x0[8], d0[8], mk[8], xh[8], dz[8], o[8];
+    pipe.read(stage, 0, x0);
+    pipe.read(stage, 1, d0);
+    if (mask) pipe.read(stage, 4, mk);
+    gn_dz8(x0, d0, k, act, p_drop, seed, mask != nullptr, mk, row * V + v, xh, dz);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = k.r[i >> 2] * (k.gam[i] * dz[i] - s1[i >> 2] - xh[i] * s2[i >> 2]);
+    if (extra) {
+      float ex[8];
+      pipe.read(stage, 2, ex);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(extra_scale, ex[i], o[i]);
+    }
+    if (acc) {
+      float old[8];
+      pipe.read(stage, 3, old);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += old[i];
+    }
+    store8(dbase + row * dld, o);
+    if (it + GN_BWD_DEPTH < n_it) issue(stage, it + GN_BWD_DEPTH);
+    P::commit();
+    stage = stage + 1 == GN_BWD_DEPTH ? 0 : stage + 1;
+  }
+}
+
+// opt a kernel in to more than 48 KB of dynamic shared memory (once per kernel instance)
+template <typename K>
+bool allow_smem(K kernel, int bytes) {
+  if (bytes <= 48 * 1024) return true;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { st_set_error("groupnorm: cudaFuncSetAttribute(%d bytes): %s", bytes, cudaGetErrorString(e)); return false; }
+  return true;
 }
 
 int check_geom(int C1, int C2, int G) {
@@ -406,7 +461,7 @@ int check_geom(int C1, int C2, int G) {
 // pixel chunks per image so that the grid is a few waves of 148 SMs x 8 resident blocks
 int chunks_for(int n_img, int hw, int V) {
   int lanes = 256 / V;
-  int max_chunks = (hw + UNR * lanes - 1) / (UNR * lanes);   // at least one full iteration per block
+  int max_chunks = (hw + GN_DEPTH * lanes - 1) / (GN_DEPTH * lanes);   // at least one full pipeline per block
   int want = (st_num_sms() * 8 + n_img - 1) / n_img;
   int c = want < max_chunks ? want : max_chunks;
   if (c > 65535) c = 65535;
@@ -421,7 +476,10 @@ extern "C" __attribute__((visibility("default"))) int st_gn_stats(const void* x1
   ST_CHECK_ARG(splits >= 1 && splits <= 65535, "st_gn_stats: bad splits");
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
-    gn_stats_kernel<T><<<dim3(n_img, splits), 256, 0, (cudaStream_t)stream>>>(s, hw, G, splits, part);
+    constexpr int smem = Pipe<T, 1, GN_DEPTH>::BYTES;
+    static bool smem_ok = false;
+    if (!smem_ok) { if (!allow_smem(gn_stats_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
+    gn_stats_kernel<T><<<dim3(n_img, splits), 256, smem, (cudaStream_t)stream>>>(s, hw, G, splits, part);
   });
   ST_CHECK_LAUNCH("st_gn_stats");
   return 0;
@@ -444,7 +502,10 @@ extern "C" __attribute__((visibility("default"))) int st_gn_apply(const void* x1
   const int V = (C1 + C2) / 8;
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
-    gn_apply_kernel<T><<<dim3(chunks_for(n_img, hw, V), n_img), 256, 0, (cudaStream_t)stream>>>(
+    constexpr int smem = Pipe<T, 2, GN_DEPTH>::BYTES;
+    static bool smem_ok = false;
+    if (!smem_ok) { if (!allow_smem(gn_apply_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
+    gn_apply_kernel<T><<<dim3(chunks_for(n_img, hw, V), n_img), 256, smem, (cudaStream_t)stream>>>(
         s, hw, G, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, (T*)y);
   });
   ST_CHECK_LAUNCH("st_gn_apply");
@@ -457,10 +518,12 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_reduce(const voi
                                 int splits, float* red, void* stream) {
   if (int e = check_geom(C1, C2, G)) return e;
   const int V = (C1 + C2) / 8;
-  const int lanes = 256 / V;
-  const size_t smem = (size_t)lanes * V * 16 * sizeof(float);     // <= 16 KB
+  (void)V;
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
+    constexpr int smem = Pipe<T, 3, GN_DEPTH>::BYTES;      // >= the 16 KB the final lane reduction reuses
+    static bool smem_ok = false;
+    if (!smem_ok) { if (!allow_smem(gn_bwd_reduce_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
     gn_bwd_reduce_kernel<T><<<dim3(n_img, splits), 256, smem, (cudaStream_t)stream>>>(
         s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, red);
   });
@@ -484,7 +547,10 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_apply(const void
   const int V = (C1 + C2) / 8;
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
-    gn_bwd_apply_kernel<T><<<dim3(chunks_for(n_img, hw, V), n_img), 256, 0, (cudaStream_t)stream>>>(
+    constexpr int smem = Pipe<T, 5, GN_BWD_DEPTH>::BYTES;
+    static bool smem_ok = false;
+    if (!smem_ok) { if (!allow_smem(gn_bwd_apply_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
+    gn_bwd_apply_kernel<T><<<dim3(chunks_for(n_img, hw, V), n_img), 256, smem, (cudaStream_t)stream>>>(
         s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, red,
         (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2);
   });
