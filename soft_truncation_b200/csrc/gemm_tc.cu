@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
 //     its slice into every CTA of the cluster (L2 -> SM traffic for B drops by `cluster`),
 //   * weight gradients run transposed (A = shifted NHWC boxes MN-major, B = dY MN-major, C stored transposed) so
 //     that the big dimension taps*Cin is M and the dY tile is the multicast operand.
-constexpr int NUM_THREADS2 = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int NUM_THREADS2 = 352;     // warp 0 TMA (A operand), warp 1 MMA, warps 2..9 epilogue, warp 10 TMA (B operand)
 
 // MH = number of 128-row accumulators per CTA tile: the tile is (128*MH) x BN with MH*BN <= 256 TMEM columns per
 // buffer.  MH = 2 (256 x 128) is the N <= 128 counterpart of the 128 x 256 tile: both stream 48 KB per K block
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full0 + 8 * s, 1);
+      mbar_init(full0 + 8 * s, 2);          // one arrive.expect_tx from each of the two producer warps
       mbar_init(empty0 + 8 * s, cs);
     }
     for (int b = 0; b < 2; ++b) {
@@ -492,8 +492,11 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
 
   // Both single-thread loops below are latency-bound chains of dependent scalar instructions, so they are written
   // with incremental state only: no integer division, no modulo, descriptors advanced by adding constants.
-  if (warp == 0) {
-    // ===================================================== TMA producer (whole warp walks the loop, one elected lane issues)
+  if (warp == 0 || warp == 10) {
+    // ===================================================== TMA producers: warp 0 streams the A operand, warp 10 the B operand
+    // (a single elected thread cannot issue the 4-6 boxes per K block of the MN-major forms fast enough);
+    // the whole warp walks the loop, one elected lane issues
+    const bool do_a = (warp == 0);
     {
       int s = 0;
       uint32_t par = 1;                 // parity to wait on empty[s]: a fresh barrier passes parity 1 immediately
@@ -537,7 +540,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
           const uint32_t bar = full0 + 8 * s;
           const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
           if (elect_one()) {
-          mbar_expect_tx(bar, STAGE_BYTES);
+          mbar_expect_tx(bar, do_a ? A_BYTES : B_STAGE_BYTES);
+          if (do_a) {
           // ---- A (private to this CTA): MH blocks of 128 rows, 16 KB each
           if (p.a_kind == KMAJOR) {
 #pragma unroll
@@ -560,6 +564,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
               else tma_load_4d(sa + j * 8192, &mapA1, bar, a_c[j], x0 + a_dx[j], y0 + a_dy[j], i0);
             }
           }
+          } else {
           // ---- B: this CTA's slice, multicast to the whole cluster
           if (p.b_kind == KMAJOR) {
             if (cs > 1) {
@@ -578,6 +583,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
               if (cs > 1) tma_load_3d_mc(sb + j * 8192, &mapB0, bar, c0, c1, c2, mc_mask);
               else tma_load_3d(sb + j * 8192, &mapB0, bar, c0, c1, c2);
             }
+          }
           }
           }
           __syncwarp();
