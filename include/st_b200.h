@@ -108,16 +108,17 @@ int st_gn_finalize(const float* part, int n_img, int splits, int G, int64_t coun
                    float* mean, float* rstd, void* stream);
 /* y = dropout( act( gamma*(x-mean)*rstd + beta ) );  act: 0 none, 1 SiLU.
  * dropout: keep-mask multiplies by 1/(1-p); `mask` (same dtype/shape as y, already scaled) is used
- * when non-NULL, else if p > 0 a counter-based RNG keyed by (seed, element index). */
+ * when non-NULL, else if p > 0 a counter-based RNG keyed by (seed, element index).  `keepbits` (optional,
+ * n_img*hw*C/8 bytes) receives the drawn keep flags, one bit per element, for the backward kernels. */
 int st_gn_apply(const void* x1, const void* x2, int dtype, int n_img, int hw, int C1, int C2, int G,
                 const float* gamma, const float* beta, const float* mean, const float* rstd, int act,
-                float p_drop, uint64_t seed, const void* mask, void* y, void* stream);
+                float p_drop, uint64_t seed, const void* mask, uint8_t* keepbits, void* y, void* stream);
 /* backward, pass 1: per (image, pixel split, channel) sums  red[n_img][splits][C][2] = (sum dz, sum dz*xhat) where
  * dz = dy * dropout_mask * act'(.)  */
 int st_gn_bwd_reduce(const void* x1, const void* x2, const void* dy, int dtype, int n_img, int hw, int C1,
                      int C2, int G, const float* gamma, const float* beta, const float* mean,
                      const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
-                     int splits, float* red, void* stream);
+                     const uint8_t* keepbits, int splits, float* red, void* stream);
 /* dgamma[c] += sum_r red[r][c][1], dbeta[c] += sum_r red[r][c][0], r over rows = n_img*splits */
 int st_gn_bwd_params(const float* red, int rows, int C, float* dgamma, float* dbeta, void* stream);
 /* backward, pass 2: dx = rstd*(gamma*dz - mean_g(gamma*dz) - xhat*mean_g(gamma*dz*xhat))
@@ -126,7 +127,7 @@ int st_gn_bwd_params(const float* red, int rows, int C, float* dgamma, float* db
 int st_gn_bwd_apply(const void* x1, const void* x2, const void* dy, int dtype, int n_img, int hw, int C1,
                     int C2, int G, const float* gamma, const float* beta, const float* mean,
                     const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
-                    int splits, const float* red, const void* extra, float extra_scale, void* dx1, int accum1,
+                    const uint8_t* keepbits, int splits, const float* red, const void* extra, float extra_scale, void* dx1, int accum1,
                     void* dx2, int accum2, void* stream);
 
 /* ------------------------------------------------------------------ elementwise / small

@@ -63,11 +63,12 @@ __device__ __forceinline__ void store4(bf16* p, const float v[4]) {
   *reinterpret_cast<uint2*>(p) = t;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// MUFU-based sigmoid (ex2 + rcp, ~2 ulp): these kernels are issue-bound, an IEEE division costs ~8 extra instructions
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 // d/dx [x*sigmoid(x)] = s*(1 + x*(1-s))
 __device__ __forceinline__ float silu_grad_f(float x) {
-  float s = 1.f / (1.f + __expf(-x));
-  return s * (1.f + x * (1.f - s));
+  float s = __fdividef(1.f, 1.f + __expf(-x));
+  return s * fmaf(x, 1.f - s, 1.f);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -76,12 +77,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Counter-based RNG (Philox-4x32-10): 4 uniform 32-bit words per (seed, counter).
+// Counter-based RNG (Philox-4x32-7): 4 uniform 32-bit words per (seed, counter).
 __device__ __forceinline__ uint4 philox4(uint64_t seed, uint64_t ctr) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x5eed5eedu, c3 = 0x0b200b20u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < 7; ++r) {      // Philox-4x32-7 (Crush-resistant per the Random123 paper; dropout needs no more)
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;

@@ -998,7 +998,9 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   int MH = 1;
   if (BN == 128 && env_int("ST_TC_MH", 2) == 2) {
     const long long tiles2 = (long long)((M + 255) / 256) * ((N + BN - 1) / BN) * p.batch * p.split_k;
-    if (tiles2 >= 120) MH = 2;
+    // weight gradients with a short M' = taps*Cin axis keep 128-row tiles (4 gathered A boxes per K block would
+    // make the A producer the bottleneck, and 1152 rows quantise badly into 256-row tiles)
+    if (tiles2 >= 120 && !(wgrad && M < 2048)) MH = 2;
   }
   p.m_tiles = (M + BM * MH - 1) / (BM * MH);
   p.n_tiles = (N + BN - 1) / BN;
@@ -1077,15 +1079,10 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
 int st_gemm_tc1(const st_gemm_args* a, cudaStream_t stream);
 
 int st_gemm_tc(const st_gemm_args* a, cudaStream_t stream) {
-  // ST_TC_VARIANT: 1 = one tile per CTA, two CTAs per SM; 2 = persistent double-buffered kernel; 0 (default) =
-  // measured best per operand form on B200 (tools/gemm_bench.py, profiles/): the persistent kernel everywhere except
-  // 3x3 weight gradients with fewer than 256 output channels, where the transposed form needs 6 TMA boxes per K block
-  // and the two-CTAs-per-SM kernel is faster.
-  const int variant = env_int("ST_TC_VARIANT", 0);
-  if (variant == 1) return st_gemm_tc1(a, stream);
-  if (variant == 2) return st_gemm_tc2(a, stream);
-  const bool small_wgrad = a->b_mode == ST_OP_GATHER && a->M < 256 && a->kh * a->kw > 1;
-  return small_wgrad ? st_gemm_tc1(a, stream) : st_gemm_tc2(a, stream);
+  // ST_TC_VARIANT=1 selects the first-generation kernel (one tile per CTA, two CTAs per SM), kept as an on-device
+  // cross-check; the persistent kernel is faster on every shape of the workload (tools/gemm_bench.py, profiles/).
+  if (env_int("ST_TC_VARIANT", 2) == 1) return st_gemm_tc1(a, stream);
+  return st_gemm_tc2(a, stream);
 }
 
 int st_gemm_tc1(const st_gemm_args* a, cudaStream_t stream) {

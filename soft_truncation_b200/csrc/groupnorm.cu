@@ -75,17 +75,28 @@ struct Pipe {
 constexpr int GN_DEPTH = 8;       // slots per thread (forward passes, backward reduction)
 constexpr int GN_BWD_DEPTH = 4;   // backward apply streams up to 5 inputs per pixel
 
-// keep-multipliers (0 or 1/(1-p)) of 8 consecutive elements: one Philox call, 16 random bits per element
-__device__ __forceinline__ void dropout8(uint64_t seed, uint64_t oct, float p, float keep[8]) {
+// keep-multipliers (0 or 1/(1-p)) of 8 consecutive elements: one Philox call, 16 random bits per element.
+// Returns the 8 keep flags as a byte (bit i = element i kept) so that the backward pass can reload them
+// (1 byte per 8 elements) instead of re-running the generator twice.
+__device__ __forceinline__ uint32_t dropout8(uint64_t seed, uint64_t oct, float p, float keep[8]) {
   uint4 r = philox4(seed, oct);
   const float inv = 1.f / (1.f - p);
   const uint32_t thr = (uint32_t)(p * 65536.f);
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t bits = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    keep[2 * i] = (w[i] & 0xFFFFu) >= thr ? inv : 0.f;
-    keep[2 * i + 1] = (w[i] >> 16) >= thr ? inv : 0.f;
+    const bool k0 = (w[i] & 0xFFFFu) >= thr, k1 = (w[i] >> 16) >= thr;
+    keep[2 * i] = k0 ? inv : 0.f;
+    keep[2 * i + 1] = k1 ? inv : 0.f;
+    bits |= (k0 ? 1u : 0u) << (2 * i) | (k1 ? 1u : 0u) << (2 * i + 1);
   }
+  return bits;
+}
+__device__ __forceinline__ void keep_from_bits(uint32_t bits, float p, float keep[8]) {
+  const float inv = 1.f / (1.f - p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) keep[i] = (bits >> i) & 1u ? inv : 0.f;
 }
 
 template <typename T>
@@ -189,7 +200,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> s, int hw, int G, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float* __restrict__ mean,
                                                        const float* __restrict__ rstd, int act, float p_drop, uint64_t seed,
-                                                       const T* mask, T* y) {
+                                                       const T* mask, uint8_t* keepbits, T* y) {
   extern __shared__ __align__(16) uint8_t gsm[];
   using P = Pipe<T, 2, GN_DEPTH>;
   const P pipe(gsm);
@@ -232,7 +243,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> s, int hw, int G,
       for (int i = 0; i < 8; ++i) o[i] *= mk[i];
     } else if (p_drop > 0.f) {
       float keep[8];
-      dropout8(seed, (uint64_t)oct, p_drop, keep);
+      const uint32_t bits = dropout8(seed, (uint64_t)oct, p_drop, keep);
+      if (keepbits) keepbits[oct] = (uint8_t)bits;
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] *= keep[i];
     }
@@ -246,9 +258,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> s, int hw, int G,
 // dz and xhat of one 8-vector (shared by both backward passes)
 // `mk` holds the injected mask values when has_mask, else it is filled here (in-kernel RNG or ones)
 __device__ __forceinline__ void gn_dz8(const float x[8], const float dyv[8], const ChanConst& k, int act, float p_drop,
-                                       uint64_t seed, bool has_mask, float mk[8], long long oct, float xhat[8], float dz[8]) {
+                                       uint64_t seed, bool has_mask, float mk[8], const uint8_t* keepbits, long long oct,
+                                       float xhat[8], float dz[8]) {
   if (!has_mask) {
-    if (p_drop > 0.f) dropout8(seed, (uint64_t)oct, p_drop, mk);
+    if (p_drop > 0.f && keepbits) keep_from_bits(keepbits[oct], p_drop, mk);
+    else if (p_drop > 0.f) dropout8(seed, (uint64_t)oct, p_drop, mk);
     else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) mk[i] = 1.f;
@@ -269,7 +283,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                            int act, float p_drop, uint64_t seed, const T* mask, float* red) {
+                                                            int act, float p_drop, uint64_t seed, const T* mask,
+                                                            const uint8_t* __restrict__ keepbits, float* red) {
   const int Ct = s.C1 + s.C2, V = Ct / 8, cpg = Ct / G;
   const int n = blockIdx.x, sp = blockIdx.y;
   const int lanes = 256 / V;
@@ -305,7 +320,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> s, const T* 
     pipe.read(stage, 0, x0);
     pipe.read(stage, 1, d0);
     if (mask) pipe.read(stage, 2, mk);
-    gn_dz8(x0, d0, k, act, p_drop, seed, mask != nullptr, mk, oct, xh, dz);
+    gn_dz8(x0, d0, k, act, p_drop, seed, mask != nullptr, mk, keepbits, oct, xh, dz);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
     if (it + GN_DEPTH < n_it) issue(stage, it + GN_DEPTH);
@@ -362,6 +377,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> s, const T* d
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            int act, float p_drop, uint64_t seed, const T* mask,
+                                                           const uint8_t* __restrict__ keepbits,
                                                            const float* __restrict__ red, const T* extra, float extra_scale,
                                                            T* dx1, int accum1, T* dx2, int accum2) {
   extern __shared__ __align__(16) uint8_t gsm[];
@@ -419,7 +435,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> s, const T* d
     pipe.read(stage, 0, x0);
     pipe.read(stage, 1, d0);
     if (mask) pipe.read(stage, 4, mk);
-    gn_dz8(x0, d0, k, act, p_drop, seed, mask != nullptr, mk, row * V + v, xh, dz);
+    gn_dz8(x0, d0, k, act, p_drop, seed, mask != nullptr, mk, keepbits, row * V + v, xh, dz);
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = k.r[i >> 2] * (k.gam[i] * dz[i] - s1[i >> 2] - xh[i] * s2[i >> 2]);
     if (extra) {
@@ -496,7 +512,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_finalize(const float
 
 extern "C" __attribute__((visibility("default"))) int st_gn_apply(const void* x1, const void* x2, int dtype, int n_img, int hw, int C1, int C2, int G,
                            const float* gamma, const float* beta, const float* mean, const float* rstd, int act,
-                           float p_drop, uint64_t seed, const void* mask, void* y, void* stream) {
+                           float p_drop, uint64_t seed, const void* mask, uint8_t* keepbits, void* y, void* stream) {
   if (int e = check_geom(C1, C2, G)) return e;
   ST_CHECK_ARG(n_img <= 65535, "st_gn_apply: more than 65535 images");
   const int V = (C1 + C2) / 8;
@@ -506,7 +522,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_apply(const void* x1
     static bool smem_ok = false;
     if (!smem_ok) { if (!allow_smem(gn_apply_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
     gn_apply_kernel<T><<<dim3(chunks_for(n_img, hw, V), n_img), 256, smem, (cudaStream_t)stream>>>(
-        s, hw, G, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, (T*)y);
+        s, hw, G, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, keepbits, (T*)y);
   });
   ST_CHECK_LAUNCH("st_gn_apply");
   return 0;
@@ -515,7 +531,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_apply(const void* x1
 extern "C" __attribute__((visibility("default"))) int st_gn_bwd_reduce(const void* x1, const void* x2, const void* dy, int dtype, int n_img, int hw, int C1,
                                 int C2, int G, const float* gamma, const float* beta, const float* mean,
                                 const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
-                                int splits, float* red, void* stream) {
+                                const uint8_t* keepbits, int splits, float* red, void* stream) {
   if (int e = check_geom(C1, C2, G)) return e;
   const int V = (C1 + C2) / 8;
   (void)V;
@@ -525,7 +541,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_reduce(const voi
     static bool smem_ok = false;
     if (!smem_ok) { if (!allow_smem(gn_bwd_reduce_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
     gn_bwd_reduce_kernel<T><<<dim3(n_img, splits), 256, smem, (cudaStream_t)stream>>>(
-        s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, red);
+        s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, keepbits, red);
   });
   ST_CHECK_LAUNCH("st_gn_bwd_reduce");
   return 0;
@@ -540,7 +556,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_params(const flo
 extern "C" __attribute__((visibility("default"))) int st_gn_bwd_apply(const void* x1, const void* x2, const void* dy, int dtype, int n_img, int hw, int C1,
                                int C2, int G, const float* gamma, const float* beta, const float* mean,
                                const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
-                               int splits, const float* red, const void* extra, float extra_scale, void* dx1,
+                               const uint8_t* keepbits, int splits, const float* red, const void* extra, float extra_scale, void* dx1,
                                int accum1, void* dx2, int accum2, void* stream) {
   if (int e = check_geom(C1, C2, G)) return e;
   ST_CHECK_ARG(n_img <= 65535, "st_gn_bwd_apply: more than 65535 images");
@@ -551,7 +567,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_apply(const void
     static bool smem_ok = false;
     if (!smem_ok) { if (!allow_smem(gn_bwd_apply_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
     gn_bwd_apply_kernel<T><<<dim3(chunks_for(n_img, hw, V), n_img), 256, smem, (cudaStream_t)stream>>>(
-        s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, red,
+        s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, keepbits, red,
         (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2);
   });
   ST_CHECK_LAUNCH("st_gn_bwd_apply");

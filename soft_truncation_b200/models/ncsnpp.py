@@ -159,13 +159,15 @@ class ResBlock:
     h1 = ops.conv_fwd(a0, P.c(pre + 'Conv_0.weight'), self.cout, bias=P.f(pre + 'Conv_0.bias'),
                       rowbias=net.dense[:, self.dense_off:], rowbias_ld=net.dense.shape[1])
     st1 = ops.gn_stats(h1, None, self.G1)
-    p_drop, seed, mask = 0., 0, None
+    p_drop, seed, mask, keepbits = 0., 0, None, None
     if net.train and m.dropout > 0:
       mask = m._mask_for(self.idx, h1)
       if mask is None:
         p_drop, seed = m.dropout, m._next_seed(self.idx)
+        if net.tape.enabled:      # keep flags (1 bit per element) for the two backward passes
+          keepbits = torch.empty(h1.numel() // 8, dtype=torch.uint8, device=h1.device)
     a1 = ops.gn_apply(h1, None, self.G1, P.f(pre + 'GroupNorm_1.weight'), P.f(pre + 'GroupNorm_1.bias'), st1, act=1,
-                      p_drop=p_drop, seed=seed, mask=mask)
+                      p_drop=p_drop, seed=seed, mask=mask, keepbits=keepbits)
     if self.shortcut:
       if xr is not None:
         sc = ops.conv_fwd(xr, P.c(pre + 'Conv_2.weight'), self.cout, 1, 1, bias=P.f(pre + 'Conv_2.bias'))
@@ -177,7 +179,7 @@ class ResBlock:
                        alpha=self.scale)
     y = Act(out, net.tape)
     if net.tape.enabled:
-      saved = (x1, x2, st0, a0, xr, h1, st1, a1, p_drop, seed, mask)
+      saved = (x1, x2, st0, a0, xr, h1, st1, a1, p_drop, seed, mask, keepbits)
       net.tape.record(lambda g, acc: self.bwd(net, saved, g, acc), (xa.id,) + ((xb.id,) if xb is not None else ()), y.id)
     if net.taps is not None:
       net.taps[self.idx] = out
@@ -187,7 +189,7 @@ class ResBlock:
     """g: d(out); acc: existing gradient tensors of (xa[, xb]) to accumulate into, or None."""
     P = net.m.P
     pre, s = self.pre, self.scale
-    x1, x2, st0, a0, xr, h1, st1, a1, p_drop, seed, mask = saved
+    x1, x2, st0, a0, xr, h1, st1, a1, p_drop, seed, mask, keepbits = saved
     B, H, W, Co = g.shape
     npix = B * H * W
     g2 = g.view(npix, Co)
@@ -198,7 +200,7 @@ class ResBlock:
     # ---- GroupNorm_1 + SiLU + dropout
     dh1, _ = ops.gn_backward(h1, None, da1, self.G1, P.f(pre + 'GroupNorm_1.weight'), P.f(pre + 'GroupNorm_1.bias'),
                              st1, 1, P.g(pre + 'GroupNorm_1.weight'), P.g(pre + 'GroupNorm_1.bias'), p_drop=p_drop,
-                             seed=seed, mask=mask)
+                             seed=seed, mask=mask, keepbits=keepbits)
     del da1
     # ---- Conv_0 bias, temb projection (per-image column sums), weights, data
     dd = torch.empty((B, Co), dtype=torch.float32, device=g.device)

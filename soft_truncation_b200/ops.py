@@ -164,17 +164,18 @@ def gn_stats(x, x2, G, eps=1e-6):
   return stats
 
 
-def gn_apply(x, x2, G, gamma, beta, stats, act, p_drop=0., seed=0, mask=None):
+def gn_apply(x, x2, G, gamma, beta, stats, act, p_drop=0., seed=0, mask=None, keepbits=None):
+  """`keepbits`: optional uint8 tensor (B*H*W*C/8 bytes) that receives the dropout keep flags drawn by the kernel."""
   B, H, W, C1 = x.shape
   C2 = 0 if x2 is None else x2.shape[3]
   y = torch.empty((B, H, W, C1 + C2), dtype=x.dtype, device=x.device)
   check(lib.st_gn_apply(ptr(x), ptr(x2), dt(x), B, H * W, C1, C2, G, ptr(gamma), ptr(beta), ptr(stats[0]),
-                        ptr(stats[1]), int(act), float(p_drop), int(seed), ptr(mask), ptr(y), stream()))
+                        ptr(stats[1]), int(act), float(p_drop), int(seed), ptr(mask), ptr(keepbits), ptr(y), stream()))
   return y
 
 
 def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0., seed=0, mask=None, extra=None,
-                extra_scale=1.0, dx1=None, accum1=False, dx2=None, accum2=False):
+                extra_scale=1.0, dx1=None, accum1=False, dx2=None, accum2=False, keepbits=None):
   """Returns (dx1, dx2); accumulates dgamma/dbeta (fp32 views into the flat gradient buffer)."""
   B, H, W, C1 = x.shape
   C2 = 0 if x2 is None else x2.shape[3]
@@ -182,7 +183,7 @@ def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0.,
   splits = _gn_splits(B, hw)
   red = torch.empty((B, splits, Ct, 2), dtype=torch.float32, device=x.device)
   common = (ptr(x), ptr(x2), ptr(dy), dt(x), B, hw, C1, C2, G, ptr(gamma), ptr(beta), ptr(stats[0]), ptr(stats[1]),
-            int(act), float(p_drop), int(seed), ptr(mask), splits, ptr(red))
+            int(act), float(p_drop), int(seed), ptr(mask), ptr(keepbits), splits, ptr(red))
   check(lib.st_gn_bwd_reduce(*common, stream()))
   check(lib.st_gn_bwd_params(ptr(red), B * splits, Ct, ptr(dgamma), ptr(dbeta), stream()))
   if dx1 is None:
