@@ -41,9 +41,24 @@ __device__ __forceinline__ void store8(bf16* p, const float v[8]) {
 template <typename T, int NS, int DEPTH>
 struct Pipe {
   static constexpr int PARTS = (int)sizeof(T) * 8 / 16;              // 16-byte pieces per vector (1 bf16, 2 fp32)
-  static constexpr int BYTES = DEPTH * NS * PARTS * 256 * 16;        // shared memory of one block
+  static constexpr int VEC_BYTES = DEPTH * NS * PARTS * 256 * 16;
+  static constexpr int BYTES = VEC_BYTES + DEPTH * 256 * 4;          // + one 4-byte side slot per stage (keep bits)
   uint32_t base;                                                     // shared address of this thread's first slot
-  __device__ __forceinline__ explicit Pipe(uint8_t* smem) { base = (uint32_t)__cvta_generic_to_shared(smem) + threadIdx.x * 16; }
+  uint32_t side;                                                     // ... and of its first 4-byte side slot
+  __device__ __forceinline__ explicit Pipe(uint8_t* smem) {
+    base = (uint32_t)__cvta_generic_to_shared(smem) + threadIdx.x * 16;
+    side = (uint32_t)__cvta_generic_to_shared(smem) + VEC_BYTES + threadIdx.x * 4;
+  }
+  // the byte `bits[idx]` travels inside its aligned 4-byte word
+  __device__ __forceinline__ void issue_byte(int stage, const uint8_t* bits, long long idx) const {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(side + (uint32_t)(stage * 256 * 4)), "l"(bits + (idx & ~3LL))
+                 : "memory");
+  }
+  __device__ __forceinline__ uint32_t read_byte(int stage, long long idx) const {
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(side + (uint32_t)(stage * 256 * 4)));
+    return (w >> (8 * (int)(idx & 3))) & 0xFFu;
+  }
   __device__ __forceinline__ uint32_t slot(int stage, int stream, int part) const {
     return base + (uint32_t)(((stage * NS + stream) * PARTS + part) * 256 * 16);
   }
@@ -195,14 +210,14 @@ __global__ void gn_finalize_kernel(const float* part, int n_img, int splits, int
 }
 
 // ---------------------------------------------------------------- apply
-// grid (chunks, n_img); streams: 0 = x, 1 = injected dropout mask (parity tests)
+// grid (chunks, n_img); pipelined stream: x (an injected dropout mask - parity tests only - is read directly)
 template <typename T>
 __global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> s, int hw, int G, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float* __restrict__ mean,
                                                        const float* __restrict__ rstd, int act, float p_drop, uint64_t seed,
                                                        const T* mask, uint8_t* keepbits, T* y) {
   extern __shared__ __align__(16) uint8_t gsm[];
-  using P = Pipe<T, 2, GN_DEPTH>;
+  using P = Pipe<T, 1, GN_DEPTH>;
   const P pipe(gsm);
   const int Ct = s.C1 + s.C2, V = Ct / 8, cpg = Ct / G;
   const int n = blockIdx.y;
@@ -219,7 +234,6 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> s, int hw, int G,
   auto issue = [&](int stage, int j) {
     const long long row = row0 + (long long)j * lanes;
     pipe.issue(stage, 0, s.at(row, c0));
-    if (mask) pipe.issue(stage, 1, mask + (row * V + v) * 8);
   };
   for (int d = 0; d < GN_DEPTH; ++d) {
     if (d < n_it) issue(d, d);
@@ -238,7 +252,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> s, int hw, int G,
     }
     if (mask) {
       float mk[8];
-      pipe.read(stage, 1, mk);
+      load8(mask + oct * 8, mk);
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] *= mk[i];
     } else if (p_drop > 0.f) {
@@ -258,10 +272,10 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> s, int hw, int G,
 // dz and xhat of one 8-vector (shared by both backward passes)
 // `mk` holds the injected mask values when has_mask, else it is filled here (in-kernel RNG or ones)
 __device__ __forceinline__ void gn_dz8(const float x[8], const float dyv[8], const ChanConst& k, int act, float p_drop,
-                                       uint64_t seed, bool has_mask, float mk[8], const uint8_t* keepbits, long long oct,
+                                       uint64_t seed, bool has_mask, float mk[8], bool has_bits, uint32_t bits, long long oct,
                                        float xhat[8], float dz[8]) {
   if (!has_mask) {
-    if (p_drop > 0.f && keepbits) keep_from_bits(keepbits[oct], p_drop, mk);
+    if (p_drop > 0.f && has_bits) keep_from_bits(bits, p_drop, mk);
     else if (p_drop > 0.f) dropout8(seed, (uint64_t)oct, p_drop, mk);
     else {
 #pragma unroll
@@ -280,7 +294,7 @@ __device__ __forceinline__ void gn_dz8(const float x[8], const float dyv[8], con
 // ---------------------------------------------------------------- backward pass 1
 // grid (n_img, splits): red[n][split][c][2] = (sum dz, sum dz*xhat) over the split's pixels
 template <typename T>
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
+__global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             int act, float p_drop, uint64_t seed, const T* mask,
@@ -296,7 +310,8 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> s, const T* 
   float a[8], b[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.f;
-  using P = Pipe<T, 3, GN_DEPTH>;            // streams: x, dy, injected mask
+  using P = Pipe<T, 2, GN_DEPTH>;            // streams: x, dy (+ the keep-bits side stream)
+  const bool use_bits = keepbits != nullptr && p_drop > 0.f && mask == nullptr;
   const P pipe(gsm);
   const int n_it = (lane < lanes && p1 > p0 + lane) ? (p1 - p0 - lane + lanes - 1) / lanes : 0;
   const long long row0 = (long long)n * hw + p0 + lane;
@@ -306,7 +321,7 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> s, const T* 
     const long long row = row0 + (long long)j * lanes;
     pipe.issue(stage, 0, s.at(row, c0));
     pipe.issue(stage, 1, dy + (row * V + v) * 8);
-    if (mask) pipe.issue(stage, 2, mask + (row * V + v) * 8);
+    if (use_bits) pipe.issue_byte(stage, keepbits, row * V + v);
   };
   for (int d = 0; d < GN_DEPTH; ++d) {
     if (d < n_it) issue(d, d);
@@ -319,8 +334,8 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(Src2<T> s, const T* 
     float x0[8], d0[8], mk[8], xh[8], dz[8];
     pipe.read(stage, 0, x0);
     pipe.read(stage, 1, d0);
-    if (mask) pipe.read(stage, 2, mk);
-    gn_dz8(x0, d0, k, act, p_drop, seed, mask != nullptr, mk, keepbits, oct, xh, dz);
+    if (mask) load8(mask + oct * 8, mk);
+    gn_dz8(x0, d0, k, act, p_drop, seed, mask != nullptr, mk, use_bits, use_bits ? pipe.read_byte(stage, oct) : 0u, oct, xh, dz);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
     if (it + GN_DEPTH < n_it) issue(stage, it + GN_DEPTH);
@@ -373,7 +388,7 @@ __global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restr
 // ---------------------------------------------------------------- backward pass 2
 // grid (chunks, n_img)
 template <typename T>
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
+__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            int act, float p_drop, uint64_t seed, const T* mask,
@@ -411,7 +426,8 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> s, const T* d
   const int acc = c0 < s.C1 ? accum1 : accum2;
   const int per = (hw + gridDim.x - 1) / gridDim.x;
   const int p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
-  using P = Pipe<T, 5, GN_BWD_DEPTH>;        // streams: x, dy, extra, old destination, injected mask
+  using P = Pipe<T, 4, GN_BWD_DEPTH>;        // streams: x, dy, extra, old destination (+ the keep-bits side stream)
+  const bool use_bits = keepbits != nullptr && p_drop > 0.f && mask == nullptr;
   const P pipe(gsm);
   const int n_it = p1 > p0 + lane ? (p1 - p0 - lane + lanes - 1) / lanes : 0;
   const long long row0 = (long long)n * hw + p0 + lane;
@@ -421,7 +437,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> s, const T* d
     pipe.issue(stage, 1, dy + (row * V + v) * 8);
     if (extra) pipe.issue(stage, 2, extra + (row * V + v) * 8);
     if (acc) pipe.issue(stage, 3, dbase + row * dld);
-    if (mask) pipe.issue(stage, 4, mask + (row * V + v) * 8);
+    if (use_bits) pipe.issue_byte(stage, keepbits, row * V + v);
   };
   for (int d = 0; d < GN_BWD_DEPTH; ++d) {
     if (d < n_it) issue(d, d);
@@ -434,8 +450,9 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(Src2<T> s, const T* d
     float x0[8], d0[8], mk[8], xh[8], dz[8], o[8];
     pipe.read(stage, 0, x0);
     pipe.read(stage, 1, d0);
-    if (mask) pipe.read(stage, 4, mk);
-    gn_dz8(x0, d0, k, act, p_drop, seed, mask != nullptr, mk, keepbits, row * V + v, xh, dz);
+    if (mask) load8(mask + (row * V + v) * 8, mk);
+    gn_dz8(x0, d0, k, act, p_drop, seed, mask != nullptr, mk, use_bits, use_bits ? pipe.read_byte(stage, row * V + v) : 0u,
+           row * V + v, xh, dz);
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = k.r[i >> 2] * (k.gam[i] * dz[i] - s1[i >> 2] - xh[i] * s2[i >> 2]);
     if (extra) {
@@ -518,7 +535,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_apply(const void* x1
   const int V = (C1 + C2) / 8;
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
-    constexpr int smem = Pipe<T, 2, GN_DEPTH>::BYTES;
+    constexpr int smem = Pipe<T, 1, GN_DEPTH>::BYTES;
     static bool smem_ok = false;
     if (!smem_ok) { if (!allow_smem(gn_apply_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
     gn_apply_kernel<T><<<dim3(chunks_for(n_img, hw, V), n_img), 256, smem, (cudaStream_t)stream>>>(
@@ -537,7 +554,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_reduce(const voi
   (void)V;
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
-    constexpr int smem = Pipe<T, 3, GN_DEPTH>::BYTES;      // >= the 16 KB the final lane reduction reuses
+    constexpr int smem = Pipe<T, 2, GN_DEPTH>::BYTES;      // >= the 16 KB the final lane reduction reuses
     static bool smem_ok = false;
     if (!smem_ok) { if (!allow_smem(gn_bwd_reduce_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
     gn_bwd_reduce_kernel<T><<<dim3(n_img, splits), 256, smem, (cudaStream_t)stream>>>(
@@ -563,7 +580,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_apply(const void
   const int V = (C1 + C2) / 8;
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
-    constexpr int smem = Pipe<T, 5, GN_BWD_DEPTH>::BYTES;
+    constexpr int smem = Pipe<T, 4, GN_BWD_DEPTH>::BYTES;
     static bool smem_ok = false;
     if (!smem_ok) { if (!allow_smem(gn_bwd_apply_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
     gn_bwd_apply_kernel<T><<<dim3(chunks_for(n_img, hw, V), n_img), 256, smem, (cudaStream_t)stream>>>(
