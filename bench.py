@@ -134,7 +134,8 @@ def run_b200(args):
   torch.cuda.set_device(local)
   dev = torch.device('cuda', local)
   if world > 1:
-    dist.init_process_group('nccl', device_id=dev)
+    import datetime
+    dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
   cfg = configs.cifar10_ddpmpp_nll_st()
   cfg.device = dev
   cfg.model.compute_dtype = args.dtype
@@ -187,20 +188,23 @@ def run_b200(args):
   # ---- dominant kernel: every st_gemm launch of one step bracketed by CUDA events (outside the timed region)
   pk, pk_kind = peaks()
   roof = None
-  if rank == 0:
-    recs = []
-    orig = ops._gemm
+  # every rank runs the instrumented step (it contains the gradient all-reduce); rank 0 reports
+  recs = []
+  orig = ops._gemm
 
-    def spy(**kw):
-      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-      a.record()
-      orig(**kw)
-      b.record()
-      recs.append((a, b, 2.0 * kw['M'] * kw['N'] * kw['K'] * kw.get('batch', 1)))
-    ops._gemm = spy
+  def spy(**kw):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    orig(**kw)
+    b.record()
+    recs.append((a, b, 2.0 * kw['M'] * kw['N'] * kw['K'] * kw.get('batch', 1)))
+  ops._gemm = spy
+  try:
     step_fn(state, batch_dev)
     torch.cuda.synchronize()
+  finally:
     ops._gemm = orig
+  if rank == 0:
     t_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
     flops = sum(f for _, _, f in recs)
     achieved = flops / (t_ms * 1e-3) / 1e12

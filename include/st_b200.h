@@ -128,7 +128,11 @@ int st_gn_bwd_apply(const void* x1, const void* x2, const void* dy, int dtype, i
                     int C2, int G, const float* gamma, const float* beta, const float* mean,
                     const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
                     const uint8_t* keepbits, int splits, const float* red, const void* extra, float extra_scale, void* dx1, int accum1,
-                    void* dx2, int accum2, void* stream);
+                    void* dx2, int accum2, int chunks, float* csum, void* stream);
+/* pixel chunks per image the backward-apply launch uses by default (grid.x); with `csum` != NULL the caller passes
+ * this count explicitly and receives csum[n_img][chunks][C]: the column sums of the gradient contribution the
+ * kernel produced (extra included, accumulated destination excluded). */
+int st_gn_chunks(int n_img, int hw, int C);
 
 /* ------------------------------------------------------------------ elementwise / small
  * All take element counts; pointers must be 16-byte aligned. */
@@ -143,8 +147,9 @@ int st_silu_bwd(const void* x, const void* dy, void* dx, int dtype, int64_t n, v
  * The input may be a channel concatenation of two tensors. */
 int st_resample2x(const void* x1, const void* x2, void* y, int dtype, int n_img, int H, int W, int C1,
                   int C2, int dir, float scale, void* stream);
-/* out[g][c] = sum over rows r in group g of x[r][c];  x is [groups*rows_per_group][C] */
-int st_colsum(const void* x, int dtype, int64_t groups, int64_t rows_per_group, int C, float scale,
+/* out[g][c] (+)= scale * sum over rows r in group g of x[r][c];  x is [groups*rows_per_group] rows of C columns,
+ * consecutive rows ld elements apart */
+int st_colsum(const void* x, int dtype, int64_t groups, int64_t rows_per_group, int C, int64_t ld, float scale,
               float* out, int accumulate, void* stream);
 /* row softmax of scale*logits: logits fp32 [rows][L] -> p (dtype) */
 int st_softmax_fwd(const float* logits, void* p, int dtype, int64_t rows, int L, float scale, void* stream);

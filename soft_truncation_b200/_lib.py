@@ -43,13 +43,14 @@ SIGNATURES = {
                          c_u64, c_p, c_p, c_int, c_p, c_p],
     'st_gn_bwd_params': [c_p, c_int, c_int, c_p, c_p, c_p],
     'st_gn_bwd_apply': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f,
-                        c_u64, c_p, c_p, c_int, c_p, c_p, c_f, c_p, c_int, c_p, c_int, c_p],
+                        c_u64, c_p, c_p, c_int, c_p, c_p, c_f, c_p, c_int, c_p, c_int, c_int, c_p, c_p],
+    'st_gn_chunks': [c_int, c_int, c_int],
     'st_cast': [c_p, c_int, c_p, c_int, c_i64, c_p],
     'st_axpby': [c_p, c_p, c_p, c_int, c_f, c_f, c_i64, c_p],
     'st_silu': [c_p, c_p, c_int, c_i64, c_p],
     'st_silu_bwd': [c_p, c_p, c_p, c_int, c_i64, c_p],
     'st_resample2x': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f, c_p],
-    'st_colsum': [c_p, c_int, c_i64, c_i64, c_int, c_f, c_p, c_int, c_p],
+    'st_colsum': [c_p, c_int, c_i64, c_i64, c_int, c_i64, c_f, c_p, c_int, c_p],
     'st_softmax_fwd': [c_p, c_p, c_int, c_i64, c_int, c_f, c_p],
     'st_softmax_bwd': [c_p, c_p, c_p, c_int, c_i64, c_int, c_f, c_p],
     'st_timestep_embedding': [c_p, c_p, c_p, c_int, c_int, c_p],

@@ -105,17 +105,17 @@ __global__ void down2_kernel(const T* x1, const T* x2, T* y, long long total_qua
 // ---------------------------------------------------------------- column sums
 // grid (groups, ceil(C/128)), block 256 = 8 row-lanes x 32 quad-lanes
 template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long rows_per_group, int C, float scale,
-                                                     float* out, int accumulate) {
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long rows_per_group, int C, long long ld,
+                                                     float scale, float* out, int accumulate) {
   const long long g = blockIdx.x;
   const int c0 = (blockIdx.y * 32 + threadIdx.x % 32) * 4;
   const int rl = threadIdx.x / 32;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   if (c0 < C) {
-    const T* base = x + g * rows_per_group * C + c0;
+    const T* base = x + g * rows_per_group * ld + c0;
     for (long long r = rl; r < rows_per_group; r += 8) {
       float v[4];
-      load4(base + r * C, v);
+      load4(base + r * ld, v);
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[k] += v[k];
     }
@@ -483,12 +483,12 @@ extern "C" __attribute__((visibility("default"))) int st_resample2x(const void* 
   return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) int st_colsum(const void* x, int dtype, int64_t groups, int64_t rows_per_group, int C, float scale, float* out,
-                         int accumulate, void* stream) {
-  ST_CHECK_ARG(C % 4 == 0, "st_colsum: C must be a multiple of 4");
+extern "C" __attribute__((visibility("default"))) int st_colsum(const void* x, int dtype, int64_t groups, int64_t rows_per_group, int C, int64_t ld, float scale,
+                         float* out, int accumulate, void* stream) {
+  ST_CHECK_ARG(C % 4 == 0 && ld % 4 == 0 && ld >= C, "st_colsum: C and ld must be multiples of 4, ld >= C");
   ST_CHECK_ARG(groups >= 1 && groups < (1LL << 31), "st_colsum: bad groups");
   dim3 grid((unsigned)groups, (C + 127) / 128);
-  ST_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<grid, 256, 0, S>>>((const T*)x, rows_per_group, C, scale, out, accumulate)));
+  ST_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<grid, 256, 0, S>>>((const T*)x, rows_per_group, C, ld, scale, out, accumulate)));
   ST_CHECK_LAUNCH("st_colsum");
   return 0;
 }

@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T
                                                            int act, float p_drop, uint64_t seed, const T* mask,
                                                            const uint8_t* __restrict__ keepbits,
                                                            const float* __restrict__ red, const T* extra, float extra_scale,
-                                                           T* dx1, int accum1, T* dx2, int accum2) {
+                                                           T* dx1, int accum1, T* dx2, int accum2, float* csum) {
   extern __shared__ __align__(16) uint8_t gsm[];
   const int Ct = s.C1 + s.C2, V = Ct / 8, cpg = Ct / G;
   const int n = blockIdx.y;
@@ -415,11 +415,14 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T
   __syncthreads();
   const int lanes = 256 / V;
   const int v = threadIdx.x % V, lane = threadIdx.x / V;
-  if (lane >= lanes) return;
-  const int c0 = v * 8;
+  const bool active = lane < lanes;
+  const int c0 = active ? v * 8 : 0;
   ChanConst k;
   load_consts(k, n, c0, G, cpg, gamma, beta, mean, rstd);
   const float s1[2] = {sh1[k.g[0]], sh1[k.g[1]]}, s2[2] = {sh2[k.g[0]], sh2[k.g[1]]};
+  float cs[8];                               // column sums of this thread's contributions (optional output)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cs[i] = 0.f;
   // destination of this thread's channels (first or second tensor of the concatenation)
   T* const dbase = c0 < s.C1 ? dx1 + c0 : dx2 + (c0 - s.C1);
   const int dld = c0 < s.C1 ? s.C1 : s.C2;
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T
   using P = Pipe<T, 4, GN_BWD_DEPTH>;        // streams: x, dy, extra, old destination (+ the keep-bits side stream)
   const bool use_bits = keepbits != nullptr && p_drop > 0.f && mask == nullptr;
   const P pipe(gsm);
-  const int n_it = p1 > p0 + lane ? (p1 - p0 - lane + lanes - 1) / lanes : 0;
+  const int n_it = (active && p1 > p0 + lane) ? (p1 - p0 - lane + lanes - 1) / lanes : 0;
   const long long row0 = (long long)n * hw + p0 + lane;
   auto issue = [&](int stage, int j) {
     const long long row = row0 + (long long)j * lanes;
@@ -461,6 +464,8 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = fmaf(extra_scale, ex[i], o[i]);
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs[i] += o[i];
     if (acc) {
       float old[8];
       pipe.read(stage, 3, old);
@@ -471,6 +476,23 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T
     if (it + GN_BWD_DEPTH < n_it) issue(stage, it + GN_BWD_DEPTH);
     P::commit();
     stage = stage + 1 == GN_BWD_DEPTH ? 0 : stage + 1;
+  }
+  if (csum) {
+    // csum[n][chunk][c] = sum over this block's pixels of the gradient it contributed (fixed-order lane reduction
+    // through the drained pipeline memory): the caller turns these into bias / time-embedding gradients without
+    // another pass over the tensor
+    __syncthreads();
+    float* s_cs = reinterpret_cast<float*>(gsm);
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_cs[(lane * V + v) * 8 + i] = cs[i];
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < Ct; col += 256) {
+      float t = 0.f;
+      for (int l = 0; l < lanes; ++l) t += s_cs[l * Ct + col];
+      csum[((long long)n * gridDim.x + blockIdx.x) * Ct + col] = t;
+    }
   }
 }
 
@@ -502,6 +524,10 @@ int chunks_for(int n_img, int hw, int V) {
 }
 
 }  // namespace
+
+extern "C" __attribute__((visibility("default"))) int st_gn_chunks(int n_img, int hw, int C) {
+  return chunks_for(n_img, hw, C / 8);
+}
 
 extern "C" __attribute__((visibility("default"))) int st_gn_stats(const void* x1, const void* x2, int dtype, int n_img, int hw, int C1, int C2, int G,
                            int splits, float* part, void* stream) {
@@ -574,18 +600,21 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_apply(const void
                                int C2, int G, const float* gamma, const float* beta, const float* mean,
                                const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
                                const uint8_t* keepbits, int splits, const float* red, const void* extra, float extra_scale, void* dx1,
-                               int accum1, void* dx2, int accum2, void* stream) {
+                               int accum1, void* dx2, int accum2, int chunks, float* csum, void* stream) {
   if (int e = check_geom(C1, C2, G)) return e;
   ST_CHECK_ARG(n_img <= 65535, "st_gn_bwd_apply: more than 65535 images");
   const int V = (C1 + C2) / 8;
+  ST_CHECK_ARG(!csum || chunks > 0, "st_gn_bwd_apply: csum needs an explicit chunk count");
+  if (chunks <= 0) chunks = chunks_for(n_img, hw, V);
+  ST_CHECK_ARG(chunks <= 65535, "st_gn_bwd_apply: too many chunks");
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
     constexpr int smem = Pipe<T, 4, GN_BWD_DEPTH>::BYTES;
     static bool smem_ok = false;
     if (!smem_ok) { if (!allow_smem(gn_bwd_apply_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
-    gn_bwd_apply_kernel<T><<<dim3(chunks_for(n_img, hw, V), n_img), 256, smem, (cudaStream_t)stream>>>(
+    gn_bwd_apply_kernel<T><<<dim3(chunks, n_img), 256, smem, (cudaStream_t)stream>>>(
         s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, keepbits, red,
-        (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2);
+        (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2, csum);
   });
   ST_CHECK_LAUNCH("st_gn_bwd_apply");
   return 0;

@@ -91,6 +91,25 @@ class NetCtx:
     self.drop_calls = 0
 
 
+def bias_grad(dst, g2, gs, scale=1.0):
+  """dst[c] += scale * sum_rows g2[row][c].  `gs` = list of fp32 (rows, C)-shaped column-sum partials that the
+  producers of `g2` emitted as a by-product of their GroupNorm backward kernels (then no pass over g2 is
+  needed), or None."""
+  C = g2.shape[-1]
+  if gs:
+    for part in gs:
+      ops.colsum(part, 1, part.shape[0], C, dst, scale=scale, accumulate=True, ld=part.stride(0))
+  else:
+    ops.colsum(g2, 1, g2.shape[0], C, dst, scale=scale, accumulate=True)
+
+
+def _split_csum(cs, C1, C2):
+  """(B, chunks, C1+C2) partial column sums -> 2-D views for the two concatenated inputs."""
+  rows = cs.shape[0] * cs.shape[1]
+  flat = cs.view(rows, C1 + C2)
+  return flat[:, :C1], (flat[:, C1:] if C2 else None)
+
+
 class ResBlock:
   """ResnetBlockBigGANpp (reference models/layerspp.py:225-287)."""
 
@@ -180,13 +199,15 @@ class ResBlock:
     y = Act(out, net.tape)
     if net.tape.enabled:
       saved = (x1, x2, st0, a0, xr, h1, st1, a1, p_drop, seed, mask, keepbits)
-      net.tape.record(lambda g, acc: self.bwd(net, saved, g, acc), (xa.id,) + ((xb.id,) if xb is not None else ()), y.id)
+      net.tape.record(lambda g, acc, gs: self.bwd(net, saved, g, acc, gs),
+                      (xa.id,) + ((xb.id,) if xb is not None else ()), y.id)
     if net.taps is not None:
       net.taps[self.idx] = out
     return y
 
-  def bwd(self, net, saved, g, acc):
-    """g: d(out); acc: existing gradient tensors of (xa[, xb]) to accumulate into, or None."""
+  def bwd(self, net, saved, g, acc, gs=None):
+    """g: d(out); acc: existing gradient tensors of (xa[, xb]) to accumulate into, or None; gs: column-sum
+    partials of g (see bias_grad).  Returns (input gradients, their column-sum partials)."""
     P = net.m.P
     pre, s = self.pre, self.scale
     x1, x2, st0, a0, xr, h1, st1, a1, p_drop, seed, mask, keepbits = saved
@@ -194,25 +215,27 @@ class ResBlock:
     npix = B * H * W
     g2 = g.view(npix, Co)
     # ---- Conv_1 (and the 1/sqrt2 output scale)
-    ops.colsum(g2, 1, npix, Co, P.g(pre + 'Conv_1.bias'), scale=s, accumulate=True)
+    bias_grad(P.g(pre + 'Conv_1.bias'), g2, gs, s)
     ops.conv_wgrad(g, a1, P.g(pre + 'Conv_1.weight'), alpha=s)
     da1 = ops.conv_dgrad(g, P.c(pre + 'Conv_1.weight'), Co, alpha=s)
     # ---- GroupNorm_1 + SiLU + dropout
-    dh1, _ = ops.gn_backward(h1, None, da1, self.G1, P.f(pre + 'GroupNorm_1.weight'), P.f(pre + 'GroupNorm_1.bias'),
-                             st1, 1, P.g(pre + 'GroupNorm_1.weight'), P.g(pre + 'GroupNorm_1.bias'), p_drop=p_drop,
-                             seed=seed, mask=mask, keepbits=keepbits)
+    dh1, _, cs1 = ops.gn_backward(h1, None, da1, self.G1, P.f(pre + 'GroupNorm_1.weight'),
+                                  P.f(pre + 'GroupNorm_1.bias'), st1, 1, P.g(pre + 'GroupNorm_1.weight'),
+                                  P.g(pre + 'GroupNorm_1.bias'), p_drop=p_drop, seed=seed, mask=mask, keepbits=keepbits,
+                                  want_csum=True)
     del da1
-    # ---- Conv_0 bias, temb projection (per-image column sums), weights, data
+    # ---- temb projection gradient = per-image column sums of dh1 (by-product of the kernel above); their sum over
+    # images is the Conv_0.bias / Dense_0.bias gradient (TimeEmbedding.bwd)
     dd = torch.empty((B, Co), dtype=torch.float32, device=g.device)
-    ops.colsum(dh1.view(npix, Co), B, H * W, Co, dd)
-    net.d_dense[:, self.dense_off:self.dense_off + Co].copy_(dd)     # Conv_0.bias gradient = its column sums (temb.bwd)
+    ops.colsum(cs1, B, cs1.shape[1], Co, dd)
+    net.d_dense[:, self.dense_off:self.dense_off + Co].copy_(dd)
     ops.conv_wgrad(dh1, a0, P.g(pre + 'Conv_0.weight'))
     da0 = ops.conv_dgrad(dh1, P.c(pre + 'Conv_0.weight'), self.cin)
     del dh1
     # ---- shortcut
     extra, extra_scale = None, 1.0
     if self.shortcut:
-      ops.colsum(g2, 1, npix, Co, P.g(pre + 'Conv_2.bias'), scale=s, accumulate=True)
+      bias_grad(P.g(pre + 'Conv_2.bias'), g2, gs, s)
       if xr is not None:
         ops.conv_wgrad(g, xr, P.g(pre + 'Conv_2.weight'), 1, 1, alpha=s)
       else:
@@ -226,11 +249,12 @@ class ResBlock:
     # ---- GroupNorm_0 + SiLU, plus the shortcut gradient, split over the two inputs
     a1_acc = acc[0]
     a2_acc = acc[1] if x2 is not None else None
-    dx1, dx2 = ops.gn_backward(x1, x2, da0, self.G0, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'),
-                               st0, 1, P.g(pre + 'GroupNorm_0.weight'), P.g(pre + 'GroupNorm_0.bias'), extra=extra,
-                               extra_scale=extra_scale, dx1=a1_acc, accum1=a1_acc is not None, dx2=a2_acc,
-                               accum2=a2_acc is not None)
-    return (dx1,) if x2 is None else (dx1, dx2)
+    dx1, dx2, cs0 = ops.gn_backward(x1, x2, da0, self.G0, P.f(pre + 'GroupNorm_0.weight'),
+                                    P.f(pre + 'GroupNorm_0.bias'), st0, 1, P.g(pre + 'GroupNorm_0.weight'),
+                                    P.g(pre + 'GroupNorm_0.bias'), extra=extra, extra_scale=extra_scale, dx1=a1_acc,
+                                    accum1=a1_acc is not None, dx2=a2_acc, accum2=a2_acc is not None, want_csum=True)
+    c1, c2 = _split_csum(cs0, x1.shape[3], 0 if x2 is None else x2.shape[3])
+    return ((dx1,), (c1,)) if x2 is None else ((dx1, dx2), (c1, c2))
 
 
 class AttnBlock:
@@ -277,12 +301,12 @@ class AttnBlock:
     y = Act(out, net.tape)
     if net.tape.enabled:
       saved = (x, st, h, qkv, p, o)
-      net.tape.record(lambda g, acc: self.bwd(net, saved, g, acc), (xa.id,), y.id)
+      net.tape.record(lambda g, acc, gs: self.bwd(net, saved, g, acc, gs), (xa.id,), y.id)
     if net.taps is not None:
       net.taps[self.idx] = out
     return y
 
-  def bwd(self, net, saved, g, acc):
+  def bwd(self, net, saved, g, acc, gs=None):
     P = net.m.P
     pre, C, s = self.pre, self.c, self.scale
     x, st, h, qkv, p, o = saved
@@ -290,7 +314,7 @@ class AttnBlock:
     L, npix = H * W, B * H * W
     g2 = g.view(npix, C)
     # ---- NIN_3
-    ops.colsum(g2, 1, npix, C, P.g(pre + 'NIN_3.b'), scale=s, accumulate=True)
+    bias_grad(P.g(pre + 'NIN_3.b'), g2, gs, s)
     ops.gemm_tn(g2, o.view(npix, C), C, C, npix, out=P.g(pre + 'NIN_3.W'), alpha=s, accumulate=True)
     do = ops.gemm_nn(g2, P.c(pre + 'NIN_3.W'), C, alpha=s)              # (npix, C): g W3 (W3 is [out][in])
     # ---- attention core
@@ -314,10 +338,10 @@ class AttnBlock:
     ops.gemm_tn(dqkv, h.view(npix, C), 3 * C, C, npix, out=P.g_group(self.names_w), accumulate=True)
     dh = ops.gemm_nn(dqkv, P.c_group(self.names_w), C).view(B, H, W, C)
     # ---- GroupNorm (no activation) + residual
-    dx, _ = ops.gn_backward(x, None, dh, self.G, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st, 0,
-                            P.g(pre + 'GroupNorm_0.weight'), P.g(pre + 'GroupNorm_0.bias'), extra=g, extra_scale=s,
-                            dx1=acc[0], accum1=acc[0] is not None)
-    return (dx,)
+    dx, _, cs = ops.gn_backward(x, None, dh, self.G, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st,
+                                0, P.g(pre + 'GroupNorm_0.weight'), P.g(pre + 'GroupNorm_0.bias'), extra=g,
+                                extra_scale=s, dx1=acc[0], accum1=acc[0] is not None, want_csum=True)
+    return (dx,), (_split_csum(cs, C, 0)[0],)
 
 
 class ConvBlock:
@@ -340,24 +364,24 @@ class ConvBlock:
     y = Act(out, net.tape)
     if net.tape.enabled:
       x = xa.t
-      net.tape.record(lambda g, acc: self.bwd(net, x, g, acc, need_dx=net.need_dx or not self.is_input), (xa.id,),
-                      y.id)
+      net.tape.record(lambda g, acc, gs: self.bwd(net, x, g, acc, need_dx=net.need_dx or not self.is_input, gs=gs),
+                      (xa.id,), y.id)
     if net.taps is not None and record_tap:
       net.taps[self.idx] = out
     return y
 
-  def bwd(self, net, x, g, acc, need_dx=True):
+  def bwd(self, net, x, g, acc, need_dx=True, gs=None):
     P = net.m.P
     B, H, W, Co = g.shape
-    ops.colsum(g.view(-1, Co), 1, B * H * W, Co, P.g(self.pre + 'bias'), accumulate=True)
+    bias_grad(P.g(self.pre + 'bias'), g.view(-1, Co), gs)
     ops.conv_wgrad(g, x, P.g(self.pre + 'weight'), self.k, self.k)
     if not need_dx:
-      return (None,)
+      return (None,), (None,)
     dx = ops.conv_dgrad(g, P.c(self.pre + 'weight'), self.cin, self.k, self.k)
     if acc[0] is not None:
       ops.axpby(acc[0], dx, out=acc[0])
       dx = acc[0]
-    return (dx,)
+    return (dx,), (None,)
 
 
 class NormActConv:
@@ -382,23 +406,25 @@ class NormActConv:
     y = Act(out, net.tape)
     if net.tape.enabled:
       ids = (xa.id,) + ((res.id,) if res is not None else ())
-      net.tape.record(lambda g, acc: self.bwd(net, (x, st, a), g, acc), ids, y.id)
+      net.tape.record(lambda g, acc, gs: self.bwd(net, (x, st, a), g, acc, gs), ids, y.id)
     if net.taps is not None:
       net.taps[self.idx_conv] = out
     return y
 
-  def bwd(self, net, saved, g, acc):
+  def bwd(self, net, saved, g, acc, gs=None):
     P = net.m.P
     x, st, a = saved
-    (da,) = self.conv.bwd(net, a, g, (None,))
-    dx, _ = ops.gn_backward(x, None, da, self.G, P.f(self.pg + 'weight'), P.f(self.pg + 'bias'), st, 1,
-                            P.g(self.pg + 'weight'), P.g(self.pg + 'bias'), dx1=acc[0], accum1=acc[0] is not None)
+    (da,), _ = self.conv.bwd(net, a, g, (None,), gs=gs)
+    dx, _, cs = ops.gn_backward(x, None, da, self.G, P.f(self.pg + 'weight'), P.f(self.pg + 'bias'), st, 1,
+                                P.g(self.pg + 'weight'), P.g(self.pg + 'bias'), dx1=acc[0], accum1=acc[0] is not None,
+                                want_csum=True)
+    c = _split_csum(cs, x.shape[3], 0)[0]
     if len(acc) == 1:
-      return (dx,)
+      return (dx,), (c,)
     if acc[1] is not None:
       ops.axpby(acc[1], g, out=acc[1])
-      return (dx, acc[1])
-    return (dx, g)
+      return (dx, acc[1]), (c, None)
+    return (dx, g), (c, None)
 
 
 class ImageResample:
@@ -423,14 +449,14 @@ class ImageResample:
   def fwd(self, net, xa, image_side_input=False):
     y = Act(self._run(net, xa.t, self.up), net.tape)
     if net.tape.enabled:
-      def bwd(g, acc):
+      def bwd(g, acc, gs=None):
         if image_side_input and not net.need_dx:
-          return (None,)
+          return (None,), (None,)
         d = self._adj(net, g, self.up)
         if acc[0] is not None:
           ops.axpby(acc[0], d, out=acc[0])
           d = acc[0]
-        return (d,)
+        return (d,), (None,)
       net.tape.record(bwd, (xa.id,), y.id)
     return y
 
@@ -450,17 +476,17 @@ class CombineBlock:
     y = Act(out, net.tape)
     if net.tape.enabled:
       x = pyr.t
-      net.tape.record(lambda g, acc: self.bwd(net, x, g, acc), (pyr.id, ha.id), y.id)
+      net.tape.record(lambda g, acc, gs: self.bwd(net, x, g, acc, gs), (pyr.id, ha.id), y.id)
     if net.taps is not None:
       net.taps[self.idx] = out
     return y
 
-  def bwd(self, net, x, g, acc):
-    (dp,) = self.conv.bwd(net, x, g, (acc[0],), need_dx=net.need_dx)
+  def bwd(self, net, x, g, acc, gs=None):
+    (dp,), _ = self.conv.bwd(net, x, g, (acc[0],), need_dx=net.need_dx, gs=gs)
     if acc[1] is not None:
       ops.axpby(acc[1], g, out=acc[1])
-      return (dp, acc[1])
-    return (dp, g)
+      return (dp, acc[1]), (None, None)
+    return (dp, g), (None, None)
 
 
 class PyramidDownConv:
@@ -488,32 +514,32 @@ class PyramidDownConv:
                       residual=ha.t.view(-1, self.cout), alpha=self.scale).view(B, H // 2, W // 2, self.cout)
     o = Act(out, net.tape)
     if net.tape.enabled:
-      net.tape.record(lambda g, acc: self.bwd(net, (cols, x.shape, y.shape), g, acc), (pyr.id, ha.id), o.id)
+      net.tape.record(lambda g, acc, gs: self.bwd(net, (cols, x.shape, y.shape), g, acc, gs), (pyr.id, ha.id), o.id)
     if net.taps is not None:
       net.taps[self.idx] = out
     return o
 
-  def bwd(self, net, saved, g, acc):
+  def bwd(self, net, saved, g, acc, gs=None):
     P, m, s = net.m.P, net.m, self.scale
     cols, xshape, yshape = saved
     B, H, W, C = xshape
     g2 = g.view(-1, self.cout)
     rows = g2.shape[0]
-    ops.colsum(g2, 1, rows, self.cout, P.g(self.pre + 'bias'), scale=s, accumulate=True)
+    bias_grad(P.g(self.pre + 'bias'), g2, gs, s)
     ops.gemm_tn(g2, cols, self.cout, cols.shape[1], rows, out=P.g(self.pre + 'weight'), alpha=s, accumulate=True)
     if acc[1] is not None:
       dh = ops.axpby(acc[1], g, 1.0, s, out=acc[1])
     else:
       dh = ops.axpby(g, None, s)
     if self.image_side and not net.need_dx:
-      return (None, dh)
+      return (None, dh), (None, None)
     dcols = ops.gemm_nn(g2, P.c(self.pre + 'weight'), cols.shape[1], alpha=s)
     dy = ops.col2im(dcols, yshape, 3, 3, 2, 0, H // 2, W // 2)
     dp = ops.upfirdn2d_nhwc(dy, m._fir_down, pad=(1, 1)) if self.fir else dy
     if acc[0] is not None:
       ops.axpby(acc[0], dp, out=acc[0])
       dp = acc[0]
-    return (dp, dh)
+    return (dp, dh), (None, None)
 
 
 class TimeEmbedding:
@@ -951,14 +977,22 @@ class NCSNpp(nn.Module):
       dout = dout * net.out_scale[:, None, None, None]
     net.need_dx = need_dx
     grads = {net.out_id: ops.nchw_to_nhwc(dout, self.compute_dtype, CPAD)}
+    # gsum[id]: column-sum partials of grads[id] emitted by the kernels that produced it (a list), or False once a
+    # contribution arrived without partials (then the consumer reduces the tensor itself)
+    gsum = {}
     for bwd, in_ids, out_id in reversed(net.tape.ops):
       g = grads.pop(out_id, None)
       if g is None:
         continue
-      res = bwd(g, tuple(grads.get(i) for i in in_ids))
-      for i, r in zip(in_ids, res):
+      gs = gsum.pop(out_id, None)
+      res, css = bwd(g, tuple(grads.get(i) for i in in_ids), gs if gs else None)
+      for i, r, c in zip(in_ids, res, css):
         if r is not None:
           grads[i] = r
+          if c is None or gsum.get(i) is False:
+            gsum[i] = False
+          else:
+            gsum.setdefault(i, []).append(c)
     self.temb.bwd(net)
     net.tape.ops = []
     if need_dx:

@@ -175,8 +175,9 @@ def gn_apply(x, x2, G, gamma, beta, stats, act, p_drop=0., seed=0, mask=None, ke
 
 
 def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0., seed=0, mask=None, extra=None,
-                extra_scale=1.0, dx1=None, accum1=False, dx2=None, accum2=False, keepbits=None):
-  """Returns (dx1, dx2); accumulates dgamma/dbeta (fp32 views into the flat gradient buffer)."""
+                extra_scale=1.0, dx1=None, accum1=False, dx2=None, accum2=False, keepbits=None, want_csum=False):
+  """Returns (dx1, dx2[, csum]); accumulates dgamma/dbeta (fp32 views into the flat gradient buffer).
+  csum (want_csum): fp32 (B, chunks, C1+C2) column sums of the gradient this call contributed."""
   B, H, W, C1 = x.shape
   C2 = 0 if x2 is None else x2.shape[3]
   hw, Ct = H * W, C1 + C2
@@ -192,9 +193,13 @@ def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0.,
   if x2 is not None and dx2 is None:
     dx2 = torch.empty_like(x2)
     accum2 = False
+  chunks, csum = 0, None
+  if want_csum:
+    chunks = lib.st_gn_chunks(B, hw, Ct)
+    csum = torch.empty((B, chunks, Ct), dtype=torch.float32, device=x.device)
   check(lib.st_gn_bwd_apply(*common, ptr(extra), float(extra_scale), ptr(dx1), int(accum1), ptr(dx2), int(accum2),
-                            stream()))
-  return dx1, dx2
+                            chunks, ptr(csum), stream()))
+  return (dx1, dx2, csum) if want_csum else (dx1, dx2)
 
 
 # ------------------------------------------------------------------------------------ elementwise
@@ -234,19 +239,20 @@ def resample2x(x, x2, direction, scale):
   return y
 
 
-def colsum(x, groups, rows_per_group, C, out, scale=1.0, accumulate=False):
-  """out[g][c] (+)= scale * sum of x[g*rows_per_group + r][c].  A single long group (bias gradients over every
-  pixel) is reduced in two deterministic passes so that the first one fills the GPU."""
-  if groups == 1 and rows_per_group >= 4096:
+def colsum(x, groups, rows_per_group, C, out, scale=1.0, accumulate=False, ld=None):
+  """out[g][c] (+)= scale * sum of x[g*rows_per_group + r][c] (rows `ld` elements apart).  A single long group
+  (bias gradients over every pixel) is reduced in two deterministic passes so that the first one fills the GPU."""
+  ld = ld or C
+  if groups == 1 and rows_per_group >= 4096 and ld == C:
     chunks = 1
     while chunks < 256 and rows_per_group % (chunks * 2) == 0 and rows_per_group // (chunks * 2) >= 32:
       chunks *= 2
     if chunks > 1:
       part = torch.empty((chunks, C), dtype=torch.float32, device=x.device)
-      check(lib.st_colsum(ptr(x), dt(x), chunks, rows_per_group // chunks, C, 1.0, ptr(part), 0, stream()))
-      check(lib.st_colsum(ptr(part), F32, 1, chunks, C, float(scale), ptr(out), int(accumulate), stream()))
+      check(lib.st_colsum(ptr(x), dt(x), chunks, rows_per_group // chunks, C, C, 1.0, ptr(part), 0, stream()))
+      check(lib.st_colsum(ptr(part), F32, 1, chunks, C, C, float(scale), ptr(out), int(accumulate), stream()))
       return out
-  check(lib.st_colsum(ptr(x), dt(x), groups, rows_per_group, C, float(scale), ptr(out), int(accumulate), stream()))
+  check(lib.st_colsum(ptr(x), dt(x), groups, rows_per_group, C, ld, float(scale), ptr(out), int(accumulate), stream()))
   return out
 
 

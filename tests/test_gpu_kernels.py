@@ -219,6 +219,12 @@ def test_groupnorm_fwd_bwd(dtype, shape, act):
                              extra=nhwc(extra).to(dtype), extra_scale=0.5)
   dx = torch.cat([dx1, dx2], -1) if C2 else dx1
   assert rel_l2(nchw(dx.float()), xq.grad + 0.5 * exq) < 2 * tol(dtype)
+  # optional by-product: per-(image, chunk) column sums of the produced gradient
+  _, _, cs = ops.gn_backward(x1, x2, nhwc(dy).to(dtype), G, gamma, beta, st, act, torch.zeros_like(dgam),
+                             torch.zeros_like(dbet), mask=mk, extra=nhwc(extra).to(dtype), extra_scale=0.5, want_csum=True)
+  assert cs.shape[0] == B and cs.shape[2] == C
+  want_cs = (xq.grad + 0.5 * exq).sum(dim=(2, 3))                    # (B, C)
+  assert rel_l2(cs.sum(1), want_cs) < 1e-4 + (2e-3 if dtype == torch.bfloat16 else 0)
   assert rel_l2(dgam - 1, gam.grad) < 2 * tol(dtype)
   assert rel_l2(dbet - 1, bet.grad) < 2 * tol(dtype)
   # accumulate-into-destination variant
@@ -265,6 +271,10 @@ def test_resample_colsum_softmax(dtype):
   out = torch.ones(6, 64, device=dev())
   ops.colsum(m, 6, 40, 64, out, scale=0.5, accumulate=True)
   assert rel_l2(out, 1 + 0.5 * m.float().reshape(6, 40, 64).sum(1)) < 2e-5
+  wide = rnd(50, 96, seed=7)                                         # strided rows: columns 32..63 of a 96-wide matrix
+  out2 = torch.zeros(32, device=dev())
+  ops.colsum(wide[:, 32:64], 1, 50, 32, out2, ld=96)
+  assert rel_l2(out2, wide[:, 32:64].sum(0)) < 2e-6
   lg = rnd(10, 37, seed=3) * 3
   p = ops.softmax_fwd(lg, 37, 0.3, dtype)
   assert rel_l2(p.float(), torch.softmax(lg * 0.3, -1)) < tol(dtype)
