@@ -103,29 +103,30 @@ __global__ void down2_kernel(const T* x1, const T* x2, T* y, long long total_qua
 }
 
 // ---------------------------------------------------------------- column sums
-// grid (groups, ceil(C/128)), block 256 = 8 row-lanes x 32 quad-lanes
+// grid (groups, ceil(C/128)), block 1024 = 32 row-lanes x 32 quad-lanes
 template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long rows_per_group, int C, long long ld,
-                                                     float scale, float* out, int accumulate) {
+__global__ void __launch_bounds__(1024) colsum_kernel(const T* __restrict__ x, long long rows_per_group, int C, long long ld,
+                                                      float scale, float* out, int accumulate) {
+  constexpr int RL = 32;
   const long long g = blockIdx.x;
   const int c0 = (blockIdx.y * 32 + threadIdx.x % 32) * 4;
   const int rl = threadIdx.x / 32;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   if (c0 < C) {
     const T* base = x + g * rows_per_group * ld + c0;
-    for (long long r = rl; r < rows_per_group; r += 8) {
+    for (long long r = rl; r < rows_per_group; r += RL) {
       float v[4];
       load4(base + r * ld, v);
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[k] += v[k];
     }
   }
-  __shared__ float4 sm[256];
+  __shared__ float4 sm[1024];
   sm[threadIdx.x] = make_float4(acc[0], acc[1], acc[2], acc[3]);
   __syncthreads();
   if (rl == 0 && c0 < C) {
     float4 t = sm[threadIdx.x];
-    for (int l = 1; l < 8; ++l) {
+    for (int l = 1; l < RL; ++l) {
       float4 u = sm[l * 32 + threadIdx.x];
       t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
     }
@@ -488,7 +489,7 @@ extern "C" __attribute__((visibility("default"))) int st_colsum(const void* x, i
   ST_CHECK_ARG(C % 4 == 0 && ld % 4 == 0 && ld >= C, "st_colsum: C and ld must be multiples of 4, ld >= C");
   ST_CHECK_ARG(groups >= 1 && groups < (1LL << 31), "st_colsum: bad groups");
   dim3 grid((unsigned)groups, (C + 127) / 128);
-  ST_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<grid, 256, 0, S>>>((const T*)x, rows_per_group, C, ld, scale, out, accumulate)));
+  ST_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<grid, 1024, 0, S>>>((const T*)x, rows_per_group, C, ld, scale, out, accumulate)));
   ST_CHECK_LAUNCH("st_colsum");
   return 0;
 }

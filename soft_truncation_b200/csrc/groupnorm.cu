@@ -360,26 +360,27 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(Src2<T> s, const 
 }
 
 // dgamma[c] += sum_rows red[row][c][1]; dbeta[c] += sum_rows red[row][c][0]
-// block = 32 channels x 8 row lanes (coalesced float2 reads), fixed-order reduction
-__global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restrict__ red, int rows, int C, float* dgamma,
+// block = 16 channels x 32 row lanes (float2 reads), fixed-order reduction; the input is tiny (rows x C x 8 bytes),
+// the kernel is latency-bound, so the rows are spread over as many lanes as a block holds
+__global__ void __launch_bounds__(512) gn_bwd_params_kernel(const float* __restrict__ red, int rows, int C, float* dgamma,
                                                             float* dbeta) {
-  const int c = blockIdx.x * 32 + threadIdx.x % 32;
-  const int rl = threadIdx.x / 32;
+  const int c = blockIdx.x * 16 + threadIdx.x % 16;
+  const int rl = threadIdx.x / 16;
   float a = 0.f, b = 0.f;
   if (c < C) {
-    for (int r = rl; r < rows; r += 8) {
+    for (int r = rl; r < rows; r += 32) {
       float2 v = *reinterpret_cast<const float2*>(red + ((long long)r * C + c) * 2);
       a += v.x;
       b += v.y;
     }
   }
-  __shared__ float sa[256], sb[256];
+  __shared__ float sa[512], sb[512];
   sa[threadIdx.x] = a;
   sb[threadIdx.x] = b;
   __syncthreads();
   if (rl == 0 && c < C) {
     double ta = 0., tb = 0.;
-    for (int l = 0; l < 8; ++l) { ta += (double)sa[l * 32 + threadIdx.x]; tb += (double)sb[l * 32 + threadIdx.x]; }
+    for (int l = 0; l < 32; ++l) { ta += (double)sa[l * 16 + threadIdx.x]; tb += (double)sb[l * 16 + threadIdx.x]; }
     dbeta[c] += (float)ta;
     dgamma[c] += (float)tb;
   }
@@ -387,8 +388,8 @@ __global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restr
 
 // ---------------------------------------------------------------- backward pass 2
 // grid (chunks, n_img)
-template <typename T>
-__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
+template <typename T, bool CSUM>
+__global__ void __launch_bounds__(256, CSUM ? 2 : 3) gn_bwd_apply_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            int act, float p_drop, uint64_t seed, const T* mask,
@@ -464,8 +465,10 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = fmaf(extra_scale, ex[i], o[i]);
     }
+    if constexpr (CSUM) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) cs[i] += o[i];
+      for (int i = 0; i < 8; ++i) cs[i] += o[i];
+    }
     if (acc) {
       float old[8];
       pipe.read(stage, 3, old);
@@ -477,7 +480,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T
     P::commit();
     stage = stage + 1 == GN_BWD_DEPTH ? 0 : stage + 1;
   }
-  if (csum) {
+  if constexpr (CSUM) {
     // csum[n][chunk][c] = sum over this block's pixels of the gradient it contributed (fixed-order lane reduction
     // through the drained pipeline memory): the caller turns these into bias / time-embedding gradients without
     // another pass over the tensor
@@ -591,7 +594,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_reduce(const voi
 }
 
 extern "C" __attribute__((visibility("default"))) int st_gn_bwd_params(const float* red, int rows, int C, float* dgamma, float* dbeta, void* stream) {
-  gn_bwd_params_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(red, rows, C, dgamma, dbeta);
+  gn_bwd_params_kernel<<<(C + 15) / 16, 512, 0, (cudaStream_t)stream>>>(red, rows, C, dgamma, dbeta);
   ST_CHECK_LAUNCH("st_gn_bwd_params");
   return 0;
 }
@@ -611,10 +614,18 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_apply(const void
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
     constexpr int smem = Pipe<T, 4, GN_BWD_DEPTH>::BYTES;
     static bool smem_ok = false;
-    if (!smem_ok) { if (!allow_smem(gn_bwd_apply_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
-    gn_bwd_apply_kernel<T><<<dim3(chunks, n_img), 256, smem, (cudaStream_t)stream>>>(
-        s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, keepbits, red,
-        (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2, csum);
+    if (!smem_ok) {
+      if (!allow_smem(gn_bwd_apply_kernel<T, false>, smem) || !allow_smem(gn_bwd_apply_kernel<T, true>, smem)) return ST_ERR_CUDA;
+      smem_ok = true;
+    }
+    if (csum)
+      gn_bwd_apply_kernel<T, true><<<dim3(chunks, n_img), 256, smem, (cudaStream_t)stream>>>(
+          s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, keepbits, red,
+          (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2, csum);
+    else
+      gn_bwd_apply_kernel<T, false><<<dim3(chunks, n_img), 256, smem, (cudaStream_t)stream>>>(
+          s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, keepbits, red,
+          (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2, csum);
   });
   ST_CHECK_LAUNCH("st_gn_bwd_apply");
   return 0;

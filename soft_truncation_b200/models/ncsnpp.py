@@ -15,6 +15,7 @@ Numeric modes: `compute_dtype=torch.bfloat16` (tensor-core path, fp32 accumulati
 `torch.float32` (parity path).  Parameters, gradients, optimizer state and all statistics stay fp32.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -25,6 +26,9 @@ from . import utils
 from .params import (ParamStore, _logical_view, _phys_view, init_conv, init_ones, init_zeros, register_owner)
 
 SQRT2 = math.sqrt(2.)
+# Emit bias / time-embedding gradient partial sums from the GroupNorm backward kernel instead of re-reading the
+# gradient tensors (ST_FUSE_CSUM=0 switches back to explicit column-sum passes; both paths are parity-tested).
+FUSE_CSUM = os.environ.get('ST_FUSE_CSUM', '1') != '0'
 CPAD = 64     # physical channel count of the 3-channel image-side tensors
 
 
@@ -219,15 +223,18 @@ class ResBlock:
     ops.conv_wgrad(g, a1, P.g(pre + 'Conv_1.weight'), alpha=s)
     da1 = ops.conv_dgrad(g, P.c(pre + 'Conv_1.weight'), Co, alpha=s)
     # ---- GroupNorm_1 + SiLU + dropout
-    dh1, _, cs1 = ops.gn_backward(h1, None, da1, self.G1, P.f(pre + 'GroupNorm_1.weight'),
-                                  P.f(pre + 'GroupNorm_1.bias'), st1, 1, P.g(pre + 'GroupNorm_1.weight'),
-                                  P.g(pre + 'GroupNorm_1.bias'), p_drop=p_drop, seed=seed, mask=mask, keepbits=keepbits,
-                                  want_csum=True)
+    r1 = ops.gn_backward(h1, None, da1, self.G1, P.f(pre + 'GroupNorm_1.weight'), P.f(pre + 'GroupNorm_1.bias'), st1, 1,
+                         P.g(pre + 'GroupNorm_1.weight'), P.g(pre + 'GroupNorm_1.bias'), p_drop=p_drop, seed=seed,
+                         mask=mask, keepbits=keepbits, want_csum=FUSE_CSUM)
+    dh1 = r1[0]
     del da1
-    # ---- temb projection gradient = per-image column sums of dh1 (by-product of the kernel above); their sum over
-    # images is the Conv_0.bias / Dense_0.bias gradient (TimeEmbedding.bwd)
+    # ---- temb projection gradient = per-image column sums of dh1 (by-product of the kernel above, or an explicit
+    # pass); their sum over images is the Conv_0.bias / Dense_0.bias gradient (TimeEmbedding.bwd)
     dd = torch.empty((B, Co), dtype=torch.float32, device=g.device)
-    ops.colsum(cs1, B, cs1.shape[1], Co, dd)
+    if FUSE_CSUM:
+      ops.colsum(r1[2], B, r1[2].shape[1], Co, dd)
+    else:
+      ops.colsum(dh1.view(npix, Co), B, H * W, Co, dd)
     net.d_dense[:, self.dense_off:self.dense_off + Co].copy_(dd)
     ops.conv_wgrad(dh1, a0, P.g(pre + 'Conv_0.weight'))
     da0 = ops.conv_dgrad(dh1, P.c(pre + 'Conv_0.weight'), self.cin)
@@ -249,11 +256,12 @@ class ResBlock:
     # ---- GroupNorm_0 + SiLU, plus the shortcut gradient, split over the two inputs
     a1_acc = acc[0]
     a2_acc = acc[1] if x2 is not None else None
-    dx1, dx2, cs0 = ops.gn_backward(x1, x2, da0, self.G0, P.f(pre + 'GroupNorm_0.weight'),
-                                    P.f(pre + 'GroupNorm_0.bias'), st0, 1, P.g(pre + 'GroupNorm_0.weight'),
-                                    P.g(pre + 'GroupNorm_0.bias'), extra=extra, extra_scale=extra_scale, dx1=a1_acc,
-                                    accum1=a1_acc is not None, dx2=a2_acc, accum2=a2_acc is not None, want_csum=True)
-    c1, c2 = _split_csum(cs0, x1.shape[3], 0 if x2 is None else x2.shape[3])
+    r0 = ops.gn_backward(x1, x2, da0, self.G0, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st0, 1,
+                         P.g(pre + 'GroupNorm_0.weight'), P.g(pre + 'GroupNorm_0.bias'), extra=extra,
+                         extra_scale=extra_scale, dx1=a1_acc, accum1=a1_acc is not None, dx2=a2_acc,
+                         accum2=a2_acc is not None, want_csum=FUSE_CSUM)
+    dx1, dx2 = r0[0], r0[1]
+    c1, c2 = _split_csum(r0[2], x1.shape[3], 0 if x2 is None else x2.shape[3]) if FUSE_CSUM else (None, None)
     return ((dx1,), (c1,)) if x2 is None else ((dx1, dx2), (c1, c2))
 
 
@@ -338,10 +346,10 @@ class AttnBlock:
     ops.gemm_tn(dqkv, h.view(npix, C), 3 * C, C, npix, out=P.g_group(self.names_w), accumulate=True)
     dh = ops.gemm_nn(dqkv, P.c_group(self.names_w), C).view(B, H, W, C)
     # ---- GroupNorm (no activation) + residual
-    dx, _, cs = ops.gn_backward(x, None, dh, self.G, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st,
-                                0, P.g(pre + 'GroupNorm_0.weight'), P.g(pre + 'GroupNorm_0.bias'), extra=g,
-                                extra_scale=s, dx1=acc[0], accum1=acc[0] is not None, want_csum=True)
-    return (dx,), (_split_csum(cs, C, 0)[0],)
+    r = ops.gn_backward(x, None, dh, self.G, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st, 0,
+                        P.g(pre + 'GroupNorm_0.weight'), P.g(pre + 'GroupNorm_0.bias'), extra=g, extra_scale=s,
+                        dx1=acc[0], accum1=acc[0] is not None, want_csum=FUSE_CSUM)
+    return (r[0],), ((_split_csum(r[2], C, 0)[0] if FUSE_CSUM else None),)
 
 
 class ConvBlock:
@@ -415,10 +423,11 @@ class NormActConv:
     P = net.m.P
     x, st, a = saved
     (da,), _ = self.conv.bwd(net, a, g, (None,), gs=gs)
-    dx, _, cs = ops.gn_backward(x, None, da, self.G, P.f(self.pg + 'weight'), P.f(self.pg + 'bias'), st, 1,
-                                P.g(self.pg + 'weight'), P.g(self.pg + 'bias'), dx1=acc[0], accum1=acc[0] is not None,
-                                want_csum=True)
-    c = _split_csum(cs, x.shape[3], 0)[0]
+    r = ops.gn_backward(x, None, da, self.G, P.f(self.pg + 'weight'), P.f(self.pg + 'bias'), st, 1,
+                        P.g(self.pg + 'weight'), P.g(self.pg + 'bias'), dx1=acc[0], accum1=acc[0] is not None,
+                        want_csum=FUSE_CSUM)
+    dx = r[0]
+    c = _split_csum(r[2], x.shape[3], 0)[0] if FUSE_CSUM else None
     if len(acc) == 1:
       return (dx,), (c,)
     if acc[1] is not None:
