@@ -300,3 +300,122 @@ def test_fir_and_pyramid_variants_vs_reference_fixture(golden, tag):
   params = dict(net.named_parameters())
   gn = np.array([params[k].grad.double().norm().item() if params[k].requires_grad else 0. for k in names])
   np.testing.assert_allclose(gn, g[f'{tag}_gnorm'], rtol=2e-3, atol=1e-6 * g[f'{tag}_gnorm'].max())
+
+
+def test_pc_sampler_ve_langevin_vs_reference_fixture(golden):
+  """4-step reverse-diffusion predictor + Langevin corrector (VE) on the reduced C5 network: pins the
+  ReverseDiffusionPredictor / LangevinCorrector updates, the on-device batch norms and the final VE denoise step."""
+  from soft_truncation_b200 import sampling, sde_lib
+  g = golden('sampler_golden.npz')
+  cfg = _reduced('c5')
+  cfg.model.num_scales = 2000
+  cfg.sampling.method = 'pc'
+  model, _, _ = _model(cfg, 5, torch.float32)
+  sde4 = sde_lib.VESDE(sigma_min=cfg.model.sigma_min, sigma_max=cfg.model.sigma_max, N=4)
+  shape = (2, 3, 32, 32)
+  fn = sampling.get_sampling_fn(cfg, sde4, shape, lambda v: v, float(g['ve_eps']))
+  trace = []
+  x, nfe = fn(model, x_init=torch.tensor(g['ve_xT']), noises=[torch.tensor(z) for z in g['ve_z']], trace=trace)
+  assert nfe == int(g['ve_nfe'])
+  for i, st in enumerate(trace):
+    assert rel_l2(st, g['ve_trace'][i]) < 2e-4, i
+  assert rel_l2(x, g['ve_x']) < 2e-4
+
+
+def _fake_score(x, t):
+  return -0.3 * x + 0.1 * t[:, None, None, None]
+
+
+@pytest.mark.parametrize('kind', ['vp', 've'])
+def test_fused_predictors_and_correctors_match_the_reference_formulas(kind):
+  """Every registered predictor / corrector (sampling.py:185-340) against the reference's update formulas written
+  with plain torch ops, for an analytic score function."""
+  from soft_truncation_b200 import sampling, sde_lib
+  from soft_truncation_b200 import configs
+  cfg = configs.cifar10_ddpmpp_nll_st()
+  sde = sde_lib.VPSDE(N=50) if kind == 'vp' else sde_lib.VESDE(N=50)
+  gen = torch.Generator().manual_seed(3)
+  x = torch.randn(3, 3, 8, 8, generator=gen).to(DEV)
+  t = torch.tensor([0.9, 0.5, 0.11], device=DEV)
+  z = torch.randn(3, 3, 8, 8, generator=gen).to(DEV)
+  bc = lambda v: v[:, None, None, None]
+  score = _fake_score(x, t)
+  # Euler-Maruyama (sampling.py:190-196)
+  p = sampling.EulerMaruyamaPredictor(cfg, sde, _fake_score)
+  p.noise_source = [z.clone()]
+  got, got_mean = p.update_fn(x, t)
+  dt = -1. / sde.N
+  f, gdiff = sde.sde(x, t)
+  drift = f - bc(gdiff) ** 2 * score
+  want_mean = x + drift * dt
+  assert rel_l2(got_mean, want_mean) < 1e-5
+  assert rel_l2(got, want_mean + bc(gdiff) * np.sqrt(-dt) * z) < 1e-5
+  # reverse diffusion (sampling.py:205-210)
+  p = sampling.ReverseDiffusionPredictor(cfg, sde, _fake_score)
+  p.noise_source = [z.clone()]
+  got, got_mean = p.update_fn(x, t)
+  fd, G = sde.discretize(x, t)
+  want_mean = x - (fd - bc(G) ** 2 * score)
+  assert rel_l2(got_mean, want_mean) < 1e-5
+  assert rel_l2(got, want_mean + bc(G) * z) < 1e-5
+  # ancestral sampling (sampling.py:225-250)
+  p = sampling.AncestralSamplingPredictor(cfg, sde, _fake_score)
+  p.noise_source = [z.clone()]
+  got, got_mean = p.update_fn(x, t)
+  ts = (t * (sde.N - 1) / sde.T).long()
+  if kind == 'vp':
+    beta = sde.discrete_betas.to(DEV)[ts]
+    want_mean = (x + bc(beta) * score) / bc(torch.sqrt(1. - beta))
+    want = want_mean + bc(torch.sqrt(beta)) * z
+  else:
+    sig = sde.discrete_sigmas.to(DEV)
+    s0, s1 = sig[ts], torch.where(ts == 0, torch.zeros_like(t), sig[ts - 1])
+    want_mean = x + score * bc(s0 ** 2 - s1 ** 2)
+    want = want_mean + bc(torch.sqrt(s1 ** 2 * (s0 ** 2 - s1 ** 2) / s0 ** 2)) * z
+  assert rel_l2(got_mean, want_mean) < 1e-5 and rel_l2(got, want) < 1e-5
+  # Langevin and annealed Langevin correctors (sampling.py:272-329), two inner steps
+  z2 = torch.randn(3, 3, 8, 8, generator=gen).to(DEV)
+  alpha = sde.alphas.to(DEV)[ts] if kind == 'vp' else torch.ones_like(t)
+  for name in ('langevin', 'ald'):
+    c = sampling.get_corrector(name)(sde, _fake_score, 0.16, 2)
+    c.noise_source = [z.clone(), z2.clone()]
+    got, got_mean = c.update_fn(x, t)
+    xr = x
+    for noise in (z, z2):
+      grad = _fake_score(xr, t)
+      if name == 'langevin':
+        gn = torch.norm(grad.reshape(3, -1), dim=-1).mean()
+        nn_ = torch.norm(noise.reshape(3, -1), dim=-1).mean()
+        step = (0.16 * nn_ / gn) ** 2 * 2 * alpha
+      else:
+        step = (0.16 * sde.marginal_prob(xr, t)[1]) ** 2 * 2 * alpha
+      xm = xr + bc(step) * grad
+      xr = xm + bc(torch.sqrt(step * 2)) * noise
+    assert rel_l2(got_mean, xm) < 1e-5 and rel_l2(got, xr) < 1e-5, name
+  assert sampling.NonePredictor(sde, _fake_score).update_fn(x, t)[0] is x
+  assert sampling.NoneCorrector(sde, _fake_score, 0.1, 1).update_fn(x, t)[1] is x
+
+
+def test_step_fn_mixed_and_ode_sampler_run():
+  """step_fn_mixed (losses.py:295-320) and the probability-flow ODE sampler (sampling.py:436-504): shape, finiteness
+  and consistency with the plain pieces they are made of."""
+  from soft_truncation_b200 import losses, sampling
+  from soft_truncation_b200.models import utils as mutils
+  from soft_truncation_b200.models.ema import ExponentialMovingAverage
+  cfg = _cfg(dropout=0.)
+  cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks = 128, (1, 2), 1
+  cfg.training.mixed, cfg.optim.warmup = True, 0
+  model, sde, _ = _model(cfg, 0, torch.float32)
+  state = dict(optimizer=losses.get_optimizer(cfg, model.parameters()), model=model,
+               ema=ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate), step=0)
+  step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+  batch = (torch.rand(8, 3, 32, 32, generator=torch.Generator().manual_seed(1)) * 2 - 1).to(DEV)
+  before = mutils.unwrap(model)._flat.clone()
+  out = step_fn(state, batch)
+  assert out.shape == (4,) and torch.isfinite(out).all() and state['step'] == 1
+  assert not torch.equal(before, mutils.unwrap(model)._flat)
+  cfg.sampling.method = 'ode'
+  fn = sampling.get_ode_sampler(cfg, sde, (2, 3, 32, 32), lambda v: v, denoise=True, rtol=1e-2, atol=1e-2,
+                                eps=1e-3, device=cfg.device)
+  x, nfe = fn(model)
+  assert x.shape == (2, 3, 32, 32) and torch.isfinite(x).all() and nfe > 5
