@@ -1,11 +1,13 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short --timeout 600 -k "langevin or predictors or mixed" > gpurun_out/t5_new.log 2>&1
-tail -n 30 gpurun_out/t5_new.log
-timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/launches_train18.csv python tools/profile_step.py --batch 512 > gpurun_out/prof18.log 2>&1
-tail -n 2 gpurun_out/prof18.log
-GP_CASE=fwd256 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc2 -s 2 -c 1 -f -o gpurun_out/r18_gemm_fwd256 python tools/gemm_probe.py > gpurun_out/ncu18a.log 2>&1
-GP_CASE=wgrad128 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc2 -s 2 -c 1 -f -o gpurun_out/r18_gemm_wgrad128 python tools/gemm_probe.py > gpurun_out/ncu18b.log 2>&1
-timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gn_ -s 40 -c 5 -f -o gpurun_out/r18_gn python tools/profile_step.py --batch 512 > gpurun_out/ncu18c.log 2>&1
-tail -n 2 gpurun_out/ncu18a.log gpurun_out/ncu18b.log gpurun_out/ncu18c.log
-ls -la gpurun_out/*.ncu-rep
+timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --tb=short --timeout 300 > gpurun_out/t1_kernels.log 2>&1
+tail -n 5 gpurun_out/t1_kernels.log
+timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short --timeout 900 > gpurun_out/t4_parity.log 2>&1
+tail -n 5 gpurun_out/t4_parity.log
+timeout 600 python tools/gn_bench.py > gpurun_out/gn_bench19.txt 2>&1
+cat gpurun_out/gn_bench19.txt
+timeout 600 python tools/gemm_shapes.py > gpurun_out/gemm_shapes19.txt 2>&1
+head -n 45 gpurun_out/gemm_shapes19.txt
+ST_GN_CSUM_OCC=3 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench19_occ3.json 2> gpurun_out/bench19_occ3.err
+ST_GN_CSUM_OCC=2 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench19_occ2.json 2> gpurun_out/bench19_occ2.err
+cat gpurun_out/bench19_*.json | cut -c1-200; tail -n 3 gpurun_out/bench19_*.err

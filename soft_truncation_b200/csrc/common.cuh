@@ -63,12 +63,20 @@ __device__ __forceinline__ void store4(bf16* p, const float v[4]) {
   *reinterpret_cast<uint2*>(p) = t;
 }
 
-// MUFU-based sigmoid (ex2 + rcp, ~2 ulp): these kernels are issue-bound, an IEEE division costs ~8 extra instructions
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
-// d/dx [x*sigmoid(x)] = s*(1 + x*(1-s))
+// MUFU-based sigmoid: FMUL, MUFU.EX2, FADD, MUFU.RCP (~2 ulp).  The streaming kernels are issue-bound; the .ftz forms
+// drop the denormal fix-up code that __expf/__fdividef carry without -use_fast_math (x < -87 gives exactly 0, x > 87
+// exactly 1 - both correct to fp32 precision).
+__device__ __forceinline__ float sigmoid_f(float x) {
+  float e, s;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.f + e));
+  return s;
+}
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
+// d/dx [x*sigmoid(x)] = s + x*s*(1-s)
 __device__ __forceinline__ float silu_grad_f(float x) {
-  float s = __fdividef(1.f, 1.f + __expf(-x));
-  return s * fmaf(x, 1.f - s, 1.f);
+  float s = sigmoid_f(x);
+  return fmaf(x, fmaf(-s, s, s), s);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -7,6 +7,10 @@
 // (16-byte bf16 / 32-byte fp32 vectors) of one image and walks that image's pixels, so per-channel constants
 // (gamma, beta, mean, rstd) sit in registers and the inner loop has no integer division; two pixels are in
 // flight per iteration.  Reductions are deterministic (fixed-order shared-memory trees, no float atomics).
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -50,14 +54,16 @@ struct Pipe {
     side = (uint32_t)__cvta_generic_to_shared(smem) + VEC_BYTES + threadIdx.x * 4;
   }
   // the byte `bits[idx]` travels inside its aligned 4-byte word
-  __device__ __forceinline__ void issue_byte(int stage, const uint8_t* bits, long long idx) const {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(side + (uint32_t)(stage * 256 * 4)), "l"(bits + (idx & ~3LL))
+  __device__ __forceinline__ void issue_byte(int stage, const uint8_t* byte) const {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(side + (uint32_t)(stage * 256 * 4)),
+                 "l"(reinterpret_cast<uintptr_t>(byte) & ~(uintptr_t)3)
                  : "memory");
   }
-  __device__ __forceinline__ uint32_t read_byte(int stage, long long idx) const {
+  // `idx` = index of that byte in its (4-byte aligned) array; only its low two bits are used
+  __device__ __forceinline__ uint32_t read_byte(int stage, uint32_t idx) const {
     uint32_t w;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(side + (uint32_t)(stage * 256 * 4)));
-    return (w >> (8 * (int)(idx & 3))) & 0xFFu;
+    return (w >> (8 * (idx & 3u))) & 0xFFu;
   }
   __device__ __forceinline__ uint32_t slot(int stage, int stream, int part) const {
     return base + (uint32_t)(((stage * NS + stream) * PARTS + part) * 256 * 16);
@@ -140,38 +146,87 @@ __device__ __forceinline__ void load_consts(ChanConst& k, int n, int c0, int G, 
   k.mu[1] = mean[n * G + k.g[1]]; k.r[1] = rstd[n * G + k.g[1]];
 }
 
+// Software-pipeline driver shared by all streaming kernels: `issue(stage)` copies the next row of every input stream
+// into `stage` and advances the stream pointers, `body(stage)` consumes the oldest row.  The ring is walked by a loop
+// unrolled DEPTH times so that every shared-memory slot address is an immediate and no ring index is kept.
+template <int DEPTH, typename Issue, typename Body>
+__device__ __forceinline__ void run_pipeline(int n_it, Issue&& issue, Body&& body) {
+#pragma unroll
+  for (int d = 0; d < DEPTH; ++d) {
+    if (d < n_it) issue(d);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  int rem = n_it;
+  while (rem > 0) {
+#pragma unroll
+    for (int st = 0; st < DEPTH; ++st) {
+      if (rem <= 0) break;
+      asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+      body(st);
+      if (rem > DEPTH) issue(st);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      --rem;
+    }
+  }
+}
+
+// thread -> (pixel lane, 8-channel vector) mapping and the walk of one thread over its pixels
+struct Walk {
+  int V, lanes, v, lane, c0, n_it;
+  long long row0;                    // first pixel row (n*hw + p) of this thread
+  __device__ __forceinline__ Walk(int Ct, int n, int hw, int part, int parts) {
+    V = Ct / 8;
+    lanes = 256 / V;
+    v = threadIdx.x % V;
+    lane = threadIdx.x / V;
+    c0 = v * 8;
+    const int per = (hw + parts - 1) / parts;
+    const int p0 = part * per, p1 = min(hw, p0 + per);
+    n_it = (lane < lanes && p1 > p0 + lane) ? (p1 - p0 - lane + lanes - 1) / lanes : 0;
+    row0 = (long long)n * hw + p0 + lane;
+  }
+};
+
+// one input stream of a thread: pointer to the next row to copy, advanced by `step` elements per row walked
+template <typename T>
+struct Stream {
+  const T* p;
+  int step;
+  __device__ __forceinline__ const T* next() { const T* q = p; p += step; return q; }
+};
+template <typename T>
+__device__ __forceinline__ Stream<T> stream_of(const Src2<T>& s, const Walk& w) {     // (possibly concatenated) input
+  const bool first = w.c0 < s.C1;
+  const int ld = first ? s.C1 : s.C2;
+  const T* base = first ? s.x1 + w.c0 : s.x2 + (w.c0 - s.C1);
+  return Stream<T>{base + w.row0 * ld, w.lanes * ld};
+}
+template <typename T>
+__device__ __forceinline__ Stream<T> stream_of(const T* t, int Ct, const Walk& w) {    // plain [rows][Ct] tensor
+  return Stream<T>{t + w.row0 * Ct + w.c0, w.lanes * Ct};
+}
+
 // ---------------------------------------------------------------- stats
 // grid (n_img, splits): part[n][split][G][2] = (sum, sum of squares) over the split's pixels
 template <typename T>
-__global__ void __launch_bounds__(256) gn_stats_kernel(Src2<T> s, int hw, int G, int splits, float* part) {
+__global__ void __launch_bounds__(256, 4) gn_stats_kernel(Src2<T> s, int hw, int G, int splits, float* part) {
   extern __shared__ __align__(16) uint8_t gsm[];
   using P = Pipe<T, 1, GN_DEPTH>;
   const P pipe(gsm);
-  const int Ct = s.C1 + s.C2, V = Ct / 8, cpg = Ct / G;
+  const int Ct = s.C1 + s.C2, cpg = Ct / G;
   const int n = blockIdx.x, sp = blockIdx.y;
-  const int lanes = 256 / V;
-  const int v = threadIdx.x % V, lane = threadIdx.x / V;
-  const int per = (hw + splits - 1) / splits;
-  const int p0 = sp * per, p1 = min(hw, p0 + per);
+  const Walk w(Ct, n, hw, sp, splits);
+  const int V = w.V, lanes = w.lanes;
   float sum[2] = {0.f, 0.f}, sq[2] = {0.f, 0.f};
-  const int c0 = v * 8;
-  const int n_it = (lane < lanes && p1 > p0 + lane) ? (p1 - p0 - lane + lanes - 1) / lanes : 0;
-  const long long row0 = (long long)n * hw + p0 + lane;
-  for (int d = 0; d < GN_DEPTH; ++d) {
-    if (d < n_it) pipe.issue(d, 0, s.at(row0 + (long long)d * lanes, c0));
-    P::commit();
-  }
-  int stage = 0;
-  for (int it = 0; it < n_it; ++it) {
-    P::wait();
-    float a[8];
-    pipe.read(stage, 0, a);
+  Stream<T> xs = stream_of(s, w);
+  run_pipeline<GN_DEPTH>(
+      w.n_it, [&](int st) { pipe.issue(st, 0, xs.next()); },
+      [&](int st) {
+        float a[8];
+        pipe.read(st, 0, a);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { sum[i >> 2] += a[i]; sq[i >> 2] = fmaf(a[i], a[i], sq[i >> 2]); }
-    if (it + GN_DEPTH < n_it) pipe.issue(stage, 0, s.at(row0 + (long long)(it + GN_DEPTH) * lanes, c0));
-    P::commit();
-    stage = stage + 1 == GN_DEPTH ? 0 : stage + 1;
-  }
+        for (int i = 0; i < 8; ++i) { sum[i >> 2] += a[i]; sq[i >> 2] = fmaf(a[i], a[i], sq[i >> 2]); }
+      });
   // quad q = 2*v + half holds channels [4q, 4q+4): whole quads never straddle a group (cpg % 4 == 0)
   __shared__ float s_sum[512], s_sq[512];
   s_sum[2 * threadIdx.x] = sum[0]; s_sum[2 * threadIdx.x + 1] = sum[1];
@@ -209,139 +264,149 @@ __global__ void gn_finalize_kernel(const float* part, int n_img, int splits, int
   rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// Dropout handling is a template parameter so that the streaming loops carry no run-time mode branches:
+//   DROP_NONE  p == 0
+//   DROP_FAST  forward: in-kernel Philox, keep bits written;  backward: keep bits read back through the pipeline
+//   DROP_SLOW  injected mask (parity tests) or, in the backward passes, the generator re-run (no keep bits kept)
+enum { DROP_NONE = 0, DROP_FAST = 1, DROP_SLOW = 2 };
+
 // ---------------------------------------------------------------- apply
 // grid (chunks, n_img); pipelined stream: x (an injected dropout mask - parity tests only - is read directly)
-template <typename T>
-__global__ void __launch_bounds__(256) gn_apply_kernel(Src2<T> s, int hw, int G, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, const float* __restrict__ mean,
-                                                       const float* __restrict__ rstd, int act, float p_drop, uint64_t seed,
-                                                       const T* mask, uint8_t* keepbits, T* y) {
+template <typename T, bool ACT, int DROP>
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(Src2<T> s, int hw, int G, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ mean,
+                                                          const float* __restrict__ rstd, float p_drop, uint64_t seed,
+                                                          const T* mask, uint8_t* keepbits, T* y) {
   extern __shared__ __align__(16) uint8_t gsm[];
   using P = Pipe<T, 1, GN_DEPTH>;
   const P pipe(gsm);
-  const int Ct = s.C1 + s.C2, V = Ct / 8, cpg = Ct / G;
+  const int Ct = s.C1 + s.C2, cpg = Ct / G;
   const int n = blockIdx.y;
-  const int lanes = 256 / V;
-  const int v = threadIdx.x % V, lane = threadIdx.x / V;
-  if (lane >= lanes) return;
-  const int c0 = v * 8;
+  const Walk w(Ct, n, hw, blockIdx.x, gridDim.x);
+  if (w.lane >= w.lanes) return;
   ChanConst k;
-  load_consts(k, n, c0, G, cpg, gamma, beta, mean, rstd);
-  const int per = (hw + gridDim.x - 1) / gridDim.x;
-  const int p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
-  const int n_it = p1 > p0 + lane ? (p1 - p0 - lane + lanes - 1) / lanes : 0;
-  const long long row0 = (long long)n * hw + p0 + lane;
-  auto issue = [&](int stage, int j) {
-    const long long row = row0 + (long long)j * lanes;
-    pipe.issue(stage, 0, s.at(row, c0));
-  };
-  for (int d = 0; d < GN_DEPTH; ++d) {
-    if (d < n_it) issue(d, d);
-    P::commit();
+  load_consts(k, n, w.c0, G, cpg, gamma, beta, mean, rstd);
+  // y = x*A + B with A = rstd*gamma, B = beta - mean*rstd*gamma
+  float A[8], Bc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    A[i] = k.r[i >> 2] * k.gam[i];
+    Bc[i] = fmaf(-k.mu[i >> 2], A[i], k.bet[i]);
   }
-  int stage = 0;
-  for (int it = 0; it < n_it; ++it) {
-    P::wait();
-    const long long oct = (row0 + (long long)it * lanes) * V + v;
-    float x[8], o[8];
-    pipe.read(stage, 0, x);
+  Stream<T> xs = stream_of(s, w);
+  long long oct = w.row0 * w.V + w.v;              // index of the 8-vector being produced
+  const int octstep = w.lanes * w.V;
+  run_pipeline<GN_DEPTH>(
+      w.n_it, [&](int st) { pipe.issue(st, 0, xs.next()); },
+      [&](int st) {
+        float x[8], o[8];
+        pipe.read(st, 0, x);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float u = fmaf((x[i] - k.mu[i >> 2]) * k.r[i >> 2], k.gam[i], k.bet[i]);
-      o[i] = act ? silu_f(u) : u;
-    }
-    if (mask) {
-      float mk[8];
-      load8(mask + oct * 8, mk);
+        for (int i = 0; i < 8; ++i) {
+          const float u = fmaf(x[i], A[i], Bc[i]);
+          o[i] = ACT ? silu_f(u) : u;
+        }
+        if constexpr (DROP == DROP_FAST) {
+          float keep[8];
+          const uint32_t bits = dropout8(seed, (uint64_t)oct, p_drop, keep);
+          if (keepbits) keepbits[oct] = (uint8_t)bits;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] *= mk[i];
-    } else if (p_drop > 0.f) {
-      float keep[8];
-      const uint32_t bits = dropout8(seed, (uint64_t)oct, p_drop, keep);
-      if (keepbits) keepbits[oct] = (uint8_t)bits;
+          for (int i = 0; i < 8; ++i) o[i] *= keep[i];
+        } else if constexpr (DROP == DROP_SLOW) {
+          float mk[8];
+          load8(mask + oct * 8, mk);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] *= keep[i];
-    }
-    store8(y + oct * 8, o);
-    if (it + GN_DEPTH < n_it) issue(stage, it + GN_DEPTH);
-    P::commit();
-    stage = stage + 1 == GN_DEPTH ? 0 : stage + 1;
-  }
+          for (int i = 0; i < 8; ++i) o[i] *= mk[i];
+        }
+        store8(y + oct * 8, o);
+        oct += octstep;
+      });
 }
 
-// dz and xhat of one 8-vector (shared by both backward passes)
-// `mk` holds the injected mask values when has_mask, else it is filled here (in-kernel RNG or ones)
-__device__ __forceinline__ void gn_dz8(const float x[8], const float dyv[8], const ChanConst& k, int act, float p_drop,
-                                       uint64_t seed, bool has_mask, float mk[8], bool has_bits, uint32_t bits, long long oct,
-                                       float xhat[8], float dz[8]) {
-  if (!has_mask) {
-    if (p_drop > 0.f && has_bits) keep_from_bits(bits, p_drop, mk);
-    else if (p_drop > 0.f) dropout8(seed, (uint64_t)oct, p_drop, mk);
-    else {
+// per-thread constants of the backward passes: xhat = x*r + nmr, pre-activation u = x*rg + bc
+struct BwdConst {
+  float rg[8], bc[8], r[2], nmr[2];
+  __device__ __forceinline__ explicit BwdConst(const ChanConst& k) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mk[i] = 1.f;
+    for (int h = 0; h < 2; ++h) { r[h] = k.r[h]; nmr[h] = -k.mu[h] * k.r[h]; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      rg[i] = k.r[i >> 2] * k.gam[i];
+      bc[i] = fmaf(-k.mu[i >> 2], rg[i], k.bet[i]);
+    }
+  }
+};
+
+// dz and xhat of one 8-vector (shared by both backward passes)
+template <bool ACT, int DROP>
+__device__ __forceinline__ void gn_dz8(const float x[8], const float dyv[8], const BwdConst& k,
+                                       float p_drop, float inv_keep, uint64_t seed, const float* mkv, uint32_t bits,
+                                       long long oct, float xhat[8], float dz[8]) {
+  float mk[8];
+  if constexpr (DROP == DROP_SLOW) {
+    if (mkv) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mk[i] = mkv[i];
+    } else {
+      dropout8(seed, (uint64_t)oct, p_drop, mk);
     }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    xhat[i] = (x[i] - k.mu[i >> 2]) * k.r[i >> 2];
-    float d = dyv[i] * mk[i];
-    if (act) d *= silu_grad_f(fmaf(xhat[i], k.gam[i], k.bet[i]));
+    xhat[i] = fmaf(x[i], k.r[i >> 2], k.nmr[i >> 2]);
+    float d = dyv[i];
+    if constexpr (DROP == DROP_FAST) d = (bits >> i) & 1u ? d * inv_keep : 0.f;
+    if constexpr (DROP == DROP_SLOW) d *= mk[i];
+    if constexpr (ACT) d *= silu_grad_f(fmaf(x[i], k.rg[i], k.bc[i]));
     dz[i] = d;
   }
 }
 
 // ---------------------------------------------------------------- backward pass 1
 // grid (n_img, splits): red[n][split][c][2] = (sum dz, sum dz*xhat) over the split's pixels
-template <typename T>
+template <typename T, bool ACT, int DROP>
 __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                            int act, float p_drop, uint64_t seed, const T* mask,
+                                                            float p_drop, uint64_t seed, const T* mask,
                                                             const uint8_t* __restrict__ keepbits, float* red) {
-  const int Ct = s.C1 + s.C2, V = Ct / 8, cpg = Ct / G;
-  const int n = blockIdx.x, sp = blockIdx.y;
-  const int lanes = 256 / V;
-  const int v = threadIdx.x % V, lane = threadIdx.x / V;
   extern __shared__ __align__(16) uint8_t gsm[];
-  const int per = (hw + splits - 1) / splits;
-  const int p0 = sp * per, p1 = min(hw, p0 + per);
-  const int c0 = v * 8;
+  const int Ct = s.C1 + s.C2, cpg = Ct / G;
+  const int n = blockIdx.x, sp = blockIdx.y;
+  const Walk w(Ct, n, hw, sp, splits);
+  const int V = w.V, lanes = w.lanes, v = w.v, lane = w.lane;
   float a[8], b[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.f;
   using P = Pipe<T, 2, GN_DEPTH>;            // streams: x, dy (+ the keep-bits side stream)
-  const bool use_bits = keepbits != nullptr && p_drop > 0.f && mask == nullptr;
   const P pipe(gsm);
-  const int n_it = (lane < lanes && p1 > p0 + lane) ? (p1 - p0 - lane + lanes - 1) / lanes : 0;
-  const long long row0 = (long long)n * hw + p0 + lane;
-  ChanConst k;
-  if (lane < lanes) load_consts(k, n, c0, G, cpg, gamma, beta, mean, rstd);
-  auto issue = [&](int stage, int j) {
-    const long long row = row0 + (long long)j * lanes;
-    pipe.issue(stage, 0, s.at(row, c0));
-    pipe.issue(stage, 1, dy + (row * V + v) * 8);
-    if (use_bits) pipe.issue_byte(stage, keepbits, row * V + v);
-  };
-  for (int d = 0; d < GN_DEPTH; ++d) {
-    if (d < n_it) issue(d, d);
-    P::commit();
-  }
-  int stage = 0;
-  for (int it = 0; it < n_it; ++it) {
-    P::wait();
-    const long long oct = (row0 + (long long)it * lanes) * V + v;
-    float x0[8], d0[8], mk[8], xh[8], dz[8];
-    pipe.read(stage, 0, x0);
-    pipe.read(stage, 1, d0);
-    if (mask) load8(mask + oct * 8, mk);
-    gn_dz8(x0, d0, k, act, p_drop, seed, mask != nullptr, mk, use_bits, use_bits ? pipe.read_byte(stage, oct) : 0u, oct, xh, dz);
+  ChanConst kc;
+  load_consts(kc, n, lane < lanes ? w.c0 : 0, G, cpg, gamma, beta, mean, rstd);
+  const BwdConst k(kc);
+  const float inv_keep = 1.f / (1.f - p_drop);
+  Stream<T> xs = stream_of(s, w), ds = stream_of(dy, Ct, w);
+  const int octstep = lanes * V;
+  long long oct = w.row0 * V + v;                    // vector being consumed
+  Stream<uint8_t> bs{keepbits + oct, octstep};       // its keep bits
+  run_pipeline<GN_DEPTH>(
+      w.n_it,
+      [&](int st) {
+        pipe.issue(st, 0, xs.next());
+        pipe.issue(st, 1, ds.next());
+        if constexpr (DROP == DROP_FAST) pipe.issue_byte(st, bs.next());
+      },
+      [&](int st) {
+        float x0[8], d0[8], mk[8], xh[8], dz[8];
+        pipe.read(st, 0, x0);
+        pipe.read(st, 1, d0);
+        uint32_t bits = 0;
+        if constexpr (DROP == DROP_FAST) bits = pipe.read_byte(st, (uint32_t)oct);
+        if constexpr (DROP == DROP_SLOW) { if (mask) load8(mask + oct * 8, mk); }
+        gn_dz8<ACT, DROP>(x0, d0, k, p_drop, inv_keep, seed, mask ? mk : nullptr, bits, oct, xh, dz);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
-    if (it + GN_DEPTH < n_it) issue(stage, it + GN_DEPTH);
-    P::commit();
-    stage = stage + 1 == GN_DEPTH ? 0 : stage + 1;
-  }
+        for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
+        if constexpr (DROP != DROP_NONE) oct += octstep;
+      });
   // reduce over pixel lanes: smem [lane][V][16] (reuses the pipeline's shared memory once it has drained)
   __syncthreads();
   float* s_red = reinterpret_cast<float*>(gsm);
@@ -388,16 +453,16 @@ __global__ void __launch_bounds__(512) gn_bwd_params_kernel(const float* __restr
 
 // ---------------------------------------------------------------- backward pass 2
 // grid (chunks, n_img)
-template <typename T, bool CSUM>
-__global__ void __launch_bounds__(256, CSUM ? 2 : 3) gn_bwd_apply_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
+template <typename T, bool ACT, int DROP, bool CSUM, int OCC>
+__global__ void __launch_bounds__(256, OCC) gn_bwd_apply_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                           int act, float p_drop, uint64_t seed, const T* mask,
+                                                           float p_drop, uint64_t seed, const T* mask,
                                                            const uint8_t* __restrict__ keepbits,
                                                            const float* __restrict__ red, const T* extra, float extra_scale,
                                                            T* dx1, int accum1, T* dx2, int accum2, float* csum) {
   extern __shared__ __align__(16) uint8_t gsm[];
-  const int Ct = s.C1 + s.C2, V = Ct / 8, cpg = Ct / G;
+  const int Ct = s.C1 + s.C2, cpg = Ct / G;
   const int n = blockIdx.y;
   __shared__ float sh1[64], sh2[64];
   if (threadIdx.x < G) {
@@ -414,72 +479,72 @@ __global__ void __launch_bounds__(256, CSUM ? 2 : 3) gn_bwd_apply_kernel(Src2<T>
     sh2[g] = (float)(b * inv);
   }
   __syncthreads();
-  const int lanes = 256 / V;
-  const int v = threadIdx.x % V, lane = threadIdx.x / V;
+  Walk w(Ct, n, hw, blockIdx.x, gridDim.x);
+  const int V = w.V, lanes = w.lanes, v = w.v, lane = w.lane;
   const bool active = lane < lanes;
-  const int c0 = active ? v * 8 : 0;
-  ChanConst k;
-  load_consts(k, n, c0, G, cpg, gamma, beta, mean, rstd);
-  const float s1[2] = {sh1[k.g[0]], sh1[k.g[1]]}, s2[2] = {sh2[k.g[0]], sh2[k.g[1]]};
+  if (!active) w.c0 = 0;
+  const int c0 = w.c0;
+  ChanConst kc;
+  load_consts(kc, n, c0, G, cpg, gamma, beta, mean, rstd);
+  const BwdConst k(kc);
+  // dx = rstd*gamma*dz - rstd*s1 - rstd*s2*xhat
+  const float rs1[2] = {-kc.r[0] * sh1[kc.g[0]], -kc.r[1] * sh1[kc.g[1]]}, rs2[2] = {-kc.r[0] * sh2[kc.g[0]], -kc.r[1] * sh2[kc.g[1]]};
+  const float inv_keep = 1.f / (1.f - p_drop);
   float cs[8];                               // column sums of this thread's contributions (optional output)
 #pragma unroll
   for (int i = 0; i < 8; ++i) cs[i] = 0.f;
   // destination of this thread's channels (first or second tensor of the concatenation)
-  T* const dbase = c0 < s.C1 ? dx1 + c0 : dx2 + (c0 - s.C1);
-  const int dld = c0 < s.C1 ? s.C1 : s.C2;
-  const int acc = c0 < s.C1 ? accum1 : accum2;
-  const int per = (hw + gridDim.x - 1) / gridDim.x;
-  const int p0 = blockIdx.x * per, p1 = min(hw, p0 + per);
+  const bool first = c0 < s.C1;
+  const int dld = first ? s.C1 : s.C2;
+  const int acc = first ? accum1 : accum2;
+  T* dp = (first ? dx1 + c0 : dx2 + (c0 - s.C1)) + w.row0 * dld;          // destination row being produced
+  const int dstep = lanes * dld;
   using P = Pipe<T, 4, GN_BWD_DEPTH>;        // streams: x, dy, extra, old destination (+ the keep-bits side stream)
-  const bool use_bits = keepbits != nullptr && p_drop > 0.f && mask == nullptr;
   const P pipe(gsm);
-  const int n_it = (active && p1 > p0 + lane) ? (p1 - p0 - lane + lanes - 1) / lanes : 0;
-  const long long row0 = (long long)n * hw + p0 + lane;
-  auto issue = [&](int stage, int j) {
-    const long long row = row0 + (long long)j * lanes;
-    pipe.issue(stage, 0, s.at(row, c0));
-    pipe.issue(stage, 1, dy + (row * V + v) * 8);
-    if (extra) pipe.issue(stage, 2, extra + (row * V + v) * 8);
-    if (acc) pipe.issue(stage, 3, dbase + row * dld);
-    if (use_bits) pipe.issue_byte(stage, keepbits, row * V + v);
-  };
-  for (int d = 0; d < GN_BWD_DEPTH; ++d) {
-    if (d < n_it) issue(d, d);
-    P::commit();
-  }
-  int stage = 0;
-  for (int it = 0; it < n_it; ++it) {
-    P::wait();
-    const long long row = row0 + (long long)it * lanes;
-    float x0[8], d0[8], mk[8], xh[8], dz[8], o[8];
-    pipe.read(stage, 0, x0);
-    pipe.read(stage, 1, d0);
-    if (mask) load8(mask + (row * V + v) * 8, mk);
-    gn_dz8(x0, d0, k, act, p_drop, seed, mask != nullptr, mk, use_bits, use_bits ? pipe.read_byte(stage, row * V + v) : 0u,
-           row * V + v, xh, dz);
+  Stream<T> xs = stream_of(s, w), ds = stream_of(dy, Ct, w), es = stream_of(extra, Ct, w);
+  Stream<T> os{dp, dstep};
+  const int octstep = lanes * V;
+  long long oct = w.row0 * V + v;
+  Stream<uint8_t> bs{keepbits + oct, octstep};
+  run_pipeline<GN_BWD_DEPTH>(
+      w.n_it,
+      [&](int st) {
+        pipe.issue(st, 0, xs.next());
+        pipe.issue(st, 1, ds.next());
+        if (extra) pipe.issue(st, 2, es.next());
+        if (acc) pipe.issue(st, 3, os.next());
+        if constexpr (DROP == DROP_FAST) pipe.issue_byte(st, bs.next());
+      },
+      [&](int st) {
+        float x0[8], d0[8], mk[8], xh[8], dz[8], o[8];
+        pipe.read(st, 0, x0);
+        pipe.read(st, 1, d0);
+        uint32_t bits = 0;
+        if constexpr (DROP == DROP_FAST) bits = pipe.read_byte(st, (uint32_t)oct);
+        if constexpr (DROP == DROP_SLOW) { if (mask) load8(mask + oct * 8, mk); }
+        gn_dz8<ACT, DROP>(x0, d0, k, p_drop, inv_keep, seed, mask ? mk : nullptr, bits, oct, xh, dz);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = k.r[i >> 2] * (k.gam[i] * dz[i] - s1[i >> 2] - xh[i] * s2[i >> 2]);
-    if (extra) {
-      float ex[8];
-      pipe.read(stage, 2, ex);
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(k.rg[i], dz[i], fmaf(xh[i], rs2[i >> 2], rs1[i >> 2]));
+        if (extra) {
+          float ex[8];
+          pipe.read(st, 2, ex);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaf(extra_scale, ex[i], o[i]);
-    }
-    if constexpr (CSUM) {
+          for (int i = 0; i < 8; ++i) o[i] = fmaf(extra_scale, ex[i], o[i]);
+        }
+        if constexpr (CSUM) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) cs[i] += o[i];
-    }
-    if (acc) {
-      float old[8];
-      pipe.read(stage, 3, old);
+          for (int i = 0; i < 8; ++i) cs[i] += o[i];
+        }
+        if (acc) {
+          float old[8];
+          pipe.read(st, 3, old);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += old[i];
-    }
-    store8(dbase + row * dld, o);
-    if (it + GN_BWD_DEPTH < n_it) issue(stage, it + GN_BWD_DEPTH);
-    P::commit();
-    stage = stage + 1 == GN_BWD_DEPTH ? 0 : stage + 1;
-  }
+          for (int i = 0; i < 8; ++i) o[i] += old[i];
+        }
+        store8(dp, o);
+        dp += dstep;
+        if constexpr (DROP != DROP_NONE) oct += octstep;
+      });
   if constexpr (CSUM) {
     // csum[n][chunk][c] = sum over this block's pixels of the gradient it contributed (fixed-order lane reduction
     // through the drained pipeline memory): the caller turns these into bias / time-embedding gradients without
@@ -520,10 +585,22 @@ int check_geom(int C1, int C2, int G) {
 int chunks_for(int n_img, int hw, int V) {
   int lanes = 256 / V;
   int max_chunks = (hw + GN_DEPTH * lanes - 1) / (GN_DEPTH * lanes);   // at least one full pipeline per block
-  int want = (st_num_sms() * 8 + n_img - 1) / n_img;
+  static const int waves = getenv("ST_GN_CHUNK_W") ? atoi(getenv("ST_GN_CHUNK_W")) : 8;   // tuning knob
+  int want = (st_num_sms() * waves + n_img - 1) / n_img;
   int c = want < max_chunks ? want : max_chunks;
   if (c > 65535) c = 65535;
   return c < 1 ? 1 : c;
+}
+
+// run f(std::bool_constant<act>, std::integral_constant<int, drop>) for the run-time (act, drop) pair
+template <typename F>
+void dispatch_mode(int act, int drop, F&& f) {
+  auto with_act = [&](auto A) {
+    if (drop == DROP_NONE) f(A, std::integral_constant<int, DROP_NONE>{});
+    else if (drop == DROP_FAST) f(A, std::integral_constant<int, DROP_FAST>{});
+    else f(A, std::integral_constant<int, DROP_SLOW>{});
+  };
+  if (act) with_act(std::true_type{}); else with_act(std::false_type{});
 }
 
 }  // namespace
@@ -562,14 +639,21 @@ extern "C" __attribute__((visibility("default"))) int st_gn_apply(const void* x1
   if (int e = check_geom(C1, C2, G)) return e;
   ST_CHECK_ARG(n_img <= 65535, "st_gn_apply: more than 65535 images");
   const int V = (C1 + C2) / 8;
+  const int drop = mask ? DROP_SLOW : (p_drop > 0.f ? DROP_FAST : DROP_NONE);
+  int rc = 0;
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
     constexpr int smem = Pipe<T, 1, GN_DEPTH>::BYTES;
-    static bool smem_ok = false;
-    if (!smem_ok) { if (!allow_smem(gn_apply_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
-    gn_apply_kernel<T><<<dim3(chunks_for(n_img, hw, V), n_img), 256, smem, (cudaStream_t)stream>>>(
-        s, hw, G, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, keepbits, (T*)y);
+    dispatch_mode(act, drop, [&](auto A, auto D) {
+      constexpr bool ACT = decltype(A)::value;
+      constexpr int DROP = decltype(D)::value;
+      static bool smem_ok = false;
+      if (!smem_ok) { if (!allow_smem(gn_apply_kernel<T, ACT, DROP>, smem)) { rc = ST_ERR_CUDA; return; } smem_ok = true; }
+      gn_apply_kernel<T, ACT, DROP><<<dim3(chunks_for(n_img, hw, V), n_img), 256, smem, (cudaStream_t)stream>>>(
+          s, hw, G, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, (T*)y);
+    });
   });
+  if (rc) return rc;
   ST_CHECK_LAUNCH("st_gn_apply");
   return 0;
 }
@@ -579,16 +663,21 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_reduce(const voi
                                 const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
                                 const uint8_t* keepbits, int splits, float* red, void* stream) {
   if (int e = check_geom(C1, C2, G)) return e;
-  const int V = (C1 + C2) / 8;
-  (void)V;
+  const int drop = mask ? DROP_SLOW : (p_drop > 0.f ? (keepbits ? DROP_FAST : DROP_SLOW) : DROP_NONE);
+  int rc = 0;
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
     constexpr int smem = Pipe<T, 2, GN_DEPTH>::BYTES;      // >= the 16 KB the final lane reduction reuses
-    static bool smem_ok = false;
-    if (!smem_ok) { if (!allow_smem(gn_bwd_reduce_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
-    gn_bwd_reduce_kernel<T><<<dim3(n_img, splits), 256, smem, (cudaStream_t)stream>>>(
-        s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, keepbits, red);
+    dispatch_mode(act, drop, [&](auto A, auto D) {
+      constexpr bool ACT = decltype(A)::value;
+      constexpr int DROP = decltype(D)::value;
+      static bool smem_ok = false;
+      if (!smem_ok) { if (!allow_smem(gn_bwd_reduce_kernel<T, ACT, DROP>, smem)) { rc = ST_ERR_CUDA; return; } smem_ok = true; }
+      gn_bwd_reduce_kernel<T, ACT, DROP><<<dim3(n_img, splits), 256, smem, (cudaStream_t)stream>>>(
+          s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, red);
+    });
   });
+  if (rc) return rc;
   ST_CHECK_LAUNCH("st_gn_bwd_reduce");
   return 0;
 }
@@ -610,23 +699,30 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_apply(const void
   ST_CHECK_ARG(!csum || chunks > 0, "st_gn_bwd_apply: csum needs an explicit chunk count");
   if (chunks <= 0) chunks = chunks_for(n_img, hw, V);
   ST_CHECK_ARG(chunks <= 65535, "st_gn_bwd_apply: too many chunks");
+  const int drop = mask ? DROP_SLOW : (p_drop > 0.f ? (keepbits ? DROP_FAST : DROP_SLOW) : DROP_NONE);
+  int rc = 0;
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
     constexpr int smem = Pipe<T, 4, GN_BWD_DEPTH>::BYTES;
-    static bool smem_ok = false;
-    if (!smem_ok) {
-      if (!allow_smem(gn_bwd_apply_kernel<T, false>, smem) || !allow_smem(gn_bwd_apply_kernel<T, true>, smem)) return ST_ERR_CUDA;
-      smem_ok = true;
-    }
-    if (csum)
-      gn_bwd_apply_kernel<T, true><<<dim3(chunks, n_img), 256, smem, (cudaStream_t)stream>>>(
-          s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, keepbits, red,
-          (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2, csum);
-    else
-      gn_bwd_apply_kernel<T, false><<<dim3(chunks, n_img), 256, smem, (cudaStream_t)stream>>>(
-          s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, act, p_drop, seed, (const T*)mask, keepbits, red,
-          (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2, csum);
+    dispatch_mode(act, drop, [&](auto A, auto D) {
+      constexpr bool ACT = decltype(A)::value;
+      constexpr int DROP = decltype(D)::value;
+      auto launch = [&](auto CS, auto OC) {
+        constexpr bool CSUM = decltype(CS)::value;
+        constexpr int OCC = decltype(OC)::value;
+        static bool smem_ok = false;
+        if (!smem_ok) { if (!allow_smem(gn_bwd_apply_kernel<T, ACT, DROP, CSUM, OCC>, smem)) { rc = ST_ERR_CUDA; return; } smem_ok = true; }
+        gn_bwd_apply_kernel<T, ACT, DROP, CSUM, OCC><<<dim3(chunks, n_img), 256, smem, (cudaStream_t)stream>>>(
+            s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, red,
+            (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2, csum);
+      };
+      static const int csum_occ = getenv("ST_GN_CSUM_OCC") ? atoi(getenv("ST_GN_CSUM_OCC")) : 3;
+      if (!csum) launch(std::false_type{}, std::integral_constant<int, 3>{});
+      else if (csum_occ == 2) launch(std::true_type{}, std::integral_constant<int, 2>{});
+      else launch(std::true_type{}, std::integral_constant<int, 3>{});
+    });
   });
+  if (rc) return rc;
   ST_CHECK_LAUNCH("st_gn_bwd_apply");
   return 0;
 }

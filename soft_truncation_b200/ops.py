@@ -147,8 +147,11 @@ def gemm_tn(a, b, M, N, K, out=None, out_dtype=None, alpha=1.0, lda=None, ldb=No
 
 
 # ------------------------------------------------------------------------------------ GroupNorm
+_GN_SPLIT_W = int(os.environ.get('ST_GN_SPLIT_W', '4'))    # tuning knob: blocks per SM the split reductions aim for
+
+
 def _gn_splits(n_img, hw):
-  s = max(1, min((148 * 4 + n_img - 1) // n_img, hw // 64, 64))
+  s = max(1, min((148 * _GN_SPLIT_W + n_img - 1) // n_img, hw // 64, 64))
   return int(s)
 
 
