@@ -59,6 +59,8 @@ struct TcParams {
   int cluster;            // CTAs per cluster along M (B tiles are multicast across them)
   int trans_out;          // store C[n][m] instead of C[m][n] (accumulate mode)
   int m_tiles, n_tiles;
+  int epi_tma;            // epilogue writes the tile through shared memory with TMA stores (mapC / mapR are valid)
+  int rb_rows;            // distinct rowbias rows (images) one tile spans (1..4) when epi_tma
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -119,6 +121,23 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"(mask)
                : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -427,6 +446,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
                                                                    const __grid_constant__ CUtensorMap mapA1,
                                                                    const __grid_constant__ CUtensorMap mapB0,
                                                                    const __grid_constant__ CUtensorMap mapB1,
+                                                                   const __grid_constant__ CUtensorMap mapC,
+                                                                   const __grid_constant__ CUtensorMap mapR,
                                                                    const TcParams p) {
   static_assert(BN * MH <= 256, "accumulator buffer exceeds half of TMEM");
   constexpr int BMT = BM * MH;                // tile rows
@@ -441,10 +462,12 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* res_stage = smem + STAGES * STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(res_stage + RES_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_slot) + 16);     // [<=4 rows][BN] (TMA epilogue)
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
   const uint32_t tfull0 = smem_u32(bars + 2 * STAGES), tempty0 = smem_u32(bars + 2 * STAGES + 2);
+  const uint32_t rfull0 = smem_u32(bars + 2 * STAGES + 4);     // residual tile landed (one per epilogue half-group)
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int cs = p.cluster;
@@ -464,6 +487,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, 1);
       mbar_init(tempty0 + 8 * b, 8);
+      mbar_init(rfull0 + 8 * b, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -478,9 +502,13 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
   const uint32_t tmem_base = *tmem_slot;
 
   // decode a work item
+  // Tile order: CTAs that run at the same time should share operand tiles in L2.  n fastest (all N tiles of one block
+  // of rows are in flight together, the activation rows are fetched from DRAM once) except for weight gradients,
+  // whose big operands are both indexed by k: there every (m, n) tile of one K split runs together.
   auto decode = [&](int st, int& m0, int& n0, int& b, int& kt0, int& nkt) {
-    const int mg = st % m_groups;
-    const int nt = (st / m_groups) % p.n_tiles;
+    int mg, nt;
+    if (p.trans_out) { mg = st % m_groups; nt = (st / m_groups) % p.n_tiles; }
+    else { nt = st % p.n_tiles; mg = (st / p.n_tiles) % m_groups; }
     const int z = st / (m_groups * p.n_tiles);
     b = z / split;
     const int ks = z % split;
@@ -656,6 +684,169 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
     const bool vec_bias = p.bias && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     uint8_t* my_stage = res_stage + (size_t)et * 16;
     int tl = 0;
+    if (p.epi_tma) {
+      // ---------------- TMA epilogue.  Each half-group (4 warps = 128 accumulator rows) owns half of the staging region:
+      // its threads write their rows into 16 KB boxes (128 rows x 128 B, SWIZZLE_128B) and one leader thread stores the
+      // boxes with cp.async.bulk.tensor (reduce-add for split-K) - full 128-byte lines instead of row-scattered 16-byte
+      // stores, out-of-range rows / columns clipped by the tensor map.  The residual tile arrives in the same boxes by
+      // TMA and is updated in place; bias + per-image bias of the tile are staged in shared memory one tile ahead.
+      constexpr int HALF_BYTES = RES_BYTES / 2;
+      constexpr int BOXES = HALF_BYTES >= 16384 ? HALF_BYTES / 16384 : 1;     // (the host never selects this path for TC < 128)
+      const bool f32 = !p.out_bf16;
+      const int slabs = f32 ? 2 : 1;
+      const int cps = CH / slabs;                         // 32-column chunks per slab
+      const uint32_t region = smem_u32(res_stage) + (uint32_t)(half * HALF_BYTES);
+      const uint32_t rowaddr = region + (uint32_t)((q * 32 + lane) * 128);
+      const uint32_t sw = (uint32_t)(lane & 7);
+      const bool leader = ((warp - 2) % 4 == 0) && lane == 0;
+      const uint32_t rfull = rfull0 + 8 * half;
+      const int bar_id = 1 + half;
+      const bool has_bias = p.bias || p.rowbias;
+      const bool res_mode = p.residual != nullptr;
+      const int nb_vals = p.rb_rows * BN;                 // staged bias values per tile
+      const int my_rb = (p.rowbias && p.rows_per_rb < BMT) ? row / p.rows_per_rb : 0;
+      const int colbase = (MH == 2 ? 0 : half * (BN / 2));
+      const int rowbase = (MH == 2 ? half * BM : 0);
+      float pre[4] = {0.f, 0.f, 0.f, 0.f};
+      auto load_bias = [&](int tm0, int tn0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int idx = et + k * 256;
+          float v = 0.f;
+          if (idx < nb_vals) {
+            const int r = idx / BN, n = tn0 + (idx % BN);
+            if (n < p.N) {
+              if (p.bias) v = __ldg(p.bias + n);
+              if (p.rowbias) {
+                const long long img = (long long)(tm0 / p.rows_per_rb) + r;
+                if (img * p.rows_per_rb < p.M) v += __ldg(p.rowbias + img * p.ld_rb + n);
+              }
+            }
+          }
+          pre[k] = v;
+        }
+      };
+      auto issue_res = [&](int tm0, int tn0, int tb) {
+        mbar_expect_tx(rfull, BOXES * 16384);
+#pragma unroll
+        for (int bx = 0; bx < BOXES; ++bx)
+          tma_load_3d(region + bx * 16384, &mapR, rfull, tn0 + colbase + bx * 64, tm0 + rowbase, tb);
+      };
+      {
+        int m0, n0, b, kt0, nkt;
+        if (cluster_id < total) {
+          decode(cluster_id, m0, n0, b, kt0, nkt);
+          if (has_bias) load_bias(m0, n0);
+          if (res_mode && leader) issue_res(m0, n0, b);
+        }
+      }
+      for (int st = cluster_id; st < total; st += n_clusters) {
+        int m0, n0, b, kt0, nkt;
+        decode(st, m0, n0, b, kt0, nkt);
+        if (nkt <= 0) continue;
+        const int buf = tl & 1;
+        if (has_bias) {
+          named_bar(3, 256);                              // every warp has finished with the previous tile's values
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (et + k * 256 < nb_vals) sbias[et + k * 256] = pre[k];
+          named_bar(3, 256);
+          if (st + n_clusters < total) {
+            int m2, n2, b2, k2, nk2;
+            decode(st + n_clusters, m2, n2, b2, k2, nk2);
+            load_bias(m2, n2);                            // lands while this tile is processed
+          }
+        }
+        if (res_mode) mbar_wait(rfull, tl & 1);
+        mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int slab = 0; slab < slabs; ++slab) {
+          if (!res_mode) {
+            if (leader) bulk_wait_read();                 // the previous store has finished reading the boxes
+            named_bar(bar_id, 128);
+          }
+#pragma unroll 1
+          for (int cc = 0; cc < cps; ++cc) {
+            const int c = slab * cps + cc;
+            uint32_t r[32];
+            __syncwarp();
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC + half * (TC / 2) + c * 32), r);
+            if (c == CH - 1) {                            // accumulator drained: hand the TMEM buffer back to the MMA warp
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+            }
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            if (has_bias) {
+              const float4* sb = reinterpret_cast<const float4*>(sbias + my_rb * BN + colbase + c * 32);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 t = sb[g];
+                v[4 * g] += t.x; v[4 * g + 1] += t.y; v[4 * g + 2] += t.z; v[4 * g + 3] += t.w;
+              }
+            }
+            if (!f32) {
+              const uint32_t base = rowaddr + (uint32_t)((cc >> 1) * 16384);
+              const uint32_t pb = (uint32_t)((cc & 1) * 4);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t addr = base + (((pb + g) ^ sw) << 4);
+                if (res_mode) {
+                  uint4 t;
+                  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(addr));
+                  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    v[g * 8 + 2 * e] += __low2float(h[e]);
+                    v[g * 8 + 2 * e + 1] += __high2float(h[e]);
+                  }
+                }
+                uint4 o;
+                __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  ho[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e] * p.alpha, v[g * 8 + 2 * e + 1] * p.alpha);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+              }
+            } else {
+              const uint32_t base = rowaddr + (uint32_t)(cc * 16384);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const uint32_t addr = base + ((((uint32_t)g) ^ sw) << 4);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v[4 * g] * p.alpha), "f"(v[4 * g + 1] * p.alpha),
+                             "f"(v[4 * g + 2] * p.alpha), "f"(v[4 * g + 3] * p.alpha)
+                             : "memory");
+              }
+            }
+          }
+          fence_async_smem();
+          named_bar(bar_id, 128);
+          if (leader) {
+            const int cols_per_box = f32 ? 32 : 64;
+            const int rowg = m0 + rowbase;
+#pragma unroll
+            for (int bx = 0; bx < BOXES; ++bx) {
+              const int col = n0 + colbase + slab * cps * 32 + bx * cols_per_box;
+              if (col < p.N && rowg < p.M) {
+                if (p.accumulate) tma_reduce_add_3d(&mapC, region + bx * 16384, col, rowg, b);
+                else tma_store_3d(&mapC, region + bx * 16384, col, rowg, b);
+              }
+            }
+            bulk_commit();
+          }
+        }
+        if (res_mode && leader && st + n_clusters < total) {
+          int m2, n2, b2, k2, nk2;
+          decode(st + n_clusters, m2, n2, b2, k2, nk2);
+          bulk_wait_read();                               // this tile's store has read the boxes: refill them
+          issue_res(m2, n2, b2);
+        }
+        ++tl;
+      }
+      if (leader) bulk_wait_all();                        // global writes complete before the CTA retires
+    } else
     for (int st = cluster_id; st < total; st += n_clusters) {
       int m0, n0, b, kt0, nkt;
       decode(st, m0, n0, b, kt0, nkt);
@@ -821,12 +1012,12 @@ void tc_init() {
 
 // bf16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/strides innermost first; strides[i] is the byte stride of dim i+1.
 bool encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                const uint32_t* box) {
+                const uint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = g_encode(map, dtype, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -922,7 +1113,7 @@ int env_int(const char* name, int dflt) {
 
 template <int BN, int MH, int STAGES>
 int launch2(const CUtensorMap* maps, TcParams& p, int total_super, cudaStream_t stream) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES * MH + BN * 128) + BN * MH * 256 + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * (A_STAGE_BYTES * MH + BN * 128) + BN * MH * 256 + (2 * STAGES + 6) * 8 + 16 + 4 * BN * 4 + 1024;
   static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   static int max_clusters[5] = {0, 0, 0, 0, 0};
@@ -954,7 +1145,7 @@ int launch2(const CUtensorMap* maps, TcParams& p, int total_super, cudaStream_t 
   }
   int clusters = total_super < max_clusters[cs] ? total_super : max_clusters[cs];
   cfg.gridDim = dim3(clusters * cs);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   if (e != cudaSuccess) { st_set_error("st_gemm(tc2): launch failed: %s", cudaGetErrorString(e)); return ST_ERR_CUDA; }
   return 0;
 }
@@ -980,7 +1171,7 @@ bool gather_maps(CUtensorMap* m0, CUtensorMap* m1, const void* p1, const void* p
 int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   TcParams p;
   memset(&p, 0, sizeof(p));
-  CUtensorMap maps[4];
+  CUtensorMap maps[6];
   memset(maps, 0, sizeof(maps));
   const int Ct = a->C1 + a->C2;
   const bool wgrad = (a->b_mode == ST_OP_GATHER);     // runs transposed: M' = taps*Cin, N' = Cout
@@ -1000,7 +1191,7 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
     const long long tiles2 = (long long)((M + 255) / 256) * ((N + BN - 1) / BN) * p.batch * p.split_k;
     // weight gradients with a short M' = taps*Cin axis keep 128-row tiles (4 gathered A boxes per K block would
     // make the A producer the bottleneck, and 1152 rows quantise badly into 256-row tiles)
-    if (tiles2 >= 120 && !(wgrad && M < 2048)) MH = 2;
+    if (tiles2 >= 120 && !(wgrad && M < env_int("ST_TC_WGRAD_MH_MIN", 2048))) MH = 2;
   }
   p.m_tiles = (M + BM * MH - 1) / (BM * MH);
   p.n_tiles = (N + BN - 1) / BN;
@@ -1065,12 +1256,45 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   p.bias = a->bias; p.rowbias = a->rowbias; p.rows_per_rb = a->rows_per_rb > 0 ? a->rows_per_rb : 1; p.ld_rb = a->ld_rb;
   p.residual = reinterpret_cast<const bf16*>(a->residual); p.ldr = a->sRm; p.sRb = a->sRb; p.alpha = a->alpha;
 
+  // ---------------- epilogue through shared memory + TMA store (else: per-thread global stores / atomics)
+  {
+    const int BMT = BM * MH;
+    const int es = p.out_bf16 ? 2 : 4;
+    const bool has_vec = a->bias || a->rowbias;
+    bool ok = env_int("ST_TC_EPI", 1) == 1 && !wgrad && BN * MH >= 128;
+    ok = ok && aligned16(a->C) && (a->sCm * es) % 16 == 0 && (a->batch == 1 || (a->sCb * es) % 16 == 0);
+    ok = ok && !(a->accumulate && p.out_bf16);
+    ok = ok && !((a->residual || has_vec) && p.split_k > 1);
+    if (a->residual)
+      ok = ok && p.out_bf16 && aligned16(a->residual) && a->sRm % 8 == 0 && (a->batch == 1 || a->sRb % 8 == 0);
+    int rb_rows = 1;
+    if (a->rowbias) {
+      if (p.rows_per_rb % BMT == 0) rb_rows = 1;
+      else if (BMT % p.rows_per_rb == 0 && BMT / p.rows_per_rb <= 4) rb_rows = BMT / p.rows_per_rb;
+      else ok = false;
+    }
+    if (ok) {
+      const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->M, (uint64_t)a->batch};
+      const uint64_t str[2] = {(uint64_t)a->sCm * es, (uint64_t)(a->batch > 1 ? a->sCb : (int64_t)a->M * a->sCm) * es};
+      const uint32_t box[3] = {(uint32_t)(p.out_bf16 ? 64 : 32), 128, 1};
+      if (!encode_map(&maps[4], a->C, 3, dims, str, box, p.out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32))
+        return ST_ERR_CUDA;
+      if (a->residual) {
+        const uint64_t rstr[2] = {(uint64_t)a->sRm * 2, (uint64_t)(a->batch > 1 ? a->sRb : (int64_t)a->M * a->sRm) * 2};
+        const uint32_t rbox[3] = {64, 128, 1};
+        if (!encode_map(&maps[5], a->residual, 3, dims, rstr, rbox)) return ST_ERR_CUDA;
+      }
+      p.epi_tma = 1;
+      p.rb_rows = rb_rows;
+    }
+  }
+
   const int m_groups = (p.m_tiles + cs - 1) / cs;
   const long long total = (long long)p.batch * p.split_k * p.n_tiles * m_groups;
   ST_CHECK_ARG(total < (1LL << 30), "st_gemm(tc2): too many tiles");
   if (BN == 256) return launch2<256, 1, 3>(maps, p, (int)total, stream);
   if (BN == 128 && MH == 2) return launch2<128, 2, 3>(maps, p, (int)total, stream);
-  if (BN == 128) return launch2<128, 1, 6>(maps, p, (int)total, stream);
+  if (BN == 128) return launch2<128, 1, 5>(maps, p, (int)total, stream);
   return launch2<64, 1, 8>(maps, p, (int)total, stream);
 }
 

@@ -208,18 +208,18 @@ __device__ __forceinline__ Stream<T> stream_of(const T* t, int Ct, const Walk& w
 
 // ---------------------------------------------------------------- stats
 // grid (n_img, splits): part[n][split][G][2] = (sum, sum of squares) over the split's pixels
-template <typename T>
-__global__ void __launch_bounds__(256, 4) gn_stats_kernel(Src2<T> s, int hw, int G, int splits, float* part) {
+template <typename T, int DEPTH>
+__global__ void __launch_bounds__(256, DEPTH > 8 ? 3 : 4) gn_stats_kernel(Src2<T> s, int hw, int G, int splits, float* part, int swap) {
   extern __shared__ __align__(16) uint8_t gsm[];
-  using P = Pipe<T, 1, GN_DEPTH>;
+  using P = Pipe<T, 1, DEPTH>;
   const P pipe(gsm);
   const int Ct = s.C1 + s.C2, cpg = Ct / G;
-  const int n = blockIdx.x, sp = blockIdx.y;
+  const int n = swap ? blockIdx.y : blockIdx.x, sp = swap ? blockIdx.x : blockIdx.y;
   const Walk w(Ct, n, hw, sp, splits);
   const int V = w.V, lanes = w.lanes;
   float sum[2] = {0.f, 0.f}, sq[2] = {0.f, 0.f};
   Stream<T> xs = stream_of(s, w);
-  run_pipeline<GN_DEPTH>(
+  run_pipeline<DEPTH>(
       w.n_it, [&](int st) { pipe.issue(st, 0, xs.next()); },
       [&](int st) {
         float a[8];
@@ -585,7 +585,7 @@ int check_geom(int C1, int C2, int G) {
 int chunks_for(int n_img, int hw, int V) {
   int lanes = 256 / V;
   int max_chunks = (hw + GN_DEPTH * lanes - 1) / (GN_DEPTH * lanes);   // at least one full pipeline per block
-  static const int waves = getenv("ST_GN_CHUNK_W") ? atoi(getenv("ST_GN_CHUNK_W")) : 8;   // tuning knob
+  static const int waves = getenv("ST_GN_CHUNK_W") ? atoi(getenv("ST_GN_CHUNK_W")) : 4;   // tuning knob
   int want = (st_num_sms() * waves + n_img - 1) / n_img;
   int c = want < max_chunks ? want : max_chunks;
   if (c > 65535) c = 65535;
@@ -615,10 +615,20 @@ extern "C" __attribute__((visibility("default"))) int st_gn_stats(const void* x1
   ST_CHECK_ARG(splits >= 1 && splits <= 65535, "st_gn_stats: bad splits");
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
-    constexpr int smem = Pipe<T, 1, GN_DEPTH>::BYTES;
-    static bool smem_ok = false;
-    if (!smem_ok) { if (!allow_smem(gn_stats_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
-    gn_stats_kernel<T><<<dim3(n_img, splits), 256, smem, (cudaStream_t)stream>>>(s, hw, G, splits, part);
+    static const int deep = getenv("ST_GN_STATS_DEPTH") ? atoi(getenv("ST_GN_STATS_DEPTH")) : 8;     // tuning knobs
+    static const int swap = getenv("ST_GN_STATS_SWAP") ? atoi(getenv("ST_GN_STATS_SWAP")) : 0;
+    const dim3 grid = swap ? dim3(splits, n_img) : dim3(n_img, splits);
+    if (deep > 8) {
+      constexpr int smem = Pipe<T, 1, 16>::BYTES;
+      static bool smem_ok = false;
+      if (!smem_ok) { if (!allow_smem(gn_stats_kernel<T, 16>, smem)) return ST_ERR_CUDA; smem_ok = true; }
+      gn_stats_kernel<T, 16><<<grid, 256, smem, (cudaStream_t)stream>>>(s, hw, G, splits, part, swap);
+    } else {
+      constexpr int smem = Pipe<T, 1, GN_DEPTH>::BYTES;
+      static bool smem_ok = false;
+      if (!smem_ok) { if (!allow_smem(gn_stats_kernel<T, GN_DEPTH>, smem)) return ST_ERR_CUDA; smem_ok = true; }
+      gn_stats_kernel<T, GN_DEPTH><<<grid, 256, smem, (cudaStream_t)stream>>>(s, hw, G, splits, part, swap);
+    }
   });
   ST_CHECK_LAUNCH("st_gn_stats");
   return 0;
