@@ -109,10 +109,13 @@ int st_gn_finalize(const float* part, int n_img, int splits, int G, int64_t coun
 /* y = dropout( act( gamma*(x-mean)*rstd + beta ) );  act: 0 none, 1 SiLU.
  * dropout: keep-mask multiplies by 1/(1-p); `mask` (same dtype/shape as y, already scaled) is used
  * when non-NULL, else if p > 0 a counter-based RNG keyed by (seed, element index).  `keepbits` (optional,
- * n_img*hw*C/8 bytes) receives the drawn keep flags, one bit per element, for the backward kernels. */
+ * n_img*hw*C/8 bytes) receives the drawn keep flags, one bit per element, for the backward kernels.
+ * `part` != NULL (with `splits`, `count` = hw*(C/G), `eps`): the statistics are finalised inside the kernel from the
+ * partial sums of st_gn_stats - no st_gn_finalize launch - and mean / rstd are OUTPUTS (kept for the backward). */
 int st_gn_apply(const void* x1, const void* x2, int dtype, int n_img, int hw, int C1, int C2, int G,
-                const float* gamma, const float* beta, const float* mean, const float* rstd, int act,
-                float p_drop, uint64_t seed, const void* mask, uint8_t* keepbits, void* y, void* stream);
+                const float* gamma, const float* beta, float* mean, float* rstd, int act,
+                float p_drop, uint64_t seed, const void* mask, uint8_t* keepbits, void* y, const float* part,
+                int splits, int64_t count, float eps, void* stream);
 /* backward, pass 1: per (image, pixel split, channel) sums  red[n_img][splits][C][2] = (sum dz, sum dz*xhat) where
  * dz = dy * dropout_mask * act'(.)  */
 int st_gn_bwd_reduce(const void* x1, const void* x2, const void* dy, int dtype, int n_img, int hw, int C1,
@@ -123,12 +126,14 @@ int st_gn_bwd_reduce(const void* x1, const void* x2, const void* dy, int dtype, 
 int st_gn_bwd_params(const float* red, int rows, int C, float* dgamma, float* dbeta, void* stream);
 /* backward, pass 2: dx = rstd*(gamma*dz - mean_g(gamma*dz) - xhat*mean_g(gamma*dz*xhat))
  *                        + extra_scale*extra,  written split over dx1 [..][C1] and dx2 [..][C2];
- * accum1/accum2 != 0 adds into the destination instead of overwriting. */
+ * accum1/accum2 != 0 adds into the destination instead of overwriting.
+ * `dgamma`/`dbeta` != NULL: the kernel also accumulates the parameter gradients from `red` (st_gn_bwd_params is
+ * then not needed). */
 int st_gn_bwd_apply(const void* x1, const void* x2, const void* dy, int dtype, int n_img, int hw, int C1,
                     int C2, int G, const float* gamma, const float* beta, const float* mean,
                     const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
                     const uint8_t* keepbits, int splits, const float* red, const void* extra, float extra_scale, void* dx1, int accum1,
-                    void* dx2, int accum2, int chunks, float* csum, void* stream);
+                    void* dx2, int accum2, int chunks, float* csum, float* dgamma, float* dbeta, void* stream);
 /* pixel chunks per image the backward-apply launch uses by default (grid.x); with `csum` != NULL the caller passes
  * this count explicitly and receives csum[n_img][chunks][C]: the column sums of the gradient contribution the
  * kernel produced (extra included, accumulated destination excluded). */

@@ -38,12 +38,12 @@ SIGNATURES = {
     'st_gn_stats': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p],
     'st_gn_finalize': [c_p, c_int, c_int, c_int, c_i64, c_f, c_p, c_p, c_p],
     'st_gn_apply': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f, c_u64, c_p,
-                    c_p, c_p, c_p],
+                    c_p, c_p, c_p, c_int, c_i64, c_f, c_p],
     'st_gn_bwd_reduce': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f,
                          c_u64, c_p, c_p, c_int, c_p, c_p],
     'st_gn_bwd_params': [c_p, c_int, c_int, c_p, c_p, c_p],
     'st_gn_bwd_apply': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f,
-                        c_u64, c_p, c_p, c_int, c_p, c_p, c_f, c_p, c_int, c_p, c_int, c_int, c_p, c_p],
+                        c_u64, c_p, c_p, c_int, c_p, c_p, c_f, c_p, c_int, c_p, c_int, c_int, c_p, c_p, c_p, c_p],
     'st_gn_chunks': [c_int, c_int, c_int],
     'st_cast': [c_p, c_int, c_p, c_int, c_i64, c_p],
     'st_axpby': [c_p, c_p, c_p, c_int, c_f, c_f, c_i64, c_p],

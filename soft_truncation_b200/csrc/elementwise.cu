@@ -102,6 +102,70 @@ __global__ void down2_kernel(const T* x1, const T* x2, T* y, long long total_qua
   }
 }
 
+// 8-channel (16-byte bf16 / 32-byte fp32) versions with 32-bit index arithmetic: one thread per INPUT vector writes
+// its four copies (up) / one thread per OUTPUT vector sums its four inputs (down).
+__device__ __forceinline__ void ld8(const float* p, float v[8]) { load4(p, v); load4(p + 4, v + 4); }
+__device__ __forceinline__ void ld8(const bf16* p, float v[8]) {
+  uint4 t = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+__device__ __forceinline__ void st8(float* p, const float v[8]) { store4(p, v); store4(p + 4, v + 4); }
+__device__ __forceinline__ void st8(bf16* p, const float v[8]) {
+  uint4 t;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) up2v_kernel(const T* __restrict__ x1, const T* __restrict__ x2, T* __restrict__ y,
+                                                   unsigned total, int H, int W, int C1, int C2, float scale) {
+  const unsigned V = (unsigned)(C1 + C2) / 8;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {   // INPUT vectors
+    const unsigned v = i % V, row = i / V;
+    const unsigned ix = row % (unsigned)W, t = row / (unsigned)W;
+    const unsigned iy = t % (unsigned)H, n = t / (unsigned)H;
+    const int c0 = (int)v * 8;
+    float val[8];
+    ld8(c0 < C1 ? x1 + (size_t)row * C1 + c0 : x2 + (size_t)row * C2 + (c0 - C1), val);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) val[k] *= scale;
+    const size_t orow = ((size_t)n * 2 * H + 2 * iy) * (2 * W) + 2 * ix;
+    T* o = y + (orow * V + v) * 8;
+    const size_t dn = (size_t)2 * W * V * 8;
+    st8(o, val);
+    st8(o + V * 8, val);
+    st8(o + dn, val);
+    st8(o + dn + V * 8, val);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) down2v_kernel(const T* __restrict__ x1, const T* __restrict__ x2, T* __restrict__ y,
+                                                     unsigned total, int H, int W, int C1, int C2, float scale) {
+  const unsigned V = (unsigned)(C1 + C2) / 8;      // H, W are INPUT sizes
+  const unsigned Ho = H / 2, Wo = W / 2;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {   // OUTPUT vectors
+    const unsigned v = i % V, row = i / V;
+    const unsigned ox = row % Wo, t = row / Wo;
+    const unsigned oy = t % Ho, n = t / Ho;
+    const int c0 = (int)v * 8;
+    const size_t irow = ((size_t)n * H + 2 * oy) * W + 2 * ox;
+    const T* src;
+    size_t ld;
+    if (c0 < C1) { src = x1 + irow * C1 + c0; ld = C1; } else { src = x2 + irow * C2 + (c0 - C1); ld = C2; }
+    float a[8], b[8], c[8], d[8];
+    ld8(src, a);
+    ld8(src + ld, b);
+    ld8(src + (size_t)W * ld, c);
+    ld8(src + (size_t)W * ld + ld, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = (((a[k] + b[k]) + c[k]) + d[k]) * scale;     // same order as the 4-wide kernel
+    st8(y + (size_t)i * 8, a);
+  }
+}
+
 // ---------------------------------------------------------------- column sums
 // grid (groups, ceil(C/128)), block 1024 = 32 row-lanes x 32 quad-lanes
 template <typename T>
@@ -199,6 +263,23 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__
     int p = (int)(t % HW);
     long long n = t / HW;
     y[i] = from_f<T>(c < C ? alpha * x[(n * C + c) * HW + p] + beta : 0.f);
+  }
+}
+// 8 output channels (one 16-byte bf16 / 32-byte fp32 store) per thread, 32-bit index arithmetic
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_nhwc8_kernel(const float* __restrict__ x, T* __restrict__ y, unsigned total, int C,
+                                                            int HW, int Cpad, float alpha, float beta) {
+  const unsigned V = (unsigned)Cpad / 8;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned v = i % V, t = i / V;
+    const unsigned p = t % (unsigned)HW, n = t / (unsigned)HW;
+    float val[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = (int)v * 8 + k;
+      val[k] = c < C ? fmaf(alpha, x[((size_t)n * C + c) * HW + p], beta) : 0.f;
+    }
+    st8(y + (size_t)i * 8, val);
   }
 }
 template <typename T>
@@ -367,21 +448,53 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
 __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                        float* __restrict__ v, float* __restrict__ ema,
                                                        const uint8_t* __restrict__ ema_mask, bf16* __restrict__ p16,
-                                                       long long n, const float* gnorm_sq, float clip, float lr, float b1,
+                                                       long long n, long long n4, const float* gnorm_sq, float clip, float lr, float b1,
                                                        float b2, float eps, float wd, float bc1, float bc2, float decay) {
   float coef = 1.f;
   if (gnorm_sq && clip >= 0.f) coef = fminf(1.f, clip / (sqrtf(*gnorm_sq) + 1e-6f));
   const float step_size = lr / bc1, sq_bc2 = sqrtf(bc2);
-  GRID_STRIDE(i, n) {
-    float pi = p[i];
-    float gi = g[i] * coef;
+  auto update = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= coef;
     if (wd != 0.f) gi = fmaf(wd, pi, gi);
-    float mi = fmaf(b1, m[i], (1.f - b1) * gi);
-    float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    mi = fmaf(b1, mi, (1.f - b1) * gi);
+    vi = fmaf(b2, vi, (1.f - b2) * gi * gi);
+    const float denom = sqrtf(vi) / sq_bc2 + eps;
+    pi -= step_size * (mi / denom);
+  };
+  // four elements per thread (all streams 16-byte aligned: checked by the caller through n4)
+  GRID_STRIDE(i4, n4) {
+    float4 P = reinterpret_cast<float4*>(p)[i4], M = reinterpret_cast<float4*>(m)[i4], V = reinterpret_cast<float4*>(v)[i4];
+    const float4 G = reinterpret_cast<const float4*>(g)[i4];
+    update(P.x, G.x, M.x, V.x);
+    update(P.y, G.y, M.y, V.y);
+    update(P.z, G.z, M.z, V.z);
+    update(P.w, G.w, M.w, V.w);
+    reinterpret_cast<float4*>(m)[i4] = M;
+    reinterpret_cast<float4*>(v)[i4] = V;
+    reinterpret_cast<float4*>(p)[i4] = P;
+    if (ema) {
+      float4 E = reinterpret_cast<float4*>(ema)[i4];
+      uchar4 k = make_uchar4(1, 1, 1, 1);
+      if (ema_mask) k = reinterpret_cast<const uchar4*>(ema_mask)[i4];
+      if (k.x) E.x = E.x - (1.f - decay) * (E.x - P.x);
+      if (k.y) E.y = E.y - (1.f - decay) * (E.y - P.y);
+      if (k.z) E.z = E.z - (1.f - decay) * (E.z - P.z);
+      if (k.w) E.w = E.w - (1.f - decay) * (E.w - P.w);
+      reinterpret_cast<float4*>(ema)[i4] = E;
+    }
+    if (p16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(P.x, P.y), hi = __floats2bfloat162_rn(P.z, P.w);
+      uint2 t;
+      t.x = *reinterpret_cast<uint32_t*>(&lo);
+      t.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(p16)[i4] = t;
+    }
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    update(pi, g[i], mi, vi);
     m[i] = mi;
     v[i] = vi;
-    float denom = sqrtf(vi) / sq_bc2 + eps;
-    pi -= step_size * (mi / denom);
     p[i] = pi;
     if (ema && (!ema_mask || ema_mask[i])) {
       float e = ema[i];
@@ -473,7 +586,15 @@ extern "C" __attribute__((visibility("default"))) int st_resample2x(const void* 
   ST_CHECK_ARG(C1 % 4 == 0 && C2 % 4 == 0, "st_resample2x: channels must be multiples of 4");
   ST_CHECK_ARG(dir == 1 || (dir == -1 && H % 2 == 0 && W % 2 == 0), "st_resample2x: bad dir/size");
   int Q = (C1 + C2) / 4;
-  if (dir == 1) {
+  const bool vec8 = C1 % 8 == 0 && C2 % 8 == 0 && (long long)n_img * H * W * ((C1 + C2) / 8) < (1LL << 31) &&
+                    ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(y)) & 31) == 0;
+  if (vec8 && dir == 1) {
+    const unsigned total = (unsigned)((long long)n_img * H * W * ((C1 + C2) / 8));
+    ST_DISPATCH_DTYPE(dtype, T, (up2v_kernel<T><<<grid1d(total, 256), 256, 0, S>>>((const T*)x1, (const T*)x2, (T*)y, total, H, W, C1, C2, scale)));
+  } else if (vec8) {
+    const unsigned total = (unsigned)((long long)n_img * (H / 2) * (W / 2) * ((C1 + C2) / 8));
+    ST_DISPATCH_DTYPE(dtype, T, (down2v_kernel<T><<<grid1d(total, 256), 256, 0, S>>>((const T*)x1, (const T*)x2, (T*)y, total, H, W, C1, C2, scale)));
+  } else if (dir == 1) {
     long long total = (long long)n_img * (2 * H) * (2 * W) * Q;
     ST_DISPATCH_DTYPE(dtype, T, (up2_kernel<T><<<grid1d(total, 256 * 2), 256, 0, S>>>((const T*)x1, (const T*)x2, (T*)y, total, H, W, C1, C2, scale)));
   } else {
@@ -521,6 +642,10 @@ extern "C" __attribute__((visibility("default"))) int st_nchw_to_nhwc(const floa
                                float beta, void* stream) {
   ST_CHECK_ARG(Cpad >= C, "st_nchw_to_nhwc: Cpad < C");
   long long total = (long long)n_img * Cpad * H * W;
+  if (Cpad % 8 == 0 && total / 8 < (1LL << 31) && (reinterpret_cast<uintptr_t>(y) & 31) == 0) {
+    const unsigned tv = (unsigned)(total / 8);
+    ST_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc8_kernel<T><<<grid1d(tv, 256), 256, 0, S>>>(x, (T*)y, tv, C, H * W, Cpad, alpha, beta)));
+  } else
   ST_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid1d(total, 256 * 4), 256, 0, S>>>(x, (T*)y, total, C, H * W, Cpad, alpha, beta)));
   ST_CHECK_LAUNCH("st_nchw_to_nhwc");
   return 0;
@@ -575,8 +700,11 @@ extern "C" __attribute__((visibility("default"))) int st_sumsq(const float* x, i
 extern "C" __attribute__((visibility("default"))) int st_adam_ema(float* p, const float* grad, float* m, float* v, float* ema, const uint8_t* ema_mask, void* p16,
                            int64_t n, const float* gnorm_sq, float clip, float lr, float b1, float b2, float eps, float wd,
                            float bc1, float bc2, float ema_decay, void* stream) {
-  adam_ema_kernel<<<grid1d(n, 256 * 4), 256, 0, S>>>(p, grad, m, v, ema, ema_mask, (bf16*)p16, n, gnorm_sq, clip, lr, b1, b2,
-                                                     eps, wd, bc1, bc2, ema_decay);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(ema) | reinterpret_cast<uintptr_t>(p16);
+  const long long n4 = ((al & 15) == 0 && (reinterpret_cast<uintptr_t>(ema_mask) & 3) == 0) ? n / 4 : 0;
+  adam_ema_kernel<<<grid1d(n4 > 0 ? n4 : n, 256 * 2), 256, 0, S>>>(p, grad, m, v, ema, ema_mask, (bf16*)p16, n, n4, gnorm_sq, clip, lr,
+                                                                    b1, b2, eps, wd, bc1, bc2, ema_decay);
   ST_CHECK_LAUNCH("st_adam_ema");
   return 0;
 }

@@ -1185,6 +1185,11 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   for (p.logH = 0; (1 << p.logH) < a->H; ++p.logH) {}
   int BN = (N >= 256 && N % 256 == 0) ? 256 : (N > 64 ? 128 : 64);
   if (BN == 256 && env_int("ST_TC_BN", 256) == 128) BN = 128;
+  // too few 128x256 tiles to occupy the SMs (4x4 level of the U-Net): halve the tile instead of idling half the GPU
+  if (BN == 256 && !wgrad && env_int("ST_TC_SMALL", 1) == 1) {
+    const long long tiles256 = (long long)((M + BM - 1) / BM) * (N / 256) * p.batch * p.split_k;
+    if (tiles256 * 10 < (long long)st_num_sms() * 7) BN = 128;
+  }
   // 256 x 128 tiles (two accumulators sharing the B tile) when N fits 128-wide tiles and M is large
   int MH = 1;
   if (BN == 128 && env_int("ST_TC_MH", 2) == 2) {

@@ -276,16 +276,44 @@ template <typename T, bool ACT, int DROP>
 __global__ void __launch_bounds__(256, 4) gn_apply_kernel(Src2<T> s, int hw, int G, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, float p_drop, uint64_t seed,
-                                                          const T* mask, uint8_t* keepbits, T* y) {
+                                                          const T* mask, uint8_t* keepbits, T* y,
+                                                          const float* __restrict__ part, int splits, double inv_count,
+                                                          float eps, float* mean_out, float* rstd_out) {
   extern __shared__ __align__(16) uint8_t gsm[];
   using P = Pipe<T, 1, GN_DEPTH>;
   const P pipe(gsm);
   const int Ct = s.C1 + s.C2, cpg = Ct / G;
   const int n = blockIdx.y;
   const Walk w(Ct, n, hw, blockIdx.x, gridDim.x);
-  if (w.lane >= w.lanes) return;
   ChanConst k;
-  load_consts(k, n, w.c0, G, cpg, gamma, beta, mean, rstd);
+  if (part) {
+    // statistics straight from the partial sums of st_gn_stats (same arithmetic as gn_finalize_kernel); the first
+    // chunk of every image publishes mean / rstd for the backward passes
+    __shared__ float s_mean[64], s_rstd[64];
+    if (threadIdx.x < G) {
+      double a = 0., b = 0.;
+      for (int sp = 0; sp < splits; ++sp) {
+        const float* o = part + (((long long)n * splits + sp) * G + threadIdx.x) * 2;
+        a += (double)o[0];
+        b += (double)o[1];
+      }
+      const double mu = a * inv_count;
+      double var = b * inv_count - mu * mu;
+      if (var < 0.) var = 0.;
+      s_mean[threadIdx.x] = (float)mu;
+      s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+      if (blockIdx.x == 0) {
+        mean_out[n * G + threadIdx.x] = s_mean[threadIdx.x];
+        rstd_out[n * G + threadIdx.x] = s_rstd[threadIdx.x];
+      }
+    }
+    __syncthreads();
+    if (w.lane >= w.lanes) return;
+    load_consts(k, 0, w.c0, G, cpg, gamma, beta, s_mean, s_rstd);
+  } else {
+    if (w.lane >= w.lanes) return;
+    load_consts(k, n, w.c0, G, cpg, gamma, beta, mean, rstd);
+  }
   // y = x*A + B with A = rstd*gamma, B = beta - mean*rstd*gamma
   float A[8], Bc[8];
 #pragma unroll
@@ -460,11 +488,39 @@ __global__ void __launch_bounds__(256, OCC) gn_bwd_apply_kernel(Src2<T> s, const
                                                            float p_drop, uint64_t seed, const T* mask,
                                                            const uint8_t* __restrict__ keepbits,
                                                            const float* __restrict__ red, const T* extra, float extra_scale,
-                                                           T* dx1, int accum1, T* dx2, int accum2, float* csum) {
+                                                           T* dx1, int accum1, T* dx2, int accum2, float* csum,
+                                                           float* dgamma, float* dbeta) {
   extern __shared__ __align__(16) uint8_t gsm[];
   const int Ct = s.C1 + s.C2, cpg = Ct / G;
   const int n = blockIdx.y;
   __shared__ float sh1[64], sh2[64];
+  if (dgamma && blockIdx.x == 0) {
+    // parameter gradients (what st_gn_bwd_params computes), spread over the first chunk's blocks: block n reduces
+    // channels [16n, 16n+16) over all rows of `red` with 16 row lanes, fixed order
+    __shared__ float sa[256], sb[256];
+    const int rows = gridDim.y * splits;
+    for (int cb = blockIdx.y; cb * 16 < Ct; cb += gridDim.y) {
+      const int c = cb * 16 + threadIdx.x % 16, rl = threadIdx.x / 16;
+      float a = 0.f, b = 0.f;
+      if (c < Ct) {
+        for (int r = rl; r < rows; r += 16) {
+          const float2 v = *reinterpret_cast<const float2*>(red + ((long long)r * Ct + c) * 2);
+          a += v.x;
+          b += v.y;
+        }
+      }
+      sa[threadIdx.x] = a;
+      sb[threadIdx.x] = b;
+      __syncthreads();
+      if (rl == 0 && c < Ct) {
+        double ta = 0., tb = 0.;
+        for (int l = 0; l < 16; ++l) { ta += (double)sa[l * 16 + threadIdx.x]; tb += (double)sb[l * 16 + threadIdx.x]; }
+        dbeta[c] += (float)ta;
+        dgamma[c] += (float)tb;
+      }
+      __syncthreads();
+    }
+  }
   if (threadIdx.x < G) {
     const int g = threadIdx.x;
     double a = 0., b = 0.;
@@ -644,10 +700,12 @@ extern "C" __attribute__((visibility("default"))) int st_gn_finalize(const float
 }
 
 extern "C" __attribute__((visibility("default"))) int st_gn_apply(const void* x1, const void* x2, int dtype, int n_img, int hw, int C1, int C2, int G,
-                           const float* gamma, const float* beta, const float* mean, const float* rstd, int act,
-                           float p_drop, uint64_t seed, const void* mask, uint8_t* keepbits, void* y, void* stream) {
+                           const float* gamma, const float* beta, float* mean, float* rstd, int act,
+                           float p_drop, uint64_t seed, const void* mask, uint8_t* keepbits, void* y, const float* part, int splits,
+                           int64_t count, float eps, void* stream) {
   if (int e = check_geom(C1, C2, G)) return e;
   ST_CHECK_ARG(n_img <= 65535, "st_gn_apply: more than 65535 images");
+  ST_CHECK_ARG(!part || (splits >= 1 && count > 0 && mean && rstd), "st_gn_apply: partial sums need splits, count and mean/rstd outputs");
   const int V = (C1 + C2) / 8;
   const int drop = mask ? DROP_SLOW : (p_drop > 0.f ? DROP_FAST : DROP_NONE);
   int rc = 0;
@@ -660,7 +718,8 @@ extern "C" __attribute__((visibility("default"))) int st_gn_apply(const void* x1
       static bool smem_ok = false;
       if (!smem_ok) { if (!allow_smem(gn_apply_kernel<T, ACT, DROP>, smem)) { rc = ST_ERR_CUDA; return; } smem_ok = true; }
       gn_apply_kernel<T, ACT, DROP><<<dim3(chunks_for(n_img, hw, V), n_img), 256, smem, (cudaStream_t)stream>>>(
-          s, hw, G, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, (T*)y);
+          s, hw, G, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, (T*)y, part, splits,
+          part ? 1.0 / (double)count : 0.0, eps, mean, rstd);
     });
   });
   if (rc) return rc;
@@ -702,13 +761,14 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_apply(const void
                                int C2, int G, const float* gamma, const float* beta, const float* mean,
                                const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
                                const uint8_t* keepbits, int splits, const float* red, const void* extra, float extra_scale, void* dx1,
-                               int accum1, void* dx2, int accum2, int chunks, float* csum, void* stream) {
+                               int accum1, void* dx2, int accum2, int chunks, float* csum, float* dgamma, float* dbeta, void* stream) {
   if (int e = check_geom(C1, C2, G)) return e;
   ST_CHECK_ARG(n_img <= 65535, "st_gn_bwd_apply: more than 65535 images");
   const int V = (C1 + C2) / 8;
   ST_CHECK_ARG(!csum || chunks > 0, "st_gn_bwd_apply: csum needs an explicit chunk count");
   if (chunks <= 0) chunks = chunks_for(n_img, hw, V);
   ST_CHECK_ARG(chunks <= 65535, "st_gn_bwd_apply: too many chunks");
+  ST_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "st_gn_bwd_apply: dgamma and dbeta go together");
   const int drop = mask ? DROP_SLOW : (p_drop > 0.f ? (keepbits ? DROP_FAST : DROP_SLOW) : DROP_NONE);
   int rc = 0;
   ST_DISPATCH_DTYPE(dtype, T, {
@@ -724,7 +784,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_apply(const void
         if (!smem_ok) { if (!allow_smem(gn_bwd_apply_kernel<T, ACT, DROP, CSUM, OCC>, smem)) { rc = ST_ERR_CUDA; return; } smem_ok = true; }
         gn_bwd_apply_kernel<T, ACT, DROP, CSUM, OCC><<<dim3(chunks, n_img), 256, smem, (cudaStream_t)stream>>>(
             s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, red,
-            (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2, csum);
+            (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2, csum, dgamma, dbeta);
       };
       static const int csum_occ = getenv("ST_GN_CSUM_OCC") ? atoi(getenv("ST_GN_CSUM_OCC")) : 3;
       if (!csum) launch(std::false_type{}, std::integral_constant<int, 3>{});

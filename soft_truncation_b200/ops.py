@@ -60,7 +60,7 @@ def _split_k(M, N, K):
   """Split the reduction so that a weight-gradient GEMM (few output tiles, huge K) fills the GPU."""
   tiles = ((M + 127) // 128) * ((N + 127) // 128)
   want = max(1, (148 * 2) // max(tiles, 1))
-  return int(max(1, min(want, K // 2048 if K >= 4096 else 1, 64)))
+  return int(max(1, min(want, K // 1024 if K >= 2048 else 1, 64)))
 
 
 def conv_fwd(x, w, cout, kh=3, kw=3, x2=None, bias=None, rowbias=None, rowbias_ld=0, residual=None, alpha=1.0,
@@ -155,7 +155,20 @@ def _gn_splits(n_img, hw):
   return int(s)
 
 
-def gn_stats(x, x2, G, eps=1e-6):
+class GnStats:
+  """mean / rstd of one GroupNorm call: `t` is the (2, B, G) tensor; while `part` is set the statistics still live
+  as partial sums and the next gn_apply finalises them inside its own kernel (no st_gn_finalize launch)."""
+  __slots__ = ('t', 'part', 'splits', 'count', 'eps')
+
+  def __init__(self, t, part=None, splits=0, count=0, eps=0.):
+    self.t, self.part, self.splits, self.count, self.eps = t, part, splits, count, eps
+
+  def __getitem__(self, i):
+    assert self.part is None, 'statistics not finalised yet (run gn_apply first)'
+    return self.t[i]
+
+
+def gn_stats(x, x2, G, eps=1e-6, finalize=True):
   B, H, W, C1 = x.shape
   C2 = 0 if x2 is None else x2.shape[3]
   hw = H * W
@@ -163,8 +176,11 @@ def gn_stats(x, x2, G, eps=1e-6):
   part = torch.empty((B, splits, G, 2), dtype=torch.float32, device=x.device)
   stats = torch.empty((2, B, G), dtype=torch.float32, device=x.device)
   check(lib.st_gn_stats(ptr(x), ptr(x2), dt(x), B, hw, C1, C2, G, splits, ptr(part), stream()))
-  check(lib.st_gn_finalize(ptr(part), B, splits, G, hw * ((C1 + C2) // G), eps, ptr(stats[0]), ptr(stats[1]), stream()))
-  return stats
+  count = hw * ((C1 + C2) // G)
+  if not finalize:
+    return GnStats(stats, part, splits, count, eps)
+  check(lib.st_gn_finalize(ptr(part), B, splits, G, count, eps, ptr(stats[0]), ptr(stats[1]), stream()))
+  return GnStats(stats)
 
 
 def gn_apply(x, x2, G, gamma, beta, stats, act, p_drop=0., seed=0, mask=None, keepbits=None):
@@ -172,8 +188,14 @@ def gn_apply(x, x2, G, gamma, beta, stats, act, p_drop=0., seed=0, mask=None, ke
   B, H, W, C1 = x.shape
   C2 = 0 if x2 is None else x2.shape[3]
   y = torch.empty((B, H, W, C1 + C2), dtype=x.dtype, device=x.device)
-  check(lib.st_gn_apply(ptr(x), ptr(x2), dt(x), B, H * W, C1, C2, G, ptr(gamma), ptr(beta), ptr(stats[0]),
-                        ptr(stats[1]), int(act), float(p_drop), int(seed), ptr(mask), ptr(keepbits), ptr(y), stream()))
+  pending = isinstance(stats, GnStats) and stats.part is not None
+  t = stats.t if isinstance(stats, GnStats) else stats
+  check(lib.st_gn_apply(ptr(x), ptr(x2), dt(x), B, H * W, C1, C2, G, ptr(gamma), ptr(beta), ptr(t[0]),
+                        ptr(t[1]), int(act), float(p_drop), int(seed), ptr(mask), ptr(keepbits), ptr(y),
+                        ptr(stats.part) if pending else None, stats.splits if pending else 0,
+                        stats.count if pending else 0, float(stats.eps) if pending else 0., stream()))
+  if pending:
+    stats.part = None          # finalised by the kernel
   return y
 
 
@@ -189,7 +211,6 @@ def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0.,
   common = (ptr(x), ptr(x2), ptr(dy), dt(x), B, hw, C1, C2, G, ptr(gamma), ptr(beta), ptr(stats[0]), ptr(stats[1]),
             int(act), float(p_drop), int(seed), ptr(mask), ptr(keepbits), splits, ptr(red))
   check(lib.st_gn_bwd_reduce(*common, stream()))
-  check(lib.st_gn_bwd_params(ptr(red), B * splits, Ct, ptr(dgamma), ptr(dbeta), stream()))
   if dx1 is None:
     dx1 = torch.empty_like(x)
     accum1 = False
@@ -201,7 +222,7 @@ def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0.,
     chunks = lib.st_gn_chunks(B, hw, Ct)
     csum = torch.empty((B, chunks, Ct), dtype=torch.float32, device=x.device)
   check(lib.st_gn_bwd_apply(*common, ptr(extra), float(extra_scale), ptr(dx1), int(accum1), ptr(dx2), int(accum2),
-                            chunks, ptr(csum), stream()))
+                            chunks, ptr(csum), ptr(dgamma), ptr(dbeta), stream()))
   return (dx1, dx2, csum) if want_csum else (dx1, dx2)
 
 

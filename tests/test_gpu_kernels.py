@@ -256,6 +256,21 @@ def test_groupnorm_dropout_rng_is_consistent_between_fwd_and_bwd():
   assert (y2 != 0).ne(keep).any()
 
 
+def test_groupnorm_apply_finalises_statistics_in_kernel():
+  """gn_stats(finalize=False) + gn_apply == st_gn_finalize path, bit for bit (same arithmetic, one launch fewer)."""
+  B, H, W, C1, C2, G = 3, 8, 8, 64, 32, 24
+  x1, x2 = nhwc(rnd(B, C1, H, W, seed=1)).to(torch.bfloat16), nhwc(rnd(B, C2, H, W, seed=2)).to(torch.bfloat16)
+  gamma, beta = rnd(C1 + C2, seed=3), rnd(C1 + C2, seed=4)
+  st = ops.gn_stats(x1, x2, G)
+  y = ops.gn_apply(x1, x2, G, gamma, beta, st, 1)
+  lazy = ops.gn_stats(x1, x2, G, finalize=False)
+  assert lazy.part is not None
+  y2 = ops.gn_apply(x1, x2, G, gamma, beta, lazy, 1)
+  assert lazy.part is None
+  assert torch.equal(y, y2)
+  assert torch.equal(st[0], lazy[0]) and torch.equal(st[1], lazy[1])
+
+
 # ------------------------------------------------------------------------------------------------ small kernels
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_resample_colsum_softmax(dtype):
