@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "st_b200.h"
 
@@ -108,6 +109,30 @@ __device__ __forceinline__ void dropout4(uint64_t seed, uint64_t e4, float p, fl
   keep[1] = r.y >= thr ? inv : 0.f;
   keep[2] = r.z >= thr ? inv : 0.f;
   keep[3] = r.w >= thr ? inv : 0.f;
+}
+
+// Programmatic dependent launch: a kernel launched through st_launch may be scheduled while its predecessor in the
+// stream is still draining; it must execute pdl_wait() before its first global-memory access (the wait returns when
+// the predecessor grid has completed and its writes are visible).  pdl_trigger() lets the NEXT kernel be scheduled
+// once every CTA of this grid has started.  Both are no-ops for a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool st_pdl_on(cudaStream_t stream);      // ST_PDL=0 disables; never used while the stream is being captured
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t st_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = st_pdl_on(stream) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 static inline int st_num_sms() {

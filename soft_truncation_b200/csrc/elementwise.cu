@@ -172,6 +172,8 @@ template <typename T>
 __global__ void __launch_bounds__(1024) colsum_kernel(const T* __restrict__ x, long long rows_per_group, int C, long long ld,
                                                       float scale, float* out, int accumulate) {
   constexpr int RL = 32;
+  pdl_wait();
+  pdl_trigger();
   const long long g = blockIdx.x;
   const int c0 = (blockIdx.y * 32 + threadIdx.x % 32) * 4;
   const int rl = threadIdx.x / 32;
@@ -610,7 +612,7 @@ extern "C" __attribute__((visibility("default"))) int st_colsum(const void* x, i
   ST_CHECK_ARG(C % 4 == 0 && ld % 4 == 0 && ld >= C, "st_colsum: C and ld must be multiples of 4, ld >= C");
   ST_CHECK_ARG(groups >= 1 && groups < (1LL << 31), "st_colsum: bad groups");
   dim3 grid((unsigned)groups, (C + 127) / 128);
-  ST_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<grid, 1024, 0, S>>>((const T*)x, rows_per_group, C, ld, scale, out, accumulate)));
+  ST_DISPATCH_DTYPE(dtype, T, (st_launch(colsum_kernel<T>, grid, dim3(1024), 0, S, (const T*)x, rows_per_group, C, ld, scale, out, accumulate)));
   ST_CHECK_LAUNCH("st_colsum");
   return 0;
 }

@@ -479,6 +479,11 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
   const int total = p.batch * split * p.n_tiles * m_groups;
   const int kper = (p.nk + split - 1) / split;
 
+  if (threadIdx.x == 32) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB0) : "memory");
+    if (p.epi_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full0 + 8 * s, 2);          // one arrive.expect_tx from each of the two producer warps
@@ -500,6 +505,9 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
   if (cs > 1) cluster_sync_all();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation) may overlap the tail of the previous kernel in the stream
+  pdl_wait();
+  pdl_trigger();
 
   // decode a work item
   // Tile order: CTAs that run at the same time should share operand tiles in L2.  n fastest (all N tiles of one block
@@ -845,7 +853,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
         }
         ++tl;
       }
-      if (leader) bulk_wait_all();                        // global writes complete before the CTA retires
+      if (leader) bulk_wait_read();                       // the boxes must outlive the last store's reads of them
     } else
     for (int st = cluster_id; st < total; st += n_clusters) {
       int m0, n0, b, kt0, nkt;
@@ -1129,11 +1137,13 @@ int launch2(const CUtensorMap* maps, TcParams& p, int total_super, cudaStream_t 
   cfg.blockDim = dim3(NUM_THREADS2);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (max_clusters[cs] == 0) {
@@ -1145,6 +1155,7 @@ int launch2(const CUtensorMap* maps, TcParams& p, int total_super, cudaStream_t 
   }
   int clusters = total_super < max_clusters[cs] ? total_super : max_clusters[cs];
   cfg.gridDim = dim3(clusters * cs);
+  cfg.numAttrs = (cs == 1 && st_pdl_on(stream)) ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   if (e != cudaSuccess) { st_set_error("st_gemm(tc2): launch failed: %s", cudaGetErrorString(e)); return ST_ERR_CUDA; }
   return 0;

@@ -208,18 +208,20 @@ __device__ __forceinline__ Stream<T> stream_of(const T* t, int Ct, const Walk& w
 
 // ---------------------------------------------------------------- stats
 // grid (n_img, splits): part[n][split][G][2] = (sum, sum of squares) over the split's pixels
-template <typename T, int DEPTH>
-__global__ void __launch_bounds__(256, DEPTH > 8 ? 3 : 4) gn_stats_kernel(Src2<T> s, int hw, int G, int splits, float* part, int swap) {
+template <typename T>
+__global__ void __launch_bounds__(256, 4) gn_stats_kernel(Src2<T> s, int hw, int G, int splits, float* part) {
   extern __shared__ __align__(16) uint8_t gsm[];
-  using P = Pipe<T, 1, DEPTH>;
+  pdl_wait();
+  pdl_trigger();
+  using P = Pipe<T, 1, GN_DEPTH>;
   const P pipe(gsm);
   const int Ct = s.C1 + s.C2, cpg = Ct / G;
-  const int n = swap ? blockIdx.y : blockIdx.x, sp = swap ? blockIdx.x : blockIdx.y;
+  const int n = blockIdx.x, sp = blockIdx.y;
   const Walk w(Ct, n, hw, sp, splits);
   const int V = w.V, lanes = w.lanes;
   float sum[2] = {0.f, 0.f}, sq[2] = {0.f, 0.f};
   Stream<T> xs = stream_of(s, w);
-  run_pipeline<DEPTH>(
+  run_pipeline<GN_DEPTH>(
       w.n_it, [&](int st) { pipe.issue(st, 0, xs.next()); },
       [&](int st) {
         float a[8];
@@ -280,6 +282,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(Src2<T> s, int hw, int
                                                           const float* __restrict__ part, int splits, double inv_count,
                                                           float eps, float* mean_out, float* rstd_out) {
   extern __shared__ __align__(16) uint8_t gsm[];
+  pdl_wait();
+  pdl_trigger();
   using P = Pipe<T, 1, GN_DEPTH>;
   const P pipe(gsm);
   const int Ct = s.C1 + s.C2, cpg = Ct / G;
@@ -399,6 +403,8 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(Src2<T> s, const 
                                                             float p_drop, uint64_t seed, const T* mask,
                                                             const uint8_t* __restrict__ keepbits, float* red) {
   extern __shared__ __align__(16) uint8_t gsm[];
+  pdl_wait();
+  pdl_trigger();
   const int Ct = s.C1 + s.C2, cpg = Ct / G;
   const int n = blockIdx.x, sp = blockIdx.y;
   const Walk w(Ct, n, hw, sp, splits);
@@ -481,8 +487,8 @@ __global__ void __launch_bounds__(512) gn_bwd_params_kernel(const float* __restr
 
 // ---------------------------------------------------------------- backward pass 2
 // grid (chunks, n_img)
-template <typename T, bool ACT, int DROP, bool CSUM, int OCC>
-__global__ void __launch_bounds__(256, OCC) gn_bwd_apply_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
+template <typename T, bool ACT, int DROP, bool CSUM>
+__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            float p_drop, uint64_t seed, const T* mask,
@@ -491,6 +497,8 @@ __global__ void __launch_bounds__(256, OCC) gn_bwd_apply_kernel(Src2<T> s, const
                                                            T* dx1, int accum1, T* dx2, int accum2, float* csum,
                                                            float* dgamma, float* dbeta) {
   extern __shared__ __align__(16) uint8_t gsm[];
+  pdl_wait();
+  pdl_trigger();
   const int Ct = s.C1 + s.C2, cpg = Ct / G;
   const int n = blockIdx.y;
   __shared__ float sh1[64], sh2[64];
@@ -671,20 +679,10 @@ extern "C" __attribute__((visibility("default"))) int st_gn_stats(const void* x1
   ST_CHECK_ARG(splits >= 1 && splits <= 65535, "st_gn_stats: bad splits");
   ST_DISPATCH_DTYPE(dtype, T, {
     Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
-    static const int deep = getenv("ST_GN_STATS_DEPTH") ? atoi(getenv("ST_GN_STATS_DEPTH")) : 8;     // tuning knobs
-    static const int swap = getenv("ST_GN_STATS_SWAP") ? atoi(getenv("ST_GN_STATS_SWAP")) : 0;
-    const dim3 grid = swap ? dim3(splits, n_img) : dim3(n_img, splits);
-    if (deep > 8) {
-      constexpr int smem = Pipe<T, 1, 16>::BYTES;
-      static bool smem_ok = false;
-      if (!smem_ok) { if (!allow_smem(gn_stats_kernel<T, 16>, smem)) return ST_ERR_CUDA; smem_ok = true; }
-      gn_stats_kernel<T, 16><<<grid, 256, smem, (cudaStream_t)stream>>>(s, hw, G, splits, part, swap);
-    } else {
-      constexpr int smem = Pipe<T, 1, GN_DEPTH>::BYTES;
-      static bool smem_ok = false;
-      if (!smem_ok) { if (!allow_smem(gn_stats_kernel<T, GN_DEPTH>, smem)) return ST_ERR_CUDA; smem_ok = true; }
-      gn_stats_kernel<T, GN_DEPTH><<<grid, 256, smem, (cudaStream_t)stream>>>(s, hw, G, splits, part, swap);
-    }
+    constexpr int smem = Pipe<T, 1, GN_DEPTH>::BYTES;
+    static bool smem_ok = false;
+    if (!smem_ok) { if (!allow_smem(gn_stats_kernel<T>, smem)) return ST_ERR_CUDA; smem_ok = true; }
+    st_launch(gn_stats_kernel<T>, dim3(n_img, splits), dim3(256), smem, (cudaStream_t)stream, s, hw, G, splits, part);
   });
   ST_CHECK_LAUNCH("st_gn_stats");
   return 0;
@@ -717,7 +715,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_apply(const void* x1
       constexpr int DROP = decltype(D)::value;
       static bool smem_ok = false;
       if (!smem_ok) { if (!allow_smem(gn_apply_kernel<T, ACT, DROP>, smem)) { rc = ST_ERR_CUDA; return; } smem_ok = true; }
-      gn_apply_kernel<T, ACT, DROP><<<dim3(chunks_for(n_img, hw, V), n_img), 256, smem, (cudaStream_t)stream>>>(
+      st_launch(gn_apply_kernel<T, ACT, DROP>, dim3(chunks_for(n_img, hw, V), n_img), dim3(256), smem, (cudaStream_t)stream,
           s, hw, G, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, (T*)y, part, splits,
           part ? 1.0 / (double)count : 0.0, eps, mean, rstd);
     });
@@ -742,7 +740,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_reduce(const voi
       constexpr int DROP = decltype(D)::value;
       static bool smem_ok = false;
       if (!smem_ok) { if (!allow_smem(gn_bwd_reduce_kernel<T, ACT, DROP>, smem)) { rc = ST_ERR_CUDA; return; } smem_ok = true; }
-      gn_bwd_reduce_kernel<T, ACT, DROP><<<dim3(n_img, splits), 256, smem, (cudaStream_t)stream>>>(
+      st_launch(gn_bwd_reduce_kernel<T, ACT, DROP>, dim3(n_img, splits), dim3(256), smem, (cudaStream_t)stream,
           s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, red);
     });
   });
@@ -777,19 +775,15 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_apply(const void
     dispatch_mode(act, drop, [&](auto A, auto D) {
       constexpr bool ACT = decltype(A)::value;
       constexpr int DROP = decltype(D)::value;
-      auto launch = [&](auto CS, auto OC) {
+      auto launch = [&](auto CS) {
         constexpr bool CSUM = decltype(CS)::value;
-        constexpr int OCC = decltype(OC)::value;
         static bool smem_ok = false;
-        if (!smem_ok) { if (!allow_smem(gn_bwd_apply_kernel<T, ACT, DROP, CSUM, OCC>, smem)) { rc = ST_ERR_CUDA; return; } smem_ok = true; }
-        gn_bwd_apply_kernel<T, ACT, DROP, CSUM, OCC><<<dim3(chunks, n_img), 256, smem, (cudaStream_t)stream>>>(
-            s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, red,
-            (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2, csum, dgamma, dbeta);
+        if (!smem_ok) { if (!allow_smem(gn_bwd_apply_kernel<T, ACT, DROP, CSUM>, smem)) { rc = ST_ERR_CUDA; return; } smem_ok = true; }
+        st_launch(gn_bwd_apply_kernel<T, ACT, DROP, CSUM>, dim3(chunks, n_img), dim3(256), smem, (cudaStream_t)stream,
+                  s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, red,
+                  (const T*)extra, extra_scale, (T*)dx1, accum1, (T*)dx2, accum2, csum, dgamma, dbeta);
       };
-      static const int csum_occ = getenv("ST_GN_CSUM_OCC") ? atoi(getenv("ST_GN_CSUM_OCC")) : 3;
-      if (!csum) launch(std::false_type{}, std::integral_constant<int, 3>{});
-      else if (csum_occ == 2) launch(std::true_type{}, std::integral_constant<int, 2>{});
-      else launch(std::true_type{}, std::integral_constant<int, 3>{});
+      if (csum) launch(std::true_type{}); else launch(std::false_type{});
     });
   });
   if (rc) return rc;
