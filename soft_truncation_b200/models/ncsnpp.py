@@ -897,6 +897,10 @@ class NCSNpp(nn.Module):
       if e.trainable and p.grad is None:
         p.grad = _logical_view(self._grad, e)
 
+  def buffers_for_graph_key(self):
+    """Tensors whose addresses a captured CUDA graph of this network depends on."""
+    return [self._flat, self._comp]
+
   def sync_compute_weights(self):
     """Refresh the compute-dtype copy of the parameters (one cast kernel over the flat buffer)."""
     if self._comp is not self._flat:

@@ -321,6 +321,7 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
     return x
 
   use_graph = bool(config.sampling.get('cuda_graph', True)) if hasattr(config.sampling, 'get') else True
+  graph_cache = {}
 
   def pc_sampler(model, x_init=None, noises=None, trace=None):
     with torch.no_grad():
@@ -344,25 +345,36 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
             trace.append(x.clone())
       else:
         # One reverse step captured into a CUDA graph and replayed: the step index lives on the device,
-        # so all N steps are enqueued back to back with no host round trip.
-        step = torch.zeros(1, dtype=torch.long, device=device)
-        sx, sx_mean = x.clone(), x.clone()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-          for _ in range(2):                       # warm-up outside capture (allocator, lazy inits)
-            one_step(sx, torch.ones(B, device=device) * timesteps[0])
-        torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-          vec_t = torch.ones(B, device=device) * timesteps.index_select(0, step)
-          nx, nx_mean = one_step(sx, vec_t)
-          sx.copy_(nx)
-          sx_mean.copy_(nx_mean)
-          step.add_(1)
+        # so all N steps are enqueued back to back with no host round trip.  The graph is kept for later calls
+        # with the same network buffers (it holds raw pointers into them).
+        net = mutils.unwrap(model)
+        key = (id(net),) + tuple(int(t.data_ptr()) for t in net.buffers_for_graph_key())
+        g = graph_cache.get('g')
+        if g is None or g['key'] != key:
+          step = torch.zeros(1, dtype=torch.long, device=device)
+          sx, sx_mean = x.clone(), x.clone()
+          sts = timesteps.clone()
+          side = torch.cuda.Stream()
+          side.wait_stream(torch.cuda.current_stream())
+          with torch.cuda.stream(side):
+            for _ in range(2):                       # warm-up outside capture (allocator, lazy inits)
+              one_step(sx, torch.ones(B, device=device) * sts[0])
+          torch.cuda.current_stream().wait_stream(side)
+          graph = torch.cuda.CUDAGraph()
+          with torch.cuda.graph(graph):
+            vec_t = torch.ones(B, device=device) * sts.index_select(0, step)
+            nx, nx_mean = one_step(sx, vec_t)
+            sx.copy_(nx)
+            sx_mean.copy_(nx_mean)
+            step.add_(1)
+          g = dict(key=key, graph=graph, step=step, sx=sx, sx_mean=sx_mean, sts=sts)
+          graph_cache['g'] = g
+        g['sx'].copy_(x)
+        g['sts'].copy_(timesteps)
+        g['step'].zero_()
         for _ in range(sde.N):
-          graph.replay()
-        x, x_mean = sx, sx_mean
+          g['graph'].replay()
+        x, x_mean = g['sx'].clone(), g['sx_mean'].clone()
 
       x_mean = x = denoise_update_fn(model, x_mean if denoise else x)
       return inverse_scaler(x_mean if denoise else x), sde.N * (n_steps + 1)

@@ -239,6 +239,10 @@ def test_pc_sampler_cuda_graph_matches_eager():
   # when the streams differ, exactly when they coincide
   if not torch.allclose(outs[0], outs[1], rtol=1e-4, atol=1e-4):
     assert abs(outs[0].std().item() - outs[1].std().item()) < 0.2 * outs[0].std().item()
+  # a second call replays the cached graph: same seeds, same samples
+  torch.cuda.manual_seed(12)
+  again, _ = fn(model, x_init=x0)
+  assert torch.allclose(again, outs[1], rtol=1e-5, atol=1e-6)
 
 
 def test_score_fn_and_state_dict_roundtrip():
