@@ -31,6 +31,9 @@ if ROOT not in sys.path:
 
 TRAIN_GF_PER_IMG = 65.08      # 3 x 21.693 GF forward (conv/linear/NIN/attention MACs x 2)
 FWD_GF_PER_IMG = 21.693
+# DRAM bytes per GEMM launch (average over the 430 launches of one B=512 bf16 step): 54.15 GB / 430, from the ncu launch
+# list committed as profiles/r01_launches_train_step.md (dram__bytes_read.sum + dram__bytes_write.sum)
+GEMM_DRAM_BYTES_PER_LAUNCH = 54.149e9 / 430
 METRIC = 'DDPM++ CIFAR-10 train images/sec'
 
 
@@ -210,7 +213,10 @@ def run_b200(args):
     achieved = flops / (t_ms * 1e-3) / 1e12
     peak = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
     roof = {'bound': 'tensor', 'kernel': 'gemm_tc2_kernel (persistent tcgen05 implicit-GEMM conv / GEMM, all st_gemm launches of one step)' if ops.tc_available() and args.dtype == 'bf16' else 'gemm_simt_kernel',
-            'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+            'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+            'traffic': GEMM_DRAM_BYTES_PER_LAUNCH if B == 512 and args.dtype == 'bf16' else None,
+            'traffic_source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 430 GEMM launches of one B=512 step '
+                              '/ 430 (profiles/r01_launches_train_step.md); algorithmic operand+output bytes of the same launches: see DESIGN.md',
             'peak_source': pk_kind + ' (sustained cuBLAS bf16)', 'launches': len(recs), 'gemm_ms_per_step': t_ms,
             'gemm_share_of_step': t_ms / (ms / args.steps),
             'whole_step_frac': value / world * TRAIN_GF_PER_IMG / 1e3 / peak}
@@ -232,7 +238,7 @@ def run_b200(args):
             'steps_timed': N + 1, 'sample_steps_per_sec': sps * SB * world,
             'frac_of_tensor_roofline': sps * SB * FWD_GF_PER_IMG / 1e3 / pk.get('bf16_tflops_sustained', 1400.),
             'note': f'{N} Euler-Maruyama steps of an N={N} VP schedule + final denoise through sampling.get_sampling_fn; '
-                    'one reverse step is captured in a CUDA graph and replayed (capture time is inside the timed call)'}
+                    'one reverse step is captured in a CUDA graph once (untimed first call) and replayed'}
   except Exception as ex:   # the headline metric must still print
     samp = {'error': repr(ex)[:300]}
 

@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(Src2<T> s, int hw, int
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float u = fmaf(x[i], A[i], Bc[i]);
-          o[i] = ACT ? silu_f(u) : u;
+          o[i] = ACT ? silu_t<T>(u) : u;
         }
         if constexpr (DROP == DROP_FAST) {
           float keep[8];
@@ -370,7 +370,7 @@ struct BwdConst {
 };
 
 // dz and xhat of one 8-vector (shared by both backward passes)
-template <bool ACT, int DROP>
+template <typename T, bool ACT, int DROP>
 __device__ __forceinline__ void gn_dz8(const float x[8], const float dyv[8], const BwdConst& k,
                                        float p_drop, float inv_keep, uint64_t seed, const float* mkv, uint32_t bits,
                                        long long oct, float xhat[8], float dz[8]) {
@@ -389,7 +389,7 @@ __device__ __forceinline__ void gn_dz8(const float x[8], const float dyv[8], con
     float d = dyv[i];
     if constexpr (DROP == DROP_FAST) d = (bits >> i) & 1u ? d * inv_keep : 0.f;
     if constexpr (DROP == DROP_SLOW) d *= mk[i];
-    if constexpr (ACT) d *= silu_grad_f(fmaf(x[i], k.rg[i], k.bc[i]));
+    if constexpr (ACT) d *= silu_grad_t<T>(fmaf(x[i], k.rg[i], k.bc[i]));
     dz[i] = d;
   }
 }
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(Src2<T> s, const 
         uint32_t bits = 0;
         if constexpr (DROP == DROP_FAST) bits = pipe.read_byte(st, (uint32_t)oct);
         if constexpr (DROP == DROP_SLOW) { if (mask) load8(mask + oct * 8, mk); }
-        gn_dz8<ACT, DROP>(x0, d0, k, p_drop, inv_keep, seed, mask ? mk : nullptr, bits, oct, xh, dz);
+        gn_dz8<T, ACT, DROP>(x0, d0, k, p_drop, inv_keep, seed, mask ? mk : nullptr, bits, oct, xh, dz);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
         if constexpr (DROP != DROP_NONE) oct += octstep;
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T
         uint32_t bits = 0;
         if constexpr (DROP == DROP_FAST) bits = pipe.read_byte(st, (uint32_t)oct);
         if constexpr (DROP == DROP_SLOW) { if (mask) load8(mask + oct * 8, mk); }
-        gn_dz8<ACT, DROP>(x0, d0, k, p_drop, inv_keep, seed, mask ? mk : nullptr, bits, oct, xh, dz);
+        gn_dz8<T, ACT, DROP>(x0, d0, k, p_drop, inv_keep, seed, mask ? mk : nullptr, bits, oct, xh, dz);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = fmaf(k.rg[i], dz[i], fmaf(xh[i], rs2[i >> 2], rs1[i >> 2]));
         if (extra) {

@@ -356,10 +356,12 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
           sts = timesteps.clone()
           side = torch.cuda.Stream()
           side.wait_stream(torch.cuda.current_stream())
+          rng = torch.cuda.get_rng_state(device)     # the warm-up draws must not shift the caller's noise stream
           with torch.cuda.stream(side):
             for _ in range(2):                       # warm-up outside capture (allocator, lazy inits)
               one_step(sx, torch.ones(B, device=device) * sts[0])
           torch.cuda.current_stream().wait_stream(side)
+          torch.cuda.set_rng_state(rng, device)
           graph = torch.cuda.CUDAGraph()
           with torch.cuda.graph(graph):
             vec_t = torch.ones(B, device=device) * sts.index_select(0, step)
