@@ -156,6 +156,14 @@ int st_resample2x(const void* x1, const void* x2, void* y, int dtype, int n_img,
  * consecutive rows ld elements apart */
 int st_colsum(const void* x, int dtype, int64_t groups, int64_t rows_per_group, int C, int64_t ld, float scale,
               float* out, int accumulate, void* stream);
+/* Many small fp32 column sums in ONE launch.  `jobs` is a device table of n_jobs records of 21 eight-byte fields:
+ *   part[4] (device pointers), rows[4], ld[4] (elements), dst, n_parts, kind, C, groups, rows_per_group, ld_out,
+ *   scale (double), accumulate.
+ * kind 0: dst[c] (+)= scale * sum over parts p < n_parts and rows r < rows[p] of part[p][r*ld[p] + c]
+ * kind 1: dst[g*ld_out + c] (+)= scale * sum over k < rows_per_group of part[0][(g*rows_per_group + k)*ld[0] + c], g < groups
+ * C % 4 == 0, all pointers 16-byte aligned; blocks_y >= max over jobs of ceil(C/128) (kind 0) / ceil(groups*C/4096)
+ * (kind 1).  Jobs must have distinct destinations.  Replaces the per-tensor bias reductions of a backward pass. */
+int st_colsum_batched(const void* jobs, int n_jobs, int blocks_y, void* stream);
 /* row softmax of scale*logits: logits fp32 [rows][L] -> p (dtype) */
 int st_softmax_fwd(const float* logits, void* p, int dtype, int64_t rows, int L, float scale, void* stream);
 /* ds = scale * p * (dp - sum_j dp*p) ; dp fp32, ds dtype */

@@ -52,6 +52,74 @@ __global__ void silu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ d
   GRID_STRIDE(i, n) dx[i] = from_f<T>(to_f(dy[i]) * silu_grad_f(to_f(x[i])));
 }
 
+// ---------------------------------------------------------------- batched column sums
+// One launch for every small fp32 reduction a backward pass queues up (bias / time-embedding gradients from the
+// column-sum partials of the GroupNorm backward kernels): ~150 launches of ~12 us each otherwise.
+struct ColsumJob {                 // every field is 8 bytes: built as an int64 table on the host
+  const float* part[4];            // kind 0: up to four [rows][ld] partial tables reduced into the same destination
+  long long rows[4];
+  long long ld[4];
+  float* dst;
+  long long n_parts;
+  long long kind;                  // 0: dst[c] (+)= scale * sum_parts sum_rows part[r][c];  1: dst[g][c] = sum_k part0[g*K + k][c]
+  long long C;
+  long long groups, rows_per_group, ld_out;
+  double scale;
+  long long accumulate;
+};
+__global__ void __launch_bounds__(1024) colsum_batched_kernel(const ColsumJob* __restrict__ jobs) {
+  pdl_wait();
+  pdl_trigger();
+  const ColsumJob& j = jobs[blockIdx.x];
+  const int C = (int)j.C;
+  if (j.kind == 0) {
+    if ((int)blockIdx.y * 128 >= C) return;
+    const int c0 = (blockIdx.y * 32 + threadIdx.x % 32) * 4;
+    const int rl = threadIdx.x / 32;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < C) {
+      for (int p = 0; p < (int)j.n_parts; ++p) {
+        const float* base = j.part[p] + c0;
+        const long long rows = j.rows[p], ld = j.ld[p];
+        for (long long r = rl; r < rows; r += 32) {
+          const float4 v = *reinterpret_cast<const float4*>(base + r * ld);
+          acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+        }
+      }
+    }
+    __shared__ float4 sm[1024];
+    sm[threadIdx.x] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    __syncthreads();
+    if (rl == 0 && c0 < C) {
+      float4 t = sm[threadIdx.x];
+      for (int l = 1; l < 32; ++l) {
+        const float4 u = sm[l * 32 + threadIdx.x];
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      const float sc = (float)j.scale;
+      float* o = j.dst + c0;
+      if (j.accumulate) { o[0] += sc * t.x; o[1] += sc * t.y; o[2] += sc * t.z; o[3] += sc * t.w; }
+      else { o[0] = sc * t.x; o[1] = sc * t.y; o[2] = sc * t.z; o[3] = sc * t.w; }
+    }
+  } else {
+    const int Q = C / 4;
+    const long long idx = (long long)blockIdx.y * 1024 + threadIdx.x;
+    if (idx >= j.groups * Q) return;
+    const long long g = idx / Q;
+    const int q = (int)(idx % Q);
+    const float* base = j.part[0] + g * j.rows_per_group * j.ld[0] + q * 4;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long k = 0; k < j.rows_per_group; ++k) {
+      const float4 v = *reinterpret_cast<const float4*>(base + k * j.ld[0]);
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    const float sc = (float)j.scale;
+    float* o = j.dst + g * j.ld_out + q * 4;
+    if (j.accumulate) { o[0] += sc * t.x; o[1] += sc * t.y; o[2] += sc * t.z; o[3] += sc * t.w; }
+    else { o[0] = sc * t.x; o[1] = sc * t.y; o[2] = sc * t.z; o[3] = sc * t.w; }
+  }
+}
+
 // ---------------------------------------------------------------- 2x resampling
 // dir=+1: y[n][2i+a][2j+b][c] = scale*x[n][i][j][c];  dir=-1: y[n][i][j][c] = scale*sum_ab x[n][2i+a][2j+b][c]
 template <typename T>
@@ -614,6 +682,15 @@ extern "C" __attribute__((visibility("default"))) int st_colsum(const void* x, i
   dim3 grid((unsigned)groups, (C + 127) / 128);
   ST_DISPATCH_DTYPE(dtype, T, (st_launch(colsum_kernel<T>, grid, dim3(1024), 0, S, (const T*)x, rows_per_group, C, ld, scale, out, accumulate)));
   ST_CHECK_LAUNCH("st_colsum");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_colsum_batched(const void* jobs, int n_jobs, int blocks_y, void* stream) {
+  ST_CHECK_ARG(n_jobs >= 0 && blocks_y >= 1 && blocks_y <= 65535, "st_colsum_batched: bad grid");
+  static_assert(sizeof(ColsumJob) == 21 * 8, "ColsumJob is a table of 21 eight-byte fields");
+  if (n_jobs == 0) return 0;
+  st_launch(colsum_batched_kernel, dim3(n_jobs, blocks_y), dim3(1024), 0, S, (const ColsumJob*)jobs);
+  ST_CHECK_LAUNCH("st_colsum_batched");
   return 0;
 }
 

@@ -95,14 +95,16 @@ class NetCtx:
     self.drop_calls = 0
 
 
+CSQ = ops.ColsumQueue()      # reductions deferred to the end of NCSNpp._backward (destinations are distinct parameters)
+
+
 def bias_grad(dst, g2, gs, scale=1.0):
   """dst[c] += scale * sum_rows g2[row][c].  `gs` = list of fp32 (rows, C)-shaped column-sum partials that the
   producers of `g2` emitted as a by-product of their GroupNorm backward kernels (then no pass over g2 is
   needed), or None."""
   C = g2.shape[-1]
   if gs:
-    for part in gs:
-      ops.colsum(part, 1, part.shape[0], C, dst, scale=scale, accumulate=True, ld=part.stride(0))
+    CSQ.add_reduce(dst, list(gs), scale)       # one batched launch at the end of the backward pass
   else:
     ops.colsum(g2, 1, g2.shape[0], C, dst, scale=scale, accumulate=True)
 
@@ -230,12 +232,12 @@ class ResBlock:
     del da1
     # ---- temb projection gradient = per-image column sums of dh1 (by-product of the kernel above, or an explicit
     # pass); their sum over images is the Conv_0.bias / Dense_0.bias gradient (TimeEmbedding.bwd)
-    dd = torch.empty((B, Co), dtype=torch.float32, device=g.device)
     if FUSE_CSUM:
-      ops.colsum(r1[2], B, r1[2].shape[1], Co, dd)
+      CSQ.add_groups(net.d_dense[:, self.dense_off:self.dense_off + Co], r1[2])
     else:
+      dd = torch.empty((B, Co), dtype=torch.float32, device=g.device)
       ops.colsum(dh1.view(npix, Co), B, H * W, Co, dd)
-    net.d_dense[:, self.dense_off:self.dense_off + Co].copy_(dd)
+      net.d_dense[:, self.dense_off:self.dense_off + Co].copy_(dd)
     ops.conv_wgrad(dh1, a0, P.g(pre + 'Conv_0.weight'))
     da0 = ops.conv_dgrad(dh1, P.c(pre + 'Conv_0.weight'), self.cin)
     del dh1
@@ -989,6 +991,7 @@ class NCSNpp(nn.Module):
     if net.out_scale is not None:
       dout = dout * net.out_scale[:, None, None, None]
     net.need_dx = need_dx
+    CSQ.jobs, CSQ.keep, CSQ.blocks_y = [], [], 1       # nothing may survive an aborted backward pass
     grads = {net.out_id: ops.nchw_to_nhwc(dout, self.compute_dtype, CPAD)}
     # gsum[id]: column-sum partials of grads[id] emitted by the kernels that produced it (a list), or False once a
     # contribution arrived without partials (then the consumer reduces the tensor itself)
@@ -1006,6 +1009,7 @@ class NCSNpp(nn.Module):
             gsum[i] = False
           else:
             gsum.setdefault(i, []).append(c)
+    CSQ.flush()
     self.temb.bwd(net)
     net.tape.ops = []
     if need_dx:

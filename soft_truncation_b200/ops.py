@@ -5,6 +5,7 @@ Every wrapper enqueues on torch's current CUDA stream and never synchronises.
 import ctypes
 import math
 
+import numpy as np
 import torch
 
 from ._lib import GemmArgs, check, lib
@@ -278,6 +279,61 @@ def colsum(x, groups, rows_per_group, C, out, scale=1.0, accumulate=False, ld=No
       return out
   check(lib.st_colsum(ptr(x), dt(x), groups, rows_per_group, C, ld, float(scale), ptr(out), int(accumulate), stream()))
   return out
+
+
+class ColsumQueue:
+  """Small fp32 column sums deferred to ONE st_colsum_batched launch (bias and time-embedding gradients built from the
+  column-sum partials of the GroupNorm backward kernels).  Destinations of queued jobs must be distinct."""
+
+  def __init__(self):
+    self.jobs, self.keep, self.blocks_y = [], [], 1
+
+  def _check(self, t):
+    assert t.dtype == torch.float32 and t.is_cuda and t.stride(-1) == 1 and t.data_ptr() % 16 == 0
+
+  def add_reduce(self, dst, parts, scale=1.0, accumulate=True):
+    """dst[c] (+)= scale * sum_p sum_rows parts[p][row][c]; parts: 2-D fp32 views (row stride arbitrary)."""
+    C = dst.numel()
+    for i in range(0, len(parts), 4):
+      chunk = parts[i:i + 4]
+      rec = [0] * 21
+      for k, p in enumerate(chunk):
+        self._check(p)
+        assert p.shape[1] == C and p.stride(0) % 4 == 0
+        rec[k], rec[4 + k], rec[8 + k] = p.data_ptr(), p.shape[0], p.stride(0)
+      rec[12], rec[13], rec[14], rec[15] = dst.data_ptr(), len(chunk), 0, C
+      rec[19] = np.float64(scale).view(np.int64).item()
+      rec[20] = int(accumulate or i > 0)
+      if i > 0:                       # same destination twice: keep stream order by flushing the first record
+        self.flush()
+      self.jobs.append(rec)
+      self.keep.extend(chunk)
+      self.keep.append(dst)
+      self.blocks_y = max(self.blocks_y, (C + 127) // 128)
+
+  def add_groups(self, dst, part, scale=1.0, accumulate=False):
+    """dst[g][c] (+)= scale * sum_k part[g][k][c]; part contiguous fp32 (G, K, C), dst a (G, C) view (row stride free)."""
+    self._check(part)
+    self._check(dst)
+    G, K, C = part.shape
+    assert part.is_contiguous() and dst.shape == (G, C) and dst.stride(0) % 4 == 0 and C % 4 == 0
+    rec = [0] * 21
+    rec[0], rec[4], rec[8] = part.data_ptr(), G * K, C
+    rec[12], rec[13], rec[14], rec[15] = dst.data_ptr(), 1, 1, C
+    rec[16], rec[17], rec[18] = G, K, dst.stride(0)
+    rec[19] = np.float64(scale).view(np.int64).item()
+    rec[20] = int(accumulate)
+    self.jobs.append(rec)
+    self.keep.extend((part, dst))
+    self.blocks_y = max(self.blocks_y, (G * (C // 4) + 1023) // 1024)
+
+  def flush(self):
+    if not self.jobs:
+      return
+    dev = self.keep[0].device
+    table = torch.tensor(self.jobs, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+    check(lib.st_colsum_batched(ptr(table), len(self.jobs), self.blocks_y, stream()))
+    self.jobs, self.keep, self.blocks_y = [], [], 1
 
 
 def softmax_fwd(logits, L, scale, dtype):

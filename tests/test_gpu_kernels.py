@@ -271,6 +271,26 @@ def test_groupnorm_apply_finalises_statistics_in_kernel():
   assert torch.equal(st[0], lazy[0]) and torch.equal(st[1], lazy[1])
 
 
+def test_colsum_batched_queue():
+  """st_colsum_batched: several reductions of both kinds in one launch == the individual reductions."""
+  q = ops.ColsumQueue()
+  a = rnd(6, 3, 192, seed=1)                       # (B, chunks, C1+C2) partials as the GroupNorm backward emits them
+  flat = a.view(18, 192)
+  p1, p2 = flat[:, :128], flat[:, 128:]            # column slices: row stride 192
+  b = rnd(37, 128, seed=2)
+  d1, d2 = torch.ones(128, device=dev()), torch.zeros(64, device=dev())
+  q.add_reduce(d1, [p1, b], scale=0.5)
+  q.add_reduce(d2, [p2], scale=2.0, accumulate=False)
+  big = torch.zeros(6, 512, device=dev())
+  q.add_groups(big[:, 128:320], a)
+  q.flush()
+  assert not q.jobs
+  assert torch.allclose(d1, 1 + 0.5 * (p1.sum(0) + b.sum(0)), rtol=1e-5, atol=1e-5)
+  assert torch.allclose(d2, 2.0 * p2.sum(0), rtol=1e-5, atol=1e-5)
+  assert torch.allclose(big[:, 128:320], a.sum(1), rtol=1e-5, atol=1e-5)
+  assert big[:, :128].abs().sum() == 0 and big[:, 320:].abs().sum() == 0
+
+
 # ------------------------------------------------------------------------------------------------ small kernels
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_resample_colsum_softmax(dtype):
