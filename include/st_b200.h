@@ -156,6 +156,13 @@ int st_resample2x(const void* x1, const void* x2, void* y, int dtype, int n_img,
  * consecutive rows ld elements apart */
 int st_colsum(const void* x, int dtype, int64_t groups, int64_t rows_per_group, int C, int64_t ld, float scale,
               float* out, int accumulate, void* stream);
+/* dst[off + (ci*taps + taps-1-t)*Co + co] = src[off + (co*taps + t)*Ci + ci] for every convolution weight
+ * [Co][taps][Ci] listed in `table` (n_entries rows of {off, Co, taps, Ci}, device memory; `tile_prefix[e]` = number of
+ * 32x32 tiles of the entries before e, total_tiles = their sum): the data gradient of a convolution
+ * (torch conv2d backward w.r.t. input, reference models/layers.py ddpm_conv3x3 via autograd) is then a forward
+ * convolution over dY with these weights. */
+int st_transpose_conv_weights(const void* src, void* dst, int dtype, const int64_t* table, const int64_t* tile_prefix,
+                              int n_entries, int64_t total_tiles, void* stream);
 /* Many small fp32 column sums in ONE launch.  `jobs` is a device table of n_jobs records of 21 eight-byte fields:
  *   part[4] (device pointers), rows[4], ld[4] (elements), dst, n_parts, kind, C, groups, rows_per_group, ld_out,
  *   scale (double), accumulate.

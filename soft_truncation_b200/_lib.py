@@ -52,6 +52,7 @@ SIGNATURES = {
     'st_resample2x': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f, c_p],
     'st_colsum': [c_p, c_int, c_i64, c_i64, c_int, c_i64, c_f, c_p, c_int, c_p],
     'st_colsum_batched': [c_p, c_int, c_int, c_p],
+    'st_transpose_conv_weights': [c_p, c_p, c_int, c_p, c_p, c_int, c_i64, c_p],
     'st_softmax_fwd': [c_p, c_p, c_int, c_i64, c_int, c_f, c_p],
     'st_softmax_bwd': [c_p, c_p, c_p, c_int, c_i64, c_int, c_f, c_p],
     'st_timestep_embedding': [c_p, c_p, c_p, c_int, c_int, c_p],

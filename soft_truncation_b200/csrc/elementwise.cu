@@ -52,6 +52,43 @@ __global__ void silu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ d
   GRID_STRIDE(i, n) dx[i] = from_f<T>(to_f(dy[i]) * silu_grad_f(to_f(x[i])));
 }
 
+// ---------------------------------------------------------------- transposed conv weights for the data gradient
+// dst[ci][taps-1-t][co] = src[co][t][ci] for every convolution of the table, one launch: the data gradient of a
+// convolution then runs as a forward convolution over dY with a K-major weight operand (one 256-row TMA box per K
+// block instead of four MN-major 64x64 boxes: +8 % at 16x16, +28 % at 8x8, tools/mn_probe.py).
+// table[e] = {offset (elements), Co, taps, Ci}; tile_prefix[e] = first 32x32 tile of entry e.
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_conv_weights_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                                     const long long* __restrict__ table,
+                                                                     const long long* __restrict__ tile_prefix, int n_entries) {
+  __shared__ T tile[32][33];
+  const long long t = blockIdx.x;
+  int lo = 0, hi = n_entries - 1;              // last entry whose first tile is <= t
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_prefix[mid] <= t) lo = mid; else hi = mid - 1;
+  }
+  const long long off = table[4 * lo];
+  const int Co = (int)table[4 * lo + 1], taps = (int)table[4 * lo + 2], Ci = (int)table[4 * lo + 3];
+  const int tci = (Ci + 31) / 32, tco = (Co + 31) / 32;
+  int r = (int)(t - tile_prefix[lo]);
+  const int tap = r / (tco * tci);
+  r -= tap * tco * tci;
+  const int co0 = (r / tci) * 32, ci0 = (r % tci) * 32;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int co = co0 + ty + 8 * k, ci = ci0 + tx;
+    if (co < Co && ci < Ci) tile[ty + 8 * k][tx] = src[off + ((long long)co * taps + tap) * Ci + ci];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ci = ci0 + ty + 8 * k, co = co0 + tx;
+    if (co < Co && ci < Ci) dst[off + ((long long)ci * taps + (taps - 1 - tap)) * Co + co] = tile[tx][ty + 8 * k];
+  }
+}
+
 // ---------------------------------------------------------------- batched column sums
 // One launch for every small fp32 reduction a backward pass queues up (bias / time-embedding gradients from the
 // column-sum partials of the GroupNorm backward kernels): ~150 launches of ~12 us each otherwise.
@@ -682,6 +719,16 @@ extern "C" __attribute__((visibility("default"))) int st_colsum(const void* x, i
   dim3 grid((unsigned)groups, (C + 127) / 128);
   ST_DISPATCH_DTYPE(dtype, T, (st_launch(colsum_kernel<T>, grid, dim3(1024), 0, S, (const T*)x, rows_per_group, C, ld, scale, out, accumulate)));
   ST_CHECK_LAUNCH("st_colsum");
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int st_transpose_conv_weights(const void* src, void* dst, int dtype, const int64_t* table,
+                                          const int64_t* tile_prefix, int n_entries, int64_t total_tiles, void* stream) {
+  ST_CHECK_ARG(n_entries >= 0 && total_tiles >= 0 && total_tiles < (1LL << 31), "st_transpose_conv_weights: bad table");
+  if (n_entries == 0 || total_tiles == 0) return 0;
+  ST_DISPATCH_DTYPE(dtype, T, (transpose_conv_weights_kernel<T><<<(unsigned)total_tiles, 256, 0, S>>>(
+                                  (const T*)src, (T*)dst, (const long long*)table, (const long long*)tile_prefix, n_entries)));
+  ST_CHECK_LAUNCH("st_transpose_conv_weights");
   return 0;
 }
 

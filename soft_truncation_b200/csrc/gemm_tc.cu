@@ -570,6 +570,21 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
             }
           }
         }
+        // gathered B operand (weight gradient with few output channels, not transposed): n = (tap, channel)
+        int b_c[BN / 64], b_dx[BN / 64], b_dy[BN / 64], b_src[BN / 64];
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) { b_c[j] = 0; b_dx[j] = 0; b_dy[j] = 0; b_src[j] = 2; }
+        if (p.b_kind == GATHER_MN) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) {
+            const int nn = n0 + 64 * j;
+            const int t = nn / p.Ct, c = nn - t * p.Ct;
+            if (t < p.ntaps) {                              // else masked columns: any in-range box
+              b_dy[j] = t / p.kw - ph; b_dx[j] = t - (t / p.kw) * p.kw - pw;
+              b_src[j] = c < p.C1 ? 0 : 1; b_c[j] = c < p.C1 ? c : c - p.C1;
+            }
+          }
+        }
         int kk = kt0 * BK;
         for (int i = 0; i < nkt; ++i) {
           mbar_wait(empty0 + 8 * s, par);
@@ -608,6 +623,14 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
               tma_load_3d_mc(sb + rank * rows * 128, &mapB0, bar, kk, n0 + rank * rows, b, mc_mask);
             } else {
               tma_load_3d(sb, &mapB0, bar, kk, n0, b);
+            }
+          } else if (p.b_kind == GATHER_MN) {
+            const int x0 = kk & Wm, y0 = (kk >> lw) & Hm, i0 = kk >> lhw;
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) {
+              if (b_src[j] == 2) tma_load_4d(sb + j * 8192, &mapB0, bar, 0, x0, y0, i0);
+              else if (b_src[j] == 0) tma_load_4d(sb + j * 8192, &mapB0, bar, b_c[j], x0 + b_dx[j], y0 + b_dy[j], i0);
+              else tma_load_4d(sb + j * 8192, &mapB1, bar, b_c[j], x0 + b_dx[j], y0 + b_dy[j], i0);
             }
           } else {
             const int per = (BN / 64) / cs;       // host guarantees cs <= BN/64
@@ -1185,7 +1208,14 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   CUtensorMap maps[6];
   memset(maps, 0, sizeof(maps));
   const int Ct = a->C1 + a->C2;
-  const bool wgrad = (a->b_mode == ST_OP_GATHER);     // runs transposed: M' = taps*Cin, N' = Cout
+  // Weight gradients run transposed (M' = taps*Cin, N' = Cout) unless the layer has <= 128 output channels: then the
+  // transposed form would be stuck with 128-wide MMAs and 128x128 tiles at the shared-memory read limit, and the
+  // direct form (A = dY MN-major, B = shifted NHWC boxes, 128x256 tiles, TMA reduce-add epilogue) is used instead.
+  const bool wgrad_any = (a->b_mode == ST_OP_GATHER);
+  const bool wgrad_nt = wgrad_any && a->M <= 128 && a->N >= 256 && a->accumulate && a->out_dtype == ST_F32 &&
+                        env_int("ST_TC_WGRAD_NT", 1) == 1 && env_int("ST_TC_EPI", 1) == 1 &&
+                        aligned16(a->C) && (a->sCm * 4) % 16 == 0;
+  const bool wgrad = wgrad_any && !wgrad_nt;
   const int M = wgrad ? a->N : a->M, N = wgrad ? a->M : a->N;
   p.M = M; p.N = N; p.batch = a->batch; p.split_k = a->split_k > 1 ? a->split_k : 1;
   p.H = a->H; p.W = a->W; p.kh = a->kh; p.kw = a->kw; p.ntaps = a->kh * a->kw; p.Ct = Ct; p.C1 = a->C1;
@@ -1194,7 +1224,7 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   p.c1blocks = a->C1 / 64;
   for (p.logW = 0; (1 << p.logW) < a->W; ++p.logW) {}
   for (p.logH = 0; (1 << p.logH) < a->H; ++p.logH) {}
-  int BN = (N >= 256 && N % 256 == 0) ? 256 : (N > 64 ? 128 : 64);
+  int BN = (N >= 256 && (N % 256 == 0 || wgrad_nt)) ? 256 : (N > 64 ? 128 : 64);
   if (BN == 256 && env_int("ST_TC_BN", 256) == 128) BN = 128;
   // too few 128x256 tiles to occupy the SMs (4x4 level of the U-Net): halve the tile instead of idling half the GPU
   if (BN == 256 && !wgrad && env_int("ST_TC_SMALL", 1) == 1) {
@@ -1211,6 +1241,13 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   }
   p.m_tiles = (M + BM * MH - 1) / (BM * MH);
   p.n_tiles = (N + BN - 1) / BN;
+  if (wgrad_nt && p.split_k > 1) {
+    // the caller sized split-K for 128x128 tiles: re-derive it so that the work items fill two waves of the SMs
+    const int tiles = p.m_tiles * p.n_tiles * p.batch;
+    int sk = (2 * st_num_sms()) / (tiles > 0 ? tiles : 1);
+    const int cap = p.nk / 16 > 0 ? p.nk / 16 : 1;
+    p.split_k = sk < 1 ? 1 : (sk > cap ? cap : sk);
+  }
 
   // B kind first (it bounds the cluster size)
   const bool b_kmajor = !wgrad && a->b_mode == ST_OP_STRIDED && a->sBk == 1;
@@ -1241,7 +1278,10 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
     if (!encode_map(&maps[0], a->A, 3, dims, str, box)) return ST_ERR_CUDA;
   }
   // ---------------- B
-  if (wgrad) {
+  if (wgrad_nt) {
+    p.b_kind = GATHER_MN;
+    if (!gather_maps(&maps[2], &maps[3], a->B, a->B2, a->C1, a->C2, a->W, a->H, a->n_img, 64)) return ST_ERR_CUDA;
+  } else if (wgrad) {
     p.b_kind = MNMAJOR;        // dY[pixel][co]: n' = co contiguous, k = pixel
     const uint64_t dims[3] = {(uint64_t)a->M, (uint64_t)a->K, 1};
     const uint64_t str[2] = {(uint64_t)a->sAk * 2, (uint64_t)a->K * a->sAk * 2};

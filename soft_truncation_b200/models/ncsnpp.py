@@ -22,6 +22,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from .._lib import check, lib
 from . import utils
 from .params import (ParamStore, _logical_view, _phys_view, init_conv, init_ones, init_zeros, register_owner)
 
@@ -93,6 +94,17 @@ class NetCtx:
     self.d_dense = None        # its gradient, filled slice by slice during backward
     self.taps = model._taps
     self.drop_calls = 0
+
+
+USE_WT = os.environ.get('ST_DGRAD_WT', '1') != '0'    # data gradients as forward convs over transposed weight copies
+
+
+def conv_dgrad_w(P, dy, name, cin, kh=3, kw=3, alpha=1.0):
+  """Data gradient of the convolution whose weight is `name`."""
+  wt = P.ct(name)
+  if wt is not None and dy.shape[3] % 64 == 0:
+    return ops.conv_fwd(dy, wt, cin, kh, kw, alpha=alpha)
+  return ops.conv_dgrad(dy, P.c(name), cin, kh, kw, alpha=alpha)
 
 
 CSQ = ops.ColsumQueue()      # reductions deferred to the end of NCSNpp._backward (destinations are distinct parameters)
@@ -223,7 +235,7 @@ class ResBlock:
     # ---- Conv_1 (and the 1/sqrt2 output scale)
     bias_grad(P.g(pre + 'Conv_1.bias'), g2, gs, s)
     ops.conv_wgrad(g, a1, P.g(pre + 'Conv_1.weight'), alpha=s)
-    da1 = ops.conv_dgrad(g, P.c(pre + 'Conv_1.weight'), Co, alpha=s)
+    da1 = conv_dgrad_w(P, g, pre + 'Conv_1.weight', Co, alpha=s)
     # ---- GroupNorm_1 + SiLU + dropout
     r1 = ops.gn_backward(h1, None, da1, self.G1, P.f(pre + 'GroupNorm_1.weight'), P.f(pre + 'GroupNorm_1.bias'), st1, 1,
                          P.g(pre + 'GroupNorm_1.weight'), P.g(pre + 'GroupNorm_1.bias'), p_drop=p_drop, seed=seed,
@@ -239,7 +251,7 @@ class ResBlock:
       ops.colsum(dh1.view(npix, Co), B, H * W, Co, dd)
       net.d_dense[:, self.dense_off:self.dense_off + Co].copy_(dd)
     ops.conv_wgrad(dh1, a0, P.g(pre + 'Conv_0.weight'))
-    da0 = ops.conv_dgrad(dh1, P.c(pre + 'Conv_0.weight'), self.cin)
+    da0 = conv_dgrad_w(P, dh1, pre + 'Conv_0.weight', self.cin)
     del dh1
     # ---- shortcut
     extra, extra_scale = None, 1.0
@@ -249,7 +261,7 @@ class ResBlock:
         ops.conv_wgrad(g, xr, P.g(pre + 'Conv_2.weight'), 1, 1, alpha=s)
       else:
         ops.conv_wgrad(g, x1, P.g(pre + 'Conv_2.weight'), 1, 1, x2=x2, alpha=s)
-      extra = ops.conv_dgrad(g, P.c(pre + 'Conv_2.weight'), self.cin, 1, 1, alpha=s)
+      extra = conv_dgrad_w(P, g, pre + 'Conv_2.weight', self.cin, 1, 1, alpha=s)
     else:
       extra, extra_scale = g, s
     if self.up or self.down:
@@ -387,7 +399,7 @@ class ConvBlock:
     ops.conv_wgrad(g, x, P.g(self.pre + 'weight'), self.k, self.k)
     if not need_dx:
       return (None,), (None,)
-    dx = ops.conv_dgrad(g, P.c(self.pre + 'weight'), self.cin, self.k, self.k)
+    dx = conv_dgrad_w(P, g, self.pre + 'weight', self.cin, self.k, self.k)
     if acc[0] is not None:
       ops.axpby(acc[0], dx, out=acc[0])
       dx = acc[0]
@@ -647,6 +659,19 @@ class _ParamAccess:
   def c(self, name):
     return self._view('_comp', name)
 
+  def ct(self, name):
+    """[Ci][reversed taps][Co] copy of a convolution weight (see NCSNpp._sync_transposed), or None in fp32 mode."""
+    if self.model._compT is None:
+      return None
+    key = ('_compT', name)
+    v = self._cache.get(key)
+    if v is None:
+      e = self.model.store.by_name[name]
+      co, ci, kh, kw = e.shape
+      v = self.model._compT[e.offset:e.offset + e.numel].view(e.pad[1], kh * kw * e.pad[0])
+      self._cache[key] = v
+    return v
+
   def f(self, name):
     return self._view('_flat', name)
 
@@ -859,6 +884,19 @@ class NCSNpp(nn.Module):
       self._comp = self._flat
     else:
       self._comp = torch.empty(self._flat.shape, dtype=self.compute_dtype, device=self._flat.device)
+    # transposed copies of the convolution weights for the data-gradient GEMMs (tensor-core path only)
+    self._compT = None
+    if self.compute_dtype != torch.float32 and self._flat.is_cuda and USE_WT:
+      convs = [e for e in self.store.entries if e.kind == 'conv']
+      rows, prefix = [], [0]
+      for e in convs:
+        co, ci, kh, kw = e.shape
+        rows.append([e.offset, e.pad[0], kh * kw, e.pad[1]])
+        prefix.append(prefix[-1] + kh * kw * ((e.pad[0] + 31) // 32) * ((e.pad[1] + 31) // 32))
+      self._compT = torch.zeros(self._flat.shape, dtype=self.compute_dtype, device=self._flat.device)
+      self._wt_table = torch.tensor(rows, dtype=torch.int64, device=self._flat.device)
+      self._wt_prefix = torch.tensor(prefix, dtype=torch.int64, device=self._flat.device)
+      self._wt_tiles = prefix[-1]
     taps = self.config.model.fir_kernel
     self._fir_up = _fir_kernel(taps, 4., self._flat.device)
     self._fir_down = _fir_kernel(taps, 1., self._flat.device)
@@ -898,6 +936,13 @@ class NCSNpp(nn.Module):
       p = self._params[e.name]
       if e.trainable and p.grad is None:
         p.grad = _logical_view(self._grad, e)
+
+  def _sync_transposed(self):
+    """Refresh the [Ci][reversed taps][Co] weight copies from the compute-dtype weights (one launch)."""
+    if self._compT is not None:
+      check(lib.st_transpose_conv_weights(ops.ptr(self._comp), ops.ptr(self._compT), ops.dt(self._comp),
+                                          ops.ptr(self._wt_table), ops.ptr(self._wt_prefix), self._wt_table.shape[0],
+                                          self._wt_tiles, ops.stream()))
 
   def buffers_for_graph_key(self):
     """Tensors whose addresses a captured CUDA graph of this network depends on."""
@@ -992,6 +1037,7 @@ class NCSNpp(nn.Module):
       dout = dout * net.out_scale[:, None, None, None]
     net.need_dx = need_dx
     CSQ.jobs, CSQ.keep, CSQ.blocks_y = [], [], 1       # nothing may survive an aborted backward pass
+    self._sync_transposed()
     grads = {net.out_id: ops.nchw_to_nhwc(dout, self.compute_dtype, CPAD)}
     # gsum[id]: column-sum partials of grads[id] emitted by the kernels that produced it (a list), or False once a
     # contribution arrived without partials (then the consumer reduces the tensor itself)

@@ -271,6 +271,39 @@ def test_groupnorm_apply_finalises_statistics_in_kernel():
   assert torch.equal(st[0], lazy[0]) and torch.equal(st[1], lazy[1])
 
 
+def test_dgrad_as_forward_conv_over_transposed_weights():
+  """st_transpose_conv_weights: [Co][t][Ci] -> [Ci][T-1-t][Co] for a table of weights in one launch, and the data
+  gradient computed as a forward convolution over dY with the transposed copy == the MN-major dgrad path."""
+  from soft_truncation_b200._lib import check, lib
+  BF = torch.bfloat16
+  shapes = [(128, 9, 64), (64, 1, 128), (256, 9, 128)]                 # (Co, taps, Ci)
+  sizes = [co * t * ci for co, t, ci in shapes]
+  flat = rnd(sum(sizes), seed=5, scale=0.05).to(BF)
+  rows, prefix, off = [], [0], 0
+  for (co, t, ci), n in zip(shapes, sizes):
+    rows.append([off, co, t, ci])
+    prefix.append(prefix[-1] + t * (co // 32) * (ci // 32))
+    off += n
+  table = torch.tensor(rows, dtype=torch.int64, device=dev())
+  pre = torch.tensor(prefix, dtype=torch.int64, device=dev())
+  out = torch.zeros_like(flat)
+  check(lib.st_transpose_conv_weights(ops.ptr(flat), ops.ptr(out), ops.dt(flat), ops.ptr(table), ops.ptr(pre), len(rows),
+                                      prefix[-1], ops.stream()))
+  off = 0
+  for (co, t, ci), n in zip(shapes, sizes):
+    w = flat[off:off + n].view(co, t, ci)
+    want = w.flip(1).permute(2, 1, 0).contiguous()
+    assert torch.equal(out[off:off + n].view(ci, t, co), want)
+    off += n
+  co, t, ci = shapes[2]
+  w = flat[off - sizes[2]:off].view(co, t * ci)
+  wt = out[off - sizes[2]:off].view(ci, t * co)
+  dy = rnd(4, 16, 16, co, seed=6).to(BF)
+  ref = ops.conv_dgrad(dy, w, ci)
+  got = ops.conv_fwd(dy, wt, ci)
+  assert rel_l2(got.float(), ref.float()) < 5e-3
+
+
 def test_colsum_batched_queue():
   """st_colsum_batched: several reductions of both kinds in one launch == the individual reductions."""
   q = ops.ColsumQueue()

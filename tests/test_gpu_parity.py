@@ -265,6 +265,54 @@ def test_score_fn_and_state_dict_roundtrip():
     mutils.unwrap(model)(x, t)          # CPU tensors: no fallback
 
 
+def test_checkpoint_roundtrip_in_the_reference_format(tmp_path):
+  """utils.save_checkpoint / restore_checkpoint (reference utils.py:13-36): the file holds the reference's structures
+  (`module.`-prefixed OIHW state_dict, torch Adam state_dict, EMA shadow list) and restores a bit-identical run."""
+  from soft_truncation_b200 import losses, utils
+  from soft_truncation_b200.models import utils as mutils
+  from soft_truncation_b200.models.ema import ExponentialMovingAverage
+
+  def fresh(seed):
+    cfg = _cfg(dropout=0.)
+    cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks = 128, (1, 2), 1
+    cfg.optim.warmup = 0
+    model, sde, _ = _model(cfg, seed, torch.float32)
+    state = dict(optimizer=losses.get_optimizer(cfg, model.parameters()), model=model,
+                 ema=ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate), step=0)
+    return cfg, sde, state
+
+  cfg, sde, state = fresh(3)
+  step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+  batch = (torch.rand(4, 3, 32, 32, generator=torch.Generator().manual_seed(1)) * 2 - 1).to(DEV)
+  for _ in range(2):
+    step_fn(state, batch)
+  path = str(tmp_path / 'checkpoint_2.pth')
+  utils.save_checkpoint(cfg, path, state)
+  raw = torch.load(path, map_location='cpu', weights_only=False)
+  assert set(raw) == {'optimizer', 'model', 'ema', 'step'} and raw['step'] == 2
+  assert all(k.startswith('module.') for k in raw['model'])
+  assert raw['model']['module.all_modules.3.Conv_0.weight'].shape[2:] == (3, 3)          # OIHW
+  assert set(raw['ema']) == {'decay', 'num_updates', 'shadow_params'} and raw['ema']['num_updates'] == 2
+  n_params = len(list(state['model'].parameters()))
+  assert len(raw['optimizer']['state']) == n_params and 'exp_avg_sq' in raw['optimizer']['state'][0]
+  cfg2, sde2, state2 = fresh(4)                                                          # different weights
+  state2 = utils.restore_checkpoint(cfg2, path, state2, torch.device(DEV))
+  assert state2['step'] == 2
+  a, b = mutils.unwrap(state['model']), mutils.unwrap(state2['model'])
+  assert torch.equal(a._flat, b._flat)
+  np.random.seed(5); torch.manual_seed(5); torch.cuda.manual_seed(5)
+  l1 = step_fn(state, batch)
+  step_fn2 = losses.get_step_fn(cfg2, sde2, train=True, optimize_fn=losses.optimization_manager(cfg2))
+  np.random.seed(5); torch.manual_seed(5); torch.cuda.manual_seed(5)
+  l2 = step_fn2(state2, batch)
+  assert torch.equal(l1.cpu(), l2.cpu())
+  assert torch.equal(a._flat, b._flat)
+  for p, q in zip(state['ema'].shadow_params, state2['ema'].shadow_params):
+    assert torch.equal(p, q)
+  # a missing file leaves the state untouched
+  assert utils.restore_checkpoint(cfg2, str(tmp_path / 'none' / 'x.pth'), state2, torch.device(DEV)) is state2
+
+
 def _reduced(tag):
   from soft_truncation_b200 import configs
   if tag == 'c3':       # RVE, FIR res-blocks, 'residual' input pyramid (configs/ve/CELEBA/uncsnpp_st.py, reduced width)
