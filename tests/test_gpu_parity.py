@@ -306,9 +306,10 @@ def test_checkpoint_roundtrip_in_the_reference_format(tmp_path):
   np.random.seed(5); torch.manual_seed(5); torch.cuda.manual_seed(5)
   l2 = step_fn2(state2, batch)
   assert torch.equal(l1.cpu(), l2.cpu())
-  assert torch.equal(a._flat, b._flat)
+  # split-K weight gradients accumulate with atomics (summation order differs run to run): compare to fp32 rounding
+  assert rel_l2(a._flat, b._flat) < 1e-6
   for p, q in zip(state['ema'].shadow_params, state2['ema'].shadow_params):
-    assert torch.equal(p, q)
+    assert rel_l2(p, q) < 1e-6
   # a missing file leaves the state untouched
   assert utils.restore_checkpoint(cfg2, str(tmp_path / 'none' / 'x.pth'), state2, torch.device(DEV)) is state2
 
