@@ -138,6 +138,18 @@ int st_gn_bwd_apply(const void* x1, const void* x2, const void* dy, int dtype, i
  * this count explicitly and receives csum[n_img][chunks][C]: the column sums of the gradient contribution the
  * kernel produced (extra included, accumulated destination excluded). */
 int st_gn_chunks(int n_img, int hw, int C);
+/* Both backward passes in ONE launch: a thread-block cluster of `chunks` CTAs owns an image, reduces its pixel chunks
+ * into red[n_img][chunks][C][2], synchronises (barrier.cluster) and produces dx: one launch and no
+ * stream-ordered round trip of `red` (the second read of x / dy hits L2 only for what the resident wave leaves
+ * there).  csum (optional) is [n_img][chunks][C].  The parameter gradients are left to the caller (st_gn_bwd_params or a kind-2 st_colsum_batched job over `red`, rows = n_img*chunks).
+ * st_gn_bwd_fused_chunks returns the cluster size the library would use for this shape (`streams` = 2 + extra + an
+ * accumulated destination), 0 = use the two-pass form (measured slower there, too few CTAs, or ST_GN_FUSED=0). */
+int st_gn_bwd_fused_chunks(int n_img, int hw, int C, int dtype, int streams);
+int st_gn_bwd_fused(const void* x1, const void* x2, const void* dy, int dtype, int n_img, int hw, int C1,
+                    int C2, int G, const float* gamma, const float* beta, const float* mean,
+                    const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
+                    const uint8_t* keepbits, int chunks, float* red, const void* extra, float extra_scale,
+                    void* dx1, int accum1, void* dx2, int accum2, float* csum, void* stream);
 
 /* ------------------------------------------------------------------ elementwise / small
  * All take element counts; pointers must be 16-byte aligned. */

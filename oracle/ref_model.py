@@ -185,7 +185,8 @@ def unet_forward(sd, cfg, x, time_cond, train=False, drop_masks=None, taps_out=N
   else:
     used_sigmas = sd.get('sigmas', sd.get('module.sigmas'))
     used_sigmas = used_sigmas[time_cond.long()] if used_sigmas is not None else None
-    temb = positional_embedding(time_cond, m.nf)
+    # model.lsgm: `embedding_dim`-wide sinusoidal embedding (reference models/ncsnpp.py:279-283)
+    temb = positional_embedding(time_cond, m.embedding_dim if getattr(m, 'lsgm', False) else m.nf)
   if m.conditional:
     p = P.take()
     temb = F.linear(temb, p['weight'], p['bias'])
@@ -310,7 +311,10 @@ def make_state_dict(cfg, seed=0, rezero=True):
     return {name + '.W': fan_avg_uniform((cin, cout), scale, gen=gen), name + '.b': torch.zeros(cout)}
 
   nf = m.nf
-  temb_dim = nf * 4
+  # Dense_0 input width = 4 * embed_dim_2 (reference models/ncsnpp.py:76-91,135): nf for Fourier features, else the
+  # sinusoidal width (embedding_dim when model.lsgm, nf otherwise)
+  lsgm = m.embedding_type.lower() == 'positional' and getattr(m, 'lsgm', False)
+  temb_dim = 4 * (m.embedding_dim if lsgm else nf)
 
   def resblock(cin, cout=None, up=False, down=False):
     cout = cout or cin
@@ -336,7 +340,7 @@ def make_state_dict(cfg, seed=0, rezero=True):
     add({'W': torch.randn(nf, generator=gen) * m.fourier_scale})
     embed_dim = 2 * nf
   else:
-    embed_dim = nf
+    embed_dim = m.embedding_dim if lsgm else nf
   if m.conditional:
     add(lin(embed_dim, temb_dim))
     add(lin(temb_dim, temb_dim))

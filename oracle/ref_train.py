@@ -140,10 +140,12 @@ def score_fn(sd, cfg, sde, x, t, train=False, drop_masks=None):
   return sde.score_from_out(out, t)
 
 
-def dsm_losses(sd, cfg, sde, batch, u, z, t_min, train=True, drop_masks=None):
-  """Per-sample losses of reference losses.py:101-132 for injected uniforms `u` and noise `z`."""
+def dsm_losses(sd, cfg, sde, batch, u, z, t_min, train=True, drop_masks=None, importance_sampling=None):
+  """Per-sample losses of reference losses.py:101-132 for injected uniforms `u` and noise `z`.
+  `importance_sampling` (the loss_fn ARGUMENT, :101,112) only selects how the times are drawn; the loss formula is keyed
+  on the config (:122) - the two differ inside step_fn_mixed."""
   tr = cfg.training
-  t, Z = sde.time_from_uniform(u, t_min, tr.importance_sampling)
+  t, Z = sde.time_from_uniform(u, t_min, tr.importance_sampling if importance_sampling is None else importance_sampling)
   std = sde.std(t)
   x_t = sde.mean_coeff(t)[:, None, None, None] * batch + std[:, None, None, None] * z
   score = score_fn(sd, cfg, sde, x_t, t, train=train, drop_masks=drop_masks)
@@ -176,14 +178,26 @@ class TrainState:
 
 
 def train_step(state, cfg, sde, batch, u, z, U_tmin, train=True, drop_masks=None):
-  """One optimizer step (reference losses.py:262-293) with injected randomness.
+  """One optimizer step (reference losses.py:262-293, or :295-320 when training.mixed) with injected randomness.
   Returns (per-sample losses, {name: grad})."""
   o = cfg.optim
   for k in state.trainable:
     state.sd[k].requires_grad_(True)
     state.sd[k].grad = None
   t_min = sde.t_min_from_uniform(cfg, U_tmin)
-  losses = dsm_losses(state.sd, cfg, sde, batch, u, z, t_min, train=train, drop_masks=drop_masks)
+  if cfg.training.mixed:
+    # step_fn_mixed (:295-320), one micro-batch: first half of the batch with importance-sampled times, second half
+    # with uniform times, combined per sample pair
+    assert o.num_micro_batch == 1 and drop_masks is None
+    h = batch.shape[0] // 2
+    l_is = dsm_losses(state.sd, cfg, sde, batch[:h], u[:h], z[:h], t_min, train=train, importance_sampling=True)
+    l_dd = dsm_losses(state.sd, cfg, sde, batch[h:], u[h:], z[h:], t_min, train=train, importance_sampling=False)
+    wgt = cfg.training.ddpm_weight
+    if cfg.training.balanced:
+      wgt = wgt * torch.mean(l_is / l_dd).detach().item()
+    losses = l_is + wgt * l_dd
+  else:
+    losses = dsm_losses(state.sd, cfg, sde, batch, u, z, t_min, train=train, drop_masks=drop_masks)
   torch.mean(losses).backward()
   grads = {k: state.sd[k].grad.detach().clone() for k in state.trainable}
   with torch.no_grad():

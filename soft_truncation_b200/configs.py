@@ -79,6 +79,19 @@ def cifar10_ddpmpp_nll_st():
       model=dict(scale_by_sigma=False, ema_rate=0.9999, embedding_type='positional'))
 
 
+def cifar10_ddpmpp_fid_st_deepest():
+  """The README's headline FID model: DDPM++ "deepest" - nf=512, three 32x32/16x16/8x8 levels of 8
+  res-blocks, FIR resampling, `lsgm` time embedding, mixed importance-sampled + uniform-time loss (step_fn_mixed)."""
+  return _base(
+      training=dict(sde='vpsde', continuous=True, reduce_mean=True, likelihood_weighting=False,
+                    importance_sampling=False, st=True, k=0.9, mixed=True, ddpm_weight=100.0,
+                    truncation_time=1e-5),
+      sampling=dict(method='pc', predictor='euler_maruyama', corrector='none'),
+      data=dict(centered=True),
+      model=dict(scale_by_sigma=False, ema_rate=0.9999, nf=512, ch_mult=(1, 1, 1), num_res_blocks=8, fir=True,
+                 embedding_type='positional', embedding_dim=128, dropout=0.2, lsgm=True))
+
+
 def imagenet32_ddpmpp_nll():
   """DDPM++ (VP) on ImageNet32 with likelihood weighting (C4)."""
   return _base(
@@ -137,6 +150,7 @@ def celebahq_uncsnpp_st():
 
 _REGISTRY = {
     'vp/CIFAR10/ddpmpp_nll_st': cifar10_ddpmpp_nll_st,
+    'vp/CIFAR10/ddpmpp_fid_st_deepest': cifar10_ddpmpp_fid_st_deepest,
     'vp/IMAGENET32/ddpmpp_nll': imagenet32_ddpmpp_nll,
     've/CELEBA/uncsnpp_st': celeba_uncsnpp_st,
     've/celebahq/uncsnpp_st': celebahq_uncsnpp_st,

@@ -99,6 +99,7 @@ struct ColsumJob {                 // every field is 8 bytes: built as an int64 
   float* dst;
   long long n_parts;
   long long kind;                  // 0: dst[c] (+)= scale * sum_parts sum_rows part[r][c];  1: dst[g][c] = sum_k part0[g*K + k][c]
+                                   // 2: GroupNorm dgamma (dst) / dbeta (part[1]) += column sums of red = part[0] [rows][C][2]
   long long C;
   long long groups, rows_per_group, ld_out;
   double scale;
@@ -137,6 +138,35 @@ __global__ void __launch_bounds__(1024) colsum_batched_kernel(const ColsumJob* _
       float* o = j.dst + c0;
       if (j.accumulate) { o[0] += sc * t.x; o[1] += sc * t.y; o[2] += sc * t.z; o[3] += sc * t.w; }
       else { o[0] = sc * t.x; o[1] = sc * t.y; o[2] = sc * t.z; o[3] = sc * t.w; }
+    }
+  } else if (j.kind == 2) {
+    // GroupNorm parameter gradients from the backward reduction buffer red[rows][C][2] = (sum dz, sum dz*xhat):
+    // dst[c] += sum_rows red[r][c][1] (dgamma), part[1][c] += sum_rows red[r][c][0] (dbeta); a float4 = 2 channels
+    const int C2 = 2 * C;
+    if ((int)blockIdx.y * 128 >= C2) return;
+    const int c0 = (blockIdx.y * 32 + threadIdx.x % 32) * 4;
+    const int rl = threadIdx.x / 32;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < C2) {
+      const float* base = j.part[0] + c0;
+      for (long long r = rl; r < j.rows[0]; r += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(base + r * C2);
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      }
+    }
+    __shared__ float4 sm2[1024];
+    sm2[threadIdx.x] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    __syncthreads();
+    if (rl == 0 && c0 < C2) {
+      double t[4] = {0., 0., 0., 0.};
+      for (int l = 0; l < 32; ++l) {
+        const float4 u = sm2[l * 32 + threadIdx.x];
+        t[0] += (double)u.x; t[1] += (double)u.y; t[2] += (double)u.z; t[3] += (double)u.w;
+      }
+      float* dgamma = j.dst + c0 / 2;
+      float* dbeta = const_cast<float*>(j.part[1]) + c0 / 2;
+      dbeta[0] += (float)t[0]; dgamma[0] += (float)t[1];
+      dbeta[1] += (float)t[2]; dgamma[1] += (float)t[3];
     }
   } else {
     const int Q = C / 4;

@@ -396,17 +396,15 @@ __device__ __forceinline__ void gn_dz8(const float x[8], const float dyv[8], con
 
 // ---------------------------------------------------------------- backward pass 1
 // grid (n_img, splits): red[n][split][c][2] = (sum dz, sum dz*xhat) over the split's pixels
+// (body shared by the stand-alone kernel and the fused two-phase kernel; image n, pixel split sp of `splits`)
 template <typename T, bool ACT, int DROP>
-__global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
-                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                            float p_drop, uint64_t seed, const T* mask,
-                                                            const uint8_t* __restrict__ keepbits, float* red) {
+__device__ __forceinline__ void gn_bwd_reduce_body(const Src2<T>& s, const T* dy, int hw, int G, int splits,
+                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                   float p_drop, uint64_t seed, const T* mask,
+                                                   const uint8_t* __restrict__ keepbits, float* red, int n, int sp) {
   extern __shared__ __align__(16) uint8_t gsm[];
-  pdl_wait();
-  pdl_trigger();
   const int Ct = s.C1 + s.C2, cpg = Ct / G;
-  const int n = blockIdx.x, sp = blockIdx.y;
   const Walk w(Ct, n, hw, sp, splits);
   const int V = w.V, lanes = w.lanes, v = w.v, lane = w.lane;
   float a[8], b[8];
@@ -458,6 +456,18 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(Src2<T> s, const 
   }
 }
 
+template <typename T, bool ACT, int DROP>
+__global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            float p_drop, uint64_t seed, const T* mask,
+                                                            const uint8_t* __restrict__ keepbits, float* red) {
+  pdl_wait();
+  pdl_trigger();
+  gn_bwd_reduce_body<T, ACT, DROP>(s, dy, hw, G, splits, gamma, beta, mean, rstd, p_drop, seed, mask, keepbits, red,
+                                   blockIdx.x, blockIdx.y);
+}
+
 // dgamma[c] += sum_rows red[row][c][1]; dbeta[c] += sum_rows red[row][c][0]
 // block = 16 channels x 32 row lanes (float2 reads), fixed-order reduction; the input is tiny (rows x C x 8 bytes),
 // the kernel is latency-bound, so the rows are spread over as many lanes as a block holds
@@ -487,27 +497,26 @@ __global__ void __launch_bounds__(512) gn_bwd_params_kernel(const float* __restr
 
 // ---------------------------------------------------------------- backward pass 2
 // grid (chunks, n_img)
+// (body shared with the fused kernel; image n of n_img, pixel chunk `chunk` of `chunks`; `red` is read with plain
+// loads - in the fused kernel other CTAs of the cluster wrote it moments ago)
 template <typename T, bool ACT, int DROP, bool CSUM>
-__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
-                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                           float p_drop, uint64_t seed, const T* mask,
-                                                           const uint8_t* __restrict__ keepbits,
-                                                           const float* __restrict__ red, const T* extra, float extra_scale,
-                                                           T* dx1, int accum1, T* dx2, int accum2, float* csum,
-                                                           float* dgamma, float* dbeta) {
+__device__ __forceinline__ void gn_bwd_apply_body(const Src2<T>& s, const T* dy, int hw, int G, int splits,
+                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                  float p_drop, uint64_t seed, const T* mask,
+                                                  const uint8_t* __restrict__ keepbits,
+                                                  const float* red, const T* extra, float extra_scale,
+                                                  T* dx1, int accum1, T* dx2, int accum2, float* csum,
+                                                  float* dgamma, float* dbeta, int n, int n_img, int chunk, int chunks) {
   extern __shared__ __align__(16) uint8_t gsm[];
-  pdl_wait();
-  pdl_trigger();
   const int Ct = s.C1 + s.C2, cpg = Ct / G;
-  const int n = blockIdx.y;
   __shared__ float sh1[64], sh2[64];
-  if (dgamma && blockIdx.x == 0) {
+  if (dgamma && chunk == 0) {
     // parameter gradients (what st_gn_bwd_params computes), spread over the first chunk's blocks: block n reduces
     // channels [16n, 16n+16) over all rows of `red` with 16 row lanes, fixed order
     __shared__ float sa[256], sb[256];
-    const int rows = gridDim.y * splits;
-    for (int cb = blockIdx.y; cb * 16 < Ct; cb += gridDim.y) {
+    const int rows = n_img * splits;
+    for (int cb = n; cb * 16 < Ct; cb += n_img) {
       const int c = cb * 16 + threadIdx.x % 16, rl = threadIdx.x / 16;
       float a = 0.f, b = 0.f;
       if (c < Ct) {
@@ -535,15 +544,15 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T
     for (int sp = 0; sp < splits; ++sp)
       for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
         const float* o = red + (((long long)n * splits + sp) * Ct + c) * 2;
-        a += (double)gamma[c] * (double)o[0];
-        b += (double)gamma[c] * (double)o[1];
+        a += (double)gamma[c] * (double)__ldcg(o);
+        b += (double)gamma[c] * (double)__ldcg(o + 1);
       }
     const double inv = 1.0 / ((double)hw * cpg);
     sh1[g] = (float)(a * inv);
     sh2[g] = (float)(b * inv);
   }
   __syncthreads();
-  Walk w(Ct, n, hw, blockIdx.x, gridDim.x);
+  Walk w(Ct, n, hw, chunk, chunks);
   const int V = w.V, lanes = w.lanes, v = w.v, lane = w.lane;
   const bool active = lane < lanes;
   if (!active) w.c0 = 0;
@@ -623,9 +632,52 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T
     for (int col = threadIdx.x; col < Ct; col += 256) {
       float t = 0.f;
       for (int l = 0; l < lanes; ++l) t += s_cs[l * Ct + col];
-      csum[((long long)n * gridDim.x + blockIdx.x) * Ct + col] = t;
+      csum[((long long)n * chunks + chunk) * Ct + col] = t;
     }
   }
+}
+
+template <typename T, bool ACT, int DROP, bool CSUM>
+__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(Src2<T> s, const T* dy, int hw, int G, int splits,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           float p_drop, uint64_t seed, const T* mask,
+                                                           const uint8_t* __restrict__ keepbits,
+                                                           const float* red, const T* extra, float extra_scale,
+                                                           T* dx1, int accum1, T* dx2, int accum2, float* csum,
+                                                           float* dgamma, float* dbeta) {
+  pdl_wait();
+  pdl_trigger();
+  gn_bwd_apply_body<T, ACT, DROP, CSUM>(s, dy, hw, G, splits, gamma, beta, mean, rstd, p_drop, seed, mask, keepbits, red,
+                                        extra, extra_scale, dx1, accum1, dx2, accum2, csum, dgamma, dbeta, blockIdx.y,
+                                        gridDim.y, blockIdx.x, gridDim.x);
+}
+
+// Both backward passes in one launch: a thread-block cluster of `chunks` CTAs owns one image; every CTA reduces its
+// pixel chunk (phase 1, writes red[n][chunk]), the cluster synchronises, and every CTA produces dx for the same chunk
+// (phase 2).  Saves a launch and the stream-ordered round trip of `red`; the second read of x and dy hits L2 only
+// partly (see fused_chunks_for for the measured policy).  grid (chunks, n_img).
+template <typename T, bool ACT, int DROP, bool CSUM>
+__global__ void __launch_bounds__(256, 3) gn_bwd_fused_kernel(Src2<T> s, const T* dy, int hw, int G,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           float p_drop, uint64_t seed, const T* mask,
+                                                           const uint8_t* __restrict__ keepbits,
+                                                           float* red, const T* extra, float extra_scale,
+                                                           T* dx1, int accum1, T* dx2, int accum2, float* csum) {
+  pdl_wait();
+  pdl_trigger();
+  const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  gn_bwd_reduce_body<T, ACT, DROP>(s, dy, hw, G, chunks, gamma, beta, mean, rstd, p_drop, seed, mask, keepbits, red, n, chunk);
+  __threadfence();
+  __syncthreads();
+  if (chunks > 1) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  gn_bwd_apply_body<T, ACT, DROP, CSUM>(s, dy, hw, G, chunks, gamma, beta, mean, rstd, p_drop, seed, mask, keepbits, red,
+                                        extra, extra_scale, dx1, accum1, dx2, accum2, csum, nullptr, nullptr, n,
+                                        (int)gridDim.y, chunk, chunks);
 }
 
 // opt a kernel in to more than 48 KB of dynamic shared memory (once per kernel instance)
@@ -788,5 +840,86 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_apply(const void
   });
   if (rc) return rc;
   ST_CHECK_LAUNCH("st_gn_bwd_apply");
+  return 0;
+}
+
+// ---------------------------------------------------------------- fused backward (one launch, cluster per image)
+namespace {
+// Pixel chunks per image (= cluster size) of the fused backward kernel, or 0 when the two-kernel path should run.
+// Measured on B200 at B=512 (tools/gn_bench.py, profiles/r01_gn_fused.txt): the saving is the second launch and the
+// reduction buffer round trip, not HBM traffic - a resident wave of CTAs touches more x/dy than L2 retains, and finer
+// chunks (clusters of 4-16) are bound by the per-CTA latency chain (constants, pipeline fill, cluster barrier).
+// One CTA per image wins up to 8x8, a pair at 16x16, and at >= 32x32 a pair only for the 2-stream form (x, dy); with
+// `extra` / accumulate streams the two-kernel form stays ahead there.
+int fused_chunks_for(int n_img, int hw, int Ct, int elem_bytes, int streams) {
+  static const int mode = getenv("ST_GN_FUSED") ? atoi(getenv("ST_GN_FUSED")) : 1;
+  static const int force = getenv("ST_GN_FUSED_CHUNKS") ? atoi(getenv("ST_GN_FUSED_CHUNKS")) : 0;
+  (void)Ct; (void)elem_bytes;
+  if (!mode) return 0;
+  int c = hw <= 64 ? 1 : 2;
+  if (hw >= 1024 && streams > 2) c = 0;
+  if (force > 0) c = force > 16 ? 16 : force;
+  if (c > hw) c = hw;
+  if ((long long)n_img * c < st_num_sms()) return 0;                  // too few CTAs: the two-kernel path splits finer
+  return c;
+}
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int st_gn_bwd_fused_chunks(int n_img, int hw, int C, int dtype, int streams) {
+  return fused_chunks_for(n_img, hw, C, dtype == ST_BF16 ? 2 : 4, streams);
+}
+
+extern "C" __attribute__((visibility("default"))) int st_gn_bwd_fused(const void* x1, const void* x2, const void* dy, int dtype, int n_img, int hw, int C1,
+                               int C2, int G, const float* gamma, const float* beta, const float* mean,
+                               const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
+                               const uint8_t* keepbits, int chunks, float* red, const void* extra, float extra_scale,
+                               void* dx1, int accum1, void* dx2, int accum2, float* csum, void* stream) {
+  if (int e = check_geom(C1, C2, G)) return e;
+  ST_CHECK_ARG(n_img <= 65535, "st_gn_bwd_fused: more than 65535 images");
+  ST_CHECK_ARG(chunks >= 1 && chunks <= 16, "st_gn_bwd_fused: chunks (cluster size) must be 1..16, got %d", chunks);
+  const int drop = mask ? DROP_SLOW : (p_drop > 0.f ? (keepbits ? DROP_FAST : DROP_SLOW) : DROP_NONE);
+  int rc = 0;
+  ST_DISPATCH_DTYPE(dtype, T, {
+    Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
+    constexpr int smem_a = Pipe<T, 2, GN_DEPTH>::BYTES, smem_b = Pipe<T, 4, GN_BWD_DEPTH>::BYTES;
+    constexpr int smem = smem_a > smem_b ? smem_a : smem_b;
+    dispatch_mode(act, drop, [&](auto A, auto D) {
+      constexpr bool ACT = decltype(A)::value;
+      constexpr int DROP = decltype(D)::value;
+      auto launch = [&](auto CS) {
+        constexpr bool CSUM = decltype(CS)::value;
+        auto kernel = gn_bwd_fused_kernel<T, ACT, DROP, CSUM>;
+        static bool attr_ok = false;
+        if (!attr_ok) {
+          if (!allow_smem(kernel, smem)) { rc = ST_ERR_CUDA; return; }
+          cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+          if (e != cudaSuccess) { st_set_error("st_gn_bwd_fused: cluster attribute: %s", cudaGetErrorString(e)); rc = ST_ERR_CUDA; return; }
+          attr_ok = true;
+        }
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(chunks, n_img);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = chunks;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = st_pdl_on((cudaStream_t)stream) ? 2 : 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, s, (const T*)dy, hw, G, gamma, beta, mean, rstd, p_drop, seed,
+                                           (const T*)mask, keepbits, red, (const T*)extra, extra_scale, (T*)dx1, accum1,
+                                           (T*)dx2, accum2, csum);
+        if (e != cudaSuccess) { st_set_error("st_gn_bwd_fused: launch: %s", cudaGetErrorString(e)); rc = ST_ERR_CUDA; }
+      };
+      if (csum) launch(std::true_type{}); else launch(std::false_type{});
+    });
+  });
+  if (rc) return rc;
+  ST_CHECK_LAUNCH("st_gn_bwd_fused");
   return 0;
 }

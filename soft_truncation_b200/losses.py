@@ -292,19 +292,31 @@ def get_step_fn(config, sde, train, optimize_fn=None):
     _finish(state, model)
     return torch.cat(pieces).cpu()
 
-  def step_fn_mixed(state, batch):
+  def step_fn_mixed(state, batch, injected=None):
+    """Reference losses.py:295-320.  `injected` = dict(t_min=, u=(B,), z=(B,C,H,W)) replaces the draws, rows in batch
+    order (per micro-batch: the importance-sampled half, then the uniform-time half)."""
     model = state['model']
     optimizer = state['optimizer']
+    if not train:
+      raise NotImplementedError('step_fn_mixed(train=False) is undefined in the reference as well (losses.py:299,318)')
     optimizer.zero_grad()
     B = batch.shape[0]
     nmb = config.optim.num_micro_batch
     mb = B // nmb
     half = B // (2 * nmb)
     pieces = []
-    t_min = _t_min()
+    t_min = injected['t_min'] if injected is not None and 't_min' in injected else _t_min()
+
+    def inj(lo, hi):
+      if injected is None:
+        return None
+      return {key: v[lo:hi] for key, v in injected.items() if key in ('u', 'z')}
+
     for k in range(nmb):
-      l_is = loss_fn(model, batch[mb * k: mb * k + half], importance_sampling=True, t_min=t_min)
-      l_dd = loss_fn(model, batch[mb * k + half: mb * (k + 1)], importance_sampling=False, t_min=t_min)
+      l_is = loss_fn(model, batch[mb * k: mb * k + half], importance_sampling=True, t_min=t_min,
+                     injected=inj(mb * k, mb * k + half))
+      l_dd = loss_fn(model, batch[mb * k + half: mb * (k + 1)], importance_sampling=False, t_min=t_min,
+                     injected=inj(mb * k + half, mb * (k + 1)))
       wgt = tr.ddpm_weight
       if tr.balanced:
         wgt = wgt * torch.mean(l_is / l_dd).detach().item()

@@ -239,7 +239,7 @@ class ResBlock:
     # ---- GroupNorm_1 + SiLU + dropout
     r1 = ops.gn_backward(h1, None, da1, self.G1, P.f(pre + 'GroupNorm_1.weight'), P.f(pre + 'GroupNorm_1.bias'), st1, 1,
                          P.g(pre + 'GroupNorm_1.weight'), P.g(pre + 'GroupNorm_1.bias'), p_drop=p_drop, seed=seed,
-                         mask=mask, keepbits=keepbits, want_csum=FUSE_CSUM)
+                         mask=mask, keepbits=keepbits, want_csum=FUSE_CSUM, queue=CSQ)
     dh1 = r1[0]
     del da1
     # ---- temb projection gradient = per-image column sums of dh1 (by-product of the kernel above, or an explicit
@@ -273,7 +273,7 @@ class ResBlock:
     r0 = ops.gn_backward(x1, x2, da0, self.G0, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st0, 1,
                          P.g(pre + 'GroupNorm_0.weight'), P.g(pre + 'GroupNorm_0.bias'), extra=extra,
                          extra_scale=extra_scale, dx1=a1_acc, accum1=a1_acc is not None, dx2=a2_acc,
-                         accum2=a2_acc is not None, want_csum=FUSE_CSUM)
+                         accum2=a2_acc is not None, want_csum=FUSE_CSUM, queue=CSQ)
     dx1, dx2 = r0[0], r0[1]
     c1, c2 = _split_csum(r0[2], x1.shape[3], 0 if x2 is None else x2.shape[3]) if FUSE_CSUM else (None, None)
     return ((dx1,), (c1,)) if x2 is None else ((dx1, dx2), (c1, c2))
@@ -362,7 +362,7 @@ class AttnBlock:
     # ---- GroupNorm (no activation) + residual
     r = ops.gn_backward(x, None, dh, self.G, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st, 0,
                         P.g(pre + 'GroupNorm_0.weight'), P.g(pre + 'GroupNorm_0.bias'), extra=g, extra_scale=s,
-                        dx1=acc[0], accum1=acc[0] is not None, want_csum=FUSE_CSUM)
+                        dx1=acc[0], accum1=acc[0] is not None, want_csum=FUSE_CSUM, queue=CSQ)
     return (r[0],), ((_split_csum(r[2], C, 0)[0] if FUSE_CSUM else None),)
 
 
@@ -439,7 +439,7 @@ class NormActConv:
     (da,), _ = self.conv.bwd(net, a, g, (None,), gs=gs)
     r = ops.gn_backward(x, None, da, self.G, P.f(self.pg + 'weight'), P.f(self.pg + 'bias'), st, 1,
                         P.g(self.pg + 'weight'), P.g(self.pg + 'bias'), dx1=acc[0], accum1=acc[0] is not None,
-                        want_csum=FUSE_CSUM)
+                        want_csum=FUSE_CSUM, queue=CSQ)
     dx = r[0]
     c = _split_csum(r[2], x.shape[3], 0)[0] if FUSE_CSUM else None
     if len(acc) == 1:
@@ -573,6 +573,8 @@ class TimeEmbedding:
     m = model.config.model
     nf = m.nf
     self.fourier = m.embedding_type.lower() == 'fourier'
+    if not self.fourier and m.embedding_type.lower() != 'positional':
+      raise ValueError(f'embedding type {m.embedding_type} unknown.')
     i = first_idx
     if self.fourier:
       model._add_param(f'all_modules.{i}.W', (nf,), trainable=False,
@@ -581,12 +583,15 @@ class TimeEmbedding:
       i += 1
       self.embed_dim = 2 * nf
     else:
-      self.embed_dim = nf
+      # `model.lsgm`: the sinusoidal embedding has `embedding_dim` entries instead of nf and the whole time-embedding
+      # MLP (and every Dense_0 input) is 4*embedding_dim wide (reference models/ncsnpp.py:86-91,135,279-283)
+      self.embed_dim = m.embedding_dim if getattr(m, 'lsgm', False) else nf
+    td = self.td = model.temb_dim
     self.l0, self.l1 = f'all_modules.{i}.', f'all_modules.{i + 1}.'
-    model._add_param(self.l0 + 'weight', (4 * nf, self.embed_dim), 'linear', init=init_conv(1.))
-    model._add_param(self.l0 + 'bias', (4 * nf,), init=init_zeros)
-    model._add_param(self.l1 + 'weight', (4 * nf, 4 * nf), 'linear', init=init_conv(1.))
-    model._add_param(self.l1 + 'bias', (4 * nf,), init=init_zeros)
+    model._add_param(self.l0 + 'weight', (td, self.embed_dim), 'linear', init=init_conv(1.))
+    model._add_param(self.l0 + 'bias', (td,), init=init_zeros)
+    model._add_param(self.l1 + 'weight', (td, td), 'linear', init=init_conv(1.))
+    model._add_param(self.l1 + 'bias', (td,), init=init_zeros)
     self.next_idx = i + 2
 
   def fwd(self, net, time_cond):
@@ -603,7 +608,7 @@ class TimeEmbedding:
     temb = ops.gemm_nt(a0_c, P.c(self.l1 + 'weight'), out_dtype=torch.float32, bias=P.f(self.l1 + 'bias'))
     at = ops.silu(temb)
     at_c = ops.cast(at, cd) if cd != torch.float32 else at
-    wd, bd = P.c_region('dense_w').view(-1, 4 * m.config.model.nf), P.f_region('dense_b')
+    wd, bd = P.c_region('dense_w').view(-1, self.td), P.f_region('dense_b')
     net.dense = ops.gemm_nt(at_c, wd, out_dtype=torch.float32, bias=bd)      # (B, sum Cout)
     if net.tape.enabled:
       net.d_dense = torch.zeros_like(net.dense)
@@ -615,7 +620,7 @@ class TimeEmbedding:
     emb_c, e0, a0_c, temb, at_c = net.temb_saved
     B = emb_c.shape[0]
     nd = net.d_dense.shape[1]
-    td = 4 * m.config.model.nf
+    td = self.td
     dd = net.d_dense
     # column sums of d_dense are the gradient of every Dense_0.bias AND of every Conv_0.bias (both are added to
     # the same pre-GroupNorm_1 activation); the two bias regions are laid out in the same block order
@@ -756,7 +761,8 @@ class NCSNpp(nn.Module):
     cd = compute_dtype or getattr(m, 'compute_dtype', None) or torch.bfloat16
     self.compute_dtype = {'bf16': torch.bfloat16, 'fp32': torch.float32}.get(cd, cd) if isinstance(cd, str) else cd
     self.nf = nf = m.nf
-    self.temb_dim = nf * 4
+    positional_lsgm = m.embedding_type.lower() == 'positional' and getattr(m, 'lsgm', False)
+    self.temb_dim = 4 * (m.embedding_dim if positional_lsgm else nf)
     self.dropout = m.dropout
     self.scale_by_sigma = m.scale_by_sigma
     self.conditional = m.conditional

@@ -201,23 +201,41 @@ def gn_apply(x, x2, G, gamma, beta, stats, act, p_drop=0., seed=0, mask=None, ke
 
 
 def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0., seed=0, mask=None, extra=None,
-                extra_scale=1.0, dx1=None, accum1=False, dx2=None, accum2=False, keepbits=None, want_csum=False):
+                extra_scale=1.0, dx1=None, accum1=False, dx2=None, accum2=False, keepbits=None, want_csum=False,
+                queue=None, fused_chunks=None):
   """Returns (dx1, dx2[, csum]); accumulates dgamma/dbeta (fp32 views into the flat gradient buffer).
-  csum (want_csum): fp32 (B, chunks, C1+C2) column sums of the gradient this call contributed."""
+  csum (want_csum): fp32 (B, chunks, C1+C2) column sums of the gradient this call contributed.
+  `queue`: a ColsumQueue that takes the dgamma/dbeta reduction of the fused (single-launch) form; `fused_chunks`:
+  cluster size override (0 = two-kernel form, None = the library decides)."""
   B, H, W, C1 = x.shape
   C2 = 0 if x2 is None else x2.shape[3]
   hw, Ct = H * W, C1 + C2
-  splits = _gn_splits(B, hw)
-  red = torch.empty((B, splits, Ct, 2), dtype=torch.float32, device=x.device)
-  common = (ptr(x), ptr(x2), ptr(dy), dt(x), B, hw, C1, C2, G, ptr(gamma), ptr(beta), ptr(stats[0]), ptr(stats[1]),
-            int(act), float(p_drop), int(seed), ptr(mask), ptr(keepbits), splits, ptr(red))
-  check(lib.st_gn_bwd_reduce(*common, stream()))
   if dx1 is None:
     dx1 = torch.empty_like(x)
     accum1 = False
   if x2 is not None and dx2 is None:
     dx2 = torch.empty_like(x2)
     accum2 = False
+  head = (ptr(x), ptr(x2), ptr(dy), dt(x), B, hw, C1, C2, G, ptr(gamma), ptr(beta), ptr(stats[0]), ptr(stats[1]),
+          int(act), float(p_drop), int(seed), ptr(mask), ptr(keepbits))
+  n_streams = 2 + (extra is not None) + bool(accum1 or accum2)
+  fc = lib.st_gn_bwd_fused_chunks(B, hw, Ct, dt(x), n_streams) if fused_chunks is None else int(fused_chunks)
+  if fc > 0:
+    # one launch: a cluster of `fc` CTAs per image reduces, synchronises and applies; the parameter gradients are
+    # column sums of `red` over all images (deferred to the batched reduction when a queue is given)
+    red = torch.empty((B, fc, Ct, 2), dtype=torch.float32, device=x.device)
+    csum = torch.empty((B, fc, Ct), dtype=torch.float32, device=x.device) if want_csum else None
+    check(lib.st_gn_bwd_fused(*head, fc, ptr(red), ptr(extra), float(extra_scale), ptr(dx1), int(accum1), ptr(dx2),
+                              int(accum2), ptr(csum), stream()))
+    if queue is not None:
+      queue.add_gn_params(dgamma, dbeta, red.view(B * fc, Ct, 2))
+    else:
+      check(lib.st_gn_bwd_params(ptr(red), B * fc, Ct, ptr(dgamma), ptr(dbeta), stream()))
+    return (dx1, dx2, csum) if want_csum else (dx1, dx2)
+  splits = _gn_splits(B, hw)
+  red = torch.empty((B, splits, Ct, 2), dtype=torch.float32, device=x.device)
+  common = head + (splits, ptr(red))
+  check(lib.st_gn_bwd_reduce(*common, stream()))
   chunks, csum = 0, None
   if want_csum:
     chunks = lib.st_gn_chunks(B, hw, Ct)
@@ -326,6 +344,20 @@ class ColsumQueue:
     self.jobs.append(rec)
     self.keep.extend((part, dst))
     self.blocks_y = max(self.blocks_y, (G * (C // 4) + 1023) // 1024)
+
+  def add_gn_params(self, dgamma, dbeta, red):
+    """dgamma[c] += sum_rows red[row][c][1]; dbeta[c] += sum_rows red[row][c][0]; red contiguous fp32 (rows, C, 2)."""
+    self._check(red)
+    rows, C, two = red.shape
+    assert two == 2 and red.is_contiguous() and C % 2 == 0 and dgamma.numel() == C and dbeta.numel() == C
+    assert dgamma.dtype == torch.float32 and dbeta.dtype == torch.float32 and dgamma.is_contiguous() and dbeta.is_contiguous()
+    rec = [0] * 21
+    rec[0], rec[1], rec[4], rec[8] = red.data_ptr(), dbeta.data_ptr(), rows, 2 * C
+    rec[12], rec[13], rec[14], rec[15] = dgamma.data_ptr(), 1, 2, C
+    rec[20] = 1
+    self.jobs.append(rec)
+    self.keep.extend((red, dgamma, dbeta))
+    self.blocks_y = max(self.blocks_y, (2 * C + 127) // 128)
 
   def flush(self):
     if not self.jobs:

@@ -97,7 +97,7 @@ def sample_idx(numel, k=6):
 def golden_configs(R):
   out = {}
   for path in ('vp/CIFAR10/ddpmpp_nll_st', 'vp/IMAGENET32/ddpmpp_nll', 've/CELEBA/uncsnpp_st',
-               've/celebahq/uncsnpp_st'):
+               've/celebahq/uncsnpp_st', 'vp/CIFAR10/ddpmpp_fid_st_deepest'):
     d = ref_config(path).to_dict()
     d.pop('device', None)
     d.get('data', {}).pop('tfrecords_path', None)
@@ -288,6 +288,56 @@ def golden_variants(R):
   np.savez_compressed(os.path.join(HERE, 'variants_golden.npz'), **out)
 
 
+def reduced_deepest(cfg):
+  """configs/vp/CIFAR10/ddpmpp_fid_st_deepest.py at reduced width: keeps ch_mult (1,1,1), FIR resampling, attention at
+  16x16, the `lsgm` embedding and training.mixed / ddpm_weight 100; dropout off and warm-up 0 for the trajectory."""
+  cfg.model.dropout = 0.
+  cfg.optim.warmup = 0
+  return reduced(cfg, nf=32, num_res_blocks=2, embedding_dim=16)
+
+
+def golden_deepest(R):
+  """the README's headline FID config (nf=512, ch_mult (1,1,1), 8 res-blocks, FIR, lsgm embedding, mixed
+  IS + uniform-time loss).  Score + 3 optimizer steps of step_fn_mixed with replayed draws."""
+  cfg = reduced_deepest(ref_config('vp/CIFAR10/ddpmpp_fid_st_deepest'))
+  seed, B, steps = 7, 4, 3
+  model, sde, _ = build_ref_model(R, cfg, seed=seed)
+  g = torch.Generator().manual_seed(21)
+  x = torch.rand(2, 3, 32, 32, generator=g) * 2. - 1.
+  labels = torch.tensor([3.7, 911.2])
+  model.eval()
+  out = model(x, labels).detach()
+  wrapped = torch.nn.DataParallel(model)
+  optimizer = R.losses.get_optimizer(cfg, wrapped.parameters())
+  ema = R.ema.ExponentialMovingAverage(wrapped.parameters(), decay=cfg.model.ema_rate)
+  state = dict(optimizer=optimizer, model=wrapped, ema=ema, step=0)
+  step_fn = R.losses.get_step_fn(cfg, sde, train=True, optimize_fn=R.losses.optimization_manager(cfg))
+  assert step_fn.__name__ == 'step_fn_mixed'
+  batch = torch.rand(B, 3, 32, 32, generator=g) * 2. - 1.
+  h = B // 2
+  losses, Us, us, zs = [], [], [], []
+  for s in range(steps):
+    np.random.seed(300 + s)
+    torch.manual_seed(400 + s)
+    # replay of the draws step_fn_mixed is about to make: t_min (NumPy), then per half u (rand) and z (randn)
+    Us.append(np.random.rand())
+    u_is, z_is = torch.rand(h), torch.randn(h, 3, 32, 32)
+    u_dd, z_dd = torch.rand(h), torch.randn(h, 3, 32, 32)
+    us.append(torch.cat([u_is, u_dd]).numpy())
+    zs.append(torch.cat([z_is, z_dd]).numpy())
+    np.random.seed(300 + s)
+    torch.manual_seed(400 + s)
+    losses.append(step_fn(state, batch).numpy())
+  names = [k for k, _ in model.named_parameters()]
+  params = list(model.parameters())
+  pnorm = np.array([p.double().norm().item() for p in params])
+  enorm = np.array([e.double().norm().item() for e in ema.shadow_params])
+  np.savez_compressed(os.path.join(HERE, 'deepest_golden.npz'), seed=seed, x=x.numpy(), labels=labels.numpy(),
+                      out=out.numpy(), batch=batch.numpy(), U=np.array(Us), u=np.stack(us),
+                      z=np.stack(zs).astype(np.float32), losses=np.stack(losses), pnorm=pnorm, enorm=enorm,
+                      names=np.array(names))
+
+
 def golden_sde(R):
   out = {}
   u = torch.linspace(0.01, 0.99, 7)
@@ -351,7 +401,7 @@ def main(which):
   torch.set_num_threads(8)
   R = import_reference()
   jobs = dict(configs=golden_configs, ops=golden_ops, sde=golden_sde, unet=golden_unet_cifar,
-              variants=golden_variants, sampler=golden_sampler, train=golden_train)
+              variants=golden_variants, sampler=golden_sampler, train=golden_train, deepest=golden_deepest)
   for name in (which or jobs):
     print('golden:', name, flush=True)
     jobs[name](R)

@@ -192,8 +192,11 @@ def test_gemm_rejects_bad_arguments():
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('shape', [(3, 8, 8, 64, 0), (2, 16, 16, 256, 128), (2, 4, 4, 128, 128), (130, 2, 2, 64, 0)])
 @pytest.mark.parametrize('act', [0, 1])
-def test_groupnorm_fwd_bwd(dtype, shape, act):
+@pytest.mark.parametrize('form', ['two_pass', 'fused'])
+def test_groupnorm_fwd_bwd(dtype, shape, act, form):
   B, H, W, C1, C2 = shape
+  # fused: one launch, a cluster of fc CTAs per image (8 = portable maximum; (130,2,2): one pixel per CTA)
+  fc = 0 if form == 'two_pass' else {(3, 8, 8): 2, (2, 16, 16): 8, (2, 4, 4): 1, (130, 2, 2): 4}[shape[:3]]
   C = C1 + C2
   G = min(C // 4, 32)
   x = rnd(B, C, H, W, seed=1) * 1.5 + 0.3
@@ -216,13 +219,14 @@ def test_groupnorm_fwd_bwd(dtype, shape, act):
   assert rel_l2(nchw(y.float()), y_ref) < tol(dtype)
   dgam, dbet = torch.ones(C, device=dev()), torch.ones(C, device=dev())
   dx1, dx2 = ops.gn_backward(x1, x2, nhwc(dy).to(dtype), G, gamma, beta, st, act, dgam, dbet, mask=mk,
-                             extra=nhwc(extra).to(dtype), extra_scale=0.5)
+                             extra=nhwc(extra).to(dtype), extra_scale=0.5, fused_chunks=fc)
   dx = torch.cat([dx1, dx2], -1) if C2 else dx1
   assert rel_l2(nchw(dx.float()), xq.grad + 0.5 * exq) < 2 * tol(dtype)
   # optional by-product: per-(image, chunk) column sums of the produced gradient
   _, _, cs = ops.gn_backward(x1, x2, nhwc(dy).to(dtype), G, gamma, beta, st, act, torch.zeros_like(dgam),
-                             torch.zeros_like(dbet), mask=mk, extra=nhwc(extra).to(dtype), extra_scale=0.5, want_csum=True)
-  assert cs.shape[0] == B and cs.shape[2] == C
+                             torch.zeros_like(dbet), mask=mk, extra=nhwc(extra).to(dtype), extra_scale=0.5, want_csum=True,
+                             fused_chunks=fc)
+  assert cs.shape[0] == B and cs.shape[2] == C and (fc == 0 or cs.shape[1] == fc)
   want_cs = (xq.grad + 0.5 * exq).sum(dim=(2, 3))                    # (B, C)
   assert rel_l2(cs.sum(1), want_cs) < 1e-4 + (2e-3 if dtype == torch.bfloat16 else 0)
   assert rel_l2(dgam - 1, gam.grad) < 2 * tol(dtype)
@@ -231,7 +235,7 @@ def test_groupnorm_fwd_bwd(dtype, shape, act):
   base1 = torch.ones_like(dx1)
   base2 = torch.ones_like(dx2) if C2 else None
   a1, a2 = ops.gn_backward(x1, x2, nhwc(dy).to(dtype), G, gamma, beta, st, act, dgam, dbet, mask=mk, dx1=base1,
-                           accum1=True, dx2=base2, accum2=True)
+                           accum1=True, dx2=base2, accum2=True, fused_chunks=fc)
   got = torch.cat([a1, a2], -1) if C2 else a1
   assert rel_l2(nchw(got.float()) - 1., xq.grad) < 3 * tol(dtype) + (2e-2 if dtype == torch.bfloat16 else 0)
 
@@ -254,6 +258,37 @@ def test_groupnorm_dropout_rng_is_consistent_between_fwd_and_bwd():
   assert torch.allclose(db, want, rtol=1e-5)
   y2 = ops.gn_apply(x, None, 16, gamma, beta, st, 0, p_drop=0.25, seed=99)
   assert (y2 != 0).ne(keep).any()
+
+
+@pytest.mark.parametrize('shape', [(6, 32, 32, 128, 0, 8), (5, 16, 16, 256, 128, 4), (7, 16, 16, 256, 0, 16), (9, 4, 4, 256, 256, 1)])
+def test_groupnorm_fused_backward_matches_two_pass(shape):
+  """bf16 + SiLU + in-kernel dropout (keep bits from the forward kernel) + column sums, parameter gradients through
+  the batched reduction queue: the single-launch cluster form against the two-kernel form on the same inputs."""
+  B, H, W, C1, C2, fc = shape
+  C, bf = C1 + C2, torch.bfloat16
+  G = min(C // 4, 32)
+  x1 = nhwc(rnd(B, C1, H, W, seed=1)).to(bf)
+  x2 = nhwc(rnd(B, C2, H, W, seed=2)).to(bf) if C2 else None
+  dy, extra = nhwc(rnd(B, C, H, W, seed=3)).to(bf), nhwc(rnd(B, C, H, W, seed=4)).to(bf)
+  gamma, beta = rnd(C, seed=5) * 0.2 + 1., rnd(C, seed=6) * 0.2
+  bits = torch.empty(B * H * W * C // 8, dtype=torch.uint8, device=dev())
+  st = ops.gn_stats(x1, x2, G)
+  ops.gn_apply(x1, x2, G, gamma, beta, st, 1, p_drop=0.1, seed=77, keepbits=bits)
+  res = []
+  for form in (0, fc):
+    dg, db = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
+    q = ops.ColsumQueue()
+    d1, d2, cs = ops.gn_backward(x1, x2, dy, G, gamma, beta, st, 1, dg, db, p_drop=0.1, seed=77, keepbits=bits, extra=extra,
+                                 extra_scale=0.7, want_csum=True, queue=q, fused_chunks=form)
+    q.flush()
+    res.append((d1.float(), d2.float() if C2 else None, cs.sum(1), dg, db))
+  two, one = res
+  assert torch.equal(two[0], one[0]) or rel_l2(one[0], two[0]) < 3e-3     # bf16 outputs, fp32 sums in another order
+  if C2:
+    assert rel_l2(one[1], two[1]) < 3e-3
+  assert rel_l2(one[2], two[2]) < 1e-3
+  assert rel_l2(one[3], two[3]) < 1e-5 and rel_l2(one[4], two[4]) < 1e-5
+  assert two[3].abs().sum() > 0
 
 
 def test_groupnorm_apply_finalises_statistics_in_kernel():

@@ -355,6 +355,48 @@ def test_fir_and_pyramid_variants_vs_reference_fixture(golden, tag):
   np.testing.assert_allclose(gn, g[f'{tag}_gnorm'], rtol=2e-3, atol=1e-6 * g[f'{tag}_gnorm'].max())
 
 
+def test_deepest_lsgm_mixed_step_vs_reference_fixture(golden):
+  """reduced-width copy of configs/vp/CIFAR10/ddpmpp_fid_st_deepest.py (lsgm embedding, FIR res-blocks,
+  ch_mult (1,1,1), attention at 16x16) - network output, then three optimizer steps of step_fn_mixed
+  (reference losses.py:295-320: importance-sampled half + 100 x uniform-time half) with replayed draws."""
+  from soft_truncation_b200 import configs, losses
+  from soft_truncation_b200.models import utils as mutils
+  from soft_truncation_b200.models.ema import ExponentialMovingAverage
+  g = golden('deepest_golden.npz')
+  cfg = configs.cifar10_ddpmpp_fid_st_deepest()
+  cfg.model.nf, cfg.model.num_res_blocks, cfg.model.embedding_dim = 32, 2, 16
+  cfg.model.dropout = 0.
+  cfg.optim.warmup = 0
+  cfg.device = torch.device(DEV)
+  model, sde, _ = _model(cfg, int(g['seed']), torch.float32)
+  net = mutils.unwrap(model)
+  names = [k for k, _ in net.named_parameters()]
+  assert names == list(g['names'])
+  model.eval()
+  with torch.no_grad():
+    out = model(torch.tensor(g['x'], device=DEV), torch.tensor(g['labels'], device=DEV))
+  assert rel_l2(out, g['out']) < 2e-5
+  model.train()
+  optimizer = losses.get_optimizer(cfg, model.parameters())
+  ema = ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate)
+  state = dict(optimizer=optimizer, model=model, ema=ema, step=0)
+  step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+  assert step_fn.__name__ == 'step_fn_mixed'
+  batch = torch.tensor(g['batch'], device=DEV)
+  vp = ref_train.make_sde(cfg)
+  for s in range(g['losses'].shape[0]):
+    inj = dict(u=torch.tensor(g['u'][s]), z=torch.tensor(g['z'][s]), t_min=vp.t_min_from_uniform(cfg, float(g['U'][s])))
+    got = step_fn(state, batch, injected=inj)
+    assert got.device.type == 'cpu' and got.shape == (2,)
+    np.testing.assert_allclose(got.numpy(), g['losses'][s], rtol=5e-4, err_msg=f'step {s}')
+  params = dict(net.named_parameters())
+  pn = np.array([params[k].double().norm().item() for k in names])
+  np.testing.assert_allclose(pn, g['pnorm'], rtol=2e-4, atol=2e-6)
+  shadow = [p for p in ema.shadow_params]
+  en = np.array([t.double().norm().item() for t in shadow])
+  np.testing.assert_allclose(en, g['enorm'], rtol=2e-4, atol=2e-6)
+
+
 def test_pc_sampler_ve_langevin_vs_reference_fixture(golden):
   """4-step reverse-diffusion predictor + Langevin corrector (VE) on the reduced C5 network: pins the
   ReverseDiffusionPredictor / LangevinCorrector updates, the on-device batch norms and the final VE denoise step."""

@@ -32,6 +32,14 @@ def _reduced_c5():
   return cfg
 
 
+def _reduced_deepest():
+  cfg = configs.cifar10_ddpmpp_fid_st_deepest()
+  cfg.model.nf, cfg.model.num_res_blocks, cfg.model.embedding_dim = 32, 2, 16
+  cfg.model.dropout = 0.
+  cfg.optim.warmup = 0
+  return cfg
+
+
 def test_configs_match_reference():
   want = json.load(open(os.path.join(GOLDEN, 'configs_golden.json')))
   for path, ref in want.items():
@@ -201,6 +209,28 @@ def test_unet_oracle_vs_reference_variants(golden, tag):
   torch.mean(losses).backward()
   gn = np.array([0. if state.sd[k].grad is None else state.sd[k].grad.double().norm().item() for k in names])
   np.testing.assert_allclose(gn, g[f'{tag}_gnorm'], rtol=2e-3, atol=1e-6 * g[f'{tag}_gnorm'].max())
+
+
+def test_deepest_lsgm_mixed_step_oracle_vs_reference(golden):
+  """reduced-width "deepest" DDPM++ (lsgm embedding, FIR, ch_mult (1,1,1)) and three optimizer steps of
+  step_fn_mixed (reference losses.py:295-320) with replayed draws."""
+  g = golden('deepest_golden.npz')
+  cfg = _reduced_deepest()
+  sd = ref_model.make_state_dict(cfg, seed=int(g['seed']))
+  names = [k for k in sd if k != 'sigmas']
+  assert names == list(g['names'])
+  out = ref_model.unet_forward(sd, cfg, torch.tensor(g['x']), torch.tensor(g['labels']))
+  assert rel_l2(out, g['out']) < 2e-5
+  sde = ref_train.make_sde(cfg)
+  state = ref_train.TrainState(sd)
+  batch = torch.tensor(g['batch'])
+  for s in range(g['losses'].shape[0]):
+    losses, _ = ref_train.train_step(state, cfg, sde, batch, torch.tensor(g['u'][s]), torch.tensor(g['z'][s]), float(g['U'][s]))
+    np.testing.assert_allclose(losses.numpy(), g['losses'][s], rtol=5e-4)
+  pn = np.array([state.sd[k].double().norm().item() for k in names])
+  en = np.array([state.ema[k].double().norm().item() for k in names])
+  np.testing.assert_allclose(pn, g['pnorm'], rtol=1e-4, atol=2e-6)     # Adam turns noise-level gradients into lr-sized steps
+  np.testing.assert_allclose(en, g['enorm'], rtol=1e-4, atol=2e-6)
 
 
 @pytest.mark.parametrize('tag', ['w5000', 'w0'])

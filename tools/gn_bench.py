@@ -66,9 +66,25 @@ def main():
       t_red = timed(only('reduce', **kw))
       ops.lib.st_gn_bwd_apply = orig_app
       res.append((t_red, t_all - t_red))
+    # single-launch cluster form (cluster size fc) against the two-kernel total, parameter gradients deferred
+    q = ops.ColsumQueue()
+    fused = []
+    for kw in (dict(), dict(p_drop=0.1, seed=5, keepbits=bits, want_csum=True), dict(extra=dy, extra_scale=0.7, want_csum=True)):
+      row = []
+      for fc in (0, 1, 2, 4, 8, 16):
+        if fc > max(1, H * H // (256 // (Ct // 8))):
+          continue
+
+        def run(fc=fc, kw=kw):
+          ops.gn_backward(x, x2, dy, G, gamma, beta, stats, True, dgamma, dbeta, queue=q, fused_chunks=fc, **kw)
+          q.jobs, q.keep = [], []
+        row.append(f'{fc}:{timed(run):.1f}')
+      fused.append(' '.join(row))
     f = lambda t, units: f'{t:7.1f} ({units * nbytes / t / 1e3:5.0f})'
     print(H, C1, C2, '|', f(t_stats, 1), '|', f(t_apply, 2), '|', f(t_applyd, 2), '|', f(res[0][0], 2), '|', f(res[0][1], 3), '|',
           f(res[1][0], 2), '|', f(res[1][1], 3), flush=True)
+    print('      backward total us by cluster size (0 = two kernels): plain [', fused[0], '] drop+csum [', fused[1], '] extra+csum [', fused[2], ']',
+          f'ideal 3-pass at 6.5 TB/s: {3 * nbytes / 6.5e6:.1f}', flush=True)
 
 
 if __name__ == '__main__':
