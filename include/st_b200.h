@@ -151,6 +151,14 @@ int st_gn_bwd_fused(const void* x1, const void* x2, const void* dy, int dtype, i
                     const uint8_t* keepbits, int chunks, float* red, const void* extra, float extra_scale,
                     void* dx1, int accum1, void* dx2, int accum2, float* csum, void* stream);
 
+/* ------------------------------------------------------------------ training-batch preparation
+ * Replaces the float pipeline of datasets.py:56-62,117,311-326 + run_lib.py:73-75: src uint8 [n_img][H][W][C] ->
+ * dst fp32 [n_img][C][H][W] = a * deq(flip(src)/255) + b, deq(x) = (255 x + u)/256 when dequant == 1.  `flip`
+ * (optional) holds one byte per image (non-zero = mirror left-right); `u` (optional, fp32 NCHW in [0,1)) replaces the
+ * in-kernel generator keyed by (seed, element). */
+int st_prep_batch(const uint8_t* src, const float* u, const uint8_t* flip, float* dst, int n_img, int C, int H,
+                  int W, int dequant, uint64_t seed, float a, float b, void* stream);
+
 /* ------------------------------------------------------------------ elementwise / small
  * All take element counts; pointers must be 16-byte aligned. */
 int st_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);

@@ -48,6 +48,7 @@ SIGNATURES = {
     'st_gn_bwd_fused_chunks': [c_int, c_int, c_int, c_int, c_int],
     'st_gn_bwd_fused': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f,
                         c_u64, c_p, c_p, c_int, c_p, c_p, c_f, c_p, c_int, c_p, c_int, c_p, c_p],
+    'st_prep_batch': [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_f, c_f, c_p],
     'st_cast': [c_p, c_int, c_p, c_int, c_i64, c_p],
     'st_axpby': [c_p, c_p, c_p, c_int, c_f, c_f, c_i64, c_p],
     'st_silu': [c_p, c_p, c_int, c_i64, c_p],

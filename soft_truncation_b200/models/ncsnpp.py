@@ -115,6 +115,8 @@ def bias_grad(dst, g2, gs, scale=1.0):
   producers of `g2` emitted as a by-product of their GroupNorm backward kernels (then no pass over g2 is
   needed), or None."""
   C = g2.shape[-1]
+  if not ops.PARAM_GRADS:
+    return
   if gs:
     CSQ.add_reduce(dst, list(gs), scale)       # one batched launch at the end of the backward pass
   else:
@@ -244,7 +246,9 @@ class ResBlock:
     del da1
     # ---- temb projection gradient = per-image column sums of dh1 (by-product of the kernel above, or an explicit
     # pass); their sum over images is the Conv_0.bias / Dense_0.bias gradient (TimeEmbedding.bwd)
-    if FUSE_CSUM:
+    if not ops.PARAM_GRADS:
+      pass                                    # input-gradient-only pass (likelihood divergence): temb is a constant
+    elif FUSE_CSUM:
       CSQ.add_groups(net.d_dense[:, self.dense_off:self.dense_off + Co], r1[2])
     else:
       dd = torch.empty((B, Co), dtype=torch.float32, device=g.device)
@@ -337,7 +341,8 @@ class AttnBlock:
     g2 = g.view(npix, C)
     # ---- NIN_3
     bias_grad(P.g(pre + 'NIN_3.b'), g2, gs, s)
-    ops.gemm_tn(g2, o.view(npix, C), C, C, npix, out=P.g(pre + 'NIN_3.W'), alpha=s, accumulate=True)
+    if ops.PARAM_GRADS:
+      ops.gemm_tn(g2, o.view(npix, C), C, C, npix, out=P.g(pre + 'NIN_3.W'), alpha=s, accumulate=True)
     do = ops.gemm_nn(g2, P.c(pre + 'NIN_3.W'), C, alpha=s)              # (npix, C): g W3 (W3 is [out][in])
     # ---- attention core
     dqkv = torch.empty_like(qkv)
@@ -356,8 +361,9 @@ class AttnBlock:
                 sCb=L * 3 * C, **bs)
     del ds
     # ---- q,k,v projections
-    ops.colsum(dqkv, 1, npix, 3 * C, P.g_group(self.names_b), accumulate=True)
-    ops.gemm_tn(dqkv, h.view(npix, C), 3 * C, C, npix, out=P.g_group(self.names_w), accumulate=True)
+    if ops.PARAM_GRADS:
+      ops.colsum(dqkv, 1, npix, 3 * C, P.g_group(self.names_b), accumulate=True)
+      ops.gemm_tn(dqkv, h.view(npix, C), 3 * C, C, npix, out=P.g_group(self.names_w), accumulate=True)
     dh = ops.gemm_nn(dqkv, P.c_group(self.names_w), C).view(B, H, W, C)
     # ---- GroupNorm (no activation) + residual
     r = ops.gn_backward(x, None, dh, self.G, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st, 0,
@@ -549,7 +555,8 @@ class PyramidDownConv:
     g2 = g.view(-1, self.cout)
     rows = g2.shape[0]
     bias_grad(P.g(self.pre + 'bias'), g2, gs, s)
-    ops.gemm_tn(g2, cols, self.cout, cols.shape[1], rows, out=P.g(self.pre + 'weight'), alpha=s, accumulate=True)
+    if ops.PARAM_GRADS:
+      ops.gemm_tn(g2, cols, self.cout, cols.shape[1], rows, out=P.g(self.pre + 'weight'), alpha=s, accumulate=True)
     if acc[1] is not None:
       dh = ops.axpby(acc[1], g, 1.0, s, out=acc[1])
     else:
@@ -1062,7 +1069,8 @@ class NCSNpp(nn.Module):
           else:
             gsum.setdefault(i, []).append(c)
     CSQ.flush()
-    self.temb.bwd(net)
+    if ops.PARAM_GRADS:
+      self.temb.bwd(net)
     net.tape.ops = []
     if need_dx:
       dx = ops.nhwc_to_nchw(grads[net.x_id], dout.shape[1])

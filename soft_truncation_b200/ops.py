@@ -93,6 +93,8 @@ def conv_dgrad(dy, w, cin, kh=3, kw=3, alpha=1.0, out=None):
 
 def conv_wgrad(dy, x, dw, kh=3, kw=3, x2=None, alpha=1.0):
   """dw[cout][taps][cin] (fp32, contiguous view into the flat gradient buffer) += alpha * dy^T * im2col(x)."""
+  if not PARAM_GRADS:
+    return
   B, H, W, Co = dy.shape
   C1 = x.shape[3]
   C2 = 0 if x2 is None else x2.shape[3]
@@ -145,6 +147,22 @@ def gemm_tn(a, b, M, N, K, out=None, out_dtype=None, alpha=1.0, lda=None, ldb=No
         B=b, C=out, sAm=1, sAk=lda or M, sAb=sAb, sBn=1, sBk=ldb or N, sBb=sBb, sCm=ldc or N, sCb=sCb,
         accumulate=int(accumulate), split_k=split_k, alpha=alpha)
   return out
+
+
+# Backward passes normally produce parameter AND input gradients.  `input_grads_only()` switches the weight / bias /
+# GroupNorm-parameter gradient work off for passes that only want d(out)/d(input): the Hutchinson divergence of the
+# likelihood ODE (reference likelihood.py:27-37) differentiates the score with respect to x with the weights fixed.
+PARAM_GRADS = True
+
+
+class input_grads_only:
+  def __enter__(self):
+    global PARAM_GRADS
+    self.prev, PARAM_GRADS = PARAM_GRADS, False
+
+  def __exit__(self, *exc):
+    global PARAM_GRADS
+    PARAM_GRADS = self.prev
 
 
 # ------------------------------------------------------------------------------------ GroupNorm
@@ -216,6 +234,8 @@ def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0.,
   if x2 is not None and dx2 is None:
     dx2 = torch.empty_like(x2)
     accum2 = False
+  if not PARAM_GRADS:
+    dgamma = dbeta = None
   head = (ptr(x), ptr(x2), ptr(dy), dt(x), B, hw, C1, C2, G, ptr(gamma), ptr(beta), ptr(stats[0]), ptr(stats[1]),
           int(act), float(p_drop), int(seed), ptr(mask), ptr(keepbits))
   n_streams = 2 + (extra is not None) + bool(accum1 or accum2)
@@ -227,7 +247,9 @@ def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0.,
     csum = torch.empty((B, fc, Ct), dtype=torch.float32, device=x.device) if want_csum else None
     check(lib.st_gn_bwd_fused(*head, fc, ptr(red), ptr(extra), float(extra_scale), ptr(dx1), int(accum1), ptr(dx2),
                               int(accum2), ptr(csum), stream()))
-    if queue is not None:
+    if dgamma is None:
+      pass
+    elif queue is not None:
       queue.add_gn_params(dgamma, dbeta, red.view(B * fc, Ct, 2))
     else:
       check(lib.st_gn_bwd_params(ptr(red), B * fc, Ct, ptr(dgamma), ptr(dbeta), stream()))

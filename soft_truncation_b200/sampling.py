@@ -15,7 +15,7 @@ import numpy as np
 import torch
 from scipy import integrate
 
-from . import ops, sde_lib
+from . import ode, ops, sde_lib
 from ._lib import check, lib
 from .models import utils as mutils
 from .models.utils import from_flattened_numpy, get_score_fn, to_flattened_numpy
@@ -385,8 +385,12 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
 
 
 def get_ode_sampler(config, sde, shape, inverse_scaler, denoise=False, rtol=1e-5, atol=1e-5, method='RK45', eps=1e-3,
-                    device='cuda'):
-  """Probability-flow ODE sampler with scipy's black-box solver (reference sampling.py:436-504)."""
+                    device='cuda', solver='device'):
+  """Probability-flow ODE sampler (reference sampling.py:436-504).  `solver='device'` integrates with
+  `ode.solve_ivp_rk45` - scipy's RK45 algorithm with the state resident on the GPU - instead of moving the state
+  through numpy for every function evaluation; `solver='scipy'` is the reference's black-box host loop."""
+  if solver == 'device' and method != 'RK45':
+    solver = 'scipy'
 
   def denoise_update_fn(model, x):
     score_fn = get_score_fn(config, sde, model, train=False, continuous=True)
@@ -404,14 +408,25 @@ def get_ode_sampler(config, sde, shape, inverse_scaler, denoise=False, rtol=1e-5
     with torch.no_grad():
       x = (sde.prior_sampling(shape) if x_init is None else x_init).to(device)
 
-      def ode_func(t, x):
-        x = from_flattened_numpy(x, shape).to(device).type(torch.float32)
-        vec_t = torch.ones(shape[0], device=x.device) * t
-        return to_flattened_numpy(drift_fn(model, x, vec_t))
+      if solver == 'device':
+        def rhs(t, state):
+          xs = state.reshape(shape).float()
+          return drift_fn(model, xs, torch.ones(shape[0], device=xs.device) * t).reshape(-1)
 
-      solution = integrate.solve_ivp(ode_func, (sde.T, eps), to_flattened_numpy(x), rtol=rtol, atol=atol, method=method)
-      nfe = solution.nfev
-      x = torch.tensor(solution.y[:, -1]).reshape(shape).to(device).type(torch.float32)
+        sol = ode.solve_ivp_rk45(rhs, (sde.T, eps), x.reshape(-1).double(), rtol=rtol, atol=atol)
+        if not sol.success:
+          raise RuntimeError('ODE sampler: step size underflow')
+        nfe = sol.nfev
+        x = sol.y.reshape(shape).float()
+      else:
+        def ode_func(t, x):
+          x = from_flattened_numpy(x, shape).to(device).type(torch.float32)
+          vec_t = torch.ones(shape[0], device=x.device) * t
+          return to_flattened_numpy(drift_fn(model, x, vec_t))
+
+        solution = integrate.solve_ivp(ode_func, (sde.T, eps), to_flattened_numpy(x), rtol=rtol, atol=atol, method=method)
+        nfe = solution.nfev
+        x = torch.tensor(solution.y[:, -1]).reshape(shape).to(device).type(torch.float32)
       if denoise:
         x = denoise_update_fn(model, x)
       return inverse_scaler(x), nfe

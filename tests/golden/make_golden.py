@@ -338,6 +338,59 @@ def golden_deepest(R):
                       names=np.array(names))
 
 
+def reduced_cifar(cfg):
+  return reduced(cfg, nf=32, ch_mult=(1, 2), num_res_blocks=1)
+
+
+def golden_likelihood(R):
+  """the reference's likelihood.py on a reduced-width CIFAR DDPM++ (VP): Hutchinson divergence of the
+  probability-flow drift, one bits/dim evaluation (RK45, 'correct' mode) and one NELBO sample, draws recorded."""
+  import likelihood as L
+  cfg = reduced_cifar(ref_config('vp/CIFAR10/ddpmpp_nll_st'))
+  seed, B = 13, 2
+  model, sde, _ = build_ref_model(R, cfg, seed=seed)
+  model.eval()
+  inv = lambda v: (v + 1.) / 2.          # datasets.get_data_inverse_scaler for centered data (datasets.py:65-71)
+  g = torch.Generator().manual_seed(31)
+  data = (torch.randint(0, 256, (B, 3, 32, 32), generator=g).float() / 255.) * 2. - 1.
+  out = dict(seed=seed, data=data.numpy())
+  # --- drift and divergence at fixed (x, t, eps)
+  t = torch.tensor([0.3, 0.7])
+  x = torch.randn(B, 3, 32, 32, generator=g)
+  eps_h = torch.randint(0, 2, (B, 3, 32, 32), generator=g).float() * 2 - 1.
+  score_fn = R.mutils.get_score_fn(cfg, sde, model, train=False, continuous=True)
+  rsde = sde.reverse(score_fn, probability_flow=cfg.eval.probability_flow, lambda_=cfg.eval.lambda_)
+  drift_fn = lambda xx, tt: rsde.sde(xx, tt)[0]
+  with torch.no_grad():
+    drift = drift_fn(x, t)
+    div = L.get_div_fn(drift_fn)(x.clone(), t, eps_h)
+  out.update(t=t.numpy(), x=x.numpy(), eps_h=eps_h.numpy(), drift=drift.numpy(), div=div.numpy())
+  # --- bits/dim
+  rtol = atol = 1e-3
+  lik = L.get_likelihood_fn(cfg, sde, inv, rtol=rtol, atol=atol)
+  torch.manual_seed(77)
+  epsilon = torch.randint_like(data, low=0, high=2).float() * 2 - 1.
+  z = torch.randn_like(data)
+  z_res = torch.randn_like(data)
+  torch.manual_seed(77)
+  bpd, latent, nfe = lik(model, data, eps=1e-3)
+  out.update(lik_rtol=rtol, lik_eps=1e-3, lik_epsilon=epsilon.numpy(), lik_z=z.numpy(), lik_z_res=z_res.numpy(),
+             lik_bpd=bpd.numpy(), lik_latent=latent.numpy(), lik_nfe=nfe)
+  # --- NELBO sample
+  elbo = L.get_elbo_fn(cfg, sde, inv)
+  torch.manual_seed(78)
+  u = torch.rand(B)
+  z = torch.randn_like(data)
+  epsilon = torch.randint_like(data, low=0, high=2).float() * 2 - 1.
+  lp_z = torch.randn_like(data)
+  z_res = torch.randn_like(data)
+  torch.manual_seed(78)
+  nelbo, resid = elbo(model, data, eps=1e-3)
+  out.update(elbo_eps=1e-3, elbo_u=u.numpy(), elbo_z=z.numpy(), elbo_epsilon=epsilon.numpy(), elbo_lp_z=lp_z.numpy(),
+             elbo_z_res=z_res.numpy(), elbo_nelbo=nelbo.detach().numpy(), elbo_resid=resid.detach().numpy())
+  np.savez_compressed(os.path.join(HERE, 'likelihood_golden.npz'), **out)
+
+
 def golden_sde(R):
   out = {}
   u = torch.linspace(0.01, 0.99, 7)
@@ -401,7 +454,8 @@ def main(which):
   torch.set_num_threads(8)
   R = import_reference()
   jobs = dict(configs=golden_configs, ops=golden_ops, sde=golden_sde, unet=golden_unet_cifar,
-              variants=golden_variants, sampler=golden_sampler, train=golden_train, deepest=golden_deepest)
+              variants=golden_variants, sampler=golden_sampler, train=golden_train, deepest=golden_deepest,
+              likelihood=golden_likelihood)
   for name in (which or jobs):
     print('golden:', name, flush=True)
     jobs[name](R)

@@ -523,3 +523,39 @@ def test_pc_update_and_langevin_helpers():
   check(lib.st_batch_norms(ops.ptr(s), ops.ptr(nz), ops.ptr(norms), B, D, ops.stream()))
   want = torch.stack([s.reshape(B, -1).norm(dim=-1).mean(), nz.reshape(B, -1).norm(dim=-1).mean()])
   assert torch.allclose(norms, want, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ batch preparation
+@pytest.mark.parametrize('centered,dequant,flip', [(True, 'uniform', True), (False, 'none', True), (True, 'none', False)])
+def test_prepare_batch_matches_reference_pipeline(centered, dequant, flip):
+  """st_prep_batch against the reference's float pipeline: tf convert_image_dtype (x/255), random_flip_left_right
+  (datasets.py:311-326), (255 x + u)/256 (run_lib.py:73-74), scaler (datasets.py:56-62) - bit-exact with injected draws."""
+  from soft_truncation_b200 import configs, datasets
+  cfg = configs.cifar10_ddpmpp_nll_st()
+  cfg.device = dev()
+  cfg.data.centered, cfg.data.dequantization, cfg.data.random_flip = centered, dequant, flip
+  B = 6
+  g = gen(3)
+  u8 = torch.randint(0, 256, (B, 32, 32, 3), generator=g, dtype=torch.uint8)
+  fl = torch.rand(B, generator=g) < 0.5
+  u = torch.rand(B, 3, 32, 32, generator=g)
+  got = datasets.prepare_batch(cfg, u8.pin_memory(), train=True, injected=dict(flip=fl, u=u))
+  x = u8.float() * torch.tensor(1. / 255., dtype=torch.float32)
+  if flip:
+    x = torch.where(fl[:, None, None, None], x.flip(2), x)
+  x = x.permute(0, 3, 1, 2)
+  if dequant == 'uniform':
+    x = (255. * x + u) / 256.
+  want = datasets.get_data_scaler(cfg)(x)
+  assert got.shape == (B, 3, 32, 32) and got.dtype == torch.float32
+  assert torch.equal(got.cpu(), want)
+  # evaluation batches are never flipped; in-kernel uniforms stay inside the quantisation bin
+  ev = datasets.prepare_batch(cfg, u8.to(dev()), train=False, seed=5)
+  base = (u8.float() * torch.tensor(1. / 255., dtype=torch.float32)).permute(0, 3, 1, 2)
+  inv = datasets.get_data_inverse_scaler(cfg)(ev.cpu())
+  if dequant == 'uniform':
+    d = inv * 256. - 255. * base
+    assert d.min() >= -1e-4 and d.max() < 1. + 1e-4 and 0.45 < d.mean() < 0.55
+    assert not torch.equal(ev, datasets.prepare_batch(cfg, u8.to(dev()), train=False, seed=6))
+  else:
+    assert torch.allclose(inv, base, atol=1e-6)

@@ -512,5 +512,51 @@ def test_step_fn_mixed_and_ode_sampler_run():
   cfg.sampling.method = 'ode'
   fn = sampling.get_ode_sampler(cfg, sde, (2, 3, 32, 32), lambda v: v, denoise=True, rtol=1e-2, atol=1e-2,
                                 eps=1e-3, device=cfg.device)
-  x, nfe = fn(model)
+  x_T = sde.prior_sampling((2, 3, 32, 32))
+  x, nfe = fn(model, x_init=x_T)
   assert x.shape == (2, 3, 32, 32) and torch.isfinite(x).all() and nfe > 5
+  # the device-resident RK45 takes the same steps as the reference's scipy loop
+  fn_host = sampling.get_ode_sampler(cfg, sde, (2, 3, 32, 32), lambda v: v, denoise=True, rtol=1e-2, atol=1e-2,
+                                     eps=1e-3, device=cfg.device, solver='scipy')
+  x_host, nfe_host = fn_host(model, x_init=x_T)
+  assert nfe_host == nfe and rel_l2(x, x_host) < 1e-4
+
+
+def test_likelihood_vs_reference_fixture(golden):
+  """bits/dim, Hutchinson divergence and NELBO sample of the reference's likelihood.py (fixture from
+  the reference on a reduced-width CIFAR DDPM++), here with the CUDA network: the divergence is the input-gradient-only
+  backward pass, the ODE state stays on the device."""
+  from soft_truncation_b200 import likelihood, ops
+  from soft_truncation_b200.models import utils as mutils
+  g = golden('likelihood_golden.npz')
+  cfg = _cfg()
+  cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks = 32, (1, 2), 1
+  model, sde, _ = _model(cfg, int(g['seed']), torch.float32)
+  net = mutils.unwrap(model)
+  inv = lambda v: (v + 1.) / 2.
+  score_fn = mutils.get_score_fn(cfg, sde, model, train=False, continuous=True)
+  rsde = sde.reverse(score_fn, probability_flow=cfg.eval.probability_flow, lambda_=cfg.eval.lambda_)
+  drift_fn = lambda xx, tt: rsde.sde(xx, tt)[0]
+  x, t = torch.tensor(g['x'], device=DEV), torch.tensor(g['t'], device=DEV)
+  net.zero_grad()
+  div = likelihood.get_div_fn(drift_fn)(x, t, torch.tensor(g['eps_h'], device=DEV))
+  np.testing.assert_allclose(div.cpu().numpy(), g['div'], rtol=5e-4)
+  assert float(net._grad.abs().sum()) == 0. and ops.PARAM_GRADS      # no parameter gradients were produced
+  data = torch.tensor(g['data'], device=DEV)
+  lik = likelihood.get_likelihood_fn(cfg, sde, inv, rtol=float(g['lik_rtol']), atol=float(g['lik_rtol']))
+  inj = dict(epsilon=torch.tensor(g['lik_epsilon']), z=torch.tensor(g['lik_z']), z_res=torch.tensor(g['lik_z_res']))
+  bpd, latent, nfe = lik(model, data, eps=float(g['lik_eps']), injected=inj)
+  assert abs(nfe - int(g['lik_nfe'])) <= 12          # adaptive steps may split differently at fp32 noise level
+  np.testing.assert_allclose(bpd.cpu().numpy(), g['lik_bpd'], rtol=2e-3)
+  assert rel_l2(latent, g['lik_latent']) < 5e-3
+  bpd_host, _, nfe_host = likelihood.get_likelihood_fn(cfg, sde, inv, rtol=float(g['lik_rtol']), atol=float(g['lik_rtol']),
+                                                       solver='scipy')(model, data, eps=float(g['lik_eps']), injected=inj)
+  assert nfe_host == nfe
+  np.testing.assert_allclose(bpd_host.cpu().numpy(), bpd.cpu().numpy(), rtol=1e-5)
+  elbo = likelihood.get_elbo_fn(cfg, sde, inv)
+  nelbo, resid = elbo(model, data, eps=float(g['elbo_eps']),
+                      injected=dict(u=torch.tensor(g['elbo_u']), z=torch.tensor(g['elbo_z']),
+                                    epsilon=torch.tensor(g['elbo_epsilon']), lp_z=torch.tensor(g['elbo_lp_z']),
+                                    z_res=torch.tensor(g['elbo_z_res'])))
+  np.testing.assert_allclose(nelbo.cpu().numpy(), g['elbo_nelbo'], rtol=5e-4)
+  np.testing.assert_allclose(resid.cpu().numpy(), g['elbo_resid'], rtol=5e-4)

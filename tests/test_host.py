@@ -190,3 +190,55 @@ def test_data_parallel_plumbing_gloo_world2():
   port = 29500 + os.getpid() % 1000
   mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
   assert dict(out) == {0: True, 1: True}
+
+
+def test_device_rk45_takes_the_same_steps_as_scipy():
+  """ode.solve_ivp_rk45 (state as one torch tensor, here on the CPU) against scipy.integrate.solve_ivp(RK45), the
+  solver the reference calls (sampling.py:492, likelihood.py:111): same accepted times, nfev and final state,
+  forward and backward in time."""
+  from scipy import integrate
+  from soft_truncation_b200.ode import solve_ivp_rk45
+  rng = np.random.default_rng(0)
+  A = rng.normal(size=(40, 40)) * 0.5 - np.eye(40)
+  At = torch.tensor(A)
+  y0 = rng.normal(size=40)
+  for span, rtol, atol in (((0., 2.), 1e-5, 1e-5), ((1., 1e-3), 1e-3, 1e-6), ((0., 0.5), 1e-8, 1e-10)):
+    want = integrate.solve_ivp(lambda t, y: A @ y * np.cos(3 * t) + np.sin(5 * t + y), span, y0, rtol=rtol, atol=atol,
+                               method='RK45')
+    got = solve_ivp_rk45(lambda t, y: At @ y * np.cos(3 * t) + torch.sin(5 * t + y), span, torch.tensor(y0),
+                         rtol=rtol, atol=atol)
+    assert got.success and got.nfev == want.nfev and len(got.ts) == len(want.t)
+    np.testing.assert_allclose(np.array(got.ts), want.t, rtol=1e-6, atol=1e-9)    # step factors: err_norm ** -0.2
+    np.testing.assert_allclose(got.y.numpy(), want.y[:, -1], rtol=1e-7, atol=1e-9)
+
+
+def test_u8_loader_epochs_and_scalers():
+  """datasets.U8Loader / get_batch (reference datasets.py:106-113: restart the epoch when exhausted) and the data
+  scalers (datasets.py:56-71)."""
+  from soft_truncation_b200 import configs, datasets
+  imgs = (np.arange(10 * 4 * 4 * 3) % 251).astype(np.uint8).reshape(10, 4, 4, 3)
+  ds = datasets.U8Loader(imgs, 4, shuffle=True, seed=3)
+  assert len(ds) == 2
+  it = iter(ds)
+  seen = []
+  for _ in range(5):                       # 2 batches per epoch -> crosses two epoch boundaries
+    batch, it = datasets.get_batch(None, it, ds)
+    assert batch.dtype == torch.uint8 and batch.shape == (4, 4, 4, 3)
+    seen.append(batch.numpy().copy())
+  flat = imgs.reshape(10, -1)
+  for b in seen:                           # every row is one of the source images
+    for row in b.reshape(4, -1):
+      assert (flat == row).all(1).any()
+  first_epoch = np.concatenate(seen[:2]).reshape(8, -1)
+  assert len({r.tobytes() for r in first_epoch}) == 8          # no repeats inside an epoch
+  with pytest.raises(ValueError):
+    datasets.U8Loader(imgs.astype(np.float32), 4)
+  cfg = configs.cifar10_ddpmpp_nll_st()
+  x = torch.linspace(0, 1, 7)
+  assert torch.allclose(datasets.get_data_inverse_scaler(cfg)(datasets.get_data_scaler(cfg)(x)), x)
+  assert datasets.get_data_scaler(cfg)(torch.tensor(0.)).item() == -1.
+  cfg.data.centered = False
+  assert datasets.get_data_scaler(cfg)(x) is x and datasets.get_data_inverse_scaler(cfg)(x) is x
+  with pytest.raises(RuntimeError):        # batch preparation is a CUDA kernel: no CPU fallback
+    cfg.device = torch.device('cpu')
+    datasets.prepare_batch(cfg, torch.zeros(2, 32, 32, 3, dtype=torch.uint8))

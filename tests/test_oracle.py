@@ -15,6 +15,7 @@ import torch
 from conftest import GOLDEN, rel_l2
 from oracle import ref_model, ref_ops, ref_train
 from soft_truncation_b200 import configs
+from soft_truncation_b200.models import utils as mutils
 
 
 def _reduced_c3():
@@ -231,6 +232,52 @@ def test_deepest_lsgm_mixed_step_oracle_vs_reference(golden):
   en = np.array([state.ema[k].double().norm().item() for k in names])
   np.testing.assert_allclose(pn, g['pnorm'], rtol=1e-4, atol=2e-6)     # Adam turns noise-level gradients into lr-sized steps
   np.testing.assert_allclose(en, g['enorm'], rtol=1e-4, atol=2e-6)
+
+
+class _OracleNet(torch.nn.Module):
+  """The oracle U-Net behind the model call convention, so that the host-side estimators can run on the CPU."""
+
+  def __init__(self, sd, cfg):
+    super().__init__()
+    self.sd, self.cfg = sd, cfg
+
+  def forward(self, x, labels):
+    return ref_model.unet_forward(self.sd, self.cfg, x, labels)
+
+
+def test_likelihood_host_logic_vs_reference_fixture(golden):
+  """likelihood.py + ode.py (host logic; the network is the CPU oracle here) against the reference's
+  likelihood.py: Hutchinson divergence, bits/dim through the device-resident RK45 (same nfev as scipy), NELBO sample."""
+  from soft_truncation_b200 import likelihood, sde_lib
+  g = golden('likelihood_golden.npz')
+  cfg = configs.cifar10_ddpmpp_nll_st()
+  cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks = 32, (1, 2), 1
+  sde = sde_lib.get_sde(cfg)
+  net = _OracleNet(ref_model.make_state_dict(cfg, seed=int(g['seed'])), cfg)
+  inv = lambda v: (v + 1.) / 2.
+  score_fn = mutils.get_score_fn(cfg, sde, net, train=False, continuous=True)
+  rsde = sde.reverse(score_fn, probability_flow=cfg.eval.probability_flow, lambda_=cfg.eval.lambda_)
+  drift_fn = lambda xx, tt: rsde.sde(xx, tt)[0]
+  x, t = torch.tensor(g['x']), torch.tensor(g['t'])
+  with torch.no_grad():
+    assert rel_l2(drift_fn(x, t), g['drift']) < 1e-5
+  div = likelihood.get_div_fn(drift_fn)(x, t, torch.tensor(g['eps_h']))
+  np.testing.assert_allclose(div.numpy(), g['div'], rtol=2e-4)
+  data = torch.tensor(g['data'])
+  lik = likelihood.get_likelihood_fn(cfg, sde, inv, rtol=float(g['lik_rtol']), atol=float(g['lik_rtol']))
+  bpd, latent, nfe = lik(net, data, eps=float(g['lik_eps']),
+                         injected=dict(epsilon=torch.tensor(g['lik_epsilon']), z=torch.tensor(g['lik_z']),
+                                       z_res=torch.tensor(g['lik_z_res'])))
+  assert nfe == int(g['lik_nfe'])
+  np.testing.assert_allclose(bpd.numpy(), g['lik_bpd'], rtol=1e-4)
+  assert rel_l2(latent, g['lik_latent']) < 1e-4
+  elbo = likelihood.get_elbo_fn(cfg, sde, inv)
+  nelbo, resid = elbo(net, data, eps=float(g['elbo_eps']),
+                      injected=dict(u=torch.tensor(g['elbo_u']), z=torch.tensor(g['elbo_z']),
+                                    epsilon=torch.tensor(g['elbo_epsilon']), lp_z=torch.tensor(g['elbo_lp_z']),
+                                    z_res=torch.tensor(g['elbo_z_res'])))
+  np.testing.assert_allclose(nelbo.numpy(), g['elbo_nelbo'], rtol=1e-4)
+  np.testing.assert_allclose(resid.numpy(), g['elbo_resid'], rtol=1e-4)
 
 
 @pytest.mark.parametrize('tag', ['w5000', 'w0'])
