@@ -1,6 +1,4 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "likelihood or ode_sampler or deepest" > gpurun_out/t42_gpu.log 2>&1; echo "pytest rc=$?"; tail -n 5 gpurun_out/t42_gpu.log
-for i in 1 2; do for f in 0 1; do
-ST_GN_FUSED=$f timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --sample-steps 2 > gpurun_out/bench42_f${f}_$i.json 2> gpurun_out/bench42_f${f}_$i.err; echo "bench f=$f rc=$?"; cut -c1-200 gpurun_out/bench42_f${f}_$i.json | cut -c40-200
-done; done
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sampler" > gpurun_out/t44_gpu.log 2>&1; echo "pytest rc=$?"; tail -n 5 gpurun_out/t44_gpu.log
+SWEEP_TIMEOUT=200 timeout 600 python tools/config_sweep.py c5 c3 > gpurun_out/sweep44.txt 2>&1; echo "sweep rc=$?"; cat gpurun_out/sweep44.txt

@@ -189,13 +189,13 @@ class AncestralSamplingPredictor(Predictor):
     noise = _draw(x, self.noise_source)
     score = self.score_fn(x, t)
     if isinstance(sde, sde_lib.VESDE):
-      sig = sde.discrete_sigmas.to(t.device)
+      sig = sde.table('discrete_sigmas', t.device)
       sigma = sig[timestep]
       adjacent = torch.where(timestep == 0, torch.zeros_like(t), sig[timestep - 1])
       ca, cb = torch.ones_like(t), sigma ** 2 - adjacent ** 2
       cc = torch.sqrt((adjacent ** 2 * (sigma ** 2 - adjacent ** 2)) / (sigma ** 2))
     else:
-      beta = sde.discrete_betas.to(t.device)[timestep]
+      beta = sde.table('discrete_betas', t.device)[timestep]
       ca = 1. / torch.sqrt(1. - beta)
       cb = beta * ca
       cc = torch.sqrt(beta)
@@ -216,7 +216,7 @@ class NonePredictor(Predictor):
 def _langevin_alpha(sde, t):
   if isinstance(sde, (sde_lib.VPSDE, sde_lib.subVPSDE)):
     timestep = (t * (sde.N - 1) / sde.T).long()
-    return sde.alphas.to(t.device)[timestep].float()
+    return sde.table('alphas', t.device)[timestep].float()
   return torch.ones_like(t)
 
 

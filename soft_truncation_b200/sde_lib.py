@@ -106,6 +106,18 @@ class SDE(abc.ABC):
   def reverse(self, score_fn, probability_flow=False, lambda_=1.):
     return ReverseSDE(self, score_fn, probability_flow, lambda_)
 
+  def table(self, name, device):
+    """Device-resident copy of one of the per-step tables (`discrete_sigmas`, `discrete_betas`, `alphas`, ...).  The
+    reference re-uploads (or CPU-indexes) them on every call (sde_lib.py:170-171,295); a sampler step captured in a
+    CUDA graph cannot copy from pageable host memory, so the copy is made once per device and kept."""
+    cache = self.__dict__.setdefault('_table_cache', {})
+    src = getattr(self, name)
+    key = (name, str(device))
+    t = cache.get(key)
+    if t is None or t.shape != src.shape:
+      t = cache[key] = src.to(device)
+    return t
+
 
 def _gaussian_prior_logp(z, sigma):
   n = np.prod(z.shape[1:])
@@ -156,8 +168,8 @@ class VPSDE(_LinearBeta, SDE):
     """DDPM grid step, or the exact one-interval step used by the denoiser (sde_lib.py:166-178)."""
     if next_t is None:
       idx = (t * (self.N - 1) / self.T).long()
-      beta = self.discrete_betas.to(x.device)[idx]
-      alpha = self.alphas.to(x.device)[idx]
+      beta = self.table('discrete_betas', x.device)[idx]
+      alpha = self.table('alphas', x.device)[idx]
       return _bcast(torch.sqrt(alpha)) * x - x, torch.sqrt(beta)
     G = torch.sqrt((t - next_t) * self._beta(t))
     return _bcast(torch.sqrt(1. - G ** 2)) * x - x, G
@@ -257,7 +269,7 @@ class VESDE(SDE):
     """SMLD grid step or the exact step to `next_t == 0` (sde_lib.py:288-304)."""
     if next_t is None:
       idx = (t * (self.N - 1) / self.T).long()
-      table = self.discrete_sigmas.to(t.device)   # the reference indexes the CPU table (quirk 21)
+      table = self.table('discrete_sigmas', t.device)   # the reference indexes the CPU table (quirk 21)
       sigma = table[idx]
       prev_sigma = torch.where(idx == 0, torch.zeros_like(t), table[idx - 1])
     else:

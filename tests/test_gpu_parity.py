@@ -245,6 +245,24 @@ def test_pc_sampler_cuda_graph_matches_eager():
   assert torch.allclose(again, outs[1], rtol=1e-5, atol=1e-6)
 
 
+def test_pc_sampler_ve_langevin_runs_under_cuda_graph():
+  """Reverse-diffusion predictor + Langevin corrector (VE, C5 block types) in the graph-replayed loop: the per-step
+  sigma table must already live on the device (no host copy inside the capture); replay is deterministic."""
+  from soft_truncation_b200 import sampling, sde_lib
+  cfg = _reduced('c5')
+  cfg.sampling.method = 'pc'
+  model, _, _ = _model(cfg, 5, torch.float32)
+  sde = sde_lib.VESDE(sigma_min=cfg.model.sigma_min, sigma_max=cfg.model.sigma_max, N=6)
+  shape = (2, 3, 32, 32)
+  fn = sampling.get_sampling_fn(cfg, sde, shape, lambda v: v, 1e-3)
+  x0 = torch.randn(*shape, generator=torch.Generator().manual_seed(3)) * cfg.model.sigma_max
+  torch.cuda.manual_seed(12)
+  a, nfe = fn(model, x_init=x0)
+  torch.cuda.manual_seed(12)
+  b, _ = fn(model, x_init=x0)
+  assert nfe == 12 and torch.isfinite(a).all() and torch.allclose(a, b, rtol=1e-5, atol=1e-5)
+
+
 def test_score_fn_and_state_dict_roundtrip():
   from soft_truncation_b200.models import utils as mutils
   cfg = _cfg()
