@@ -143,6 +143,8 @@ def run_b200(args):
   cfg.device = dev
   cfg.model.compute_dtype = args.dtype
   B = args.batch
+  if args.micro:
+    cfg.optim.l2_blocks = args.micro
   cfg.training.batch_size = B * world
   torch.manual_seed(42)
   np.random.seed(42)
@@ -291,6 +293,8 @@ def main():
   ap.add_argument('--sample-batch', type=int, default=1024)
   ap.add_argument('--sample-steps', type=int, default=50)
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--micro', type=int, default=0,
+                  help='L2 blocking: run the step as this many image blocks (0 = the library default for the batch)')
   args = ap.parse_args()
   if args.impl == 'reference':
     run_reference(args)

@@ -116,6 +116,15 @@ int st_gn_apply(const void* x1, const void* x2, int dtype, int n_img, int hw, in
                 const float* gamma, const float* beta, float* mean, float* rstd, int act,
                 float p_drop, uint64_t seed, const void* mask, uint8_t* keepbits, void* y, const float* part,
                 int splits, int64_t count, float eps, void* stream);
+/* Statistics + apply in ONE launch: a thread-block cluster of `chunks` CTAs keeps an image resident in shared memory
+ * (all of its cp.async copies in flight at once), exchanges per-group partial sums through distributed shared memory
+ * and writes y from the resident copy - the tensor crosses HBM once in and once out.  mean / rstd [n_img][G] are
+ * outputs (kept for the backward).  st_gn_fwd_fused_chunks returns the cluster size for a shape, 0 = the image does
+ * not fit 16 CTAs x 64 KB (or the grid would under-fill the GPU, or ST_GN_FWD_FUSED=0): use st_gn_stats + st_gn_apply. */
+int st_gn_fwd_fused_chunks(int n_img, int hw, int C);
+int st_gn_fwd_fused(const void* x1, const void* x2, int dtype, int n_img, int hw, int C1, int C2, int G,
+                    const float* gamma, const float* beta, float eps, int act, float p_drop, uint64_t seed,
+                    const void* mask, uint8_t* keepbits, void* y, float* mean, float* rstd, int chunks, void* stream);
 /* backward, pass 1: per (image, pixel split, channel) sums  red[n_img][splits][C][2] = (sum dz, sum dz*xhat) where
  * dz = dy * dropout_mask * act'(.)  */
 int st_gn_bwd_reduce(const void* x1, const void* x2, const void* dy, int dtype, int n_img, int hw, int C1,

@@ -45,6 +45,9 @@ SIGNATURES = {
     'st_gn_bwd_apply': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f,
                         c_u64, c_p, c_p, c_int, c_p, c_p, c_f, c_p, c_int, c_p, c_int, c_int, c_p, c_p, c_p, c_p],
     'st_gn_chunks': [c_int, c_int, c_int],
+    'st_gn_fwd_fused_chunks': [c_int, c_int, c_int],
+    'st_gn_fwd_fused': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_f, c_int, c_f, c_u64, c_p, c_p, c_p,
+                        c_p, c_p, c_int, c_p],
     'st_gn_bwd_fused_chunks': [c_int, c_int, c_int, c_int, c_int],
     'st_gn_bwd_fused': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f,
                         c_u64, c_p, c_p, c_int, c_p, c_p, c_f, c_p, c_int, c_p, c_int, c_p, c_p],

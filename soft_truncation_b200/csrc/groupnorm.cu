@@ -923,3 +923,235 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_fused(const void
   ST_CHECK_LAUNCH("st_gn_bwd_fused");
   return 0;
 }
+
+// ---------------------------------------------------------------- fused forward (statistics + apply, one launch)
+// A thread-block cluster of `chunks` CTAs owns one image and keeps it RESIDENT in shared memory: every thread copies
+// all of its pixels (<= GN_RES 8-channel vectors) with cp.async up front - the whole chunk is in flight at once -,
+// sums them, the CTAs exchange their per-group partial sums through distributed shared memory, and the normalised /
+// activated output is produced from the resident copy.  HBM sees the tensor once in and once out (2 passes instead of
+// the 3 of st_gn_stats + st_gn_apply) and one launch instead of two.
+namespace {
+constexpr int GN_RES = 16;        // resident 8-channel vectors per thread: 16 x 16 B x 256 threads = 64 KB (bf16)
+
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_smem_ptr, uint32_t cta) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(local_smem_ptr), ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(cta));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+template <typename T, bool ACT, int DROP>
+__global__ void __launch_bounds__(256, 3) gn_fwd_fused_kernel(Src2<T> s, int hw, int G, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, double inv_count, float eps,
+                                                              float p_drop, uint64_t seed, const T* mask, uint8_t* keepbits,
+                                                              T* y, float* mean_out, float* rstd_out) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  __shared__ float s_sum[512], s_sq[512];
+  __shared__ float s_part[128];               // this CTA's per-group (sum, sum of squares): read by the whole cluster
+  __shared__ float s_mean[64], s_rstd[64];
+  pdl_wait();
+  pdl_trigger();
+  using P = Pipe<T, 1, GN_RES>;
+  const P pipe(gsm);
+  const int Ct = s.C1 + s.C2, cpg = Ct / G;
+  const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  const Walk w(Ct, n, hw, chunk, chunks);
+  const int V = w.V, lanes = w.lanes;
+  const bool active = w.lane < lanes;
+  // ---- the whole chunk in flight
+  {
+    Stream<T> xs = stream_of(s, w);
+#pragma unroll
+    for (int st = 0; st < GN_RES; ++st) {          // one commit group per vector: the sums below start on arrival
+      if (st < w.n_it) pipe.issue(st, 0, xs.next());
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  }
+  float gam[8], bet[8];
+  load8(gamma + (active ? w.c0 : 0), gam);
+  load8(beta + (active ? w.c0 : 0), bet);
+  // ---- statistics of the resident chunk
+  float sum[2] = {0.f, 0.f}, sq[2] = {0.f, 0.f};
+  static_for<0, GN_RES>([&](auto I) {
+    constexpr int st = decltype(I)::value;
+    if (st < w.n_it) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(GN_RES - 1 - st) : "memory");
+      float a[8];
+      pipe.read(st, 0, a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sum[i >> 2] += a[i]; sq[i >> 2] = fmaf(a[i], a[i], sq[i >> 2]); }
+    }
+  });
+  s_sum[2 * threadIdx.x] = sum[0]; s_sum[2 * threadIdx.x + 1] = sum[1];
+  s_sq[2 * threadIdx.x] = sq[0]; s_sq[2 * threadIdx.x + 1] = sq[1];
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x, qpg = cpg / 4, Q = 2 * V;      // quads never straddle a group (cpg % 4 == 0)
+    double a = 0., b = 0.;
+    for (int l = 0; l < lanes; ++l)
+      for (int q = 0; q < qpg; ++q) {
+        a += (double)s_sum[l * Q + g * qpg + q];
+        b += (double)s_sq[l * Q + g * qpg + q];
+      }
+    s_part[2 * g] = (float)a;
+    s_part[2 * g + 1] = (float)b;
+  }
+  // ---- exchange across the cluster (fixed rank order: every CTA derives bit-identical statistics)
+  if (chunks > 1) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    double a = 0., b = 0.;
+    if (chunks > 1) {
+      for (int r = 0; r < chunks; ++r) {
+        a += (double)ld_dsmem_f32(&s_part[2 * g], (uint32_t)r);
+        b += (double)ld_dsmem_f32(&s_part[2 * g + 1], (uint32_t)r);
+      }
+    } else {
+      a = (double)s_part[2 * g];
+      b = (double)s_part[2 * g + 1];
+    }
+    const double mu = a * inv_count;
+    double var = b * inv_count - mu * mu;
+    if (var < 0.) var = 0.;
+    s_mean[g] = (float)mu;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    if (chunk == 0) {
+      mean_out[n * G + g] = s_mean[g];
+      rstd_out[n * G + g] = s_rstd[g];
+    }
+  }
+  if (chunks > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // done reading peers' s_part
+  __syncthreads();
+  // ---- apply from the resident copy: y = x*A + B with A = rstd*gamma, B = beta - mean*rstd*gamma
+  if (active) {
+    const int c0 = w.c0;
+    float A[8], Bc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c0 + (i & 4)) / cpg;
+      A[i] = s_rstd[g] * gam[i];
+      Bc[i] = fmaf(-s_mean[g], A[i], bet[i]);
+    }
+    long long oct = w.row0 * V + w.v;              // index of the 8-vector being produced
+    const int octstep = lanes * V;
+#pragma unroll
+    for (int st = 0; st < GN_RES; ++st)
+      if (st < w.n_it) {
+        float x[8], o[8];
+        pipe.read(st, 0, x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float u = fmaf(x[i], A[i], Bc[i]);
+          o[i] = ACT ? silu_t<T>(u) : u;
+        }
+        if constexpr (DROP == DROP_FAST) {
+          float keep[8];
+          const uint32_t bits = dropout8(seed, (uint64_t)oct, p_drop, keep);
+          if (keepbits) keepbits[oct] = (uint8_t)bits;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] *= keep[i];
+        } else if constexpr (DROP == DROP_SLOW) {
+          float mk[8];
+          load8(mask + oct * 8, mk);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] *= mk[i];
+        }
+        store8(y + oct * 8, o);
+        oct += octstep;
+      }
+  }
+  // no CTA may exit while a peer can still read its s_part
+  if (chunks > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// cluster size for the resident forward kernel, 0 = use st_gn_stats + st_gn_apply
+int fwd_fused_chunks_for(int n_img, int hw, int Ct) {
+  static const int mode = getenv("ST_GN_FWD_FUSED") ? atoi(getenv("ST_GN_FWD_FUSED")) : 1;
+  static const int max_cluster = getenv("ST_GN_FWD_CLUSTER") ? atoi(getenv("ST_GN_FWD_CLUSTER")) : 16;
+  if (!mode) return 0;
+  const int V = Ct / 8, lanes = 256 / V;
+  if (lanes < 1) return 0;
+  const int per_cta = lanes * GN_RES;                          // pixels one CTA can hold
+  const int c = (hw + per_cta - 1) / per_cta;
+  if (c > max_cluster || c > 16) return 0;
+  // every chunk must fit: chunk size = ceil(hw / c) pixels
+  if ((hw + c - 1) / c > per_cta) return 0;
+  if (mode == 1 && (long long)n_img * c < st_num_sms()) return 0;   // too few CTAs to fill the machine
+  return c;
+}
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int st_gn_fwd_fused_chunks(int n_img, int hw, int C) {
+  return fwd_fused_chunks_for(n_img, hw, C);
+}
+
+extern "C" __attribute__((visibility("default"))) int st_gn_fwd_fused(const void* x1, const void* x2, int dtype, int n_img, int hw, int C1, int C2, int G,
+                               const float* gamma, const float* beta, float eps, int act, float p_drop, uint64_t seed,
+                               const void* mask, uint8_t* keepbits, void* y, float* mean, float* rstd, int chunks,
+                               void* stream) {
+  if (int e = check_geom(C1, C2, G)) return e;
+  const int Ct = C1 + C2, V = Ct / 8, lanes = 256 / V;
+  ST_CHECK_ARG(n_img <= 65535, "st_gn_fwd_fused: more than 65535 images");
+  ST_CHECK_ARG(chunks >= 1 && chunks <= 16, "st_gn_fwd_fused: chunks (cluster size) must be 1..16, got %d", chunks);
+  ST_CHECK_ARG(lanes >= 1 && (hw + chunks - 1) / chunks <= lanes * GN_RES,
+               "st_gn_fwd_fused: a chunk of %d pixels x %d channels does not fit the resident buffer", (hw + chunks - 1) / chunks, Ct);
+  ST_CHECK_ARG(mean && rstd, "st_gn_fwd_fused: mean / rstd outputs are required");
+  const int drop = mask ? DROP_SLOW : (p_drop > 0.f ? DROP_FAST : DROP_NONE);
+  const double inv_count = 1.0 / ((double)hw * (Ct / G));
+  int rc = 0;
+  ST_DISPATCH_DTYPE(dtype, T, {
+    Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
+    constexpr int smem = Pipe<T, 1, GN_RES>::VEC_BYTES;
+    dispatch_mode(act, drop, [&](auto A, auto D) {
+      constexpr bool ACT = decltype(A)::value;
+      constexpr int DROP = decltype(D)::value;
+      auto kernel = gn_fwd_fused_kernel<T, ACT, DROP>;
+      static bool attr_ok = false;
+      if (!attr_ok) {
+        if (!allow_smem(kernel, smem)) { rc = ST_ERR_CUDA; return; }
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) { st_set_error("st_gn_fwd_fused: cluster attribute: %s", cudaGetErrorString(e)); rc = ST_ERR_CUDA; return; }
+        attr_ok = true;
+      }
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(chunks, n_img);
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = chunks;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = st_pdl_on((cudaStream_t)stream) ? 2 : 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, s, hw, G, gamma, beta, inv_count, eps, p_drop, seed, (const T*)mask,
+                                         keepbits, (T*)y, mean, rstd);
+      if (e != cudaSuccess) { st_set_error("st_gn_fwd_fused: launch: %s", cudaGetErrorString(e)); rc = ST_ERR_CUDA; }
+    });
+  });
+  if (rc) return rc;
+  ST_CHECK_LAUNCH("st_gn_fwd_fused");
+  return 0;
+}

@@ -188,8 +188,7 @@ class ResBlock:
     x1, x2 = xa.t, (xb.t if xb is not None else None)
     if x2 is not None and (self.up or self.down) and self.fir:
       raise NotImplementedError('FIR resampling of a concatenated input')
-    st0 = ops.gn_stats(x1, x2, self.G0, finalize=False)
-    a0 = ops.gn_apply(x1, x2, self.G0, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st0, act=1)
+    a0, st0 = ops.gn_norm_act(x1, x2, self.G0, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), act=1)
     xr = None
     if self.up or self.down:
       a0 = self._resample(net, a0, None)
@@ -197,7 +196,6 @@ class ResBlock:
     B, H, W, _ = a0.shape
     h1 = ops.conv_fwd(a0, P.c(pre + 'Conv_0.weight'), self.cout, bias=P.f(pre + 'Conv_0.bias'),
                       rowbias=net.dense[:, self.dense_off:], rowbias_ld=net.dense.shape[1])
-    st1 = ops.gn_stats(h1, None, self.G1, finalize=False)
     p_drop, seed, mask, keepbits = 0., 0, None, None
     if net.train and m.dropout > 0:
       mask = m._mask_for(self.idx, h1)
@@ -205,8 +203,8 @@ class ResBlock:
         p_drop, seed = m.dropout, m._next_seed(self.idx)
         if net.tape.enabled:      # keep flags (1 bit per element) for the two backward passes
           keepbits = torch.empty(h1.numel() // 8, dtype=torch.uint8, device=h1.device)
-    a1 = ops.gn_apply(h1, None, self.G1, P.f(pre + 'GroupNorm_1.weight'), P.f(pre + 'GroupNorm_1.bias'), st1, act=1,
-                      p_drop=p_drop, seed=seed, mask=mask, keepbits=keepbits)
+    a1, st1 = ops.gn_norm_act(h1, None, self.G1, P.f(pre + 'GroupNorm_1.weight'), P.f(pre + 'GroupNorm_1.bias'), act=1,
+                              p_drop=p_drop, seed=seed, mask=mask, keepbits=keepbits)
     if self.shortcut:
       if xr is not None:
         sc = ops.conv_fwd(xr, P.c(pre + 'Conv_2.weight'), self.cout, 1, 1, bias=P.f(pre + 'Conv_2.bias'))
@@ -311,8 +309,7 @@ class AttnBlock:
     x = xa.t
     B, H, W, _ = x.shape
     L, npix = H * W, B * H * W
-    st = ops.gn_stats(x, None, self.G, finalize=False)
-    h = ops.gn_apply(x, None, self.G, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st, act=0)
+    h, st = ops.gn_norm_act(x, None, self.G, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), act=0)
     wqkv, bqkv = P.c_group(self.names_w), P.f_group(self.names_b)        # (3C, C), (3C,)
     qkv = ops.gemm_nt(h.view(npix, C), wqkv, bias=bqkv)                 # (npix, 3C)
     # logits[b][i][j] = sum_c q[b,i,c] k[b,j,c]   (einsum 'bchw,bcij->bhwij')
@@ -427,8 +424,7 @@ class NormActConv:
     """`res`: optional Act added to the output (the up-sampled output pyramid, ncsnpp.py:391-396)."""
     P = net.m.P
     x = xa.t
-    st = ops.gn_stats(x, None, self.G, finalize=False)
-    a = ops.gn_apply(x, None, self.G, P.f(self.pg + 'weight'), P.f(self.pg + 'bias'), st, act=1)
+    a, st = ops.gn_norm_act(x, None, self.G, P.f(self.pg + 'weight'), P.f(self.pg + 'bias'), act=1)
     out = ops.conv_fwd(a, P.c(self.conv.pre + 'weight'), self.conv.cout, bias=P.f(self.conv.pre + 'bias'),
                        residual=res.t if res is not None else None)
     y = Act(out, net.tape)

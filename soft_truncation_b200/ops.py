@@ -218,6 +218,28 @@ def gn_apply(x, x2, G, gamma, beta, stats, act, p_drop=0., seed=0, mask=None, ke
   return y
 
 
+def gn_norm_act(x, x2, G, gamma, beta, act, p_drop=0., seed=0, mask=None, keepbits=None, eps=1e-6, fused_chunks=None):
+  """GroupNorm (+SiLU, +dropout) forward: returns (y, GnStats).  One cluster launch with the image resident in shared
+  memory when it fits (st_gn_fwd_fused), else st_gn_stats followed by st_gn_apply (which finalises the statistics)."""
+  B, H, W, C1 = x.shape
+  C2 = 0 if x2 is None else x2.shape[3]
+  if fused_chunks is not None:
+    fc = int(fused_chunks)
+  elif p_drop > 0. and mask is None:
+    fc = 0      # in-kernel dropout: the generator work overlaps the loads only in the pipelined apply kernel (measured)
+  else:
+    fc = lib.st_gn_fwd_fused_chunks(B, H * W, C1 + C2)
+  if fc <= 0:
+    st = gn_stats(x, x2, G, eps=eps, finalize=False)
+    return gn_apply(x, x2, G, gamma, beta, st, act, p_drop=p_drop, seed=seed, mask=mask, keepbits=keepbits), st
+  y = torch.empty((B, H, W, C1 + C2), dtype=x.dtype, device=x.device)
+  stats = torch.empty((2, B, G), dtype=torch.float32, device=x.device)
+  check(lib.st_gn_fwd_fused(ptr(x), ptr(x2), dt(x), B, H * W, C1, C2, G, ptr(gamma), ptr(beta), float(eps), int(act),
+                            float(p_drop), int(seed), ptr(mask), ptr(keepbits), ptr(y), ptr(stats[0]), ptr(stats[1]),
+                            fc, stream()))
+  return y, GnStats(stats)
+
+
 def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0., seed=0, mask=None, extra=None,
                 extra_scale=1.0, dx1=None, accum1=False, dx2=None, accum2=False, keepbits=None, want_csum=False,
                 queue=None, fused_chunks=None):

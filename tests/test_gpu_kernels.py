@@ -291,6 +291,55 @@ def test_groupnorm_fused_backward_matches_two_pass(shape):
   assert two[3].abs().sum() > 0
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape', [(5, 32, 32, 128, 0, 4), (3, 16, 16, 256, 128, 4), (4, 32, 32, 128, 128, 8),
+                                   (3, 32, 32, 256, 128, 16), (6, 8, 8, 256, 256, 1), (9, 4, 4, 256, 0, 1),
+                                   (3, 16, 16, 128, 0, 2), (2, 12, 12, 64, 0, 3)])
+def test_groupnorm_fused_forward(dtype, shape):
+  """st_gn_fwd_fused (cluster-resident statistics + apply) against F.group_norm and against the two-kernel path,
+  including the in-kernel dropout (same keep bits) and a cluster size that does not divide the pixel count."""
+  B, H, W, C1, C2, fc = shape
+  C = C1 + C2
+  G = min(C // 4, 32)
+  x = rnd(B, C, H, W, seed=1) * 1.5 + 0.3
+  gamma, beta = rnd(C, seed=2) * 0.2 + 1., rnd(C, seed=3) * 0.2
+  xq = x.to(dtype).float()
+  y_ref = F.group_norm(xq, G, gamma, beta, eps=1e-6)
+  y_ref = y_ref * torch.sigmoid(y_ref)
+  xh = nhwc(x).to(dtype)
+  x1, x2 = (xh[..., :C1].contiguous(), xh[..., C1:].contiguous()) if C2 else (xh, None)
+  y, st = ops.gn_norm_act(x1, x2, G, gamma, beta, 1, fused_chunks=fc)
+  assert rel_l2(nchw(y.float()), y_ref) < tol(dtype)
+  y2, st2 = ops.gn_norm_act(x1, x2, G, gamma, beta, 1, fused_chunks=0)
+  assert rel_l2(st[0], st2[0]) < 1e-5 and rel_l2(st[1], st2[1]) < 1e-5
+  mu = xq.reshape(B, G, -1).mean(-1)
+  assert torch.allclose(st[0], mu, atol=1e-4)
+  assert rel_l2(y.float(), y2.float()) < (1e-6 if dtype == torch.float32 else 4e-3)
+  # dropout: identical keep flags from both forms (keyed by seed and element index)
+  bits_a = torch.zeros(B * H * W * C // 8, dtype=torch.uint8, device=dev())
+  bits_b = torch.zeros_like(bits_a)
+  ya, _ = ops.gn_norm_act(x1, x2, G, gamma, beta, 1, p_drop=0.2, seed=99, keepbits=bits_a, fused_chunks=fc)
+  yb, _ = ops.gn_norm_act(x1, x2, G, gamma, beta, 1, p_drop=0.2, seed=99, keepbits=bits_b, fused_chunks=0)
+  assert torch.equal(bits_a, bits_b)
+  assert torch.equal(ya == 0, yb == 0) and rel_l2(ya.float(), yb.float()) < (1e-6 if dtype == torch.float32 else 4e-3)
+  # injected mask (parity mode) and no activation
+  mk = nhwc((torch.rand(B, C, H, W, generator=gen(5)) > 0.1).float().to(dev()) / 0.9).to(dtype)
+  ym, _ = ops.gn_norm_act(x1, x2, G, gamma, beta, 0, mask=mk, fused_chunks=fc)
+  want = F.group_norm(xq, G, gamma, beta, eps=1e-6) * nchw(mk.float())
+  assert rel_l2(nchw(ym.float()), want) < tol(dtype)
+
+
+def test_groupnorm_fused_forward_rejects_oversized_chunks():
+  from soft_truncation_b200._lib import StError
+  x = nhwc(rnd(2, 128, 32, 32, seed=1)).to(torch.bfloat16)
+  g, b = torch.ones(128, device=dev()), torch.zeros(128, device=dev())
+  with pytest.raises(StError):          # 1024 pixels x 128 channels do not fit one CTA's 64 KB
+    ops.gn_norm_act(x, None, 32, g, b, 1, fused_chunks=1)
+  assert ops.lib.st_gn_fwd_fused_chunks(512, 1024, 128) == 4 and ops.lib.st_gn_fwd_fused_chunks(512, 256, 256) == 2
+  assert ops.lib.st_gn_fwd_fused_chunks(512, 1024, 1024) == 0        # would need 32 CTAs per image
+  assert ops.lib.st_gn_fwd_fused_chunks(2, 1024, 128) == 0           # 8 CTAs cannot fill the GPU: two-kernel path
+
+
 def test_groupnorm_apply_finalises_statistics_in_kernel():
   """gn_stats(finalize=False) + gn_apply == st_gn_finalize path, bit for bit (same arithmetic, one launch fewer)."""
   B, H, W, C1, C2, G = 3, 8, 8, 64, 32, 24

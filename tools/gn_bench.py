@@ -53,7 +53,7 @@ def main():
     def only(which, **kw):
       # time one of the two backward passes by stubbing the other out
       def run():
-        ops.gn_backward(x, x2, dy, G, gamma, beta, stats, True, dgamma, dbeta, **kw)
+        ops.gn_backward(x, x2, dy, G, gamma, beta, stats, True, dgamma, dbeta, fused_chunks=0, **kw)
       return run
 
     t_stats = timed(lambda: ops.gn_stats(x, x2, G))
@@ -80,11 +80,19 @@ def main():
           q.jobs, q.keep = [], []
         row.append(f'{fc}:{timed(run):.1f}')
       fused.append(' '.join(row))
+    # forward: st_gn_stats + st_gn_apply against the cluster-resident single launch
+    fwd = []
+    for kw in (dict(), dict(p_drop=0.1, seed=5, keepbits=bits)):
+      t2 = timed(lambda: ops.gn_norm_act(x, x2, G, gamma, beta, True, fused_chunks=0, **kw))
+      fcs = ops.lib.st_gn_fwd_fused_chunks(B, H * H, Ct)
+      t1 = timed(lambda: ops.gn_norm_act(x, x2, G, gamma, beta, True, fused_chunks=fcs, **kw)) if fcs > 0 else float('nan')
+      fwd.append(f'two kernels {t2:.1f}, resident x{fcs} {t1:.1f}')
     f = lambda t, units: f'{t:7.1f} ({units * nbytes / t / 1e3:5.0f})'
     print(H, C1, C2, '|', f(t_stats, 1), '|', f(t_apply, 2), '|', f(t_applyd, 2), '|', f(res[0][0], 2), '|', f(res[0][1], 3), '|',
           f(res[1][0], 2), '|', f(res[1][1], 3), flush=True)
     print('      backward total us by cluster size (0 = two kernels): plain [', fused[0], '] drop+csum [', fused[1], '] extra+csum [', fused[2], ']',
           f'ideal 3-pass at 6.5 TB/s: {3 * nbytes / 6.5e6:.1f}', flush=True)
+    print('      forward total us: plain [', fwd[0], '] dropout [', fwd[1], f'] ideal 2-pass at 6.5 TB/s: {2 * nbytes / 6.5e6:.1f}', flush=True)
 
 
 if __name__ == '__main__':
