@@ -184,6 +184,40 @@ def test_train_step_bf16_close_to_fp32_fixture(golden):
     np.testing.assert_allclose(got.numpy(), g['w0_losses'][s], rtol=3e-2, err_msg=f'step {s}')
 
 
+def test_full_size_step_properties():
+  """BASELINE configs[1] at FULL size (61.8 M parameters, batch 512, bf16), where the oracle cannot follow: the
+  size-independent properties of the step.  (1) Samples are independent (GroupNorm and attention are per image): a
+  permuted batch gives the permuted losses.  (2) The gradient is linear in the batch: the step run as 4 image blocks
+  (optim.l2_blocks) accumulates the same gradient as one pass.  (3) The per-sample losses of both forms agree."""
+  from soft_truncation_b200 import losses
+  from soft_truncation_b200.models import utils as mutils
+  cfg = _cfg(dropout=0.)
+  B = 512
+  model, sde, _ = _model(cfg, 3, torch.bfloat16)
+  net = mutils.unwrap(model)
+  g = torch.Generator().manual_seed(5)
+  batch = (torch.rand(B, 3, 32, 32, generator=g) * 2 - 1).to(DEV)
+  inj = dict(u=torch.rand(B, generator=g), z=torch.randn(B, 3, 32, 32, generator=g))
+  loss_fn = losses.get_sde_loss_fn(cfg, sde, train=True)
+  with torch.no_grad():
+    base = loss_fn(model, batch, importance_sampling=True, t_min=1e-3, injected=inj)
+    perm = torch.randperm(B, generator=g)
+    got = loss_fn(model, batch[perm.to(DEV)], importance_sampling=True, t_min=1e-3,
+                  injected=dict(u=inj['u'][perm], z=inj['z'][perm]))
+  assert torch.isfinite(base).all()
+  np.testing.assert_allclose(got.cpu().numpy(), base[perm.to(DEV)].cpu().numpy(), rtol=2e-3)
+  grads, ls = [], []
+  for blocks in (1, 4):
+    cfg.optim.l2_blocks = blocks
+    step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=lambda *a, **k: None)
+    state = dict(optimizer=losses.get_optimizer(cfg, model.parameters()), model=model, ema=None, step=0)
+    ls.append(step_fn(state, batch, injected=dict(inj, t_min=1e-3)))
+    grads.append(net._grad.clone())
+  np.testing.assert_allclose(ls[1].numpy(), ls[0].numpy(), rtol=2e-3)
+  np.testing.assert_allclose(ls[0].numpy(), base.cpu().numpy(), rtol=2e-3)
+  assert rel_l2(grads[1], grads[0]) < 2e-2 and float(grads[0].abs().sum()) > 0
+
+
 def test_pc_sampler_vs_reference_fixture(golden):
   """8-step Euler-Maruyama PC sampling + denoise (BASELINE configs[0]) through sampling.get_pc_sampler."""
   from soft_truncation_b200 import sampling, sde_lib
