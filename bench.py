@@ -15,6 +15,8 @@ GPU box, so this arm runs the oracle port (oracle/ref_train.py, checked against 
 all host cores, on a bounded sample (batch 8) of the same workload.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -296,10 +298,30 @@ def main():
   ap.add_argument('--micro', type=int, default=0,
                   help='L2 blocking: run the step as this many image blocks (0 = the library default for the batch)')
   args = ap.parse_args()
-  if args.impl == 'reference':
-    run_reference(args)
-  else:
-    run_b200(args)
+  # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when
+  # the first communicator is created), so file descriptor 1 points at stderr while the benchmark runs and is restored
+  # for the result line only.
+  sys.stdout.flush()
+  real_stdout = os.dup(1)
+  os.dup2(2, 1)
+  out = io.StringIO()
+  try:
+    with contextlib.redirect_stdout(out):
+      if args.impl == 'reference':
+        run_reference(args)
+      else:
+        run_b200(args)
+  finally:
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+  lines = [ln for ln in out.getvalue().splitlines() if ln.strip()]
+  for ln in lines:
+    if not ln.startswith('{'):
+      print(ln, file=sys.stderr)
+  for ln in lines:
+    if ln.startswith('{'):
+      print(ln, flush=True)
 
 
 if __name__ == '__main__':
