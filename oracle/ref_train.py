@@ -154,7 +154,10 @@ def dsm_losses(sd, cfg, sde, batch, u, z, t_min, train=True, drop_masks=None, im
     sq = torch.square(score * std[:, None, None, None] + z)
     return 0.5 * Z * reduce(sq.reshape(sq.shape[0], -1))
   if sde.kind == 'vpsde':
-    g2 = sde.beta(t)
+    g2 = sde.beta(t)                       # diffusion^2 of the VP SDE (sde_lib.py:145-149)
+  elif sde.kind == 'vesde':
+    # diffusion = sigma(t) sqrt(2 ln(sigma_max / sigma_min)) (sde_lib.py:263-268)
+    g2 = sde.std(t) ** 2 * (2. * (np.log(sde.smax) - np.log(sde.smin)))
   else:
     raise NotImplementedError
   sq = torch.square(score + z / std[:, None, None, None])

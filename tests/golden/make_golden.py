@@ -391,6 +391,33 @@ def golden_likelihood(R):
   np.savez_compressed(os.path.join(HERE, 'likelihood_golden.npz'), **out)
 
 
+def golden_lossbranches(R):
+  """The likelihood-weighted loss branch (reference losses.py:125-129: (score + z/std)^2 * g^2, uniform times), which no
+  shipped config reaches because importance sampling is tested first (:122).  VP (reduced CIFAR net) and VE (reduced C5)."""
+  out = {}
+  for tag, path, shrink, seed in (('vp', 'vp/CIFAR10/ddpmpp_nll_st', reduced_cifar, 17),
+                                  ('ve', 've/celebahq/uncsnpp_st', reduced_c5, 18)):
+    cfg = shrink(ref_config(path))
+    cfg.model.dropout = 0.
+    cfg.training.likelihood_weighting, cfg.training.importance_sampling = True, False
+    model, sde, _ = build_ref_model(R, cfg, seed=seed)
+    g = torch.Generator().manual_seed(41)
+    x = torch.rand(2, 3, 32, 32, generator=g)
+    if cfg.data.centered:
+      x = x * 2. - 1.
+    loss_fn = R.losses.get_sde_loss_fn(cfg, sde, train=True)
+    t_min = 1e-3
+    torch.manual_seed(9)
+    u, z = torch.rand(2), torch.randn(2, 3, 32, 32)
+    torch.manual_seed(9)
+    losses = loss_fn(model, x, importance_sampling=False, t_min=t_min)
+    torch.mean(losses).backward()
+    gnorm = np.array([0. if p.grad is None else p.grad.double().norm().item() for p in model.parameters()])
+    out.update({f'{tag}_x': x.numpy(), f'{tag}_u': u.numpy(), f'{tag}_z': z.numpy(), f'{tag}_tmin': t_min,
+                f'{tag}_losses': losses.detach().numpy(), f'{tag}_gnorm': gnorm, f'{tag}_seed': seed})
+  np.savez_compressed(os.path.join(HERE, 'lossbranch_golden.npz'), **out)
+
+
 def golden_sde(R):
   out = {}
   u = torch.linspace(0.01, 0.99, 7)
@@ -455,7 +482,7 @@ def main(which):
   R = import_reference()
   jobs = dict(configs=golden_configs, ops=golden_ops, sde=golden_sde, unet=golden_unet_cifar,
               variants=golden_variants, sampler=golden_sampler, train=golden_train, deepest=golden_deepest,
-              likelihood=golden_likelihood)
+              likelihood=golden_likelihood, lossbranches=golden_lossbranches)
   for name in (which or jobs):
     print('golden:', name, flush=True)
     jobs[name](R)

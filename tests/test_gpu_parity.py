@@ -449,6 +449,31 @@ def test_deepest_lsgm_mixed_step_vs_reference_fixture(golden):
   np.testing.assert_allclose(en, g['enorm'], rtol=2e-4, atol=2e-6)
 
 
+@pytest.mark.parametrize('tag', ['vp', 've'])
+def test_likelihood_weighted_loss_branch_vs_reference_fixture(golden, tag):
+  """reference losses.py:125-129: (score + z/std)^2 g^2 with uniformly drawn times (importance sampling off,
+  likelihood weighting on) - losses and every gradient norm against the reference fixture."""
+  from soft_truncation_b200 import losses
+  from soft_truncation_b200.models import utils as mutils
+  g = golden('lossbranch_golden.npz')
+  if tag == 'vp':
+    cfg = _cfg(dropout=0.)
+    cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks = 32, (1, 2), 1
+  else:
+    cfg = _reduced('c5')
+  cfg.training.likelihood_weighting, cfg.training.importance_sampling = True, False
+  model, sde, _ = _model(cfg, int(g[f'{tag}_seed']), torch.float32)
+  net = mutils.unwrap(model)
+  loss_fn = losses.get_sde_loss_fn(cfg, sde, train=True)
+  net.zero_grad()
+  ls = loss_fn(model, torch.tensor(g[f'{tag}_x'], device=DEV), importance_sampling=False, t_min=float(g[f'{tag}_tmin']),
+               injected=dict(u=torch.tensor(g[f'{tag}_u']), z=torch.tensor(g[f'{tag}_z'])))
+  np.testing.assert_allclose(ls.detach().cpu().numpy(), g[f'{tag}_losses'], rtol=2e-4)
+  torch.mean(ls).backward()
+  gn = np.array([p.grad.double().norm().item() if p.requires_grad else 0. for _, p in net.named_parameters()])
+  np.testing.assert_allclose(gn, g[f'{tag}_gnorm'], rtol=2e-3, atol=1e-6 * g[f'{tag}_gnorm'].max())
+
+
 def test_pc_sampler_ve_langevin_vs_reference_fixture(golden):
   """4-step reverse-diffusion predictor + Langevin corrector (VE) on the reduced C5 network: pins the
   ReverseDiffusionPredictor / LangevinCorrector updates, the on-device batch norms and the final VE denoise step."""

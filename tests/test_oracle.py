@@ -234,6 +234,30 @@ def test_deepest_lsgm_mixed_step_oracle_vs_reference(golden):
   np.testing.assert_allclose(en, g['enorm'], rtol=1e-4, atol=2e-6)
 
 
+@pytest.mark.parametrize('tag', ['vp', 've'])
+def test_likelihood_weighted_loss_branch_oracle_vs_reference(golden, tag):
+  """losses.py:125-129 ((score + z/std)^2 g^2 with uniform times): reached only with importance_sampling off."""
+  g = golden('lossbranch_golden.npz')
+  if tag == 'vp':
+    cfg = configs.cifar10_ddpmpp_nll_st()
+    cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks = 32, (1, 2), 1
+  else:
+    cfg = _reduced_c5()
+  cfg.model.dropout = 0.
+  cfg.training.likelihood_weighting, cfg.training.importance_sampling = True, False
+  sde = ref_train.make_sde(cfg)
+  state = ref_train.TrainState(ref_model.make_state_dict(cfg, seed=int(g[f'{tag}_seed'])))
+  for k in state.trainable:
+    state.sd[k].requires_grad_(True)
+  losses = ref_train.dsm_losses(state.sd, cfg, sde, torch.tensor(g[f'{tag}_x']), torch.tensor(g[f'{tag}_u']),
+                                torch.tensor(g[f'{tag}_z']), float(g[f'{tag}_tmin']))
+  np.testing.assert_allclose(losses.detach().numpy(), g[f'{tag}_losses'], rtol=2e-4)
+  torch.mean(losses).backward()
+  names = [k for k in state.sd if k != 'sigmas']
+  gn = np.array([0. if state.sd[k].grad is None else state.sd[k].grad.double().norm().item() for k in names])
+  np.testing.assert_allclose(gn, g[f'{tag}_gnorm'], rtol=2e-3, atol=1e-6 * g[f'{tag}_gnorm'].max())
+
+
 class _OracleNet(torch.nn.Module):
   """The oracle U-Net behind the model call convention, so that the host-side estimators can run on the CPU."""
 
