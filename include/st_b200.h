@@ -160,6 +160,19 @@ int st_gn_bwd_fused(const void* x1, const void* x2, const void* dy, int dtype, i
                     const uint8_t* keepbits, int chunks, float* red, const void* extra, float extra_scale,
                     void* dx1, int accum1, void* dx2, int accum2, float* csum, void* stream);
 
+/* The backward with plain (not accumulated) destinations and x, dy (and `extra`, optional) read ONCE: a cluster of
+ * `chunks` CTAs keeps the image resident in shared memory between the reduction and the apply phase (dz overwrites dy's copy), exchanges
+ * the per-group sums through distributed shared memory and writes dx: 3 tensor passes over HBM instead of 5.  `red`
+ * [n_img][chunks][C][2] and csum [n_img][chunks][C] as for st_gn_bwd_fused.  st_gn_bwd_resident_chunks: cluster size
+ * for a shape and stream count (2, or 3 with `extra`), 0 = not applicable (an accumulated destination, C > 512, more
+ * than 8 CTAs x 64 KB per image, too few CTAs, or ST_GN_BWD_RESIDENT=0). */
+int st_gn_bwd_resident_chunks(int n_img, int hw, int C, int streams);
+int st_gn_bwd_resident(const void* x1, const void* x2, const void* dy, int dtype, int n_img, int hw, int C1,
+                       int C2, int G, const float* gamma, const float* beta, const float* mean,
+                       const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
+                       const uint8_t* keepbits, int chunks, float* red, const void* extra, float extra_scale,
+                       void* dx1, void* dx2, float* csum, void* stream);
+
 /* ------------------------------------------------------------------ training-batch preparation
  * Replaces the float pipeline of datasets.py:56-62,117,311-326 + run_lib.py:73-75: src uint8 [n_img][H][W][C] ->
  * dst fp32 [n_img][C][H][W] = a * deq(flip(src)/255) + b, deq(x) = (255 x + u)/256 when dequant == 1.  `flip`

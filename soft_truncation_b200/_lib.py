@@ -48,6 +48,9 @@ SIGNATURES = {
     'st_gn_fwd_fused_chunks': [c_int, c_int, c_int],
     'st_gn_fwd_fused': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_f, c_int, c_f, c_u64, c_p, c_p, c_p,
                         c_p, c_p, c_int, c_p],
+    'st_gn_bwd_resident_chunks': [c_int, c_int, c_int, c_int],
+    'st_gn_bwd_resident': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f,
+                           c_u64, c_p, c_p, c_int, c_p, c_p, c_f, c_p, c_p, c_p, c_p],
     'st_gn_bwd_fused_chunks': [c_int, c_int, c_int, c_int, c_int],
     'st_gn_bwd_fused': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f,
                         c_u64, c_p, c_p, c_int, c_p, c_p, c_f, c_p, c_int, c_p, c_int, c_p, c_p],

@@ -1155,3 +1155,297 @@ extern "C" __attribute__((visibility("default"))) int st_gn_fwd_fused(const void
   ST_CHECK_LAUNCH("st_gn_fwd_fused");
   return 0;
 }
+
+// ---------------------------------------------------------------- resident backward (x and dy read ONCE)
+// The backward without an accumulated destination (GroupNorm_1 of every res-block; GroupNorm_0 / attention norms with
+// their `extra` shortcut gradient as a third resident stream where the image is small enough) with the cluster's
+// image resident in shared memory: every thread copies its <= R pixels of x and dy (and extra) up front, phase 1 forms dz
+// (written back over dy's slot) and the per-channel sums, the cluster exchanges the gamma-weighted per-group sums through
+// distributed shared memory, phase 2 produces dx from the resident x and dz.  HBM traffic: x + dy in, dx out - 3 tensor
+// passes instead of the 5 of st_gn_bwd_reduce + st_gn_bwd_apply.  The dropout keep bits ride in registers (8 byte loads
+// issued with the copies).  `red` [n_img][chunks][C][2] is still written: the parameter gradients are its column sums.
+namespace {
+// resident pixels per thread: 8 x (x, dy) or 5 x (x, dy, extra) 16-byte vectors x 256 threads = 64 / 60 KB (bf16)
+constexpr int bres_for(int streams) { return streams == 2 ? 8 : 5; }
+
+template <typename T>
+__device__ __forceinline__ void slot_write(uint32_t addr, const float v[8]) {
+  if constexpr (sizeof(T) == 2) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
+  }
+}
+
+// sum the 8 per-thread values `val` over the pixel lanes; column (v*8+i) of the result lands in thread `col % 256`'s
+// out[col / 256] (columns = channels, <= 512).  s_red: 256*8 floats.
+__device__ __forceinline__ void lane_reduce8(const float val[8], bool active, int lane, int lanes, int V, int v, float* s_red,
+                                             float out[2]) {
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_red[(lane * V + v) * 8 + i] = val[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int col = threadIdx.x + 256 * j;
+    float t = 0.f;
+    if (col < 8 * V)
+      for (int l = 0; l < lanes; ++l) t += s_red[l * 8 * V + col];
+    out[j] = t;
+  }
+}
+
+template <typename T, bool ACT, int DROP, bool CSUM, int NS>
+__global__ void __launch_bounds__(256, 3) gn_bwd_resident_kernel(Src2<T> s, const T* dy, const T* extra, float extra_scale, int hw, int G,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 float p_drop, uint64_t seed, const T* mask,
+                                                                 const uint8_t* __restrict__ keepbits, float* red, T* dx1,
+                                                                 T* dx2, float* csum) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  __shared__ float s_red[256 * 8];
+  __shared__ float s_gpart[128];             // gamma-weighted per-group (sum dz, sum dz*xhat) of this CTA's chunk
+  __shared__ float sh1[64], sh2[64];
+  pdl_wait();
+  pdl_trigger();
+  constexpr int GN_BRES = bres_for(NS);
+  using P = Pipe<T, NS, GN_BRES>;
+  const P pipe(gsm);
+  const int Ct = s.C1 + s.C2, cpg = Ct / G;
+  const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  Walk w(Ct, n, hw, chunk, chunks);
+  const int V = w.V, lanes = w.lanes, v = w.v, lane = w.lane;
+  const bool active = lane < lanes;
+  if (!active) w.c0 = 0;
+  const int c0 = w.c0;
+  const int octstep = lanes * V;
+  const long long oct0 = w.row0 * V + v;
+  // ---- everything in flight: x, dy (cp.async, one group per pixel) and the keep bits (plain byte loads)
+  {
+    Stream<T> xs = stream_of(s, w), ds = stream_of(dy, Ct, w), es = stream_of(extra, Ct, w);
+#pragma unroll
+    for (int st = 0; st < GN_BRES; ++st) {
+      if (st < w.n_it) {
+        pipe.issue(st, 0, xs.next());
+        pipe.issue(st, 1, ds.next());
+        if constexpr (NS == 3) pipe.issue(st, 2, es.next());
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  }
+  uint32_t kb[2] = {0u, 0u};
+  if constexpr (DROP == DROP_FAST) {
+#pragma unroll
+    for (int st = 0; st < GN_BRES; ++st)
+      if (st < w.n_it) kb[st >> 2] |= (uint32_t)__ldg(keepbits + oct0 + (long long)st * octstep) << (8 * (st & 3));
+  }
+  ChanConst kc;
+  load_consts(kc, n, c0, G, cpg, gamma, beta, mean, rstd);
+  const BwdConst k(kc);
+  const float inv_keep = 1.f / (1.f - p_drop);
+  // ---- phase 1: dz (kept in dy's slot) and the per-channel sums of this thread's pixels
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = b[i] = 0.f;
+  static_for<0, GN_BRES>([&](auto I) {
+    constexpr int st = decltype(I)::value;
+    if (st < w.n_it) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(GN_BRES - 1 - st) : "memory");
+      float x0[8], d0[8], mk[8], xh[8], dz[8];
+      pipe.read(st, 0, x0);
+      pipe.read(st, 1, d0);
+      const long long oct = oct0 + (long long)st * octstep;
+      const uint32_t bits = (kb[st >> 2] >> (8 * (st & 3))) & 0xFFu;
+      if constexpr (DROP == DROP_SLOW) { if (mask) load8(mask + oct * 8, mk); }
+      gn_dz8<T, ACT, DROP>(x0, d0, k, p_drop, inv_keep, seed, mask ? mk : nullptr, bits, oct, xh, dz);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], xh[i], b[i]); }
+      if constexpr (sizeof(T) == 2) {
+        slot_write<T>(pipe.slot(st, 1, 0), dz);
+      } else {
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(pipe.slot(st, 1, 0)), "f"(dz[0]), "f"(dz[1]), "f"(dz[2]), "f"(dz[3]) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(pipe.slot(st, 1, 1)), "f"(dz[4]), "f"(dz[5]), "f"(dz[6]), "f"(dz[7]) : "memory");
+      }
+    }
+  });
+  // ---- per-channel sums of the chunk -> red (parameter gradients), gamma-weighted per-group sums -> s_gpart
+  float ta[2], tb[2];
+  lane_reduce8(a, active, lane, lanes, V, v, s_red, ta);
+  lane_reduce8(b, active, lane, lanes, V, v, s_red, tb);
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int c = threadIdx.x + 256 * j;
+    if (c < Ct) {
+      float* o = red + (((long long)n * chunks + chunk) * Ct + c) * 2;
+      o[0] = ta[j];
+      o[1] = tb[j];
+      const float gm = gamma[c];
+      s_red[c] = gm * ta[j];
+      s_red[512 + c] = gm * tb[j];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    double A = 0., Bq = 0.;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { A += (double)s_red[c]; Bq += (double)s_red[512 + c]; }
+    s_gpart[2 * g] = (float)A;
+    s_gpart[2 * g + 1] = (float)Bq;
+  }
+  if (chunks > 1) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    double A = 0., Bq = 0.;
+    if (chunks > 1) {
+      for (int r = 0; r < chunks; ++r) {
+        A += (double)ld_dsmem_f32(&s_gpart[2 * g], (uint32_t)r);
+        Bq += (double)ld_dsmem_f32(&s_gpart[2 * g + 1], (uint32_t)r);
+      }
+    } else {
+      A = (double)s_gpart[2 * g];
+      Bq = (double)s_gpart[2 * g + 1];
+    }
+    const double inv = 1.0 / ((double)hw * cpg);
+    sh1[g] = (float)(A * inv);
+    sh2[g] = (float)(Bq * inv);
+  }
+  if (chunks > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // done reading peers' s_gpart
+  __syncthreads();
+  // ---- phase 2: dx = rstd*gamma*dz - rstd*s1 - rstd*s2*xhat from the resident x and dz
+  const float rs1[2] = {-kc.r[0] * sh1[kc.g[0]], -kc.r[1] * sh1[kc.g[1]]}, rs2[2] = {-kc.r[0] * sh2[kc.g[0]], -kc.r[1] * sh2[kc.g[1]]};
+  float cs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+  const bool first = c0 < s.C1;
+  const int dld = first ? s.C1 : s.C2;
+  T* dp = (first ? dx1 + c0 : dx2 + (c0 - s.C1)) + w.row0 * dld;
+  const int dstep = lanes * dld;
+#pragma unroll
+  for (int st = 0; st < GN_BRES; ++st)
+    if (st < w.n_it) {
+      float x0[8], dz[8], o[8];
+      pipe.read(st, 0, x0);
+      pipe.read(st, 1, dz);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = fmaf(x0[i], k.r[i >> 2], k.nmr[i >> 2]);
+        o[i] = fmaf(k.rg[i], dz[i], fmaf(xh, rs2[i >> 2], rs1[i >> 2]));
+      }
+      if constexpr (NS == 3) {
+        float ex[8];
+        pipe.read(st, 2, ex);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(extra_scale, ex[i], o[i]);
+      }
+      if constexpr (CSUM) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cs[i] += o[i];
+      }
+      store8(dp, o);
+      dp += dstep;
+    }
+  if constexpr (CSUM) {
+    float tc[2];
+    lane_reduce8(cs, active, lane, lanes, V, v, s_red, tc);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = threadIdx.x + 256 * j;
+      if (c < Ct) csum[((long long)n * chunks + chunk) * Ct + c] = tc[j];
+    }
+  }
+  if (chunks > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// streams: 2 (x, dy) or 3 (+ extra); an accumulated destination is a further stream -> not applicable.
+// Measured (tools/gn_bench.py, B=512): ahead of the two-kernel and fused-pair forms up to clusters of 8; a cluster of
+// 16 (32x32x256) is slower (302 vs 257 us).
+int bwd_resident_chunks_for(int n_img, int hw, int Ct, int streams) {
+  static const int mode = getenv("ST_GN_BWD_RESIDENT") ? atoi(getenv("ST_GN_BWD_RESIDENT")) : 1;
+  static const int max_cluster = getenv("ST_GN_BWD_CLUSTER") ? atoi(getenv("ST_GN_BWD_CLUSTER")) : 8;
+  if (!mode || (streams != 2 && streams != 3) || Ct > 512) return 0;
+  const int V = Ct / 8, lanes = 256 / V;
+  if (lanes < 1) return 0;
+  const int per_cta = lanes * bres_for(streams);
+  const int c = (hw + per_cta - 1) / per_cta;
+  if (c > 16 || c > max_cluster || (hw + c - 1) / c > per_cta) return 0;
+  if (streams == 3 && c > 2) return 0;      // 5 pixels per thread: ahead only at 8x8x256 and 4x4 (89.6 vs 71.7 us at 16x16x256)
+  if (mode == 1 && (long long)n_img * c < st_num_sms()) return 0;
+  return c;
+}
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int st_gn_bwd_resident_chunks(int n_img, int hw, int C, int streams) {
+  return bwd_resident_chunks_for(n_img, hw, C, streams);
+}
+
+extern "C" __attribute__((visibility("default"))) int st_gn_bwd_resident(const void* x1, const void* x2, const void* dy, int dtype, int n_img, int hw,
+                               int C1, int C2, int G, const float* gamma, const float* beta, const float* mean,
+                               const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
+                               const uint8_t* keepbits, int chunks, float* red, const void* extra, float extra_scale,
+                               void* dx1, void* dx2, float* csum, void* stream) {
+  if (int e = check_geom(C1, C2, G)) return e;
+  const int Ct = C1 + C2, V = Ct / 8, lanes = 256 / V;
+  ST_CHECK_ARG(n_img <= 65535, "st_gn_bwd_resident: more than 65535 images");
+  ST_CHECK_ARG(Ct <= 512, "st_gn_bwd_resident: C > 512 unsupported");
+  ST_CHECK_ARG(chunks >= 1 && chunks <= 16, "st_gn_bwd_resident: chunks (cluster size) must be 1..16, got %d", chunks);
+  const int ns = extra ? 3 : 2;
+  ST_CHECK_ARG(lanes >= 1 && (hw + chunks - 1) / chunks <= lanes * bres_for(ns),
+               "st_gn_bwd_resident: a chunk of %d pixels x %d channels does not fit the resident buffer", (hw + chunks - 1) / chunks, Ct);
+  const int drop = mask ? DROP_SLOW : (p_drop > 0.f ? (keepbits ? DROP_FAST : DROP_SLOW) : DROP_NONE);
+  int rc = 0;
+  ST_DISPATCH_DTYPE(dtype, T, {
+    Src2<T> s{(const T*)x1, (const T*)x2, C1, C2};
+    dispatch_mode(act, drop, [&](auto A, auto D) {
+      constexpr bool ACT = decltype(A)::value;
+      constexpr int DROP = decltype(D)::value;
+      auto launch = [&](auto CS, auto NSt) {
+        constexpr bool CSUM = decltype(CS)::value;
+        constexpr int NS = decltype(NSt)::value;
+        constexpr int smem = Pipe<T, NS, bres_for(NS)>::VEC_BYTES;
+        auto kernel = gn_bwd_resident_kernel<T, ACT, DROP, CSUM, NS>;
+        static bool attr_ok = false;
+        if (!attr_ok) {
+          if (!allow_smem(kernel, smem)) { rc = ST_ERR_CUDA; return; }
+          cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+          if (e != cudaSuccess) { st_set_error("st_gn_bwd_resident: cluster attribute: %s", cudaGetErrorString(e)); rc = ST_ERR_CUDA; return; }
+          attr_ok = true;
+        }
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(chunks, n_img);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = chunks;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = st_pdl_on((cudaStream_t)stream) ? 2 : 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, s, (const T*)dy, (const T*)extra, extra_scale, hw, G, gamma, beta, mean,
+                                           rstd, p_drop, seed, (const T*)mask, keepbits, red, (T*)dx1, (T*)dx2, csum);
+        if (e != cudaSuccess) { st_set_error("st_gn_bwd_resident: launch: %s", cudaGetErrorString(e)); rc = ST_ERR_CUDA; }
+      };
+      auto with_ns = [&](auto CS) {
+        if (extra) launch(CS, std::integral_constant<int, 3>{}); else launch(CS, std::integral_constant<int, 2>{});
+      };
+      if (csum) with_ns(std::true_type{}); else with_ns(std::false_type{});
+    });
+  });
+  if (rc) return rc;
+  ST_CHECK_LAUNCH("st_gn_bwd_resident");
+  return 0;
+}

@@ -242,11 +242,12 @@ def gn_norm_act(x, x2, G, gamma, beta, act, p_drop=0., seed=0, mask=None, keepbi
 
 def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0., seed=0, mask=None, extra=None,
                 extra_scale=1.0, dx1=None, accum1=False, dx2=None, accum2=False, keepbits=None, want_csum=False,
-                queue=None, fused_chunks=None):
+                queue=None, fused_chunks=None, resident=None):
   """Returns (dx1, dx2[, csum]); accumulates dgamma/dbeta (fp32 views into the flat gradient buffer).
   csum (want_csum): fp32 (B, chunks, C1+C2) column sums of the gradient this call contributed.
   `queue`: a ColsumQueue that takes the dgamma/dbeta reduction of the fused (single-launch) form; `fused_chunks`:
-  cluster size override (0 = two-kernel form, None = the library decides)."""
+  cluster size override (0 = two-kernel form, None = the library decides); `resident`: cluster size of the form that
+  keeps x / dy in shared memory between the two phases (2-stream calls only; None = the library decides, 0 = off)."""
   B, H, W, C1 = x.shape
   C2 = 0 if x2 is None else x2.shape[3]
   hw, Ct = H * W, C1 + C2
@@ -261,6 +262,23 @@ def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0.,
   head = (ptr(x), ptr(x2), ptr(dy), dt(x), B, hw, C1, C2, G, ptr(gamma), ptr(beta), ptr(stats[0]), ptr(stats[1]),
           int(act), float(p_drop), int(seed), ptr(mask), ptr(keepbits))
   n_streams = 2 + (extra is not None) + bool(accum1 or accum2)
+  if resident is None:
+    ok = fused_chunks is None and not (accum1 or accum2)
+    resident = lib.st_gn_bwd_resident_chunks(B, hw, Ct, n_streams) if ok else 0
+  if resident > 0:
+    # x and dy read once: the cluster keeps the image in shared memory between the reduction and the apply phase
+    assert not (accum1 or accum2), 'the resident backward form takes no accumulated destination'
+    red = torch.empty((B, resident, Ct, 2), dtype=torch.float32, device=x.device)
+    csum = torch.empty((B, resident, Ct), dtype=torch.float32, device=x.device) if want_csum else None
+    check(lib.st_gn_bwd_resident(*head, int(resident), ptr(red), ptr(extra), float(extra_scale), ptr(dx1), ptr(dx2),
+                                 ptr(csum), stream()))
+    if dgamma is None:
+      pass
+    elif queue is not None:
+      queue.add_gn_params(dgamma, dbeta, red.view(B * resident, Ct, 2))
+    else:
+      check(lib.st_gn_bwd_params(ptr(red), B * resident, Ct, ptr(dgamma), ptr(dbeta), stream()))
+    return (dx1, dx2, csum) if want_csum else (dx1, dx2)
   fc = lib.st_gn_bwd_fused_chunks(B, hw, Ct, dt(x), n_streams) if fused_chunks is None else int(fused_chunks)
   if fc > 0:
     # one launch: a cluster of `fc` CTAs per image reduces, synchronises and applies; the parameter gradients are

@@ -340,6 +340,69 @@ def test_groupnorm_fused_forward_rejects_oversized_chunks():
   assert ops.lib.st_gn_fwd_fused_chunks(2, 1024, 128) == 0           # 8 CTAs cannot fill the GPU: two-kernel path
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('shape', [(6, 32, 32, 128, 0, 8), (5, 16, 16, 256, 0, 4), (3, 32, 32, 256, 0, 16),
+                                   (7, 8, 8, 256, 256, 2), (9, 4, 4, 256, 0, 1), (4, 16, 16, 256, 128, 7),
+                                   (2, 12, 12, 64, 0, 3)])
+def test_groupnorm_resident_backward(dtype, shape):
+  """st_gn_bwd_resident (x / dy resident in shared memory across the two phases, DSMEM exchange) against autograd and
+  against the two-kernel form: SiLU + dropout keep bits + column sums + parameter gradients through the batched queue."""
+  B, H, W, C1, C2, fc = shape
+  C = C1 + C2
+  G = min(C // 4, 32)
+  x = rnd(B, C, H, W, seed=1) * 1.5 + 0.3
+  gamma, beta = rnd(C, seed=2) * 0.2 + 1., rnd(C, seed=3) * 0.2
+  dy = rnd(B, C, H, W, seed=4)
+  xh, dyh = nhwc(x).to(dtype), nhwc(dy).to(dtype)
+  x1, x2 = (xh[..., :C1].contiguous(), xh[..., C1:].contiguous()) if C2 else (xh, None)
+  # (a) no dropout: against autograd
+  xq = x.to(dtype).float().requires_grad_(True)
+  gam, bet = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+  y_ref = F.group_norm(xq, G, gam, bet, eps=1e-6)
+  (y_ref * torch.sigmoid(y_ref)).backward(dy.to(dtype).float())
+  _, st = ops.gn_norm_act(x1, x2, G, gamma, beta, 1, fused_chunks=0)
+  dg, db = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
+  d1, d2, cs = ops.gn_backward(x1, x2, dyh, G, gamma, beta, st, 1, dg, db, want_csum=True, resident=fc)
+  dx = torch.cat([d1, d2], -1) if C2 else d1
+  assert rel_l2(nchw(dx.float()), xq.grad) < 2 * tol(dtype)
+  assert rel_l2(dg, gam.grad) < 2 * tol(dtype) and rel_l2(db, bet.grad) < 2 * tol(dtype)
+  assert cs.shape == (B, fc, C)
+  assert rel_l2(cs.sum(1), xq.grad.sum(dim=(2, 3))) < 1e-4 + (1e-2 if dtype == torch.bfloat16 else 0)
+  # (b) in-kernel dropout with the forward's keep bits: against the two-kernel form, parameter gradients via the queue
+  bits = torch.empty(B * H * W * C // 8, dtype=torch.uint8, device=dev())
+  ops.gn_norm_act(x1, x2, G, gamma, beta, 1, p_drop=0.2, seed=31, keepbits=bits, fused_chunks=0)
+  res = []
+  for form in (0, fc):
+    dg, db = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
+    q = ops.ColsumQueue()
+    d1, d2, cs = ops.gn_backward(x1, x2, dyh, G, gamma, beta, st, 1, dg, db, p_drop=0.2, seed=31, keepbits=bits,
+                                 want_csum=True, queue=q, fused_chunks=0 if form == 0 else None, resident=form)
+    q.flush()
+    res.append((torch.cat([d1, d2], -1).float() if C2 else d1.float(), cs.sum(1), dg, db))
+  two, one = res
+  lim = 1e-5 if dtype == torch.float32 else 6e-3
+  assert rel_l2(one[0], two[0]) < lim and rel_l2(one[1], two[1]) < max(lim, 1e-4)
+  assert rel_l2(one[2], two[2]) < 1e-4 and rel_l2(one[3], two[3]) < 1e-4 and two[2].abs().sum() > 0
+  # (c) the regenerated-mask path (no keep bits kept) gives the same answer
+  dg2, db2 = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
+  e1, e2 = ops.gn_backward(x1, x2, dyh, G, gamma, beta, st, 1, dg2, db2, p_drop=0.2, seed=31, resident=fc)
+  got = torch.cat([e1, e2], -1).float() if C2 else e1.float()
+  assert rel_l2(got, one[0]) < 1e-6 + (1e-3 if dtype == torch.bfloat16 else 0)
+  # (d) three resident streams (x, dy, extra): 5 pixels per thread
+  lanes = 256 // (C // 8)
+  fc3 = -(-(H * W) // (lanes * 5))
+  if fc3 <= 16:
+    extra = nhwc(rnd(B, C, H, W, seed=6)).to(dtype)
+    outs = []
+    for form in (0, fc3):
+      dg, db = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
+      r = ops.gn_backward(x1, x2, dyh, G, gamma, beta, st, 1, dg, db, extra=extra, extra_scale=0.7, want_csum=True,
+                          fused_chunks=0 if form == 0 else None, resident=form)
+      outs.append((torch.cat([r[0], r[1]], -1).float() if C2 else r[0].float(), r[2].sum(1), dg, db))
+    assert rel_l2(outs[1][0], outs[0][0]) < lim and rel_l2(outs[1][1], outs[0][1]) < max(lim, 1e-4)
+    assert rel_l2(outs[1][2], outs[0][2]) < 1e-4 and rel_l2(outs[1][3], outs[0][3]) < 1e-4
+
+
 def test_groupnorm_apply_finalises_statistics_in_kernel():
   """gn_stats(finalize=False) + gn_apply == st_gn_finalize path, bit for bit (same arithmetic, one launch fewer)."""
   B, H, W, C1, C2, G = 3, 8, 8, 64, 32, 24

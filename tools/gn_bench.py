@@ -87,11 +87,27 @@ def main():
       fcs = ops.lib.st_gn_fwd_fused_chunks(B, H * H, Ct)
       t1 = timed(lambda: ops.gn_norm_act(x, x2, G, gamma, beta, True, fused_chunks=fcs, **kw)) if fcs > 0 else float('nan')
       fwd.append(f'two kernels {t2:.1f}, resident x{fcs} {t1:.1f}')
+    # backward with x / dy resident in shared memory (2-stream form): plain and dropout + column sums
+    rc = ops.lib.st_gn_bwd_resident_chunks(B, H * H, Ct, 2)
+    resid = []
+    for kw in (dict(), dict(p_drop=0.1, seed=5, keepbits=bits, want_csum=True)):
+      def run_r(kw=kw):
+        ops.gn_backward(x, x2, dy, G, gamma, beta, stats, True, dgamma, dbeta, queue=q, resident=rc, **kw)
+        q.jobs, q.keep = [], []
+      resid.append(f'{timed(run_r):.1f}' if rc > 0 else 'n/a')
     f = lambda t, units: f'{t:7.1f} ({units * nbytes / t / 1e3:5.0f})'
     print(H, C1, C2, '|', f(t_stats, 1), '|', f(t_apply, 2), '|', f(t_applyd, 2), '|', f(res[0][0], 2), '|', f(res[0][1], 3), '|',
           f(res[1][0], 2), '|', f(res[1][1], 3), flush=True)
     print('      backward total us by cluster size (0 = two kernels): plain [', fused[0], '] drop+csum [', fused[1], '] extra+csum [', fused[2], ']',
           f'ideal 3-pass at 6.5 TB/s: {3 * nbytes / 6.5e6:.1f}', flush=True)
+    rc3 = ops.lib.st_gn_bwd_resident_chunks(B, H * H, Ct, 3)
+
+    def run_r3():
+      ops.gn_backward(x, x2, dy, G, gamma, beta, stats, True, dgamma, dbeta, queue=q, resident=rc3, extra=dy, extra_scale=0.7,
+                      want_csum=True)
+      q.jobs, q.keep = [], []
+    r3 = f'{timed(run_r3):.1f}' if rc3 > 0 else 'n/a'
+    print(f'      backward resident x{rc}: plain {resid[0]}, drop+csum {resid[1]}; with extra (x{rc3}) + csum {r3}', flush=True)
     print('      forward total us: plain [', fwd[0], '] dropout [', fwd[1], f'] ideal 2-pass at 6.5 TB/s: {2 * nbytes / 6.5e6:.1f}', flush=True)
 
 
