@@ -35,7 +35,7 @@ TRAIN_GF_PER_IMG = 65.08      # 3 x 21.693 GF forward (conv/linear
 FWD_GF_PER_IMG = 21.693
 # DRAM bytes per GEMM launch (average over the 430 launches of one B=512 bf16 step): 54.15 GB / 430, from the ncu launch
 # list committed as profiles/r01_launches_train_step.md (dram__bytes_read.sum + dram__bytes_write.sum)
-GEMM_DRAM_BYTES_PER_LAUNCH = 54.177e9 / 430
+GEMM_DRAM_BYTES_PER_LAUNCH = 54.166e9 / 430
 METRIC = 'DDPM++ CIFAR-10 train images/sec'
 
 

@@ -983,6 +983,24 @@ __global__ void __launch_bounds__(256, 3) gn_fwd_fused_kernel(Src2<T> s, int hw,
   float gam[8], bet[8];
   load8(gamma + (active ? w.c0 : 0), gam);
   load8(beta + (active ? w.c0 : 0), bet);
+  // dropout keep flags of every resident vector, drawn while the copies are in flight (the generator is ~60 ALU
+  // instructions per vector: in the store phase it would not overlap anything) and carried in registers
+  uint32_t kb[GN_RES / 4];
+#pragma unroll
+  for (int i = 0; i < GN_RES / 4; ++i) kb[i] = 0u;
+  if constexpr (DROP == DROP_FAST) {
+    const long long oct0 = w.row0 * V + w.v;
+    const int octstep = lanes * V;
+#pragma unroll
+    for (int st = 0; st < GN_RES; ++st)
+      if (st < w.n_it) {
+        float keep[8];
+        const long long oct = oct0 + (long long)st * octstep;
+        const uint32_t bits = dropout8(seed, (uint64_t)oct, p_drop, keep);
+        if (keepbits) keepbits[oct] = (uint8_t)bits;
+        kb[st >> 2] |= bits << (8 * (st & 3));
+      }
+  }
   // ---- statistics of the resident chunk
   float sum[2] = {0.f, 0.f}, sq[2] = {0.f, 0.f};
   static_for<0, GN_RES>([&](auto I) {
@@ -1064,8 +1082,7 @@ __global__ void __launch_bounds__(256, 3) gn_fwd_fused_kernel(Src2<T> s, int hw,
         }
         if constexpr (DROP == DROP_FAST) {
           float keep[8];
-          const uint32_t bits = dropout8(seed, (uint64_t)oct, p_drop, keep);
-          if (keepbits) keepbits[oct] = (uint8_t)bits;
+          keep_from_bits((kb[st >> 2] >> (8 * (st & 3))) & 0xFFu, p_drop, keep);
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] *= keep[i];
         } else if constexpr (DROP == DROP_SLOW) {

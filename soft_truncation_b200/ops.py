@@ -166,6 +166,9 @@ class input_grads_only:
 
 
 # ------------------------------------------------------------------------------------ GroupNorm
+# resident forward for the in-kernel-dropout passes: measured level with / behind the pipelined pair (94 vs 85 us at
+# 32x32x128 even with the generator moved under the loads: it is ALU-bound), so off by default
+_GN_FWD_FUSED_DROP = os.environ.get('ST_GN_FWD_FUSED_DROP', '0') != '0'
 _GN_SPLIT_W = int(os.environ.get('ST_GN_SPLIT_W', '4'))    # tuning knob: blocks per SM the split reductions aim for
 
 
@@ -225,8 +228,8 @@ def gn_norm_act(x, x2, G, gamma, beta, act, p_drop=0., seed=0, mask=None, keepbi
   C2 = 0 if x2 is None else x2.shape[3]
   if fused_chunks is not None:
     fc = int(fused_chunks)
-  elif p_drop > 0. and mask is None:
-    fc = 0      # in-kernel dropout: the generator work overlaps the loads only in the pipelined apply kernel (measured)
+  elif p_drop > 0. and mask is None and not _GN_FWD_FUSED_DROP:
+    fc = 0      # in-kernel dropout passes keep the pipelined stats + apply pair (ST_GN_FWD_FUSED_DROP=1 to fuse)
   else:
     fc = lib.st_gn_fwd_fused_chunks(B, H * W, C1 + C2)
   if fc <= 0:
