@@ -242,3 +242,22 @@ def test_u8_loader_epochs_and_scalers():
   with pytest.raises(RuntimeError):        # batch preparation is a CUDA kernel: no CPU fallback
     cfg.device = torch.device('cpu')
     datasets.prepare_batch(cfg, torch.zeros(2, 32, 32, 3, dtype=torch.uint8))
+
+
+def test_groupnorm_launch_policies_for_the_bench_shapes():
+  """The cluster-form policies are host functions of the shape (no GPU needed; 148 SMs assumed without a device):
+  pins what the B=512 training step launches (measured policy) and the fall-backs."""
+  from soft_truncation_b200._lib import lib
+  B = 512
+  # (hw, C) -> (resident forward cluster, resident backward 2-stream, 3-stream, fused-pair backward 2-stream, 3-stream)
+  want = {(1024, 128): (4, 8, 0, 2, 0), (1024, 256): (8, 0, 0, 2, 0), (1024, 384): (13, 0, 0, 2, 0),
+          (256, 256): (2, 4, 0, 2, 2), (256, 384): (4, 7, 0, 2, 2), (256, 512): (4, 8, 0, 2, 2),
+          (64, 256): (1, 1, 2, 1, 1), (64, 512): (1, 2, 0, 1, 1), (16, 256): (1, 1, 1, 1, 1), (16, 512): (1, 1, 1, 1, 1)}
+  for (hw, C), w in want.items():
+    got = (lib.st_gn_fwd_fused_chunks(B, hw, C), lib.st_gn_bwd_resident_chunks(B, hw, C, 2),
+           lib.st_gn_bwd_resident_chunks(B, hw, C, 3), lib.st_gn_bwd_fused_chunks(B, hw, C, 1, 2),
+           lib.st_gn_bwd_fused_chunks(B, hw, C, 1, 3))
+    assert got == w, ((hw, C), got, w)
+  # an image that does not fit 16 CTAs (CelebA-HQ 256x256), a batch too small to fill the GPU, a 4-stream call
+  assert lib.st_gn_fwd_fused_chunks(16, 65536, 128) == 0 and lib.st_gn_bwd_resident_chunks(4, 1024, 128, 2) == 0
+  assert lib.st_gn_bwd_resident_chunks(B, 64, 256, 4) == 0 and lib.st_gn_bwd_resident_chunks(B, 64, 1024, 2) == 0
