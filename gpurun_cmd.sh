@@ -1,4 +1,4 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/t55_gpu.log 2>&1; echo "pytest rc=$?"; tail -n 3 gpurun_out/t55_gpu.log
-timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --sample-steps 8 > gpurun_out/bench55.json 2> gpurun_out/bench55.err; echo "bench rc=$?"; cut -c1-200 gpurun_out/bench55.json
+timeout 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --sample-steps 1000 > gpurun_out/bench56_n1000.json 2> gpurun_out/bench56_n1000.err; echo "bench rc=$?"; python -c "
+import json;d=json.load(open('gpurun_out/bench56_n1000.json'));print(d['ms_per_step'], d['value']); print(d['sampler'])"
