@@ -418,6 +418,35 @@ def golden_lossbranches(R):
   np.savez_compressed(os.path.join(HERE, 'lossbranch_golden.npz'), **out)
 
 
+def golden_sde_reverse(R):
+  """a6-a9 on every SDE class incl. subVPSDE: sde / marginal_prob / prior_logp / discretize and the reverse-time SDE
+  (lambda 1), a lambda 0.5 interpolation and the probability-flow ODE (lambda 0) built by SDE.reverse with a fixed
+  analytic score (reference sde_lib.py:55-119)."""
+  out = {}
+  g = torch.Generator().manual_seed(8)
+  x = torch.randn(3, 3, 4, 4, generator=g)
+  t = torch.tensor([0.05, 0.5, 0.95])
+  score = lambda xx, tt: -0.3 * xx + 0.1 * tt[:, None, None, None]
+  sdes = dict(vp=R.sde_lib.VPSDE(truncation_time=1e-5, beta_min=0.1, beta_max=20., N=1000),
+              subvp=R.sde_lib.subVPSDE(beta_min=0.1, beta_max=20., N=1000),
+              ve=R.sde_lib.VESDE(sigma_min=0.01, sigma_max=50., N=1000))
+  for tag, sde in sdes.items():
+    f, gg = sde.sde(x, t)
+    mean, std = sde.marginal_prob(x, t)
+    fd, Gd = sde.discretize(x, t)
+    out.update({f'{tag}_f': f.numpy(), f'{tag}_g': gg.numpy(), f'{tag}_mean': mean.numpy(), f'{tag}_std': std.numpy(),
+                f'{tag}_logp': sde.prior_logp(x).numpy(), f'{tag}_fd': fd.numpy(), f'{tag}_Gd': Gd.numpy(),
+                f'{tag}_T': float(sde.T)})
+    for name, pf, lam in (('rsde', False, 1.), ('mix', False, 0.5), ('ode', True, 0.)):
+      r = sde.reverse(score, probability_flow=pf, lambda_=lam)
+      rf, rg = r.sde(x, t)
+      rfd, rGd = r.discretize(x, t)
+      out.update({f'{tag}_{name}_f': rf.numpy(), f'{tag}_{name}_g': rg.numpy(), f'{tag}_{name}_fd': rfd.numpy(),
+                  f'{tag}_{name}_Gd': rGd.numpy()})
+  out.update(x=x.numpy(), t=t.numpy())
+  np.savez_compressed(os.path.join(HERE, 'sde_reverse_golden.npz'), **out)
+
+
 def golden_sde(R):
   out = {}
   u = torch.linspace(0.01, 0.99, 7)
@@ -482,7 +511,8 @@ def main(which):
   R = import_reference()
   jobs = dict(configs=golden_configs, ops=golden_ops, sde=golden_sde, unet=golden_unet_cifar,
               variants=golden_variants, sampler=golden_sampler, train=golden_train, deepest=golden_deepest,
-              likelihood=golden_likelihood, lossbranches=golden_lossbranches)
+              likelihood=golden_likelihood, lossbranches=golden_lossbranches,
+              sde_reverse=golden_sde_reverse)
   for name in (which or jobs):
     print('golden:', name, flush=True)
     jobs[name](R)

@@ -261,3 +261,31 @@ def test_groupnorm_launch_policies_for_the_bench_shapes():
   # an image that does not fit 16 CTAs (CelebA-HQ 256x256), a batch too small to fill the GPU, a 4-stream call
   assert lib.st_gn_fwd_fused_chunks(16, 65536, 128) == 0 and lib.st_gn_bwd_resident_chunks(4, 1024, 128, 2) == 0
   assert lib.st_gn_bwd_resident_chunks(B, 64, 256, 4) == 0 and lib.st_gn_bwd_resident_chunks(B, 64, 1024, 2) == 0
+
+
+def test_sde_classes_and_reverse_sde_vs_reference_fixture():
+  """SURVEY 8(a) a6-a9 for VPSDE, subVPSDE and VESDE: sde / marginal_prob / prior_logp / discretize and the
+  reverse-time SDE, its lambda = 0.5 interpolation and the probability-flow ODE (reference sde_lib.py:55-119)."""
+  from soft_truncation_b200 import sde_lib
+  g = np.load(os.path.join(GOLDEN, 'sde_reverse_golden.npz'))
+  x, t = torch.tensor(g['x']), torch.tensor(g['t'])
+  score = lambda xx, tt: -0.3 * xx + 0.1 * tt[:, None, None, None]
+  sdes = dict(vp=sde_lib.VPSDE(truncation_time=1e-5, beta_min=0.1, beta_max=20., N=1000),
+              subvp=sde_lib.subVPSDE(beta_min=0.1, beta_max=20., N=1000),
+              ve=sde_lib.VESDE(sigma_min=0.01, sigma_max=50., N=1000))
+  close = lambda a, b: np.testing.assert_allclose(a.numpy(), b, rtol=1e-6, atol=1e-7)
+  for tag, sde in sdes.items():
+    f, gg = sde.sde(x, t)
+    mean, std = sde.marginal_prob(x, t)
+    fd, Gd = sde.discretize(x, t)
+    for got, key in ((f, 'f'), (gg, 'g'), (mean, 'mean'), (std, 'std'), (sde.prior_logp(x), 'logp'), (fd, 'fd'), (Gd, 'Gd')):
+      close(got, g[f'{tag}_{key}'])
+    assert float(sde.T) == float(g[f'{tag}_T'])
+    for name, pf, lam in (('rsde', False, 1.), ('mix', False, 0.5), ('ode', True, 0.)):
+      r = sde.reverse(score, probability_flow=pf, lambda_=lam)
+      rf, rg = r.sde(x, t)
+      rfd, rGd = r.discretize(x, t)
+      for got, key in ((rf, 'f'), (rg, 'g'), (rfd, 'fd'), (rGd, 'Gd')):
+        close(got, g[f'{tag}_{name}_{key}'])
+    with pytest.raises(AssertionError):          # probability_flow and lambda_ must agree (sde_lib.py:82)
+      sde.reverse(score, probability_flow=True, lambda_=1.)
