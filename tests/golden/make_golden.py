@@ -447,6 +447,38 @@ def golden_sde_reverse(R):
   np.savez_compressed(os.path.join(HERE, 'sde_reverse_golden.npz'), **out)
 
 
+class _LabelEcho(torch.nn.Module):
+  """Stand-in network: returns its conditioning labels broadcast over x, so that a score function's label and scale
+  conventions can be read off its output."""
+
+  def forward(self, x, labels):
+    return torch.zeros_like(x) + labels.float()[:, None, None, None]
+
+
+def golden_score_fn(R):
+  """models/utils.py:128-190 (a10): labels and output scaling of get_score_fn for VP continuous (plain and
+  `unbounded_parametrization`), VP discrete, VP without ddpm_score, VE continuous and VE discrete."""
+  out = {}
+  net = _LabelEcho()
+  x = torch.zeros(3, 3, 4, 4)
+  t = torch.tensor([0.05, 0.5, 0.95])
+  cfg = ref_config('vp/CIFAR10/ddpmpp_nll_st')
+  vp = R.sde_lib.get_sde(cfg, None)
+  out['vp_cont'] = R.mutils.get_score_fn(cfg, vp, net, train=False, continuous=True)(x, t).numpy()
+  out['vp_disc'] = R.mutils.get_score_fn(cfg, vp, net, train=False, continuous=False)(x, t).numpy()
+  cfg.training.unbounded_parametrization = True
+  out['vp_unbounded'] = R.mutils.get_score_fn(cfg, vp, net, train=False, continuous=True)(x, t).numpy()
+  cfg.training.unbounded_parametrization = False
+  cfg.training.ddpm_score = False
+  out['vp_raw'] = R.mutils.get_score_fn(cfg, vp, net, train=False, continuous=True)(x, t).numpy()
+  cfg5 = ref_config('ve/celebahq/uncsnpp_st')
+  ve = R.sde_lib.get_sde(cfg5, None)
+  out['ve_cont'] = R.mutils.get_score_fn(cfg5, ve, net, train=False, continuous=True)(x, t).numpy()
+  out['ve_disc'] = R.mutils.get_score_fn(cfg5, ve, net, train=False, continuous=False)(x, t.clone()).numpy()
+  out['t'] = t.numpy()
+  np.savez_compressed(os.path.join(HERE, 'score_fn_golden.npz'), **out)
+
+
 def golden_sde(R):
   out = {}
   u = torch.linspace(0.01, 0.99, 7)
@@ -512,7 +544,7 @@ def main(which):
   jobs = dict(configs=golden_configs, ops=golden_ops, sde=golden_sde, unet=golden_unet_cifar,
               variants=golden_variants, sampler=golden_sampler, train=golden_train, deepest=golden_deepest,
               likelihood=golden_likelihood, lossbranches=golden_lossbranches,
-              sde_reverse=golden_sde_reverse)
+              sde_reverse=golden_sde_reverse, score_fn=golden_score_fn)
   for name in (which or jobs):
     print('golden:', name, flush=True)
     jobs[name](R)

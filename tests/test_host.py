@@ -289,3 +289,33 @@ def test_sde_classes_and_reverse_sde_vs_reference_fixture():
         close(got, g[f'{tag}_{name}_{key}'])
     with pytest.raises(AssertionError):          # probability_flow and lambda_ must agree (sde_lib.py:82)
       sde.reverse(score, probability_flow=True, lambda_=1.)
+
+
+class _LabelEcho(torch.nn.Module):
+  def forward(self, x, labels):
+    return torch.zeros_like(x) + labels.float()[:, None, None, None]
+
+
+def test_score_fn_label_and_scale_conventions_vs_reference_fixture():
+  """SURVEY 8(a) a10 (models/utils.py:128-190): what get_score_fn feeds the network and how it scales the output, for
+  VP continuous (plain / unbounded parametrisation / without ddpm_score), VP discrete, VE continuous and discrete.
+  The network is a stub that echoes its labels, so the fixture pins labels and 1/std factors."""
+  from soft_truncation_b200 import configs, sde_lib
+  from soft_truncation_b200.models import utils as mutils
+  g = np.load(os.path.join(GOLDEN, 'score_fn_golden.npz'))
+  net = _LabelEcho()
+  x, t = torch.zeros(3, 3, 4, 4), torch.tensor(g['t'])
+  cfg = configs.cifar10_ddpmpp_nll_st()
+  vp = sde_lib.get_sde(cfg)
+  close = lambda a, key: np.testing.assert_allclose(a.numpy(), g[key], rtol=2e-6)
+  close(mutils.get_score_fn(cfg, vp, net, train=False, continuous=True)(x, t), 'vp_cont')
+  close(mutils.get_score_fn(cfg, vp, net, train=False, continuous=False)(x, t), 'vp_disc')
+  cfg.training.unbounded_parametrization = True
+  close(mutils.get_score_fn(cfg, vp, net, train=False, continuous=True)(x, t), 'vp_unbounded')
+  cfg.training.unbounded_parametrization = False
+  cfg.training.ddpm_score = False
+  close(mutils.get_score_fn(cfg, vp, net, train=False, continuous=True)(x, t), 'vp_raw')
+  cfg5 = configs.celebahq_uncsnpp_st()
+  ve = sde_lib.get_sde(cfg5)
+  close(mutils.get_score_fn(cfg5, ve, net, train=False, continuous=True)(x, t), 've_cont')
+  close(mutils.get_score_fn(cfg5, ve, net, train=False, continuous=False)(x, t.clone()), 've_disc')
