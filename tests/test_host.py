@@ -319,3 +319,21 @@ def test_score_fn_label_and_scale_conventions_vs_reference_fixture():
   ve = sde_lib.get_sde(cfg5)
   close(mutils.get_score_fn(cfg5, ve, net, train=False, continuous=True)(x, t), 've_cont')
   close(mutils.get_score_fn(cfg5, ve, net, train=False, continuous=False)(x, t.clone()), 've_disc')
+
+
+def test_ema_store_copy_to_restore_like_run_lib(cifar_model):
+  """The evaluation dance of run_lib.py:94-97,105-109 / models/ema.py:53-89: store the raw weights, copy the shadow in
+  (the flat parameter buffer itself changes: views stay valid), restore."""
+  from soft_truncation_b200.models.ema import ExponentialMovingAverage
+  m = cifar_model
+  ema = ExponentialMovingAverage(m.parameters(), decay=0.999)
+  raw = m._flat.clone()
+  with torch.no_grad():
+    ema.shadow_flat.mul_(0.5)                    # a shadow that differs from the weights
+  ema.store(m.parameters())
+  ema.copy_to(m.parameters())
+  first = next(p for p in m.parameters() if p.requires_grad)
+  assert torch.equal(first.data, ema.shadow_params[0]) and not torch.equal(m._flat, raw)
+  assert first.data.data_ptr() >= m._flat.data_ptr()          # still a view of the flat buffer
+  ema.restore(m.parameters())
+  assert torch.equal(m._flat, raw)
