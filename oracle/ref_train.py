@@ -6,14 +6,16 @@ network, with all randomness INJECTED:
 * VP / VE / RVE schedules            - reference sde_lib.py:121-207, 248-332, 334-430
 * time sampling + soft truncation    - reference sde_lib.py:180-207 (VP), 314-332 (VE), 421-430 (RVE)
 * score wrapper                      - reference models/utils.py:128-190
-* DSM loss                           - reference losses.py:101-132
+* DSM loss (IS / plain / likelihood-weighted branches) - reference losses.py:101-132
+* step_fn / step_fn_mixed            - reference losses.py:262-293, 295-320
 * warm-up / clip / Adam              - reference losses.py:44-58, torch.optim.Adam
 * EMA                                - reference models/ema.py:32-51
 * EM / reverse-diffusion predictors, Langevin corrector, denoise step, PC loop
                                      - reference sampling.py:185-210, 263-292, 402-431
 
-Parity pin: tests/golden/train_golden.npz / sampler_golden.npz (made from the untouched
-reference by tests/golden/make_golden.py) are checked in tests/test_oracle.py.
+Parity pin: tests/golden/train_golden.npz, sampler_golden.npz, variants_golden.npz, deepest_golden.npz and
+lossbranch_golden.npz (made from the untouched reference by tests/golden/make_golden.py) are checked in
+tests/test_oracle.py.
 """
 import math
 
