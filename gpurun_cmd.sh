@@ -1,4 +1,3 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --sample-steps 1000 > gpurun_out/bench56_n1000.json 2> gpurun_out/bench56_n1000.err; echo "bench rc=$?"; python -c "
-import json;d=json.load(open('gpurun_out/bench56_n1000.json'));print(d['ms_per_step'], d['value']); print(d['sampler'])"
+timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gn_bwd_resident_kernel -c 2 -f -o gpurun_out/ncu57_gnbwd python tools/profile_step.py --batch 512 > gpurun_out/ncu57_gnbwd.log 2>&1; echo "ncu full rc=$?"; ls -la gpurun_out/ncu57*
