@@ -337,3 +337,21 @@ def test_ema_store_copy_to_restore_like_run_lib(cifar_model):
   assert first.data.data_ptr() >= m._flat.data_ptr()          # still a view of the flat buffer
   ema.restore(m.parameters())
   assert torch.equal(m._flat, raw)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+  """bench.py contract: stdout carries ONE JSON line (library banners go to stderr); the reference arm runs the oracle
+  port of the training step on the host cores and reports it as its own cpu_baseline / e2e."""
+  import subprocess
+  import sys
+  r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                     capture_output=True, text=True, timeout=600)
+  assert r.returncode == 0, r.stderr[-2000:]
+  lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+  assert len(lines) == 1, r.stdout
+  d = json.loads(lines[0])
+  assert d['impl'] == 'reference' and d['metric'] == 'DDPM++ CIFAR-10 train images/sec' and d['unit'] == 'images/s'
+  assert d['higher_is_better'] is True and d['value'] > 0 and d['n_gpus'] == 1 and d['steps'] == 1
+  assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+  assert d['e2e'] == {'value': d['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+  assert 'workload' in d['config'] and d['vs_baseline'] is None
