@@ -1,3 +1,3 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gn_bwd_resident_kernel -c 2 -f -o gpurun_out/ncu57_gnbwd python tools/profile_step.py --batch 512 > gpurun_out/ncu57_gnbwd.log 2>&1; echo "ncu full rc=$?"; ls -la gpurun_out/ncu57*
+timeout 240 python tools/likelihood_bench.py 256 1e-3 > gpurun_out/lik58.txt 2>&1; echo "rc=$?"; tail -n 3 gpurun_out/lik58.txt | cut -c1-900
