@@ -48,14 +48,35 @@ def peaks():
 
 
 class ClockSampler:
-  """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+  """Samples SM clocks / throttle reasons while the timed region runs: in-process NVML (pynvml, initialised BEFORE the
+  timed region, one query every 100 ms from a thread - no process start-up or NVML initialisation inside the window),
+  falling back to one looping `nvidia-smi -lms 200` process when pynvml is not importable."""
   Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
   def __init__(self, index):
     self.rows, self.proc, self.index = [], None, index
+    self.nvml, self.handle, self.stop = None, None, threading.Event()
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+      phys = index
+      if visible:                                    # NVML enumerates physical devices
+        ids = [v.strip() for v in visible.split(',') if v.strip()]
+        if index < len(ids) and ids[index].isdigit():
+          phys = int(ids[index])
+      self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+      self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+      self.nvml = pynvml
+    except Exception:
+      self.nvml = None
 
   def __enter__(self):
+    if self.nvml is not None:
+      self.thread = threading.Thread(target=self._poll, daemon=True)
+      self.thread.start()
+      return self
     try:
       self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
                                     '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -65,11 +86,32 @@ class ClockSampler:
       self.proc = None
     return self
 
+  def _poll(self):
+    n = self.nvml
+    flags = (('hw_slowdown', n.nvmlClocksThrottleReasonHwSlowdown), ('hw_thermal_slowdown', n.nvmlClocksThrottleReasonHwThermalSlowdown),
+             ('sw_thermal_slowdown', n.nvmlClocksThrottleReasonSwThermalSlowdown), ('sw_power_cap', n.nvmlClocksThrottleReasonSwPowerCap))
+    while True:
+      try:
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        try:
+          power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.
+        except Exception:
+          power = 0.
+        self.rows.append([str(sm), str(self.max_sm), str(power)] + ['Active' if mask & bit else 'Not Active' for _, bit in flags])
+      except Exception:
+        pass
+      if self.stop.wait(0.1):
+        return
+
   def _read(self):
     for line in self.proc.stdout:
       self.rows.append([c.strip() for c in line.split(',')])
 
   def __exit__(self, *a):
+    self.stop.set()
+    if self.nvml is not None:
+      self.thread.join(timeout=2)
     if self.proc is not None:
       self.proc.terminate()
       try:
@@ -85,7 +127,7 @@ class ClockSampler:
       if any(len(r) >= 7 and r[col].lower().startswith('active') for r in self.rows):
         reasons.append(name)
     return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-            'samples': len(sm)}
+            'samples': len(sm), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 # ============================================================================================ reference arm
@@ -192,6 +234,28 @@ def run_b200(args):
   ms_e2e = timed(e2e_step, args.steps)
   e2e = B * world * args.steps / (ms_e2e * 1e-3)
 
+  # the same with the batch travelling as uint8 and prepared on the GPU (datasets.prepare_batch: /255, random flip,
+  # uniform dequantisation, scaler in one kernel) - SURVEY 8(f)4; informative, the headline e2e stays the fp32 form
+  e2e_u8 = None
+  try:
+    from soft_truncation_b200 import datasets
+    u8_host = torch.randint(0, 256, (B, 32, 32, 3), dtype=torch.uint8).pin_memory()
+    dq = cfg.data.dequantization
+    cfg.data.dequantization = 'uniform'
+
+    def e2e_u8_step():
+      step_fn(state, datasets.prepare_batch(cfg, u8_host, train=True))
+    try:
+      e2e_u8_step()
+      ms_u8 = timed(e2e_u8_step, args.steps)
+    finally:
+      cfg.data.dequantization = dq
+    e2e_u8 = {'value': B * world * args.steps / (ms_u8 * 1e-3), 'unit': 'images/s',
+              'h2d_bytes_per_step': u8_host.numel() * world, 'ms_per_step': ms_u8 / args.steps,
+              'note': 'uint8 pinned host batch -> datasets.prepare_batch (flip, uniform dequantisation, scaler on the GPU) -> step_fn'}
+  except Exception as ex:       # informative leg: the headline line must still print
+    e2e_u8 = {'error': repr(ex)[:300]}
+
   # ---- dominant kernel: every st_gemm launch of one step bracketed by CUDA events (outside the timed region)
   pk, pk_kind = peaks()
   roof = None
@@ -277,7 +341,7 @@ def run_b200(args):
                        'l2': 'per-step working set (>20 GB of activations) is far larger than the 126 MB L2; no flush needed'},
             'e2e': {'value': e2e, 'unit': 'images/s', 'h2d_bytes_per_step': batch_host.numel() * 4 * world,
                     'd2h_bytes_per_step': B * 4 * world, 'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'sampler': samp,
+            'e2e_u8': e2e_u8, 'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'sampler': samp,
             'tcgen05': bool(ops.tc_available())}
     print(json.dumps(line), flush=True)
   if world > 1:

@@ -1,3 +1,4 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 240 python tools/likelihood_bench.py 256 1e-3 > gpurun_out/lik58.txt 2>&1; echo "rc=$?"; tail -n 3 gpurun_out/lik58.txt | cut -c1-900
+timeout 300 python bench.py --steps 10 --warmup 3 --sample-steps 10 > gpurun_out/bench60.json 2> gpurun_out/bench60.err; echo "bench rc=$?"; python -c "
+import json;d=json.load(open('gpurun_out/bench60.json'));print(d['ms_per_step'], d['value'], d['e2e']['ms_per_step'], d['e2e_u8']['ms_per_step'], d['clocks'], d['cpu_baseline'])"; tail -n 3 gpurun_out/bench60.err
