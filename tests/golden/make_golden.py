@@ -479,6 +479,34 @@ def golden_score_fn(R):
   np.savez_compressed(os.path.join(HERE, 'score_fn_golden.npz'), **out)
 
 
+def golden_predictors(R):
+  """Every registered predictor / corrector of the reference (sampling.py:185-340) on an analytic score function:
+  outputs (x, x_mean) with the noise draws replayed, VP and VE, 50-step schedules, two inner corrector steps."""
+  out = {}
+  cfg = ref_config('vp/CIFAR10/ddpmpp_nll_st')
+  score = lambda xx, tt: -0.3 * xx + 0.1 * tt[:, None, None, None]
+  gen = torch.Generator().manual_seed(3)
+  x = torch.randn(3, 3, 8, 8, generator=gen)
+  t = torch.tensor([0.9, 0.5, 0.11])
+  out.update(x=x.numpy(), t=t.numpy())
+  for kind, sde in (('vp', R.sde_lib.VPSDE(truncation_time=1e-5, beta_min=0.1, beta_max=20., N=50)),
+                    ('ve', R.sde_lib.VESDE(sigma_min=0.01, sigma_max=50., N=50))):
+    torch.manual_seed(77)
+    z, z2 = torch.randn_like(x), torch.randn_like(x)
+    out.update({f'{kind}_z': z.numpy(), f'{kind}_z2': z2.numpy()})
+    for name in ('euler_maruyama', 'reverse_diffusion', 'ancestral_sampling'):
+      p = R.sampling.get_predictor(name)(cfg, sde, score, probability_flow=False)
+      torch.manual_seed(77)
+      a, b = p.update_fn(x.clone(), t.clone())
+      out.update({f'{kind}_{name}_x': a.numpy(), f'{kind}_{name}_mean': b.numpy()})
+    for name in ('langevin', 'ald'):
+      c = R.sampling.get_corrector(name)(sde, score, 0.16, 2)
+      torch.manual_seed(77)
+      a, b = c.update_fn(x.clone(), t.clone())
+      out.update({f'{kind}_{name}_x': a.numpy(), f'{kind}_{name}_mean': b.numpy()})
+  np.savez_compressed(os.path.join(HERE, 'predictors_golden.npz'), **out)
+
+
 def golden_sde(R):
   out = {}
   u = torch.linspace(0.01, 0.99, 7)
@@ -544,7 +572,8 @@ def main(which):
   jobs = dict(configs=golden_configs, ops=golden_ops, sde=golden_sde, unet=golden_unet_cifar,
               variants=golden_variants, sampler=golden_sampler, train=golden_train, deepest=golden_deepest,
               likelihood=golden_likelihood, lossbranches=golden_lossbranches,
-              sde_reverse=golden_sde_reverse, score_fn=golden_score_fn)
+              sde_reverse=golden_sde_reverse, score_fn=golden_score_fn,
+              predictors=golden_predictors)
   for name in (which or jobs):
     print('golden:', name, flush=True)
     jobs[name](R)

@@ -568,6 +568,29 @@ def test_fused_predictors_and_correctors_match_the_reference_formulas(kind):
   assert sampling.NoneCorrector(sde, _fake_score, 0.1, 1).update_fn(x, t)[1] is x
 
 
+@pytest.mark.parametrize('kind', ['vp', 've'])
+def test_predictors_and_correctors_vs_reference_fixture(golden, kind):
+  """Every registered predictor / corrector against the outputs of the reference's own classes (sampling.py:185-340)
+  on the same analytic score function and replayed noise draws (50-step VP / VE schedules, two inner corrector steps)."""
+  from soft_truncation_b200 import configs, sampling, sde_lib
+  g = golden('predictors_golden.npz')
+  cfg = configs.cifar10_ddpmpp_nll_st()
+  sde = sde_lib.VPSDE(truncation_time=1e-5, beta_min=0.1, beta_max=20., N=50) if kind == 'vp' else \
+      sde_lib.VESDE(sigma_min=0.01, sigma_max=50., N=50)
+  x, t = torch.tensor(g['x'], device=DEV), torch.tensor(g['t'], device=DEV)
+  z, z2 = torch.tensor(g[f'{kind}_z'], device=DEV), torch.tensor(g[f'{kind}_z2'], device=DEV)
+  for name in ('euler_maruyama', 'reverse_diffusion', 'ancestral_sampling'):
+    p = sampling.get_predictor(name)(cfg, sde, _fake_score)
+    p.noise_source = [z.clone()]
+    got, got_mean = p.update_fn(x, t)
+    assert rel_l2(got_mean, g[f'{kind}_{name}_mean']) < 2e-5 and rel_l2(got, g[f'{kind}_{name}_x']) < 2e-5, name
+  for name in ('langevin', 'ald'):
+    c = sampling.get_corrector(name)(sde, _fake_score, 0.16, 2)
+    c.noise_source = [z.clone(), z2.clone()]
+    got, got_mean = c.update_fn(x, t)
+    assert rel_l2(got_mean, g[f'{kind}_{name}_mean']) < 2e-5 and rel_l2(got, g[f'{kind}_{name}_x']) < 2e-5, name
+
+
 def test_step_fn_mixed_and_ode_sampler_run():
   """step_fn_mixed (losses.py:295-320) and the probability-flow ODE sampler (sampling.py:436-504): shape, finiteness
   and consistency with the plain pieces they are made of."""
