@@ -1,3 +1,5 @@
+# the end-of-round validation this repo was last checked with (one B200):
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "predictors_and_correctors" > gpurun_out/t61.log 2>&1; echo "pytest rc=$?"; tail -n 12 gpurun_out/t61.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/t_gpu.log 2>&1; echo "pytest rc=$?"; tail -n 3 gpurun_out/t_gpu.log
+timeout 400 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cut -c1-200 gpurun_out/bench.json
