@@ -1,18 +1,25 @@
 """Benchmark of the Soft-Truncation hot path on B200 (driver contract: one JSON line on stdout).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c2|c3|c4|c5|deepest]
+                  [--mode train|sampler] [--batch B] [--sample-steps N]
 
-Workload (BASELINE.json configs[1]): DDPM++ (VP) CIFAR-10 32x32, batch 512 per GPU, bf16 compute / fp32
-accumulate+master weights, soft-truncated importance-sampled DSM loss, dropout 0.1, grad-clip 1.0, Adam, EMA:
-one "step" = losses.get_step_fn(...)(state, batch) on synthetic images.  `value` = images/s with the batch
-resident in HBM; `e2e` = the same call fed from pinned host memory (H2D of the batch + D2H of the B losses inside
-the timed region).  A secondary figure, PC-sampler reverse steps/s (Euler-Maruyama, batch 1024), is reported in
-`sampler`.  N > 1: one process per GPU under torchrun, pure data parallel (weak scaling), one NCCL all-reduce of
-the flat gradient buffer per step.
+Default workload (BASELINE.json configs[1], `--config c2`): DDPM++ (VP) CIFAR-10 32x32, batch 512 per GPU, bf16
+compute / fp32 accumulate + master weights, soft-truncated importance-sampled DSM loss, dropout 0.1, grad-clip 1.0,
+Adam, EMA: one "step" = losses.get_step_fn(...)(state, batch) on synthetic images.  `value` = images/s with the batch
+resident in HBM; `e2e` = the same call fed from pinned host memory (H2D of the batch + D2H of the B losses inside the
+timed region).  A secondary figure, PC-sampler reverse steps/s, is reported in `sampler`.  N > 1: one process per GPU
+under torchrun, pure data parallel (weak scaling), one NCCL all-reduce of the flat gradient buffer per step.
 
-`--impl reference` times the reference's CPU path: the reference is pure Python/PyTorch and cannot travel to the
-GPU box, so this arm runs the oracle port (oracle/ref_train.py, checked against reference-generated fixtures) on
-all host cores, on a bounded sample (batch 8) of the same workload.
+`--config` selects the other BASELINE.json configurations at FULL size (c3 = configs[2] UNCSN++ RVE CelebA-64 B=128,
+c4 = configs[3] DDPM++ ImageNet32 B=512, c5 = configs[4] NCSN++ VE CelebA-HQ-256 B=16, deepest = the README's FID
+model); `--mode sampler` makes the PC sampler over the config's full schedule (`--sample-steps`, default the config's
+N = 1000 / 2000) the headline value of the line.
+
+Reference arms (the UNTOUCHED reference staged under baseline/_ref, see baseline/ref_env.py):
+  * `--impl reference`: its own `losses.get_step_fn` on the host cores at the saturated batch 64;
+    when baseline/_ref is absent the oracle port (oracle/ref_train.py) is timed instead and says so (`kind: "port"`).
+  * `gpu_reference` (inside the default run, N = 1): the same stock call on cuda:0 at batch 512 - eager fp32 (cuDNN /
+    cuBLAS sm_100 kernels) and bf16 autocast + channels_last - i.e. the "existing Blackwell kernel" bar.
 """
 import argparse
 import contextlib
@@ -31,12 +38,26 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 
-TRAIN_GF_PER_IMG = 65.08      # 3 x 21.693 GF forward (conv/linear/NIN/attention MACs x 2)
-FWD_GF_PER_IMG = 21.693
-# DRAM bytes per GEMM launch (average over the 430 launches of one B=512 bf16 step): 54.15 GB / 430, from the ncu launch
-# list committed as profiles/r01_launches_train_step.md (dram__bytes_read.sum + dram__bytes_write.sum)
+# DRAM bytes per GEMM launch (average over the GEMM launches of one B=512 bf16 c2 step), from the ncu launch list
+# committed under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum); see profiles/README.md for the file
 GEMM_DRAM_BYTES_PER_LAUNCH = 54.166e9 / 430
-METRIC = 'DDPM++ CIFAR-10 train images/sec'
+TRAFFIC_SOURCE = 'profiles/r01_launches_train_step.md'
+
+# name -> config path under the reference's configs/, per-GPU train batch, sampler batch, forward GF / image
+# (2 x MACs of conv / linear / NIN / attention products; None = not surveyed)
+WORKLOADS = {
+    'c2': dict(path='vp/CIFAR10/ddpmpp_nll_st', batch=512, sample_batch=1024, fwd_gf=21.693, baseline='configs[1]',
+               label='DDPM++ (VP) CIFAR-10 32x32', metric='DDPM++ CIFAR-10 train images/sec'),
+    'c3': dict(path='ve/CELEBA/uncsnpp_st', batch=128, sample_batch=None, fwd_gf=83.957, baseline='configs[2]',
+               label='UNCSN++ (RVE) CelebA 64x64', metric='UNCSN++ (RVE) CelebA-64 train images/sec'),
+    'c4': dict(path='vp/IMAGENET32/ddpmpp_nll', batch=512, sample_batch=1024, fwd_gf=21.693, baseline='configs[3]',
+               label='DDPM++ (VP) ImageNet32 32x32, NLL weighting', metric='DDPM++ ImageNet32 train images/sec'),
+    'c5': dict(path='ve/celebahq/uncsnpp_st', batch=16, sample_batch=16, fwd_gf=531.775, baseline='configs[4]',
+               label='NCSN++ (VE) CelebA-HQ 256x256', metric='NCSN++ CelebA-HQ-256 train images/sec'),
+    'deepest': dict(path='vp/CIFAR10/ddpmpp_fid_st_deepest', batch=128, sample_batch=256, fwd_gf=None, baseline='README FID model',
+                    label="DDPM++ 'deepest' (nf=512) CIFAR-10 32x32, step_fn_mixed", metric="DDPM++ 'deepest' CIFAR-10 train images/sec"),
+}
+METRIC = WORKLOADS['c2']['metric']
 
 
 def peaks():
@@ -131,50 +152,73 @@ class ClockSampler:
 
 
 # ============================================================================================ reference arm
-def run_reference(args):
-  rank = int(os.environ.get('RANK', '0'))
-  if rank != 0:
-    return
+def cpu_reference_sample(batch, steps, warmup):
+  """The reference training step on the host cores: the untouched reference when it is staged (baseline/_ref), else
+  the oracle port."""
+  from baseline import ref_bench
+  if ref_bench.available():
+    return ref_bench.cpu_train(batch=batch, steps=steps, warmup=warmup)
   from oracle import ref_model, ref_train
   from soft_truncation_b200 import configs
   cores = os.cpu_count() or 1
   torch.set_num_threads(cores)
   cfg = configs.cifar10_ddpmpp_nll_st()
-  B = 8
   sde = ref_train.make_sde(cfg)
   state = ref_train.TrainState(ref_model.make_state_dict(cfg, seed=0))
   gen = torch.Generator().manual_seed(1234)
-  batch = torch.rand(B, 3, 32, 32, generator=gen) * 2 - 1
-  steps, warm = min(args.steps, 4), min(args.warmup, 1)
+  x = torch.rand(batch, 3, 32, 32, generator=gen) * 2 - 1
 
-  def one(i):
-    u, z = torch.rand(B, generator=gen), torch.randn(B, 3, 32, 32, generator=gen)
-    ref_train.train_step(state, cfg, sde, batch, u, z, float(torch.rand(1, generator=gen)))
+  def one():
+    u, z = torch.rand(batch, generator=gen), torch.randn(batch, 3, 32, 32, generator=gen)
+    ref_train.train_step(state, cfg, sde, x, u, z, float(torch.rand(1, generator=gen)))
 
-  for i in range(warm):
-    one(i)
+  for _ in range(warmup):
+    one()
   t0 = time.perf_counter()
-  for i in range(steps):
-    one(i)
+  for _ in range(steps):
+    one()
   dt = time.perf_counter() - t0
-  v = B * steps / dt
+  return {'value': batch * steps / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'batch': batch, 'steps': steps,
+          'warmup': warmup, 'ms_per_step': 1e3 * dt / steps,
+          'sample': f'{steps} optimizer steps at batch {batch} (oracle/ref_train.train_step, fp32, dropout off: baseline/_ref not staged)'}
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  # bounded sample: the saturated CPU batch (BASELINE.md 4.3) and at most 4 timed steps (~10 s each on 16 cores)
+  B = int(os.environ.get('ST_BENCH_REF_BATCH', '64'))      # (the CPU test suite shrinks it)
+  steps, warm = max(1, min(args.steps, 4)), max(1, min(args.warmup, 1))
+  r = cpu_reference_sample(B, steps, warm)
+  v = r['value']
   line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
-          'warmup': warm, 'ms_per_step': 1e3 * dt / steps, 'higher_is_better': True, 'scaling': 'weak',
+          'warmup': warm, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-          'config': {'workload': 'DDPM++ (VP) CIFAR-10 32x32 soft-truncated DSM train step, CPU, bounded sample batch 8'},
-          'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                           'sample': f'{steps} optimizer steps at batch {B} (oracle/ref_train.train_step, fp32, dropout injected off)'},
+          'config': {'workload': f'DDPM++ (VP) CIFAR-10 32x32 soft-truncated DSM train step (BASELINE configs[1]), CPU, bounded sample batch {B}'},
+          'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']},
           'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
   print(json.dumps(line), flush=True)
 
 
 # ============================================================================================ our arm
+def _sampler_sde(sde_lib, cfg, N):
+  kind = cfg.training.sde.lower()
+  if kind == 'vpsde':
+    return sde_lib.VPSDE(truncation_time=cfg.training.truncation_time, beta_min=cfg.model.beta_min,
+                         beta_max=cfg.model.beta_max, N=N)
+  if kind == 'vesde':
+    return sde_lib.VESDE(sigma_min=cfg.model.sigma_min, sigma_max=cfg.model.sigma_max, N=N)
+  return None      # the reference's PC sampler does not run for the reciprocal VE SDE (SURVEY F7)
+
+
 def run_b200(args):
   import torch.distributed as dist
   from soft_truncation_b200 import _lib, configs, losses, ops, sampling, sde_lib
   from soft_truncation_b200.models import utils as mutils
   from soft_truncation_b200.models.ema import ExponentialMovingAverage
 
+  wl = WORKLOADS[args.config]
   world = int(os.environ.get('WORLD_SIZE', '1'))
   rank = int(os.environ.get('RANK', '0'))
   local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -183,24 +227,32 @@ def run_b200(args):
   if world > 1:
     import datetime
     dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
-  cfg = configs.cifar10_ddpmpp_nll_st()
+  cfg = configs.get_config(wl['path'])
   cfg.device = dev
   cfg.model.compute_dtype = args.dtype
-  B = args.batch
+  B = args.batch or wl['batch']
+  R = cfg.data.image_size
   if args.micro:
     cfg.optim.l2_blocks = args.micro
   cfg.training.batch_size = B * world
+  # every rank builds the same initial weights (and losses.sync_replicas broadcasts rank 0's anyway), then ranks seed
+  # torch apart so that their time / noise / dropout draws differ; NumPy (t_min) stays identical on all ranks
   torch.manual_seed(42)
   np.random.seed(42)
   sde = sde_lib.get_sde(cfg)
   model = mutils.create_model(cfg, sde)
+  torch.manual_seed(42 + rank)
   net = mutils.unwrap(model)
   state = dict(model=model, optimizer=losses.get_optimizer(cfg, model.parameters()),
                ema=ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate), step=0)
   step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
   gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-  batch_dev = torch.rand(B, 3, 32, 32, generator=gen, device=dev) * 2 - 1
+  batch_dev = torch.rand(B, 3, R, R, generator=gen, device=dev)
+  if cfg.data.centered:
+    batch_dev = batch_dev * 2 - 1
   batch_host = batch_dev.cpu().pin_memory()
+  pk, pk_kind = peaks()
+  peak_tf = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
 
   def barrier():
     if world > 1:
@@ -220,131 +272,202 @@ def run_b200(args):
       dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return ms.item()
 
-  for _ in range(max(args.warmup, 3)):
-    step_fn(state, batch_dev)
-  l0 = _lib.launches
-  with ClockSampler(local) as clk:
-    ms = timed(lambda: step_fn(state, batch_dev), args.steps)
-  launches = _lib.launches - l0
-  value = B * world * args.steps / (ms * 1e-3)
+  train, roof, e2e_u8 = None, None, None
+  if args.mode == 'train':
+    _lib.lib.st_gemm_simt_fallbacks(1)
+    for _ in range(max(args.warmup, 3)):
+      step_fn(state, batch_dev)
+    l0 = _lib.launches
+    with ClockSampler(local) as clk:
+      ms = timed(lambda: step_fn(state, batch_dev), args.steps)
+    launches_host = _lib.launches - l0
+    value = B * world * args.steps / (ms * 1e-3)
 
-  def e2e_step():
-    step_fn(state, batch_host.to(dev, non_blocking=True))
-  e2e_step()
-  ms_e2e = timed(e2e_step, args.steps)
-  e2e = B * world * args.steps / (ms_e2e * 1e-3)
+    def e2e_step():
+      step_fn(state, batch_host.to(dev, non_blocking=True))
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e = B * world * args.steps / (ms_e2e * 1e-3)
+    train = dict(ms=ms, value=value, ms_e2e=ms_e2e, e2e=e2e, launches_host=launches_host)
 
-  # the same with the batch travelling as uint8 and prepared on the GPU (datasets.prepare_batch: /255, random flip,
-  # uniform dequantisation, scaler in one kernel) - SURVEY 8(f)4; informative, the headline e2e stays the fp32 form
-  e2e_u8 = None
-  try:
-    if world > 1:
-      raise RuntimeError('informative leg, measured at N=1 only')
-    from soft_truncation_b200 import datasets
-    u8_host = torch.randint(0, 256, (B, 32, 32, 3), dtype=torch.uint8).pin_memory()
-    dq = cfg.data.dequantization
-    cfg.data.dequantization = 'uniform'
-
-    def e2e_u8_step():
-      step_fn(state, datasets.prepare_batch(cfg, u8_host, train=True))
+    # the same with the batch travelling as uint8 and prepared on the GPU (datasets.prepare_batch: /255, random flip,
+    # uniform dequantisation, scaler in one kernel) - SURVEY 8(f)4; informative, the headline e2e stays the fp32 form
     try:
-      e2e_u8_step()
-      ms_u8 = timed(e2e_u8_step, args.steps)
+      if world > 1:
+        raise RuntimeError('informative leg, measured at N=1 only')
+      from soft_truncation_b200 import datasets
+      u8_host = torch.randint(0, 256, (B, R, R, 3), dtype=torch.uint8).pin_memory()
+      dq = cfg.data.dequantization
+      cfg.data.dequantization = 'uniform'
+
+      def e2e_u8_step():
+        step_fn(state, datasets.prepare_batch(cfg, u8_host, train=True))
+      try:
+        e2e_u8_step()
+        ms_u8 = timed(e2e_u8_step, args.steps)
+      finally:
+        cfg.data.dequantization = dq
+      e2e_u8 = {'value': B * world * args.steps / (ms_u8 * 1e-3), 'unit': 'images/s',
+                'h2d_bytes_per_step': u8_host.numel() * world, 'ms_per_step': ms_u8 / args.steps,
+                'note': 'uint8 pinned host batch -> datasets.prepare_batch (flip, uniform dequantisation, scaler on the GPU) -> step_fn'}
+    except Exception as ex:       # informative leg: the headline line must still print
+      e2e_u8 = {'skipped': repr(ex)[:300]}
+
+    # ---- dominant kernel: every st_gemm launch of one step bracketed by CUDA events (outside the timed region, on an
+    # EAGER step: the captured-graph step the timed region replays launches exactly the same kernels)
+    recs = []
+    counts = {'calls': 0}
+    orig, orig_check = ops._gemm, _lib.check
+
+    def spy(**kw):
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      orig(**kw)
+      b.record()
+      recs.append((a, b, 2.0 * kw['M'] * kw['N'] * kw['K'] * kw.get('batch', 1)))
+    ops._gemm = spy
+    graph_was = losses._STEP_GRAPH
+    losses._STEP_GRAPH = False
+    l1 = _lib.launches
+    try:
+      step_fn(state, batch_dev)
+      torch.cuda.synchronize()
     finally:
-      cfg.data.dequantization = dq
-    e2e_u8 = {'value': B * world * args.steps / (ms_u8 * 1e-3), 'unit': 'images/s',
-              'h2d_bytes_per_step': u8_host.numel() * world, 'ms_per_step': ms_u8 / args.steps,
-              'note': 'uint8 pinned host batch -> datasets.prepare_batch (flip, uniform dequantisation, scaler on the GPU) -> step_fn'}
-  except Exception as ex:       # informative leg: the headline line must still print
-    e2e_u8 = {'skipped': repr(ex)[:300]}
+      ops._gemm = orig
+      losses._STEP_GRAPH = graph_was
+    kernel_calls = _lib.launches - l1          # C-ABI calls of one step (each enqueues >= 1 of our kernels)
+    fallbacks = int(_lib.lib.st_gemm_simt_fallbacks(0))
+    if args.dtype == 'bf16' and fallbacks:
+      raise RuntimeError(f'{fallbacks} bf16 GEMMs fell back to the SIMT kernel: {_lib.lib.st_gemm_simt_fallback_reason().decode()}')
+    if rank == 0:
+      t_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+      flops = sum(f for _, _, f in recs)
+      achieved = flops / (t_ms * 1e-3) / 1e12
+      tc = ops.tc_available() and args.dtype == 'bf16'
+      roof = {'bound': 'tensor', 'kernel': 'gemm_tc2_kernel (persistent tcgen05 implicit-GEMM conv / GEMM, all st_gemm launches of one step)' if tc else 'gemm_simt_kernel',
+              'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+              'traffic': GEMM_DRAM_BYTES_PER_LAUNCH if (args.config == 'c2' and B == 512 and args.dtype == 'bf16') else None,
+              'traffic_source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the GEMM launches of one B=512 step '
+                                f'/ their count ({TRAFFIC_SOURCE})',
+              'peak_source': pk_kind + ' (sustained cuBLAS bf16)', 'launches': len(recs), 'gemm_ms_per_step': t_ms,
+              'gemm_share_of_step': t_ms / (ms / args.steps), 'simt_fallbacks': fallbacks,
+              'whole_step_frac': (value / world * 3 * wl['fwd_gf'] / 1e3 / peak_tf) if wl['fwd_gf'] else None}
+    if world > 1:
+      dist.barrier()
+    train['kernel_calls'] = kernel_calls
 
-  # ---- dominant kernel: every st_gemm launch of one step bracketed by CUDA events (outside the timed region)
-  pk, pk_kind = peaks()
-  roof = None
-  # every rank runs the instrumented step (it contains the gradient all-reduce); rank 0 reports
-  recs = []
-  orig = ops._gemm
-
-  def spy(**kw):
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    orig(**kw)
-    b.record()
-    recs.append((a, b, 2.0 * kw['M'] * kw['N'] * kw['K'] * kw.get('batch', 1)))
-  ops._gemm = spy
-  try:
-    step_fn(state, batch_dev)
-    torch.cuda.synchronize()
-  finally:
-    ops._gemm = orig
-  if rank == 0:
-    t_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
-    flops = sum(f for _, _, f in recs)
-    achieved = flops / (t_ms * 1e-3) / 1e12
-    peak = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
-    roof = {'bound': 'tensor', 'kernel': 'gemm_tc2_kernel (persistent tcgen05 implicit-GEMM conv / GEMM, all st_gemm launches of one step)' if ops.tc_available() and args.dtype == 'bf16' else 'gemm_simt_kernel',
-            'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-            'traffic': GEMM_DRAM_BYTES_PER_LAUNCH if B == 512 and args.dtype == 'bf16' else None,
-            'traffic_source': 'ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 430 GEMM launches of one B=512 step '
-                              '/ 430 (profiles/r01_launches_train_step.md); algorithmic operand+output bytes of the same launches: see DESIGN.md',
-            'peak_source': pk_kind + ' (sustained cuBLAS bf16)', 'launches': len(recs), 'gemm_ms_per_step': t_ms,
-            'gemm_share_of_step': t_ms / (ms / args.steps),
-            'whole_step_frac': value / world * TRAIN_GF_PER_IMG / 1e3 / peak}
-  if world > 1:
-    dist.barrier()
-
-  # ---- secondary: PC sampler reverse steps/s (Euler-Maruyama, no corrector), CUDA-graph replay
+  # ---- PC sampler reverse steps/s: the config's own predictor / corrector, CUDA-graph replay
   samp = None
+  clk_s = None
   try:
-    SB, N = args.sample_batch, args.sample_steps
+    SB = args.sample_batch or wl['sample_batch']
+    if SB is None:
+      raise RuntimeError('the reference has no working PC sampler for this SDE (SURVEY F7)')
+    full = cfg.model.num_scales
+    N = args.sample_steps or (full if args.mode == 'sampler' else 50)
     cfg.sampling.method = 'pc'
-    sde_s = sde_lib.VPSDE(truncation_time=cfg.training.truncation_time, beta_min=cfg.model.beta_min,
-                          beta_max=cfg.model.beta_max, N=N)
-    fn = sampling.get_sampling_fn(cfg, sde_s, (SB, 3, 32, 32), lambda v: v, cfg.sampling.truncation_time)
-    fn(model)
-    ms_s = timed(lambda: fn(model), 1)
+    sde_s = _sampler_sde(sde_lib, cfg, N)
+    model.eval()
+    fn = sampling.get_sampling_fn(cfg, sde_s, (SB, 3, R, R), lambda v: v, cfg.sampling.truncation_time)
+    evals_per_step = 2 if cfg.sampling.corrector.lower() != 'none' else 1
+    if args.mode == 'sampler':
+      sde_w = _sampler_sde(sde_lib, cfg, 6)          # short warm-up call (captures the graph, fills the allocator)
+      sampling.get_sampling_fn(cfg, sde_w, (SB, 3, R, R), lambda v: v, cfg.sampling.truncation_time)(model)
+      with ClockSampler(local) as clk_s:
+        fn(model)                                   # first full call captures this schedule's graph: untimed
+        ms_s = timed(lambda: fn(model), 1)
+      ms_s_e2e = timed(lambda: fn(model)[0].cpu(), 1)
+    else:
+      fn(model)
+      ms_s = timed(lambda: fn(model), 1)
+      ms_s_e2e = None
     sps = (N + 1) / (ms_s * 1e-3)
+    evals = N * evals_per_step + 1
     samp = {'metric': 'PC-sampler reverse steps/sec', 'value': sps, 'unit': 'steps/s', 'batch_per_gpu': SB,
-            'steps_timed': N + 1, 'sample_steps_per_sec': sps * SB * world,
-            'frac_of_tensor_roofline': sps * SB * FWD_GF_PER_IMG / 1e3 / pk.get('bf16_tflops_sustained', 1400.),
-            'note': f'{N} Euler-Maruyama steps of an N={N} VP schedule + final denoise through sampling.get_sampling_fn; '
-                    'one reverse step is captured in a CUDA graph once (untimed first call) and replayed'}
+            'schedule_N': N, 'steps_timed': N + 1, 'network_evals': evals, 'ms_per_step': ms_s / (N + 1),
+            'sample_steps_per_sec': sps * SB * world,
+            'sampler': f'{cfg.sampling.predictor}+{cfg.sampling.corrector}',
+            'frac_of_tensor_roofline': (evals / (ms_s * 1e-3) * SB * wl['fwd_gf'] / 1e3 / peak_tf) if wl['fwd_gf'] else None,
+            'note': f'{N} reverse steps of an N={N} schedule + final denoise through sampling.get_sampling_fn; one reverse '
+                    'step is captured in a CUDA graph once (untimed first call) and replayed'}
+    if ms_s_e2e is not None:
+      samp['e2e_steps_per_sec'] = (N + 1) / (ms_s_e2e * 1e-3)
   except Exception as ex:   # the headline metric must still print
     samp = {'error': repr(ex)[:300]}
+    if args.mode == 'sampler':
+      raise
 
-  # ---- CPU baseline: the oracle port on this box's host cores, bounded sample
-  cpu = None
-  if rank == 0 and world == 1 and not args.no_cpu_baseline:
-    from oracle import ref_model, ref_train
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    ccfg = configs.cifar10_ddpmpp_nll_st()
-    cst = ref_train.TrainState(ref_model.make_state_dict(ccfg, seed=0))
-    csde = ref_train.make_sde(ccfg)
-    cb = 8
-    g2 = torch.Generator().manual_seed(1)
-    xb = torch.rand(cb, 3, 32, 32, generator=g2) * 2 - 1
-    t0 = time.perf_counter()
-    n = 0
-    while n < 3:
-      ref_train.train_step(cst, ccfg, csde, xb, torch.rand(cb, generator=g2), torch.randn(cb, 3, 32, 32, generator=g2), 0.5)
-      n += 1
-    dt = time.perf_counter() - t0
-    cpu = {'value': cb * n / dt, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-           'sample': f'{n} optimizer steps at batch {cb} of the same workload (oracle/ref_train.train_step, fp32)'}
+  # ---- free our state, then the reference legs (N = 1 only)
+  cpu, gpu_ref = None, None
+  if rank == 0 and world == 1 and args.mode == 'train' and args.config == 'c2':
+    del state, step_fn, model, net
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    if not args.no_gpu_reference:
+      from baseline import ref_bench
+      if ref_bench.available():
+        gpu_ref = {'what': 'the UNTOUCHED reference (baseline/_ref) driving its own losses.get_step_fn on cuda:0: '
+                           'cuDNN / cuBLAS / ATen sm_100 kernels under eager PyTorch ' + torch.__version__,
+                   'our_value': train['value'], 'our_e2e': train['e2e']}
+        for mode in ('fp32', 'bf16_autocast_channels_last'):
+          try:
+            r = ref_bench.gpu_train_best_batch(mode, steps=min(args.steps, 5), warmup=3)
+          except Exception as ex:
+            r = {'mode': mode, 'error': repr(ex)[:300]}
+          if 'value' in r:
+            r['ours_over_reference'] = train['value'] / r['value']
+          gpu_ref[mode] = r
+        try:
+          r = ref_bench.gpu_sampler(batch=1024, n_steps=10)
+          if samp and 'value' in samp:
+            r['ours_over_reference'] = samp['value'] / r['value']
+          gpu_ref['sampler_fp32'] = r
+        except Exception as ex:
+          gpu_ref['sampler_fp32'] = {'error': repr(ex)[:300]}
+      else:
+        gpu_ref = {'unavailable': 'baseline/_ref is not staged on this box'}
+    if not args.no_cpu_baseline:
+      r = cpu_reference_sample(64, 2, 1)
+      cpu = {'value': r['value'], 'unit': 'images/s', 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']}
 
   if rank == 0:
-    line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
-            'config': {'workload': f'DDPM++ (VP) CIFAR-10 32x32, batch {B}/GPU, {args.dtype} compute + fp32 master, '
-                                   'soft-truncated IS-DSM loss, dropout 0.1, clip+Adam+EMA (BASELINE configs[1])',
-                       'global_batch': B * world, 'parallelism': f'dp{world}',
-                       'l2': 'per-step working set (>20 GB of activations) is far larger than the 126 MB L2; no flush needed'},
-            'e2e': {'value': e2e, 'unit': 'images/s', 'h2d_bytes_per_step': batch_host.numel() * 4 * world,
-                    'd2h_bytes_per_step': B * 4 * world, 'ms_per_step': ms_e2e / args.steps},
-            'e2e_u8': e2e_u8, 'gpu_launches': launches, 'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'sampler': samp,
-            'tcgen05': bool(ops.tc_available())}
+    common = {'n_gpus': world, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
+              'data': 'synthetic', 'tcgen05': bool(ops.tc_available())}
+    if args.mode == 'train':
+      ms, value = train['ms'], train['value']
+      line = {'metric': wl['metric'], 'value': value, 'unit': 'images/s', 'steps': args.steps,
+              'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, **common,
+              'config': {'workload': f"{wl['label']}, batch {B}/GPU, {args.dtype} compute + fp32 master, "
+                                     f"{'soft-truncated ' if cfg.training.st else ''}DSM loss, dropout {cfg.model.dropout}, "
+                                     f"clip+Adam+EMA (BASELINE {wl['baseline']})",
+                         'global_batch': B * world, 'parallelism': f'dp{world}',
+                         'step_graph': bool(losses._STEP_GRAPH),
+                         'l2': 'per-step working set (>20 GB of activations) is far larger than the 126 MB L2; no flush needed'},
+              'e2e': {'value': train['e2e'], 'unit': 'images/s', 'h2d_bytes_per_step': batch_host.numel() * 4 * world,
+                      'd2h_bytes_per_step': B * 4 * world, 'ms_per_step': train['ms_e2e'] / args.steps},
+              'e2e_u8': e2e_u8,
+              # our kernels launched inside the timed region: C-ABI calls of one step (each enqueues >= 1 kernel; the
+              # captured graph replays the same launches) x steps
+              'gpu_launches': train['kernel_calls'] * args.steps, 'host_calls_in_timed_region': train['launches_host'],
+              'clocks': clk.summary(), 'roofline': roof, 'cpu_baseline': cpu, 'gpu_reference': gpu_ref, 'sampler': samp}
+    else:
+      N = samp['schedule_N']
+      line = {'metric': f"{wl['label']} PC-sampler sample-steps/sec", 'value': samp['sample_steps_per_sec'],
+              'unit': 'sample-steps/s', 'steps': samp['steps_timed'], 'warmup': 1, 'ms_per_step': samp['ms_per_step'],
+              **common,
+              'config': {'workload': f"{wl['label']}, {samp['sampler']} PC sampler, batch {samp['batch_per_gpu']}/GPU, "
+                                     f"full N={N} schedule + denoise, {args.dtype} compute (BASELINE {wl['baseline']})",
+                         'parallelism': f'{world} independent samplers', 'l2': 'activations of one network evaluation exceed L2'},
+              'steps_per_sec_per_gpu': samp['value'],
+              'e2e': {'value': samp.get('e2e_steps_per_sec', 0.) * samp['batch_per_gpu'] * world, 'unit': 'sample-steps/s',
+                      'h2d_bytes_per_step': samp['batch_per_gpu'] * 3 * R * R * 4 * world / samp['steps_timed'],
+                      'd2h_bytes_per_step': samp['batch_per_gpu'] * 3 * R * R * 4 * world / samp['steps_timed']},
+              'gpu_launches': None, 'clocks': clk_s.summary() if clk_s is not None else None,
+              'roofline': {'bound': 'tensor', 'achieved': (samp['frac_of_tensor_roofline'] or 0.) * peak_tf, 'peak': peak_tf,
+                           'unit': 'TFLOP/s', 'frac': samp['frac_of_tensor_roofline'], 'traffic': None,
+                           'kernel': 'whole reverse step (algorithmic GF of the network evaluations / time)'},
+              'cpu_baseline': None, 'sampler': samp}
     print(json.dumps(line), flush=True)
   if world > 1:
     dist.destroy_process_group()
@@ -356,11 +479,14 @@ def main():
   ap.add_argument('--steps', type=int, default=10)
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='b200')
-  ap.add_argument('--batch', type=int, default=512)
+  ap.add_argument('--config', default='c2', choices=sorted(WORKLOADS))
+  ap.add_argument('--mode', default='train', choices=['train', 'sampler'])
+  ap.add_argument('--batch', type=int, default=0, help='per-GPU train batch (0 = the workload\'s)')
   ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
-  ap.add_argument('--sample-batch', type=int, default=1024)
-  ap.add_argument('--sample-steps', type=int, default=50)
+  ap.add_argument('--sample-batch', type=int, default=0)
+  ap.add_argument('--sample-steps', type=int, default=0, help='PC schedule length (0 = 50 in train mode, the config\'s N in sampler mode)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-gpu-reference', action='store_true')
   ap.add_argument('--micro', type=int, default=0,
                   help='L2 blocking: run the step as this many image blocks (0 = the library default for the batch)')
   args = ap.parse_args()

@@ -95,6 +95,11 @@ typedef struct st_gemm_args {
 } st_gemm_args;
 
 int st_gemm(const st_gemm_args* args, void* stream);
+/* Number of bf16 problems the AUTO backend had to run on the fp32-FMA kernel because the tcgen05 path cannot express
+ * them (alignment, channel counts, non power-of-two images) since the last reset - benchmarks and full-size tests assert
+ * it is zero - and the reason given for the most recent one. */
+int st_gemm_simt_fallbacks(int reset);
+const char* st_gemm_simt_fallback_reason(void);
 
 /* ------------------------------------------------------------------ GroupNorm (+SiLU, +dropout)
  * x is NHWC [n_img][hw][C1] (+ optional second tensor [n_img][hw][C2] concatenated on channels),
@@ -116,6 +121,11 @@ int st_gn_apply(const void* x1, const void* x2, int dtype, int n_img, int hw, in
                 const float* gamma, const float* beta, float* mean, float* rstd, int act,
                 float p_drop, uint64_t seed, const void* mask, uint8_t* keepbits, void* y, const float* part,
                 int splits, int64_t count, float eps, void* stream);
+/* Device-resident 64-bit addend of the `seed` argument of every st_gn_apply / st_gn_fwd_fused launch that draws its own
+ * dropout mask (NULL = none, the default): the kernel keys its generator with seed + *ptr.  A training step captured
+ * in a CUDA graph bakes `seed` into the launch; the host advances *ptr between replays so that every step draws a
+ * fresh mask, exactly the seeds the eager path would have passed by value. */
+int st_set_dropout_seed_offset(const void* dev_u64);
 /* Statistics + apply in ONE launch: a thread-block cluster of `chunks` CTAs keeps an image resident in shared memory
  * (all of its cp.async copies in flight at once), exchanges per-group partial sums through distributed shared memory
  * and writes y from the resident copy - the tensor crosses HBM once in and once out.  mean / rstd [n_img][G] are
@@ -269,10 +279,12 @@ int st_sumsq(const float* x, int64_t n, float* acc, void* stream);
  *   coef = min(1, clip / (sqrt(*gnorm_sq) + 1e-6)) if clip >= 0 and gnorm_sq != NULL else 1
  *   g = coef*grad (+ wd*p); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2
  *   p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps);  ema -= (1-decay)*(ema - p)   (ema_mask[i]==0 skips)
- *   p16 (optional) receives bf16(p).  */
+ *   p16 (optional) receives bf16(p).
+ * `dyn` (optional, device): {lr, bc1, bc2, ema_decay} read by the kernel INSTEAD of the by-value arguments, so that a
+ * captured CUDA graph of the training step replays with the current step's warm-up / bias-correction / EMA scalars. */
 int st_adam_ema(float* p, const float* grad, float* m, float* v, float* ema, const uint8_t* ema_mask,
                 void* p16, int64_t n, const float* gnorm_sq, float clip, float lr, float b1, float b2,
-                float eps, float wd, float bc1, float bc2, float ema_decay, void* stream);
+                float eps, float wd, float bc1, float bc2, float ema_decay, const float* dyn, void* stream);
 
 /* ------------------------------------------------------------------ sampler */
 /* x_mean = ca[n]*x + cb[n]*s ; x_new = x_mean + cc[n]*noise   (fp32 [B][D]); noise may be NULL.

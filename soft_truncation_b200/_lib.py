@@ -35,6 +35,7 @@ class GemmArgs(ctypes.Structure):
 # name -> argument ctypes (every function returns int status unless noted)
 SIGNATURES = {
     'st_gemm': [ctypes.POINTER(GemmArgs), c_p],
+    'st_gemm_simt_fallbacks': [c_int],
     'st_gn_stats': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p],
     'st_gn_finalize': [c_p, c_int, c_int, c_int, c_i64, c_f, c_p, c_p, c_p],
     'st_gn_apply': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f, c_u64, c_p,
@@ -77,7 +78,8 @@ SIGNATURES = {
     'st_dsm_perturb': [c_p, c_p, c_p, c_p, c_p, c_int, c_i64, c_p],
     'st_dsm_loss': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_i64, c_int, c_p],
     'st_sumsq': [c_p, c_i64, c_p, c_p],
-    'st_adam_ema': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p] + [c_f] * 9 + [c_p],
+    'st_adam_ema': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p] + [c_f] * 9 + [c_p, c_p],
+    'st_set_dropout_seed_offset': [c_p],
     'st_pc_update': [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_i64, c_p],
     'st_batch_norms': [c_p, c_p, c_p, c_int, c_i64, c_p],
     'st_langevin_coeffs': [c_p, c_p, c_f, c_p, c_p, c_p, c_int, c_p],
@@ -99,8 +101,9 @@ def _load():
     fn = getattr(lib, name)          # AttributeError here = header/library mismatch
     fn.argtypes = args
     fn.restype = c_int
-  lib.st_last_error.argtypes = []
-  lib.st_last_error.restype = ctypes.c_char_p
+  for name in ('st_last_error', 'st_gemm_simt_fallback_reason'):
+    getattr(lib, name).argtypes = []
+    getattr(lib, name).restype = ctypes.c_char_p
   return lib
 
 

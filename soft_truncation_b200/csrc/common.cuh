@@ -138,6 +138,7 @@ __device__ __forceinline__ void dropout4(uint64_t seed, uint64_t e4, float p, fl
 // once every CTA of this grid has started.  Both are no-ops for a normal launch.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+const uint64_t* st_seed_offset();        // device addend of in-kernel dropout seeds, or nullptr (lib.cu)
 bool st_pdl_on(cudaStream_t stream);      // ST_PDL=0 disables; never used while the stream is being captured
 
 template <typename... KArgs, typename... Args>

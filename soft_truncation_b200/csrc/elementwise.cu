@@ -586,7 +586,10 @@ __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, co
                                                        float* __restrict__ v, float* __restrict__ ema,
                                                        const uint8_t* __restrict__ ema_mask, bf16* __restrict__ p16,
                                                        long long n, long long n4, const float* gnorm_sq, float clip, float lr, float b1,
-                                                       float b2, float eps, float wd, float bc1, float bc2, float decay) {
+                                                       float b2, float eps, float wd, float bc1, float bc2, float decay,
+                                                       const float* __restrict__ dyn) {
+  // step-dependent scalars from device memory (a captured CUDA graph replays with fresh values): {lr, bc1, bc2, decay}
+  if (dyn) { lr = dyn[0]; bc1 = dyn[1]; bc2 = dyn[2]; decay = dyn[3]; }
   float coef = 1.f;
   if (gnorm_sq && clip >= 0.f) coef = fminf(1.f, clip / (sqrtf(*gnorm_sq) + 1e-6f));
   const float step_size = lr / bc1, sq_bc2 = sqrtf(bc2);
@@ -855,12 +858,12 @@ extern "C" __attribute__((visibility("default"))) int st_sumsq(const float* x, i
 }
 extern "C" __attribute__((visibility("default"))) int st_adam_ema(float* p, const float* grad, float* m, float* v, float* ema, const uint8_t* ema_mask, void* p16,
                            int64_t n, const float* gnorm_sq, float clip, float lr, float b1, float b2, float eps, float wd,
-                           float bc1, float bc2, float ema_decay, void* stream) {
+                           float bc1, float bc2, float ema_decay, const float* dyn, void* stream) {
   const uintptr_t al = reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(m) |
                        reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(ema) | reinterpret_cast<uintptr_t>(p16);
   const long long n4 = ((al & 15) == 0 && (reinterpret_cast<uintptr_t>(ema_mask) & 3) == 0) ? n / 4 : 0;
   adam_ema_kernel<<<grid1d(n4 > 0 ? n4 : n, 256 * 2), 256, 0, S>>>(p, grad, m, v, ema, ema_mask, (bf16*)p16, n, n4, gnorm_sq, clip, lr,
-                                                                    b1, b2, eps, wd, bc1, bc2, ema_decay);
+                                                                    b1, b2, eps, wd, bc1, bc2, ema_decay, dyn);
   ST_CHECK_LAUNCH("st_adam_ema");
   return 0;
 }

@@ -5,6 +5,18 @@ int st_gemm_simt(const st_gemm_args* a, cudaStream_t stream);
 int st_gemm_tc(const st_gemm_args* a, cudaStream_t stream);          // gemm_tc.cu
 int st_gemm_tc_supported(const st_gemm_args* a, const char** why);   // gemm_tc.cu
 
+// bf16 problems that the AUTO backend had to route to the fp32-FMA kernel (a 50x cliff on the fast path): counted so
+// that benchmarks and the full-size tests can assert there were none, and the reason of the last one is kept.
+static int g_simt_fallbacks = 0;
+static const char* g_simt_fallback_why = "";
+
+extern "C" __attribute__((visibility("default"))) int st_gemm_simt_fallbacks(int reset) {
+  const int n = g_simt_fallbacks;
+  if (reset) g_simt_fallbacks = 0;
+  return n;
+}
+extern "C" __attribute__((visibility("default"))) const char* st_gemm_simt_fallback_reason(void) { return g_simt_fallback_why; }
+
 extern "C" __attribute__((visibility("default"))) int st_gemm(const st_gemm_args* a, void* stream) {
   ST_CHECK_ARG(a != nullptr, "st_gemm: null args");
   ST_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0, "st_gemm: empty problem M=%d N=%d K=%d batch=%d", a->M,
@@ -42,6 +54,10 @@ extern "C" __attribute__((visibility("default"))) int st_gemm(const st_gemm_args
     const char* why = nullptr;
     backend = (a->in_dtype == ST_BF16 && st_tc_available() && st_gemm_tc_supported(a, &why)) ? ST_BACKEND_TCGEN05
                                                                                             : ST_BACKEND_SIMT;
+    if (backend == ST_BACKEND_SIMT && a->in_dtype == ST_BF16) {
+      if (g_simt_fallbacks < 0x7fffffff) ++g_simt_fallbacks;
+      g_simt_fallback_why = why ? why : "no sm_100 device";
+    }
   }
   if (backend == ST_BACKEND_TCGEN05) {
     const char* why = "unsupported";

@@ -79,10 +79,12 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(Src2<T> s, int hw, int
                                                           const float* __restrict__ rstd, float p_drop, uint64_t seed,
                                                           const T* mask, uint8_t* keepbits, T* y,
                                                           const float* __restrict__ part, int splits, double inv_count,
-                                                          float eps, float* mean_out, float* rstd_out) {
+                                                          float eps, float* mean_out, float* rstd_out,
+                                                          const uint64_t* __restrict__ seed_off) {
   extern __shared__ __align__(16) uint8_t gsm[];
   pdl_wait();
   pdl_trigger();
+  if constexpr (DROP == DROP_FAST) { if (seed_off) seed += *seed_off; }
   using P = Pipe<T, 1, GN_DEPTH>;
   const P pipe(gsm);
   const int Ct = s.C1 + s.C2, cpg = Ct / G;
@@ -270,7 +272,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_apply(const void* x1
       if (!smem_ok) { if (!allow_smem(gn_apply_kernel<T, ACT, DROP>, smem)) { rc = ST_ERR_CUDA; return; } smem_ok = true; }
       st_launch(gn_apply_kernel<T, ACT, DROP>, dim3(chunks_for(n_img, hw, V), n_img), dim3(256), smem, (cudaStream_t)stream,
           s, hw, G, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, (T*)y, part, splits,
-          part ? 1.0 / (double)count : 0.0, eps, mean, rstd);
+          part ? 1.0 / (double)count : 0.0, eps, mean, rstd, st_seed_offset());
     });
   });
   if (rc) return rc;

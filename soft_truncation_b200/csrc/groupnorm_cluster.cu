@@ -144,13 +144,15 @@ template <typename T, bool ACT, int DROP>
 __global__ void __launch_bounds__(256, 3) gn_fwd_fused_kernel(Src2<T> s, int hw, int G, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, double inv_count, float eps,
                                                               float p_drop, uint64_t seed, const T* mask, uint8_t* keepbits,
-                                                              T* y, float* mean_out, float* rstd_out) {
+                                                              T* y, float* mean_out, float* rstd_out,
+                                                              const uint64_t* __restrict__ seed_off) {
   extern __shared__ __align__(16) uint8_t gsm[];
   __shared__ float s_sum[512], s_sq[512];
   __shared__ float s_part[128];               // this CTA's per-group (sum, sum of squares): read by the whole cluster
   __shared__ float s_mean[64], s_rstd[64];
   pdl_wait();
   pdl_trigger();
+  if constexpr (DROP == DROP_FAST) { if (seed_off) seed += *seed_off; }
   using P = Pipe<T, 1, GN_RES>;
   const P pipe(gsm);
   const int Ct = s.C1 + s.C2, cpg = Ct / G;
@@ -351,7 +353,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_fwd_fused(const void
       cfg.attrs = attr;
       cfg.numAttrs = st_pdl_on((cudaStream_t)stream) ? 2 : 1;
       cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, s, hw, G, gamma, beta, inv_count, eps, p_drop, seed, (const T*)mask,
-                                         keepbits, (T*)y, mean, rstd);
+                                         keepbits, (T*)y, mean, rstd, st_seed_offset());
       if (e != cudaSuccess) { st_set_error("st_gn_fwd_fused: launch: %s", cudaGetErrorString(e)); rc = ST_ERR_CUDA; }
     });
   });

@@ -13,7 +13,11 @@ Same factory surface as the reference (`get_optimizer`, `optimization_manager`, 
     and reduces gradients through GPU 0 every step, models/utils.py:94).
 """
 import ctypes
+import inspect
 import math
+import os
+import pickle
+import warnings
 
 import numpy as np
 import torch
@@ -47,11 +51,26 @@ class FusedAdam(optim.Optimizer):
     self._bind_state()
 
   def _bind_state(self):
+    step = torch.tensor(float(self.t))
     for e in self.model.store.entries:
       p = self.model._params[e.name]
       if e.trainable:
-        self.state[p] = {'step': torch.tensor(float(self.t)), 'exp_avg': _params._logical_view(self.m, e),
+        self.state[p] = {'step': step, 'exp_avg': _params._logical_view(self.m, e),
                          'exp_avg_sq': _params._logical_view(self.v, e)}
+
+  def state_dict(self):
+    """torch.optim.Adam's format; the per-parameter 'step' entries are refreshed here (not 564 tensor allocations
+    per optimizer step)."""
+    step = torch.tensor(float(self.t))
+    for st in self.state.values():
+      st['step'] = step
+    return super().state_dict()
+
+  def hyper(self):
+    """(lr, 1-b1^t, 1-b2^t) of the step that is about to be taken (self.t already advanced)."""
+    g = self.param_groups[0]
+    b1, b2 = g['betas']
+    return float(g['lr']), 1. - b1 ** self.t, 1. - b2 ** self.t
 
   def zero_grad(self, set_to_none=False):
     self.model.zero_grad()
@@ -64,22 +83,23 @@ class FusedAdam(optim.Optimizer):
     return self.gnorm_sq
 
   @torch.no_grad()
-  def step(self, closure=None, clip=-1., gnorm_sq=None, ema=None, ema_decay=0.):
+  def step(self, closure=None, clip=-1., gnorm_sq=None, ema=None, ema_decay=0., dyn=None, advance=True):
+    """`dyn`: device fp32 {lr, bc1, bc2, ema_decay} read by the kernel instead of the by-value scalars (a captured
+    graph replays with the current step's values); `advance=False`: the caller keeps the step counter itself."""
     m = self.model
     if not m._flat.is_cuda:
       raise RuntimeError('FusedAdam needs the parameters on a CUDA device')
     g = self.param_groups[0]
-    self.t += 1
+    if advance:
+      self.t += 1
     b1, b2 = g['betas']
+    lr, bc1, bc2 = self.hyper()
     p16 = m._comp if m._comp is not m._flat else None
     check(lib.st_adam_ema(ops.ptr(m._flat), ops.ptr(m._grad), ops.ptr(self.m), ops.ptr(self.v),
                           ops.ptr(ema.shadow_flat) if ema is not None else None,
                           ops.ptr(ema.mask) if ema is not None else None, ops.ptr(p16), m._flat.numel(),
-                          ops.ptr(gnorm_sq), float(clip), float(g['lr']), float(b1), float(b2), float(g['eps']),
-                          float(g['weight_decay']), 1. - b1 ** self.t, 1. - b2 ** self.t, float(ema_decay),
-                          ops.stream()))
-    for st in self.state.values():
-      st['step'] = torch.tensor(float(self.t))
+                          ops.ptr(gnorm_sq), float(clip), lr, float(b1), float(b2), float(g['eps']),
+                          float(g['weight_decay']), bc1, bc2, float(ema_decay), ops.ptr(dyn), ops.stream()))
 
   def load_state_dict(self, state_dict):
     super().load_state_dict(state_dict)
@@ -134,21 +154,30 @@ def optimization_manager(config):
     if ema is not None:
       ema.update(params)
 
+  # what the captured-graph step needs to reproduce this function without calling it (losses._StepGraph)
+  optimize_fn.st_recipe = dict(lr=config.optim.lr, warmup=config.optim.warmup, grad_clip=config.optim.grad_clip)
   return optimize_fn
 
 
 # ------------------------------------------------------------------------------------ loss
+def _dsm_loss_raw(out, z, a, b, w, reduce_mean, gvec=None):
+  """st_dsm_loss: losses[n] = w[n] * red_i (a[n]*out[n,i] + b[n]*z[n,i])^2; with `gvec` (d loss / d losses[n]) also
+  d(out).  Returns (losses, dout | None)."""
+  B, D = out.shape[0], out[0].numel()
+  losses = torch.empty(B, dtype=torch.float32, device=out.device)
+  dout = torch.empty_like(out) if gvec is not None else None
+  check(lib.st_dsm_loss(ops.ptr(out), ops.ptr(z), ops.ptr(a), ops.ptr(b), ops.ptr(w), ops.ptr(losses), ops.ptr(dout),
+                        ops.ptr(gvec), B, D, int(reduce_mean), ops.stream()))
+  return losses, dout
+
+
 class _DsmLoss(torch.autograd.Function):
-  """losses[n] = w[n] * red_i (a[n]*out[n,i] + b[n]*z[n,i])^2 (st_dsm_loss); backward returns d(out)."""
+  """Autograd node over st_dsm_loss; backward returns d(out)."""
 
   @staticmethod
   def forward(ctx, out, z, a, b, w, reduce_mean):
-    B = out.shape[0]
-    D = out[0].numel()
     out, z = out.contiguous(), z.contiguous()
-    losses = torch.empty(B, dtype=torch.float32, device=out.device)
-    check(lib.st_dsm_loss(ops.ptr(out), ops.ptr(z), ops.ptr(a), ops.ptr(b), ops.ptr(w), ops.ptr(losses), None, None,
-                          B, D, int(reduce_mean), ops.stream()))
+    losses, _ = _dsm_loss_raw(out, z, a, b, w, reduce_mean)
     ctx.save_for_backward(out, z, a, b, w)
     ctx.reduce_mean = reduce_mean
     return losses
@@ -156,11 +185,7 @@ class _DsmLoss(torch.autograd.Function):
   @staticmethod
   def backward(ctx, dl):
     out, z, a, b, w = ctx.saved_tensors
-    B, D = out.shape[0], out[0].numel()
-    dout = torch.empty_like(out)
-    scratch = torch.empty(B, dtype=torch.float32, device=out.device)
-    check(lib.st_dsm_loss(ops.ptr(out), ops.ptr(z), ops.ptr(a), ops.ptr(b), ops.ptr(w), ops.ptr(scratch),
-                          ops.ptr(dout), ops.ptr(dl.float().contiguous()), B, D, int(ctx.reduce_mean), ops.stream()))
+    _, dout = _dsm_loss_raw(out, z, a, b, w, ctx.reduce_mean, gvec=dl.float().contiguous())
     return dout, None, None, None, None, None
 
 
@@ -168,6 +193,44 @@ def _vec(v, B, device):
   if torch.is_tensor(v):
     return v.to(device=device, dtype=torch.float32).expand(B).contiguous()
   return torch.full((B,), float(v), dtype=torch.float32, device=device)
+
+
+def _dsm_inputs(config, sde, batch, t, Z, z):
+  """Everything between the random draws and the network call, and the per-sample loss coefficients
+  (reference losses.py:116-132, models/utils.py:128-190): returns (x_t, labels, a, b, w) with
+  losses[n] = w[n] * reduce((a[n]*out + b[n]*z)^2) for the raw network output `out`."""
+  tr = config.training
+  B, dev = batch.shape[0], batch.device
+  unit = torch.ones((B, 1, 1, 1), device=dev)
+  mean_coeff, std = sde.marginal_prob(unit, t)
+  mean_coeff = mean_coeff.reshape(B).float().contiguous()
+  std = std.float().contiguous()
+  xt = torch.empty_like(batch)
+  check(lib.st_dsm_perturb(ops.ptr(batch), ops.ptr(z), ops.ptr(mean_coeff), ops.ptr(std), ops.ptr(xt), B,
+                           batch[0].numel(), ops.stream()))
+  # raw network output; the score is c[n]*out with c = -1/std (VP, ddpm_score) or 1 (models/utils.py:128-190)
+  if isinstance(sde, VPSDE):
+    if tr.continuous:
+      if tr.unbounded_parametrization:
+        c0 = tr.stabilizing_constant
+        lo = sde.antiderivative(1e-5, stabilizing_constant=c0)
+        labels = (sde.antiderivative(t, stabilizing_constant=c0) - lo) / \
+                 (sde.antiderivative(sde.T, stabilizing_constant=c0) - lo) * 999.
+      else:
+        labels = t * 999
+    else:
+      raise NotImplementedError('discrete-time VP training is not built')
+    c = -1. / std if tr.ddpm_score else torch.ones_like(std)
+  else:
+    labels = std if tr.continuous else torch.round((sde.T - t) * (sde.N - 1))
+    c = torch.ones_like(std)
+  if tr.importance_sampling or not tr.likelihood_weighting:
+    # (score*std + z)^2
+    a, b, w = c * std, torch.ones_like(std), 0.5 * _vec(Z, B, dev)
+  else:
+    g2 = sde.sde(torch.zeros((B, 1, 1, 1), device=dev), t)[1] ** 2
+    a, b, w = c, 1. / std, 0.5 * _vec(Z, B, dev) * g2
+  return xt, labels, a.float().contiguous(), b.float().contiguous(), w.float().contiguous()
 
 
 def get_sde_loss_fn(config, sde, train, variance='scoreflow'):
@@ -187,65 +250,246 @@ def get_sde_loss_fn(config, sde, train, variance='scoreflow'):
     else:
       t, Z = sde.get_diffusion_time(config, B, dev, t_min, importance_sampling=importance_sampling)
     z = injected['z'].to(dev) if injected is not None and 'z' in injected else torch.randn_like(batch)
-    unit = torch.ones((B, 1, 1, 1), device=dev)
-    mean_coeff, std = sde.marginal_prob(unit, t)
-    mean_coeff = mean_coeff.reshape(B).float().contiguous()
-    std = std.float().contiguous()
     batch = batch.float().contiguous()
     z = z.float().contiguous()
-    xt = torch.empty_like(batch)
-    check(lib.st_dsm_perturb(ops.ptr(batch), ops.ptr(z), ops.ptr(mean_coeff), ops.ptr(std), ops.ptr(xt), B,
-                             batch[0].numel(), ops.stream()))
-    # raw network output; the score is c[n]*out with c = -1/std (VP, ddpm_score) or 1 (models/utils.py:128-190)
-    if isinstance(sde, VPSDE):
-      if tr.continuous:
-        if tr.unbounded_parametrization:
-          c0 = tr.stabilizing_constant
-          lo = sde.antiderivative(1e-5, stabilizing_constant=c0)
-          labels = (sde.antiderivative(t, stabilizing_constant=c0) - lo) / \
-                   (sde.antiderivative(sde.T, stabilizing_constant=c0) - lo) * 999.
-        else:
-          labels = t * 999
-      else:
-        raise NotImplementedError('discrete-time VP training is not built')
-      c = -1. / std if tr.ddpm_score else torch.ones_like(std)
-    else:
-      labels = std if tr.continuous else torch.round((sde.T - t) * (sde.N - 1))
-      c = torch.ones_like(std)
+    xt, labels, a, b, w = _dsm_inputs(config, sde, batch, t, Z, z)
     model_fn = mutils.get_model_fn(model, train=train)
     out = model_fn(xt, labels)
-    if tr.importance_sampling or not tr.likelihood_weighting:
-      # (score*std + z)^2
-      a, b, w = c * std, torch.ones_like(std), 0.5 * _vec(Z, B, dev)
-    else:
-      g2 = sde.sde(torch.zeros((B, 1, 1, 1), device=dev), t)[1] ** 2
-      a, b, w = c, 1. / std, 0.5 * _vec(Z, B, dev) * g2
-    return _DsmLoss.apply(out, z, a.float().contiguous(), b.float().contiguous(), w.float().contiguous(),
-                          bool(tr.reduce_mean))
+    return _DsmLoss.apply(out, z, a, b, w, bool(tr.reduce_mean))
 
   return loss_fn
 
 
+# ------------------------------------------------------------------------------------ data parallel
 def _world():
   return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
+def _bcast_device():
+  return torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
+
+
+def sync_numpy_rng():
+  """Give every rank rank 0's NumPy global RNG state (once, at start-up).  The soft-truncation time t_min is one
+  `np.random.rand()` per step (reference sde_lib.py:200-207, losses.py:284) and must be the same on every rank; with
+  identical generator states every rank draws it locally, so the per-step broadcast (and its host sync) of the
+  first build is gone.  The draw sequence equals the single-process reference's."""
+  if _world() == 1:
+    return
+  dev = _bcast_device()
+  blob = pickle.dumps(np.random.get_state()) if dist.get_rank() == 0 else b''
+  n = torch.tensor([len(blob)], dtype=torch.int64, device=dev)
+  dist.broadcast(n, 0)
+  buf = torch.zeros(int(n.item()), dtype=torch.uint8, device=dev)
+  if dist.get_rank() == 0:
+    buf.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+  dist.broadcast(buf, 0)
+  np.random.set_state(pickle.loads(bytes(buf.cpu().numpy().tobytes())))
+
+
+def sync_replicas(state):
+  """Make every rank's parameters, optimizer moments, EMA shadow and step counter equal to rank 0's (once at start-up
+  and after a checkpoint restore): data-parallel ranks only exchange gradients afterwards, so replicas that start
+  apart stay apart.  Ranks may (and should) seed torch differently so that their time / noise / dropout draws differ."""
+  if _world() == 1:
+    return
+  net = mutils.unwrap(state['model'])
+  bufs = []
+  if hasattr(net, '_flat'):
+    bufs.append(net._flat)
+    opt, ema = state.get('optimizer'), state.get('ema')
+    if isinstance(opt, FusedAdam):
+      bufs += [opt.m, opt.v]
+    if ema is not None and getattr(ema, 'shadow_flat', None) is not None:
+      bufs.append(ema.shadow_flat)
+  else:
+    bufs += [p.data for p in net.parameters()]
+  for b in bufs:
+    dist.broadcast(b, 0)
+  meta = torch.tensor([int(state.get('step', 0)), int(getattr(state.get('optimizer'), 't', 0)),
+                       int(getattr(state.get('ema'), 'num_updates', 0) or 0)], dtype=torch.int64, device=_bcast_device())
+  dist.broadcast(meta, 0)
+  state['step'] = int(meta[0])
+  if isinstance(state.get('optimizer'), FusedAdam):
+    state['optimizer'].t = int(meta[1])
+  if state.get('ema') is not None and getattr(state['ema'], 'num_updates', None) is not None:
+    state['ema'].num_updates = int(meta[2])
+  if hasattr(net, 'sync_compute_weights'):
+    net.sync_compute_weights()
+
+
 def shared_t_min(sde, config):
-  """The soft-truncation draw of this step (NumPy RNG, reference losses.py:284), identical on every rank:
-  rank 0 draws, the others receive it."""
-  t_min = sde.get_t_min(config)
-  if _world() > 1:
-    box = [t_min]
-    dist.broadcast_object_list(box, src=0)
-    t_min = box[0]
-  return t_min
+  """The soft-truncation draw of this step (NumPy RNG, reference losses.py:284).  Under torch.distributed every rank
+  draws from its own copy of rank 0's generator (see sync_numpy_rng) - no collective, no host sync."""
+  return sde.get_t_min(config)
+
+
+_GRAD_ALLREDUCE_BF16 = os.environ.get('ST_GRAD_ALLREDUCE', 'fp32') == 'bf16'
 
 
 def sync_gradients(model):
   """Data-parallel gradient reduction: ONE all-reduce (sum) of the flat fp32 gradient buffer.  The loss is
-  already divided by the world size, so the sum is the global-batch mean gradient."""
+  already divided by the world size, so the sum is the global-batch mean gradient.  ST_GRAD_ALLREDUCE=bf16 halves
+  the bytes on the wire (round to bf16, reduce, widen) at bf16 rounding of the summed gradient."""
   if _world() > 1:
-    dist.all_reduce(mutils.unwrap(model)._grad)
+    g = mutils.unwrap(model)._grad
+    if _GRAD_ALLREDUCE_BF16 and g.is_cuda:
+      h = ops.cast(g, torch.bfloat16)
+      dist.all_reduce(h)
+      ops.cast(h, torch.float32, out=g)
+    else:
+      dist.all_reduce(g)
+
+
+# ------------------------------------------------------------------------------------ captured training step
+_STEP_GRAPH = os.environ.get('ST_STEP_GRAPH', '1') != '0'
+_HP_BYTES = 64        # u64 dropout-seed offset | fp32 Z, A(t_min), t_min, T-t_min | fp32 lr, bc1, bc2, ema decay
+
+
+class _StepGraph:
+  """One optimizer step as two CUDA graphs: (A) perturb -> network forward -> loss -> explicit backward,
+  (B) global-norm clip + Adam + EMA; the data-parallel gradient all-reduce runs between them.
+
+  A B=512 step is ~1250 kernel launches issued through ~750 ctypes calls; eagerly the host cannot keep the GPU fed
+  through the 8x8 / 4x4 levels of the U-Net (13 us kernels against ~25 us of Python per call).  The graphs remove
+  the host from the step; what changes from step to step travels through one 64-byte pinned block that graph A
+  copies to the device as its first node: the soft-truncation scalars Z, A(t_min), t_min (sde_lib.time_consts), the
+  warm-up learning rate, Adam bias corrections and EMA decay (st_adam_ema `dyn`), and the dropout seed offset
+  (st_set_dropout_seed_offset) - so every replay draws the seeds / scalars the eager path would have used.  The
+  random draws u, z stay eager torch calls outside the graph (same generator stream as the eager path).
+  """
+
+  def __init__(self, config, sde, state, optimize_fn, batch_shape):
+    self.config, self.sde = config, sde
+    net = mutils.unwrap(state['model'])
+    dev = net._flat.device
+    self.net, self.dev = net, dev
+    B = batch_shape[0]
+    self.key = self._key(state, batch_shape)
+    self.batch = torch.empty(batch_shape, dtype=torch.float32, device=dev)
+    self.u = torch.empty(B, dtype=torch.float32, device=dev)
+    self.z = torch.empty(batch_shape, dtype=torch.float32, device=dev)
+    self.hp_host = torch.zeros(_HP_BYTES, dtype=torch.uint8).pin_memory()
+    self.hp_dev = torch.zeros(_HP_BYTES, dtype=torch.uint8, device=dev)
+    self.hp_i64, self.hp_f32 = self.hp_host[:8].view(torch.int64), self.hp_host[8:].view(torch.float32)
+    dev_f = self.hp_dev[8:].view(torch.float32)
+    self.dyn_time = {'Z': dev_f[0], 'A': dev_f[1], 't_min': dev_f[2], 'span': dev_f[3]} if self._dynamic_t_min() else None
+    self.dyn_opt = dev_f[4:8]
+    self.gvec = torch.full((B,), 1. / (B * _world()), dtype=torch.float32, device=dev)
+    self.recipe = getattr(optimize_fn, 'st_recipe', None)
+    self.fused_opt = (self.recipe is not None and isinstance(state['optimizer'], FusedAdam)
+                      and state['ema'] is not None and getattr(state['ema'], 'owner', None) is net)
+    self.calls0 = None
+    self.graph_a = self.graph_b = None
+    self.losses = None
+    self.pinned = []
+
+  @staticmethod
+  def _key(state, batch_shape):
+    net = mutils.unwrap(state['model'])
+    opt, ema = state['optimizer'], state['ema']
+    ptrs = [t.data_ptr() for t in (net._flat, net._grad, net._comp)]
+    if isinstance(opt, FusedAdam):
+      ptrs += [opt.m.data_ptr(), opt.v.data_ptr()]
+    if ema is not None and getattr(ema, 'shadow_flat', None) is not None:
+      ptrs.append(ema.shadow_flat.data_ptr())
+    return (id(net), id(opt), id(ema), tuple(batch_shape), tuple(ptrs), _world())
+
+  def _dynamic_t_min(self):
+    return isinstance(self.sde, VPSDE) and bool(self.config.training.st)
+
+  # ---- the step body (runs once, under capture)
+  def _body_a(self):
+    cfg, sde, net, tr = self.config, self.sde, self.net, self.config.training
+    self.hp_dev.copy_(self.hp_host, non_blocking=True)
+    net._grad.zero_()
+    t_min = sde.eps if self.dyn_time is not None else sde.get_t_min(cfg)     # constant when not soft-truncated
+    if self.dyn_time is not None:
+      t, Z = sde.time_from_uniform(self.u, t_min, tr.importance_sampling, consts=self.dyn_time)
+    else:
+      t, Z = sde.time_from_uniform(self.u, t_min, tr.importance_sampling)
+    xt, labels, a, b, w = _dsm_inputs(cfg, sde, self.batch, t, Z, self.z)
+    out, ctx = net._execute(xt.float().contiguous(), labels.float().contiguous(), record=True)
+    losses, dout = _dsm_loss_raw(out, self.z, a, b, w, bool(tr.reduce_mean), gvec=self.gvec)
+    net._backward(ctx, dout, need_dx=False)
+    return losses
+
+  def _body_b(self, state):
+    opt, ema = state['optimizer'], state['ema']
+    clip = self.recipe['grad_clip']
+    gn = opt.grad_norm_sq() if clip >= 0 else None
+    opt.step(clip=clip, gnorm_sq=gn, ema=ema, ema_decay=0., dyn=self.dyn_opt, advance=False)
+
+  def capture(self, state):
+    net = self.net
+    ops.ColsumQueue.reserve_pinned(8)
+    state['model'].train()
+    self.calls0 = net._calls + 1                       # _execute advances the counter before it draws seeds
+    check(lib.st_set_dropout_seed_offset(ctypes.c_void_p(self.hp_dev.data_ptr())))
+    try:
+      torch.cuda.synchronize()
+      self.graph_a = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(self.graph_a):
+        self.losses = self._body_a()
+      self.pinned = ops.ColsumQueue.take_pinned()
+      if self.fused_opt:
+        self.graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_b):
+          self._body_b(state)
+    finally:
+      check(lib.st_set_dropout_seed_offset(None))
+      net._calls = self.calls0 - 1                     # the capture pass itself executed nothing
+
+  # ---- one replayed step
+  def run(self, state, batch, optimize_fn, injected, finish):
+    cfg, sde, net = self.config, self.sde, self.net
+    t_min = injected['t_min'] if injected is not None and 't_min' in injected else shared_t_min(sde, cfg)
+    if injected is not None and 'u' in injected:
+      self.u.copy_(injected['u'], non_blocking=True)
+    else:
+      torch.rand(self.u.shape, device=self.dev, out=self.u)
+    if injected is not None and 'z' in injected:
+      self.z.copy_(injected['z'], non_blocking=True)
+    else:
+      torch.randn(self.z.shape, device=self.dev, out=self.z)
+    self.batch.copy_(batch, non_blocking=True)
+    state['model'].train()                              # the flag the eager path's model_fn(train=True) leaves behind
+    net._calls += 1
+    self.hp_i64[0] = (net._calls - self.calls0) * net.SEED_STRIDE
+    if self.dyn_time is not None:
+      self.hp_f32[0:4] = torch.tensor(sde.time_consts(t_min), dtype=torch.float32)
+    if self.fused_opt:
+      opt, ema = state['optimizer'], state['ema']
+      r = self.recipe
+      if r['warmup'] > 0:
+        for g in opt.param_groups:
+          g['lr'] = r['lr'] * np.minimum(state['step'] / r['warmup'], 1.0)
+      opt.t += 1
+      lr, bc1, bc2 = opt.hyper()
+      self.hp_f32[4:8] = torch.tensor([lr, bc1, bc2, ema.next_decay()], dtype=torch.float32)
+    self.graph_a.replay()
+    sync_gradients(state['model'])
+    if self.fused_opt:
+      self.graph_b.replay()
+      state['step'] += 1
+    else:
+      finish(state, state['model'], reduced=True)
+    return self.losses
+
+
+def _graph_eligible(config, sde, state, batch, injected):
+  if not _STEP_GRAPH or not bool(getattr(config.optim, 'cuda_graph', True)):
+    return False
+  net = mutils.unwrap(state['model'])
+  if not (hasattr(net, '_execute') and net._flat.is_cuda and batch.is_cuda):
+    return False
+  if config.optim.num_micro_batch != 1 or int(getattr(config.optim, 'l2_blocks', 1) or 1) != 1 or config.training.mixed:
+    return False
+  if net.drop_masks is not None or net._taps is not None:
+    return False                                      # injected dropout masks / activation taps: eager parity paths
+  if injected is not None and any(k not in ('t_min', 'u', 'z') for k in injected):
+    return False
+  return True
 
 
 def get_step_fn(config, sde, train, optimize_fn=None):
@@ -254,28 +498,75 @@ def get_step_fn(config, sde, train, optimize_fn=None):
     raise NotImplementedError('only continuous-time training (every BASELINE config) is built')
   loss_fn = get_sde_loss_fn(config, sde, train)
   tr = config.training
+  # decide ONCE whether the caller's optimize_fn takes the EMA (ours folds it into the Adam kernel); catching a
+  # TypeError around the call instead would re-run the optimizer when the error came from inside it
+  try:
+    takes_ema = optimize_fn is not None and 'ema' in inspect.signature(optimize_fn).parameters
+  except (TypeError, ValueError):
+    takes_ema = False
+  ctl = {'graph': None, 'eager_calls': 0, 'synced': False, 'graph_failed': False}
 
   def _t_min():
     return shared_t_min(sde, config)    # once per step, shared by the micro-batches (:284)
 
-  def _finish(state, model):
-    sync_gradients(model)
-    try:
+  def _finish(state, model, reduced=False):
+    if not reduced:
+      sync_gradients(model)
+    if takes_ema:
       optimize_fn(state['optimizer'], model.parameters(), step=state['step'], ema=state['ema'])
-      fused_ema = True
-    except TypeError:                                  # a foreign optimize_fn without the `ema` keyword
+    else:
       optimize_fn(state['optimizer'], model.parameters(), step=state['step'])
-      fused_ema = False
     state['step'] += 1
-    if not fused_ema:
+    if not takes_ema:
       state['ema'].update(model.parameters())
+
+  def _zero_grad(state):
+    net = mutils.unwrap(state['model'])
+    if hasattr(net, '_grad'):
+      # through the model: the flat gradient buffer is what the explicit backward accumulates into; torch's
+      # optimizer.zero_grad(set_to_none=True) would only drop the .grad views (and hide them from AdamW / clip)
+      net.zero_grad()
+    else:
+      state['optimizer'].zero_grad()
+
+  def _start(state):
+    if not ctl['synced']:
+      ctl['synced'] = True
+      if _world() > 1:
+        sync_numpy_rng()
+        sync_replicas(state)
+
+  def _graph_step(state, batch, injected):
+    """The captured-graph form of step_fn, or None when this call has to run eagerly."""
+    if ctl['graph_failed'] or not _graph_eligible(config, sde, state, batch, injected):
+      return None
+    ctl['eager_calls'] += 1
+    g = ctl['graph']
+    if g is not None and g.key != _StepGraph._key(state, batch.shape):
+      g = ctl['graph'] = None
+    if g is None:
+      if ctl['eager_calls'] <= 2:       # two eager steps first: lazy initialisation, allocator warm-up
+        return None
+      try:
+        g = _StepGraph(config, sde, state, optimize_fn, tuple(batch.shape))
+        g.capture(state)
+        ctl['graph'] = g
+      except Exception as ex:           # keep training eagerly (and say so) rather than fail the step
+        ctl['graph_failed'] = True
+        warnings.warn(f'soft_truncation_b200: CUDA-graph capture of the training step failed ({ex!r}); running eagerly')
+        return None
+    return g.run(state, batch, optimize_fn, injected, _finish)
 
   def step_fn(state, batch, injected=None):
     model = state['model']
-    optimizer = state['optimizer']
     if not train:
       raise NotImplementedError('step_fn(train=False) is undefined in the reference as well (losses.py:279,293)')
-    optimizer.zero_grad()
+    _start(state)
+    if batch.is_cuda:
+      losses = _graph_step(state, batch, injected)
+      if losses is not None:
+        return losses.cpu()
+    _zero_grad(state)
     B = batch.shape[0]
     nmb = config.optim.num_micro_batch
     mb = B // nmb
@@ -303,10 +594,10 @@ def get_step_fn(config, sde, train, optimize_fn=None):
     """Reference losses.py:295-320.  `injected` = dict(t_min=, u=(B,), z=(B,C,H,W)) replaces the draws, rows in batch
     order (per micro-batch: the importance-sampled half, then the uniform-time half)."""
     model = state['model']
-    optimizer = state['optimizer']
     if not train:
       raise NotImplementedError('step_fn_mixed(train=False) is undefined in the reference as well (losses.py:299,318)')
-    optimizer.zero_grad()
+    _start(state)
+    _zero_grad(state)
     B = batch.shape[0]
     nmb = config.optim.num_micro_batch
     mb = B // nmb

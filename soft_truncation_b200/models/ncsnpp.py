@@ -778,7 +778,11 @@ class NCSNpp(nn.Module):
     self._resblocks = []
     self._taps = None
     self.drop_masks = None
-    self._seed_base = 0x5eed
+    # in-kernel dropout streams are keyed by (seed base, forward-call counter, block index).  The base follows the
+    # process's torch seed and its data-parallel rank, so that `torch.manual_seed` selects the masks and ranks draw
+    # different ones (the reference draws dropout from torch's per-device CUDA generator)
+    self._seed_base = (int(torch.initial_seed()) % (2 ** 31)) ^ 0x5eed
+    self._seed_base += int(os.environ.get('RANK', '0'))
     self._calls = 0
 
     ch = config.data.num_channels
@@ -968,24 +972,32 @@ class NCSNpp(nn.Module):
     mk = self.drop_masks[idx]            # NCHW fp32 keep-mask already scaled by 1/(1-p)
     return ops.nchw_to_nhwc(mk.to(like.device).float().contiguous(), like.dtype)
 
+  SEED_STRIDE = 7919      # seed advance per forward call (a captured training graph adds it through device memory)
+
   def _next_seed(self, idx):
-    return (self._seed_base * 1000003 + self._calls * 7919 + idx) & 0xFFFFFFFFFFFF
+    return self._seed_base * 1000003 + self._calls * self.SEED_STRIDE + idx
 
   def seed_dropout(self, seed):
     self._seed_base, self._calls = int(seed), 0
 
   # ---------------------------------------------------------------- execution
-  def forward(self, x, time_cond):
+  fused_out_scale = True      # forward(..., out_scale=v) multiplies image n of the output by v[n] in the layout kernel
+
+  def forward(self, x, time_cond, out_scale=None):
+    """`out_scale` (ours, optional, inference only): per-image factor folded into the final NHWC->NCHW kernel, e.g.
+    -1/std(t) for the VP score (models/utils.py:169-170) - one elementwise pass less per sampler step."""
     if not x.is_cuda:
       raise RuntimeError('NCSNpp (B200 build) runs on CUDA tensors only; there is no CPU fallback')
     x = x.float().contiguous()
     time_cond = time_cond.float().contiguous()
     if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self._params.values())):
+      if out_scale is not None:
+        raise ValueError('out_scale is an inference-only option')
       return _UNetFn.apply(x, time_cond, self._params[self.head.conv.pre + 'weight'], self)
-    out, _ = self._execute(x, time_cond, record=False)
+    out, _ = self._execute(x, time_cond, record=False, out_scale=out_scale)
     return out
 
-  def _execute(self, x, time_cond, record):
+  def _execute(self, x, time_cond, record, out_scale=None):
     m = self.config.model
     self._calls += 1
     self.sync_compute_weights()
@@ -1037,6 +1049,9 @@ class NCSNpp(nn.Module):
     h = pyramid if self.progressive == 'output_skip' else self.head.fwd(net, h)
     net.out_id = h.id
     net.out_scale = (1. / used_sigmas).contiguous() if m.scale_by_sigma else None
+    if out_scale is not None:
+      out_scale = out_scale.float().reshape(-1)
+      net.out_scale = (out_scale if net.out_scale is None else net.out_scale * out_scale).contiguous()
     out = ops.nhwc_to_nchw(h.t, x.shape[1], net.out_scale)
     return out, net
 

@@ -66,12 +66,12 @@ def unwrap(model):
 def get_model_fn(model, train=False):
   """model_fn(x, labels) with the train/eval toggle of the reference (:97-126)."""
 
-  def model_fn(x, labels):
+  def model_fn(x, labels, **kw):
     if not train:
       model.eval()
     else:
       model.train()
-    return model(x, labels)
+    return model(x, labels, **kw)
 
   return model_fn
 
@@ -92,6 +92,10 @@ def get_score_fn(config, sde, model, train=False, continuous=False):
         else:
           labels = t * 999
         std = sde.marginal_prob(torch.zeros_like(x[:, :1, :1, :1]), t)[1]
+        if (config.training.ddpm_score and not torch.is_grad_enabled() and not x.requires_grad
+            and getattr(unwrap(model), 'fused_out_scale', False)):
+          # -out/std folded into the network's output layout kernel (no separate elementwise pass per sampler step)
+          return model_fn(x, labels, out_scale=-1. / std)
         score = model_fn(x, labels)
       else:
         labels = t * (sde.N - 1)

@@ -424,11 +424,36 @@ class ColsumQueue:
     self.keep.extend((red, dgamma, dbeta))
     self.blocks_y = max(self.blocks_y, (2 * C + 127) // 128)
 
+  # Pinned staging buffers for job tables built while a CUDA graph is being captured: pinned memory must not be
+  # allocated under capture, and the captured host->device copy re-reads the buffer at every replay, so the buffers
+  # are reserved before the capture starts and handed to the graph's owner afterwards (losses._StepGraph).
+  PINNED_ROWS = 4096
+  _pinned_free, _pinned_used = [], []
+
+  @classmethod
+  def reserve_pinned(cls, n):
+    while len(cls._pinned_free) < n:
+      cls._pinned_free.append(torch.zeros((cls.PINNED_ROWS, 21), dtype=torch.int64).pin_memory())
+
+  @classmethod
+  def take_pinned(cls):
+    used, cls._pinned_used = cls._pinned_used, []
+    return used
+
   def flush(self):
     if not self.jobs:
       return
     dev = self.keep[0].device
-    table = torch.tensor(self.jobs, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+    host = torch.tensor(self.jobs, dtype=torch.int64)
+    if torch.cuda.is_current_stream_capturing():
+      assert ColsumQueue._pinned_free and len(self.jobs) <= self.PINNED_ROWS, 'reserve_pinned() before capturing'
+      buf = ColsumQueue._pinned_free.pop()
+      ColsumQueue._pinned_used.append(buf)
+      buf[:len(self.jobs)].copy_(host)
+      table = torch.empty((len(self.jobs), 21), dtype=torch.int64, device=dev)
+      table.copy_(buf[:len(self.jobs)], non_blocking=True)
+    else:
+      table = host.pin_memory().to(dev, non_blocking=True)
     check(lib.st_colsum_batched(ptr(table), len(self.jobs), self.blocks_y, stream()))
     self.jobs, self.keep, self.blocks_y = [], [], 1
 

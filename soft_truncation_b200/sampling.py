@@ -362,15 +362,27 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
               one_step(sx, torch.ones(B, device=device) * sts[0])
           torch.cuda.current_stream().wait_stream(side)
           torch.cuda.set_rng_state(rng, device)
-          graph = torch.cuda.CUDAGraph()
-          with torch.cuda.graph(graph):
-            vec_t = torch.ones(B, device=device) * sts.index_select(0, step)
-            nx, nx_mean = one_step(sx, vec_t)
-            sx.copy_(nx)
-            sx_mean.copy_(nx_mean)
-            step.add_(1)
-          g = dict(key=key, graph=graph, step=step, sx=sx, sx_mean=sx_mean, sts=sts)
+          try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+              vec_t = torch.ones(B, device=device) * sts.index_select(0, step)
+              nx, nx_mean = one_step(sx, vec_t)
+              sx.copy_(nx)
+              sx_mean.copy_(nx_mean)
+              step.add_(1)
+            g = dict(key=key, graph=graph, step=step, sx=sx, sx_mean=sx_mean, sts=sts)
+          except Exception as ex:                    # a predictor / corrector that cannot be captured: eager loop
+            import warnings
+            warnings.warn(f'soft_truncation_b200: CUDA-graph capture of the reverse step failed ({ex!r}); sampling eagerly')
+            torch.cuda.synchronize()
+            g = dict(key=key, graph=None)
           graph_cache['g'] = g
+        if g['graph'] is None:
+          x_mean = x
+          for i in range(sde.N):
+            x, x_mean = one_step(x, torch.ones(B, device=device) * timesteps[i])
+          x_mean = x = denoise_update_fn(model, x_mean if denoise else x)
+          return inverse_scaler(x_mean if denoise else x), sde.N * (n_steps + 1)
         g['sx'].copy_(x)
         g['sts'].copy_(timesteps)
         g['step'].zero_()

@@ -101,7 +101,7 @@ class SDE(abc.ABC):
     """Euler-Maruyama default: f = drift/N, G = diffusion * sqrt(1/N) (sde_lib.py:55-73)."""
     dt = 1 / self.N
     drift, diffusion = self.sde(x, t)
-    return drift * dt, diffusion * torch.sqrt(torch.tensor(dt, device=t.device))
+    return drift * dt, diffusion * float(torch.sqrt(torch.tensor(dt)))      # fp32 sqrt on the host: graph-capturable
 
   def reverse(self, score_fn, probability_flow=False, lambda_=1.):
     return ReverseSDE(self, score_fn, probability_flow, lambda_)
@@ -186,18 +186,28 @@ class VPSDE(_LinearBeta, SDE):
   def normalizing_constant(self, t_min):
     return self.antiderivative(self.T) - self.antiderivative(t_min)
 
-  def importance_time_from_uniform(self, u, t_min):
-    """Inverse-CDF map u in [0,1) -> t for the importance-sampled time (sde_lib.py:191-196)."""
-    Z = self.normalizing_constant(t_min)
+  def importance_time_from_uniform(self, u, t_min, consts=None):
+    """Inverse-CDF map u in [0,1) -> t for the importance-sampled time (sde_lib.py:191-196).  `consts` (optional):
+    the t_min-dependent scalars as DEVICE 0-dim fp32 tensors (see `time_consts`) - same values, same operation
+    order, but a captured CUDA graph re-reads them at every replay instead of baking one step's t_min in."""
+    Z = self.normalizing_constant(t_min) if consts is None else consts['Z']
+    A = self.antiderivative(t_min) if consts is None else consts['A']
     db = self.beta_1 - self.beta_0
     t = (-self.beta_0 + torch.sqrt(self.beta_0 ** 2 + 2 * db *
-                                   torch.log(1. + torch.exp(Z * u + self.antiderivative(t_min))))) / db
+                                   torch.log(1. + torch.exp(Z * u + A)))) / db
     return t, Z.detach()
 
-  def time_from_uniform(self, u, t_min, importance_sampling=True):
+  def time_consts(self, t_min):
+    """Host-side fp32 values of everything in `time_from_uniform` that depends on t_min: [Z, A(t_min), t_min, T - t_min]
+    (Z, A evaluated exactly as the reference does, as fp32 tensor ops on the host)."""
+    return [float(self.normalizing_constant(t_min)), float(self.antiderivative(t_min)), float(t_min), float(self.T - t_min)]
+
+  def time_from_uniform(self, u, t_min, importance_sampling=True, consts=None):
     """Diffusion times for given uniforms `u` (the deterministic part of get_diffusion_time)."""
     if importance_sampling:
-      return self.importance_time_from_uniform(u, t_min)
+      return self.importance_time_from_uniform(u, t_min, consts)
+    if consts is not None:
+      return u * consts['span'] + consts['t_min'], 1
     return u * (self.T - t_min) + t_min, 1
 
   def get_diffusion_time(self, config, batch_size, batch_device, t_min, importance_sampling=True):
@@ -252,8 +262,9 @@ class VESDE(SDE):
     return self.sigma_min * (self.sigma_max / self.sigma_min) ** t
 
   def sde(self, x, t):
-    growth = torch.sqrt(torch.tensor(2 * (np.log(self.sigma_max) - np.log(self.sigma_min)),
-                                     device=t.device))
+    # the reference builds this scalar as a device tensor on every call (sde_lib.py:255); a host->device copy from
+    # pageable memory cannot be captured in a CUDA graph, so the fp32 value is computed once on the host
+    growth = float(torch.sqrt(torch.tensor(2 * (np.log(self.sigma_max) - np.log(self.sigma_min)))))
     return torch.zeros_like(x), self._sigma(t) * growth
 
   def marginal_prob(self, x, t):

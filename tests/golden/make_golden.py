@@ -566,6 +566,110 @@ def golden_ops(R):
   np.savez_compressed(os.path.join(HERE, 'ops_golden.npz'), **out)
 
 
+def reduced_ckpt(cfg):
+  cfg.model.dropout = 0.
+  cfg.optim.warmup = 0
+  return reduced(cfg, nf=16, ch_mult=(1, 2), num_res_blocks=1)
+
+
+def golden_checkpoint(R):
+  """a checkpoint WRITTEN BY THE REFERENCE - its NCSNpp (DataParallel-wrapped, `module.` keys), its
+  torch.optim.Adam and its ExponentialMovingAverage after two CPU optimizer steps, saved by the reference's own
+  utils.save_checkpoint (utils.py:29-36, imported behind the tensorflow.io.gfile stub) - plus the losses, parameter and
+  EMA norms of the reference's THIRD step, which the GPU test must reproduce after restoring the file."""
+  sys.path.insert(0, ROOT)
+  from baseline import ref_env
+  ref_env.install_shims(REF, drivers=True)
+  import utils as ref_utils
+  cfg = reduced_ckpt(ref_config('vp/CIFAR10/ddpmpp_nll_st'))
+  seed, B = 23, 4
+  model, sde, _ = build_ref_model(R, cfg, seed=seed)
+  wrapped = torch.nn.DataParallel(model)
+  optimizer = R.losses.get_optimizer(cfg, wrapped.parameters())
+  ema = R.ema.ExponentialMovingAverage(wrapped.parameters(), decay=cfg.model.ema_rate)
+  state = dict(optimizer=optimizer, model=wrapped, ema=ema, step=0)
+  step_fn = R.losses.get_step_fn(cfg, sde, train=True, optimize_fn=R.losses.optimization_manager(cfg))
+  g = torch.Generator().manual_seed(55)
+  batch = torch.rand(B, 3, 32, 32, generator=g) * 2. - 1.
+  losses = []
+  for s in range(3):
+    if s == 2:
+      ref_utils.save_checkpoint(cfg, os.path.join(HERE, 'ref_checkpoint.pth'), state)
+      np.random.seed(500 + s)
+      torch.manual_seed(600 + s)
+      U, u, z = np.random.rand(), torch.rand(B).numpy(), torch.randn(B, 3, 32, 32).numpy()
+    np.random.seed(500 + s)
+    torch.manual_seed(600 + s)
+    losses.append(step_fn(state, batch).numpy())
+  names = [k for k, _ in model.named_parameters()]
+  pnorm = np.array([p.double().norm().item() for p in model.parameters()])
+  enorm = np.array([e.double().norm().item() for e in ema.shadow_params])
+  np.savez_compressed(os.path.join(HERE, 'checkpoint_golden.npz'), seed=seed, batch=batch.numpy(), U=U, u=u,
+                      z=z.astype(np.float32), losses=np.stack(losses), pnorm=pnorm, enorm=enorm, names=np.array(names),
+                      step_after=state['step'])
+
+
+def golden_fullwidth(R):
+  """FULL-width C3 (RVE, 64x64, FIR, residual input pyramid) and C5 (VE, 256x256, 7 levels, input_skip / output_skip)
+  on ONE image: score and training loss.  Inputs and draws are regenerated from seeds by the tests (torch CPU
+  generator), weights from oracle.ref_model.make_state_dict; the fixture keeps a strided sample of the score."""
+  out = {}
+  for tag, path, seed in (('c3', 've/CELEBA/uncsnpp_st', 31), ('c5', 've/celebahq/uncsnpp_st', 32)):
+    cfg = ref_config(path)
+    cfg.model.dropout = 0.
+    Rz = cfg.data.image_size
+    model, sde, _ = build_ref_model(R, cfg, seed=seed)
+    model.eval()
+    g = torch.Generator().manual_seed(seed + 100)
+    x = torch.rand(1, 3, Rz, Rz, generator=g)
+    sig = torch.tensor([1.7])
+    with torch.no_grad():
+      score = model(x, sig)
+    loss_fn = R.losses.get_sde_loss_fn(cfg, sde, train=True)
+    t_min = sde.get_t_min(cfg)
+    torch.manual_seed(seed + 200)
+    u, z = torch.rand(1), torch.randn(1, 3, Rz, Rz)
+    torch.manual_seed(seed + 200)
+    with torch.no_grad():
+      losses = loss_fn(model, x, importance_sampling=cfg.training.importance_sampling, t_min=t_min)
+    flat = score.reshape(-1)
+    idx = np.arange(0, flat.numel(), 97)
+    out.update({f'{tag}_seed': seed, f'{tag}_sig': sig.numpy(), f'{tag}_idx': idx, f'{tag}_score_samples': flat[idx].numpy(),
+                f'{tag}_score_norm': flat.double().norm().item(), f'{tag}_tmin': t_min, f'{tag}_u': u.numpy(),
+                f'{tag}_z_checksum': z.double().sum().item(), f'{tag}_x_checksum': x.double().sum().item(),
+                f'{tag}_losses': losses.numpy(), f'{tag}_n_params': sum(p.numel() for p in model.parameters())})
+  np.savez_compressed(os.path.join(HERE, 'fullwidth_golden.npz'), **out)
+
+
+def golden_traj100(R):
+  """north_star: "score-matching loss trajectory matching the reference within tolerance" - 100 optimizer steps of the
+  reference (fp32, CPU) on the full-size CIFAR-10 DDPM++ at batch 16, dropout 0, warm-up 0, lr 2e-4, with replayable
+  draws: step s seeds NumPy with 100+s (t_min) and torch with 200+s (u = rand(B), z = randn(B,3,32,32))."""
+  cfg = ref_config('vp/CIFAR10/ddpmpp_nll_st')
+  cfg.model.dropout = 0.
+  cfg.optim.warmup = 0
+  seed, B, steps = 2, 16, 100
+  model, sde, _ = build_ref_model(R, cfg, seed=seed)
+  wrapped = torch.nn.DataParallel(model)
+  optimizer = R.losses.get_optimizer(cfg, wrapped.parameters())
+  ema = R.ema.ExponentialMovingAverage(wrapped.parameters(), decay=cfg.model.ema_rate)
+  state = dict(optimizer=optimizer, model=wrapped, ema=ema, step=0)
+  step_fn = R.losses.get_step_fn(cfg, sde, train=True, optimize_fn=R.losses.optimization_manager(cfg))
+  g = torch.Generator().manual_seed(1234)
+  batch = torch.rand(B, 3, 32, 32, generator=g) * 2. - 1.
+  losses, Us = [], []
+  for s in range(steps):
+    np.random.seed(100 + s)
+    Us.append(np.random.rand())
+    np.random.seed(100 + s)
+    torch.manual_seed(200 + s)
+    losses.append(step_fn(state, batch).numpy())
+    if s % 10 == 0:
+      print('  traj100 step', s, float(losses[-1].mean()), flush=True)
+  np.savez_compressed(os.path.join(HERE, 'traj100_golden.npz'), seed=seed, B=B, U=np.array(Us), losses=np.stack(losses),
+                      batch_checksum=batch.double().sum().item())
+
+
 def main(which):
   torch.set_num_threads(8)
   R = import_reference()
@@ -573,7 +677,8 @@ def main(which):
               variants=golden_variants, sampler=golden_sampler, train=golden_train, deepest=golden_deepest,
               likelihood=golden_likelihood, lossbranches=golden_lossbranches,
               sde_reverse=golden_sde_reverse, score_fn=golden_score_fn,
-              predictors=golden_predictors)
+              predictors=golden_predictors, checkpoint=golden_checkpoint, fullwidth=golden_fullwidth,
+              traj100=golden_traj100)
   for name in (which or jobs):
     print('golden:', name, flush=True)
     jobs[name](R)

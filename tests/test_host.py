@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
   raw = ctypes.CDLL(_lib.LIB_PATH)
   for name in declared:
     assert hasattr(raw, name), f'{name} declared in st_b200.h but not exported'
-  assert declared - {'st_last_error'} == set(_lib.SIGNATURES), 'ctypes signatures out of sync with the header'
+  assert declared - {'st_last_error', 'st_gemm_simt_fallback_reason'} == set(_lib.SIGNATURES), 'ctypes signatures out of sync with the header'
   assert _lib.lib.st_version() >= 100
   assert isinstance(_lib.lib.st_last_error(), bytes)
 
@@ -173,12 +173,23 @@ def _dp_worker(rank, world, port, out):
   m = ncsnpp.NCSNpp(cfg, None, compute_dtype=torch.float32, seed=7)
   m._grad.fill_(float(rank + 1))
   losses.sync_gradients(m)
-  np.random.seed(100 + rank)                     # ranks draw differently; rank 0's value must win
-  t_min = losses.shared_t_min(sde_lib.get_sde(cfg), cfg)
-  np.random.seed(100)
-  want = sde_lib.get_sde(cfg).get_t_min(cfg)
-  ok = bool((m._grad == sum(range(1, world + 1))).all()) and t_min == want
+  ok = bool((m._grad == sum(range(1, world + 1))).all())
   ok = ok and all(bool((p.grad == 3.).all()) for p in m.parameters() if p.requires_grad)
+  # t_min: ranks start with different NumPy generator states; after the one-time sync every rank draws rank 0's
+  # sequence locally (no per-step collective)
+  np.random.seed(100 + rank)
+  losses.sync_numpy_rng()
+  sde = sde_lib.get_sde(cfg)
+  drawn = [losses.shared_t_min(sde, cfg) for _ in range(3)]
+  np.random.seed(100)
+  ok = ok and drawn == [sde.get_t_min(cfg) for _ in range(3)]
+  # replicas that were initialised apart are made equal to rank 0's (parameters, step counter)
+  ref = m._flat.clone()                          # seed=7 on every rank: identical so far
+  with torch.no_grad():
+    m._flat.add_(float(rank))
+  state = dict(model=m, optimizer=None, ema=None, step=5 * rank + 2)
+  losses.sync_replicas(state)
+  ok = ok and bool((m._flat == ref).all()) and state['step'] == 2
   out[rank] = ok
   dist.destroy_process_group()
 
@@ -340,18 +351,53 @@ def test_ema_store_copy_to_restore_like_run_lib(cifar_model):
 
 
 def test_bench_reference_arm_prints_exactly_one_json_line():
-  """bench.py contract: stdout carries ONE JSON line (library banners go to stderr); the reference arm runs the oracle
-  port of the training step on the host cores and reports it as its own cpu_baseline / e2e."""
+  """bench.py contract: stdout carries ONE JSON line (library banners go to stderr); the reference arm runs the staged
+  reference's own training step (else the oracle port) on the host cores and reports it as its own cpu_baseline / e2e."""
   import subprocess
   import sys
   r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
-                     capture_output=True, text=True, timeout=600)
+                     capture_output=True, text=True, timeout=600, env=dict(os.environ, ST_BENCH_REF_BATCH='4'))
   assert r.returncode == 0, r.stderr[-2000:]
   lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
   assert len(lines) == 1, r.stdout
   d = json.loads(lines[0])
   assert d['impl'] == 'reference' and d['metric'] == 'DDPM++ CIFAR-10 train images/sec' and d['unit'] == 'images/s'
   assert d['higher_is_better'] is True and d['value'] > 0 and d['n_gpus'] == 1 and d['steps'] == 1
-  assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+  from baseline import ref_env
+  assert d['cpu_baseline']['kind'] == ('reference' if ref_env.locate() else 'port') and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
   assert d['e2e'] == {'value': d['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
   assert 'workload' in d['config'] and d['vs_baseline'] is None
+
+
+def test_reference_utils_drives_this_package_on_the_host():
+  """CPU half of tests/test_gpu_round2.py::test_reference_drivers_run_on_this_package: the reference's UNCHANGED utils.py,
+  imported with its module names redirected to this package behind the TensorFlow stubs,
+  builds the model / optimizer / EMA through `load_model` and the step / sampling / likelihood functions through
+  `get_loss_fns` (reference utils.py:49-82).  Runs where the reference is available (build container or staged copy)."""
+  import json
+  import subprocess
+  import sys
+  from baseline import ref_env
+  from test_gpu_round2 import _DRIVER_SCRIPT
+  if ref_env.locate(allow_source=True) is None:
+    pytest.skip('the reference is not available here')
+  r = subprocess.run([sys.executable, '-c', _DRIVER_SCRIPT.format(root=ROOT, dev='cpu')], capture_output=True, text=True, timeout=600)
+  assert r.returncode == 0, r.stderr[-3000:]
+  res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('RESULT ')][-1][7:])
+  assert res == {'model': 'soft_truncation_b200.models.ncsnpp', 'opt': 'Adam'}
+
+
+def test_reference_is_staged_and_importable():
+  """baseline/_ref (the untouched reference, staged by baseline/ref_env.stage() from /root/reference) is what
+  `bench.py --impl reference` and the `gpu_reference` leg run: it must import behind the shims and expose the path's API."""
+  from baseline import ref_env
+  if ref_env.locate() is None:
+    pytest.skip('baseline/_ref is not staged')
+  import subprocess
+  import sys
+  code = ("import sys; sys.path.insert(0, %r); from baseline import ref_env; R = ref_env.import_reference(); "
+          "c = ref_env.ref_config('vp/CIFAR10/ddpmpp_nll_st'); "
+          "assert callable(R.losses.get_step_fn) and callable(R.sampling.get_sampling_fn) and c.training.sde == 'vpsde'; "
+          "print('ok', R.root)" % ROOT)
+  r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+  assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
