@@ -141,3 +141,13 @@ def gpu_sampler(batch=1024, n_steps=10, device='cuda:0'):
   del model, fn
   torch.cuda.empty_cache()
   return out
+
+
+if __name__ == '__main__':
+  # `python -m baseline.ref_bench cpu <batch> <steps> <warmup>`: the CPU sample in a process of its own (bench.py runs it
+  # with CUDA_VISIBLE_DEVICES='' - the reference's create_model wraps the model in DataParallel over every visible GPU)
+  import json
+  import sys
+  kind, b, k, w = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+  assert kind == 'cpu'
+  print('RESULT ' + json.dumps(cpu_train(batch=b, steps=k, warmup=w)), flush=True)

@@ -157,7 +157,15 @@ def cpu_reference_sample(batch, steps, warmup):
   the oracle port."""
   from baseline import ref_bench
   if ref_bench.available():
-    return ref_bench.cpu_train(batch=batch, steps=steps, warmup=warmup)
+    # a process of its own with the GPUs hidden: the reference's create_model wraps the model in DataParallel over
+    # every visible device (models/utils.py:94), which would move a CPU run onto cuda:0
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='')
+    r = subprocess.run([sys.executable, '-m', 'baseline.ref_bench', 'cpu', str(batch), str(steps), str(warmup)], cwd=ROOT,
+                       env=env, capture_output=True, text=True, timeout=1500)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith('RESULT ')]
+    if r.returncode != 0 or not lines:
+      raise RuntimeError('reference CPU run failed: ' + (r.stderr or r.stdout)[-1500:])
+    return json.loads(lines[-1][7:])
   from oracle import ref_model, ref_train
   from soft_truncation_b200 import configs
   cores = os.cpu_count() or 1
@@ -428,8 +436,11 @@ def run_b200(args):
       else:
         gpu_ref = {'unavailable': 'baseline/_ref is not staged on this box'}
     if not args.no_cpu_baseline:
-      r = cpu_reference_sample(64, 2, 1)
-      cpu = {'value': r['value'], 'unit': 'images/s', 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']}
+      try:
+        r = cpu_reference_sample(64, 2, 1)
+        cpu = {'value': r['value'], 'unit': 'images/s', 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']}
+      except Exception as ex:       # the headline line must still print
+        cpu = {'error': repr(ex)[:300]}
 
   if rank == 0:
     common = {'n_gpus': world, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,

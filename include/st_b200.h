@@ -101,6 +101,17 @@ int st_gemm(const st_gemm_args* args, void* stream);
 int st_gemm_simt_fallbacks(int reset);
 const char* st_gemm_simt_fallback_reason(void);
 
+/* ------------------------------------------------------------------ fused attention core
+ * AttnBlockpp's  w = softmax(q k^T * scale),  o = w v  (models/layerspp.py:95-99) in ONE tcgen05 kernel: the logits live
+ * in tensor memory, the probabilities in shared memory; only q, k, v are read and o is written.
+ *   qkv   bf16 [n_img * L][3C]: q | k | v of every pixel (the packed projection st_gemm produces)
+ *   o     bf16 [n_img * L][C]
+ *   p_out bf16 [n_img][L][L] or NULL: the normalised probabilities, kept for the backward pass (training)
+ * st_attn_fwd_supported: 1 when the kernel can run the shape (sm_100, L = 256, C = 256, bf16); other shapes use the
+ * st_gemm / st_softmax_fwd path. */
+int st_attn_fwd_supported(int L, int C, int dtype);
+int st_attn_fwd(const void* qkv, void* o, void* p_out, int n_img, int L, int C, float scale, void* stream);
+
 /* ------------------------------------------------------------------ GroupNorm (+SiLU, +dropout)
  * x is NHWC [n_img][hw][C1] (+ optional second tensor [n_img][hw][C2] concatenated on channels),
  * G groups of (C1+C2)/G adjacent channels, statistics per (image, group).

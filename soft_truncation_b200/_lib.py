@@ -36,6 +36,8 @@ class GemmArgs(ctypes.Structure):
 SIGNATURES = {
     'st_gemm': [ctypes.POINTER(GemmArgs), c_p],
     'st_gemm_simt_fallbacks': [c_int],
+    'st_attn_fwd_supported': [c_int, c_int, c_int],
+    'st_attn_fwd': [c_p, c_p, c_p, c_int, c_int, c_int, c_f, c_p],
     'st_gn_stats': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p],
     'st_gn_finalize': [c_p, c_int, c_int, c_int, c_i64, c_f, c_p, c_p, c_p],
     'st_gn_apply': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f, c_u64, c_p,

@@ -24,6 +24,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -62,140 +63,6 @@ struct TcParams {
   int epi_tma;            // epilogue writes the tile through shared memory with TMA stores (mapC / mapR are valid)
   int rb_rows;            // distinct rowbias rows (images) one tile spans (1..4) when epi_tma
 };
-
-// ------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint64_t globaltimer() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// Bounded wait: a protocol bug must trap (-> launch error on the host) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  uint64_t t0 = 0;
-  for (uint32_t it = 0;; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if ((it & 1023u) == 1023u) {
-      uint64_t now = globaltimer();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) __trap();     // 4 s
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void named_bar(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
-//   K-major : rows of 128 bytes, 8-row groups SBO = 1024 bytes apart; LBO unused (1).
-//   MN-major: 64-element (128-byte) runs along M/N, k rows 128 bytes apart, 8-k groups SBO = 1024 bytes apart,
-//             successive 64-wide M/N chunks LBO bytes apart.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;          // SWIZZLE_128B
-  return d;
-}
 
 // ------------------------------------------------------------------------------------ kernel
 template <int BN, int STAGES>
@@ -441,7 +308,15 @@ constexpr int NUM_THREADS2 = 352;     // warp 0 TMA (A operand), warp 1 MMA, war
 // MH = number of 128-row accumulators per CTA tile: the tile is (128*MH) x BN with MH*BN <= 256 TMEM columns per
 // buffer.  MH = 2 (256 x 128) is the N <= 128 counterpart of the 128 x 256 tile: both stream 48 KB per K block
 // for 4.2 MFLOP, i.e. the single TMA / MMA issuing threads have 512 tensor-core cycles per K block to hide behind.
-template <int BN, int MH, int STAGES>
+//
+// CG = 2 (CTA pair, tcgen05.mma.cta_group::2): the two CTAs of a cluster compute one (2*128*MH) x BN tile.  Each CTA
+// stages its own 128*MH rows of A and HALF of the B tile (the tensor core reads the other half from the peer's shared
+// memory), so a K block costs 16*MH + BN/16 KB per SM instead of 16*MH + BN/8 and a tensor-core instruction reads
+// 4 + BN/64 KB of shared memory per SM instead of 4 + BN/32: deeper ring, less shared-memory bandwidth per flop.
+// Protocol: both CTAs' producers arm and signal the LEADER's full barrier (4 arrivals + the bytes of both CTAs); the
+// leader's MMA thread issues for the pair and commits with .multicast::cluster to the empty / accumulator-full
+// barriers of both CTAs; every epilogue warp of the pair arrives on the leader's accumulator-empty barrier.
+template <int BN, int MH, int STAGES, int CG>
 __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                    const __grid_constant__ CUtensorMap mapA1,
                                                                    const __grid_constant__ CUtensorMap mapB0,
@@ -450,9 +325,10 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
                                                                    const __grid_constant__ CUtensorMap mapR,
                                                                    const TcParams p) {
   static_assert(BN * MH <= 256, "accumulator buffer exceeds half of TMEM");
-  constexpr int BMT = BM * MH;                // tile rows
+  static_assert(CG == 1 || (BN % 128 == 0), "a CTA pair splits the B tile in 64-wide halves");
+  constexpr int BMT = BM * MH;                // tile rows of this CTA
   constexpr int A_BYTES = A_STAGE_BYTES * MH;
-  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int B_STAGE_BYTES = BN * 128 / CG;     // this CTA's share of the B tile
   constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
   constexpr int TC = BN * MH;                 // TMEM columns per accumulator buffer
   constexpr int TMEM_COLS = 2 * TC;
@@ -460,6 +336,12 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
   constexpr int RES_BYTES = TC * 256;         // 256 epilogue threads x CH chunks x 64 bytes
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  {
+    uint32_t dyn;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    constexpr uint32_t NEED = STAGES * STAGE_BYTES + TC * 256 + (2 * STAGES + 6) * 8 + 16 + 4 * BN * 4;
+    if ((uint32_t)(smem - smem_raw) + NEED > dyn) __trap();     // launched without re-alignment slack and misaligned
+  }
   uint8_t* res_stage = smem + STAGES * STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(res_stage + RES_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
@@ -470,8 +352,9 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
   const uint32_t rfull0 = smem_u32(bars + 2 * STAGES + 4);     // residual tile landed (one per epilogue half-group)
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int cs = p.cluster;
+  const int cs = CG == 2 ? 2 : p.cluster;
   const int rank = cs > 1 ? (int)cluster_ctarank() : 0;
+  const bool leader_cta = (CG == 1) || rank == 0;
   const uint16_t mc_mask = (uint16_t)((1u << cs) - 1u);
   const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
   const int split = p.split_k > 1 ? p.split_k : 1;
@@ -486,19 +369,24 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full0 + 8 * s, 2);          // one arrive.expect_tx from each of the two producer warps
-      mbar_init(empty0 + 8 * s, cs);
+      mbar_init(full0 + 8 * s, 2 * CG);     // one arrive.expect_tx from each producer warp (of both CTAs of a pair)
+      mbar_init(empty0 + 8 * s, CG == 2 ? 1 : cs);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull0 + 8 * b, 1);
-      mbar_init(tempty0 + 8 * b, 8);
+      mbar_init(tempty0 + 8 * b, 8 * CG);   // every epilogue warp (of both CTAs of a pair)
       mbar_init(rfull0 + 8 * b, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -571,13 +459,16 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
           }
         }
         // gathered B operand (weight gradient with few output channels, not transposed): n = (tap, channel)
-        int b_c[BN / 64], b_dx[BN / 64], b_dy[BN / 64], b_src[BN / 64];
+        // (a CTA of a pair only walks its own half of the 64-wide column chunks)
+        constexpr int NBJ = BN / 64 / CG;
+        const int bj0 = CG == 2 ? rank * NBJ : 0;
+        int b_c[NBJ], b_dx[NBJ], b_dy[NBJ], b_src[NBJ];
 #pragma unroll
-        for (int j = 0; j < BN / 64; ++j) { b_c[j] = 0; b_dx[j] = 0; b_dy[j] = 0; b_src[j] = 2; }
+        for (int j = 0; j < NBJ; ++j) { b_c[j] = 0; b_dx[j] = 0; b_dy[j] = 0; b_src[j] = 2; }
         if (p.b_kind == GATHER_MN) {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) {
-            const int nn = n0 + 64 * j;
+          for (int j = 0; j < NBJ; ++j) {
+            const int nn = n0 + 64 * (bj0 + j);
             const int t = nn / p.Ct, c = nn - t * p.Ct;
             if (t < p.ntaps) {                              // else masked columns: any in-range box
               b_dy[j] = t / p.kw - ph; b_dx[j] = t - (t / p.kw) * p.kw - pw;
@@ -588,31 +479,54 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
         int kk = kt0 * BK;
         for (int i = 0; i < nkt; ++i) {
           mbar_wait(empty0 + 8 * s, par);
-          const uint32_t bar = full0 + 8 * s;
+          // CG == 2: both CTAs arm and signal the pair leader's barrier (same offset, peer bit cleared)
+          const uint32_t bar = CG == 2 ? ((full0 + 8 * s) & PEER_MASK) : (full0 + 8 * s);
           const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
           if (elect_one()) {
-          mbar_expect_tx(bar, do_a ? A_BYTES : B_STAGE_BYTES);
+          if constexpr (CG == 2) mbar_expect_tx_cluster(bar, do_a ? A_BYTES : B_STAGE_BYTES);
+          else mbar_expect_tx(bar, do_a ? A_BYTES : B_STAGE_BYTES);
           if (do_a) {
           // ---- A (private to this CTA): MH blocks of 128 rows, 16 KB each
           if (p.a_kind == KMAJOR) {
 #pragma unroll
-            for (int h = 0; h < MH; ++h) tma_load_3d(sa + h * A_STAGE_BYTES, &mapA0, bar, kk, m0 + h * BM, b);
+            for (int h = 0; h < MH; ++h) ld3<CG>(sa + h * A_STAGE_BYTES, &mapA0, bar, kk, m0 + h * BM, b);
           } else if (p.a_kind == MNMAJOR) {
 #pragma unroll
-            for (int j = 0; j < 2 * MH; ++j) tma_load_3d(sa + j * 8192, &mapA0, bar, m0 + 64 * j, kk, b);
+            for (int j = 0; j < 2 * MH; ++j) ld3<CG>(sa + j * 8192, &mapA0, bar, m0 + 64 * j, kk, b);
           } else if (p.a_kind == GATHER_K) {
 #pragma unroll
             for (int h = 0; h < MH; ++h) {
-              if (cb < p.c1blocks) tma_load_4d(sa + h * A_STAGE_BYTES, &mapA0, bar, cb * 64, gx0[h] + dx, gy0[h] + dy, gn0[h]);
-              else tma_load_4d(sa + h * A_STAGE_BYTES, &mapA1, bar, (cb - p.c1blocks) * 64, gx0[h] + dx, gy0[h] + dy, gn0[h]);
+              if (cb < p.c1blocks) ld4<CG>(sa + h * A_STAGE_BYTES, &mapA0, bar, cb * 64, gx0[h] + dx, gy0[h] + dy, gn0[h]);
+              else ld4<CG>(sa + h * A_STAGE_BYTES, &mapA1, bar, (cb - p.c1blocks) * 64, gx0[h] + dx, gy0[h] + dy, gn0[h]);
             }
           } else {   // GATHER_MN as A: m = (tap, channel), k = pixel block
             const int x0 = kk & Wm, y0 = (kk >> lw) & Hm, i0 = kk >> lhw;
 #pragma unroll
             for (int j = 0; j < 2 * MH; ++j) {
-              if (a_src[j] == 2) tma_load_4d(sa + j * 8192, &mapA0, bar, 0, x0, y0, i0);
-              else if (a_src[j] == 0) tma_load_4d(sa + j * 8192, &mapA0, bar, a_c[j], x0 + a_dx[j], y0 + a_dy[j], i0);
-              else tma_load_4d(sa + j * 8192, &mapA1, bar, a_c[j], x0 + a_dx[j], y0 + a_dy[j], i0);
+              if (a_src[j] == 2) ld4<CG>(sa + j * 8192, &mapA0, bar, 0, x0, y0, i0);
+              else if (a_src[j] == 0) ld4<CG>(sa + j * 8192, &mapA0, bar, a_c[j], x0 + a_dx[j], y0 + a_dy[j], i0);
+              else ld4<CG>(sa + j * 8192, &mapA1, bar, a_c[j], x0 + a_dx[j], y0 + a_dy[j], i0);
+            }
+          }
+          } else if constexpr (CG == 2) {
+          // ---- B, CTA pair: this CTA's half of the tile (BN/2 rows or BN/128 64-wide chunks) at local offset 0
+          constexpr int HALF = BN / 2, PER = BN / 128;
+          if (p.b_kind == KMAJOR) {
+            ld3<2>(sb, &mapB0, bar, kk, n0 + rank * HALF, b);
+          } else if (p.b_kind == GATHER_MN) {
+            const int x0 = kk & Wm, y0 = (kk >> lw) & Hm, i0 = kk >> lhw;
+#pragma unroll
+            for (int jj = 0; jj < PER; ++jj) {
+              if (b_src[jj] == 2) ld4<2>(sb + jj * 8192, &mapB0, bar, 0, x0, y0, i0);
+              else if (b_src[jj] == 0) ld4<2>(sb + jj * 8192, &mapB0, bar, b_c[jj], x0 + b_dx[jj], y0 + b_dy[jj], i0);
+              else ld4<2>(sb + jj * 8192, &mapB1, bar, b_c[jj], x0 + b_dx[jj], y0 + b_dy[jj], i0);
+            }
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < PER; ++jj) {
+              const int j = rank * PER + jj;
+              if (p.b_kind == MNMAJOR) ld3<2>(sb + jj * 8192, &mapB0, bar, n0 + 64 * j, kk, b);
+              else ld3<2>(sb + jj * 8192, &mapB0, bar, n0 + 64 * j, p.ntaps - 1 - tap, cb * 64);
             }
           }
           } else {
@@ -655,11 +569,13 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (whole warp walks the loop, one elected lane issues)
-    {
+    // (CTA pair: the leader issues for both CTAs, the peer's warp 1 only owns its TMEM allocation)
+    if (leader_cta) {
       const bool a_mn = (p.a_kind == MNMAJOR || p.a_kind == GATHER_MN);
       const bool b_mn = (p.b_kind != KMAJOR);
+      // instruction descriptor: D = f32, A = B = bf16, operand majors, N >> 3, M >> 4 (M = 256 across a CTA pair)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
       // descriptor = hi32 (SBO=1024, version 1, SWIZZLE_128B) : lo32 (start>>4 | LBO>>4 << 16)
       const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t a_lo0 = (smem_base >> 4) | ((a_mn ? (8192u >> 4) : 1u) << 16);
@@ -687,11 +603,13 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
 #pragma unroll
             for (int h = 0; h < MH; ++h) {
               const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + h * (A_STAGE_BYTES >> 4) + j * a_step);
-              umma_f16(tacc + (uint32_t)(h * BN), ad, bd, idesc, accum);
+              if constexpr (CG == 2) umma_f16_2sm(tacc + (uint32_t)(h * BN), ad, bd, idesc, accum);
+              else umma_f16(tacc + (uint32_t)(h * BN), ad, bd, idesc, accum);
             }
             accum = 1;
           }
-          if (cs > 1) umma_commit_mc(empty0 + 8 * s, mc_mask);
+          if constexpr (CG == 2) umma_commit_2sm(empty0 + 8 * s, 3);      // frees the slot in both CTAs
+          else if (cs > 1) umma_commit_mc(empty0 + 8 * s, mc_mask);
           else umma_commit(empty0 + 8 * s);
           }
           __syncwarp();
@@ -700,7 +618,10 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
           b_lo += STAGE_BYTES >> 4;
           if (++s == STAGES) { s = 0; par ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
         }
-        if (elect_one()) umma_commit(tfull0 + 8 * buf);
+        if (elect_one()) {
+          if constexpr (CG == 2) umma_commit_2sm(tfull0 + 8 * buf, 3);        // accumulators of both CTAs complete
+          else umma_commit(tfull0 + 8 * buf);
+        }
         __syncwarp();
         ++tl;
       }
@@ -805,7 +726,10 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
             if (c == CH - 1) {                            // accumulator drained: hand the TMEM buffer back to the MMA warp
               asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
               __syncwarp();
-              if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+              if (lane == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster((tempty0 + 8 * buf) & PEER_MASK);
+                else mbar_arrive(tempty0 + 8 * buf);
+              }
             }
             float v[32];
 #pragma unroll
@@ -1007,16 +931,20 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
       // this warp has drained its part of the accumulator buffer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster((tempty0 + 8 * buf) & PEER_MASK);
+        else mbar_arrive(tempty0 + 8 * buf);
+      }
       ++tl;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (cs > 1) cluster_sync_all();     // no CTA may exit while peers can still multicast into it
+  if (cs > 1) cluster_sync_all();     // no CTA may exit while peers can still multicast into it / read its operands
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    if constexpr (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
 
@@ -1101,6 +1029,17 @@ extern "C" __attribute__((visibility("default"))) int st_tc_available(void) {
   return g_tc_state == 1;
 }
 
+// 2-D bf16 SWIZZLE_128B tensor map over a row-major matrix (for the other tcgen05 kernels of the library: attn_tc.cu)
+bool st_tc_encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                     uint32_t box_inner, uint32_t box_rows) {
+  tc_init();
+  if (g_tc_state != 1) { st_set_error("no sm_100 device / cuTensorMapEncodeTiled"); return false; }
+  const uint64_t dims[2] = {inner, rows};
+  const uint64_t str[1] = {row_stride_bytes};
+  const uint32_t box[2] = {box_inner, box_rows};
+  return encode_map(map, base, 2, dims, str, box);
+}
+
 // Why (or whether) the tcgen05 backend can run this problem.
 int st_gemm_tc_supported(const st_gemm_args* a, const char** why) {
 #define NO(msg) do { *why = msg; return 0; } while (0)
@@ -1142,19 +1081,22 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-template <int BN, int MH, int STAGES>
+template <int BN, int MH, int STAGES, int CG>
 int launch2(const CUtensorMap* maps, TcParams& p, int total_super, cudaStream_t stream) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES * MH + BN * 128) + BN * MH * 256 + (2 * STAGES + 6) * 8 + 16 + 4 * BN * 4 + 1024;
+  constexpr int need = STAGES * (A_STAGE_BYTES * MH + BN * 128 / CG) + BN * MH * 256 + (2 * STAGES + 6) * 8 + 16 + 4 * BN * 4;
+  // 1 KB of slack for re-aligning the dynamic shared-memory base to 1024 bytes (SWIZZLE_128B) - dropped when the
+  // configuration only fits without it: the base is 1024-aligned in practice (the kernel traps if it is not)
+  constexpr int smem = need + 1024 <= 232448 ? need + 1024 : need;
   static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   static int max_clusters[5] = {0, 0, 0, 0, 0};
-  auto kern = gemm_tc2_kernel<BN, MH, STAGES>;
+  auto kern = gemm_tc2_kernel<BN, MH, STAGES, CG>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { st_set_error("st_gemm(tc2): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ST_ERR_CUDA; }
     configured = true;
   }
-  const int cs = p.cluster;
+  const int cs = CG == 2 ? 2 : p.cluster;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.blockDim = dim3(NUM_THREADS2);
@@ -1178,7 +1120,8 @@ int launch2(const CUtensorMap* maps, TcParams& p, int total_super, cudaStream_t 
   }
   int clusters = total_super < max_clusters[cs] ? total_super : max_clusters[cs];
   cfg.gridDim = dim3(clusters * cs);
-  cfg.numAttrs = (cs == 1 && st_pdl_on(stream)) ? 2 : 1;
+  const int pdl_pairs = env_int("ST_TC_PDL2", 1);
+  cfg.numAttrs = ((cs == 1 || (CG == 2 && pdl_pairs)) && st_pdl_on(stream)) ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
   if (e != cudaSuccess) { st_set_error("st_gemm(tc2): launch failed: %s", cudaGetErrorString(e)); return ST_ERR_CUDA; }
   return 0;
@@ -1255,6 +1198,14 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   if (cs != 1 && cs != 2 && cs != 4) cs = 2;
   while (cs > 1 && cs > p.m_tiles) cs >>= 1;
   if (!b_kmajor) while (cs > 1 && cs > BN / 64) cs >>= 1;
+  // CTA pairs (tcgen05.mma.cta_group::2): the big tiles, whenever there are at least two row blocks to pair
+  // (ST_TC_CG=1 keeps every launch on single-CTA instructions; bit 0/1 of ST_TC_CG2_MASK select the 128x256 / 256x128 forms)
+  int CG = 1;
+  {
+    const int want = env_int("ST_TC_CG", 2), mask = env_int("ST_TC_CG2_MASK", 3);
+    const bool big = (BN == 256 && MH == 1 && (mask & 1)) || (BN == 128 && MH == 2 && (mask & 2));
+    if (want == 2 && big && p.m_tiles >= 2) { CG = 2; cs = 2; }
+  }
   p.cluster = cs;
 
   // ---------------- A
@@ -1348,10 +1299,12 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   const int m_groups = (p.m_tiles + cs - 1) / cs;
   const long long total = (long long)p.batch * p.split_k * p.n_tiles * m_groups;
   ST_CHECK_ARG(total < (1LL << 30), "st_gemm(tc2): too many tiles");
-  if (BN == 256) return launch2<256, 1, 3>(maps, p, (int)total, stream);
-  if (BN == 128 && MH == 2) return launch2<128, 2, 3>(maps, p, (int)total, stream);
-  if (BN == 128) return launch2<128, 1, 5>(maps, p, (int)total, stream);
-  return launch2<64, 1, 8>(maps, p, (int)total, stream);
+  if (CG == 2 && BN == 256) return launch2<256, 1, 4, 2>(maps, p, (int)total, stream);
+  if (CG == 2) return launch2<128, 2, 4, 2>(maps, p, (int)total, stream);
+  if (BN == 256) return launch2<256, 1, 3, 1>(maps, p, (int)total, stream);
+  if (BN == 128 && MH == 2) return launch2<128, 2, 3, 1>(maps, p, (int)total, stream);
+  if (BN == 128) return launch2<128, 1, 5, 1>(maps, p, (int)total, stream);
+  return launch2<64, 1, 8, 1>(maps, p, (int)total, stream);
 }
 
 }  // namespace

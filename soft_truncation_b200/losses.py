@@ -501,7 +501,8 @@ def get_step_fn(config, sde, train, optimize_fn=None):
   # decide ONCE whether the caller's optimize_fn takes the EMA (ours folds it into the Adam kernel); catching a
   # TypeError around the call instead would re-run the optimizer when the error came from inside it
   try:
-    takes_ema = optimize_fn is not None and 'ema' in inspect.signature(optimize_fn).parameters
+    sig = inspect.signature(optimize_fn).parameters
+    takes_ema = 'ema' in sig or any(q.kind == inspect.Parameter.VAR_KEYWORD for q in sig.values())
   except (TypeError, ValueError):
     takes_ema = False
   ctl = {'graph': None, 'eager_calls': 0, 'synced': False, 'graph_failed': False}
@@ -517,7 +518,7 @@ def get_step_fn(config, sde, train, optimize_fn=None):
     else:
       optimize_fn(state['optimizer'], model.parameters(), step=state['step'])
     state['step'] += 1
-    if not takes_ema:
+    if not takes_ema and state.get('ema') is not None:
       state['ema'].update(model.parameters())
 
   def _zero_grad(state):

@@ -312,13 +312,18 @@ class AttnBlock:
     h, st = ops.gn_norm_act(x, None, self.G, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), act=0)
     wqkv, bqkv = P.c_group(self.names_w), P.f_group(self.names_b)        # (3C, C), (3C,)
     qkv = ops.gemm_nt(h.view(npix, C), wqkv, bias=bqkv)                 # (npix, 3C)
-    # logits[b][i][j] = sum_c q[b,i,c] k[b,j,c]   (einsum 'bchw,bcij->bhwij')
-    logits = ops.gemm_nt(qkv, qkv[:, C:], out_dtype=torch.float32, M=L, N=L, K=C, lda=3 * C, ldb=3 * C, batch=B,
-                         sAb=L * 3 * C, sBb=L * 3 * C, sCb=L * L)
-    p = ops.softmax_fwd(logits, L, float(C) ** -0.5, x.dtype)           # (B, L, L)
-    del logits
-    o = ops.gemm_nn(p, qkv[:, 2 * C:], C, M=L, K=L, lda=L, ldb=3 * C, batch=B, sAb=L * L, sBb=L * 3 * C,
-                    sCb=L * C)                                          # (B, L, C)
+    if ops.attn_fused_ok(L, C, qkv.dtype):
+      # logits in tensor memory, probabilities in shared memory: one kernel (csrc/attn_tc.cu); p is only written
+      # when the backward pass will need it
+      o, p = ops.attn_fwd(qkv, B, L, C, float(C) ** -0.5, save_p=net.tape.enabled)
+    else:
+      # logits[b][i][j] = sum_c q[b,i,c] k[b,j,c]   (einsum 'bchw,bcij->bhwij')
+      logits = ops.gemm_nt(qkv, qkv[:, C:], out_dtype=torch.float32, M=L, N=L, K=C, lda=3 * C, ldb=3 * C, batch=B,
+                           sAb=L * 3 * C, sBb=L * 3 * C, sCb=L * L)
+      p = ops.softmax_fwd(logits, L, float(C) ** -0.5, x.dtype)           # (B, L, L)
+      del logits
+      o = ops.gemm_nn(p, qkv[:, 2 * C:], C, M=L, K=L, lda=L, ldb=3 * C, batch=B, sAb=L * L, sBb=L * 3 * C,
+                      sCb=L * C)                                          # (B, L, C)
     out = ops.gemm_nt(o.view(npix, C), P.c(pre + 'NIN_3.W'), bias=P.f(pre + 'NIN_3.b'), residual=x.view(npix, C),
                       alpha=self.scale).view(B, H, W, C)
     y = Act(out, net.tape)
@@ -598,30 +603,32 @@ class TimeEmbedding:
     self.next_idx = i + 2
 
   def fwd(self, net, time_cond):
+    """The two Linear layers of the embedding MLP run in fp32 on the master weights in every mode (the
+    sin / cos features of arguments up to 999 and what is computed from them must stay fp32; these are two
+    B x 512 x 512 GEMMs, 0.03 % of the step's flops); only the Dense_0 projections of all res-blocks - one
+    (B, 512) x (512, sum Cout) GEMM - run in the compute dtype."""
     m, P = net.m, net.m.P
     cd = m.compute_dtype
     if self.fourier:
       emb = ops.fourier_embedding(time_cond, P.f(self.w_name))
     else:
       emb = ops.timestep_embedding(time_cond, self.embed_dim)
-    emb_c = ops.cast(emb, cd) if cd != torch.float32 else emb
-    e0 = ops.gemm_nt(emb_c, P.c(self.l0 + 'weight'), out_dtype=torch.float32, bias=P.f(self.l0 + 'bias'))
+    e0 = ops.gemm_nt(emb, P.f(self.l0 + 'weight'), out_dtype=torch.float32, bias=P.f(self.l0 + 'bias'))
     a0 = ops.silu(e0)
-    a0_c = ops.cast(a0, cd) if cd != torch.float32 else a0
-    temb = ops.gemm_nt(a0_c, P.c(self.l1 + 'weight'), out_dtype=torch.float32, bias=P.f(self.l1 + 'bias'))
+    temb = ops.gemm_nt(a0, P.f(self.l1 + 'weight'), out_dtype=torch.float32, bias=P.f(self.l1 + 'bias'))
     at = ops.silu(temb)
     at_c = ops.cast(at, cd) if cd != torch.float32 else at
     wd, bd = P.c_region('dense_w').view(-1, self.td), P.f_region('dense_b')
     net.dense = ops.gemm_nt(at_c, wd, out_dtype=torch.float32, bias=bd)      # (B, sum Cout)
     if net.tape.enabled:
       net.d_dense = torch.zeros_like(net.dense)
-      net.temb_saved = (emb_c, e0, a0_c, temb, at_c)
+      net.temb_saved = (emb, e0, a0, temb, at_c)
 
   def bwd(self, net):
     m, P = net.m, net.m.P
     cd = m.compute_dtype
-    emb_c, e0, a0_c, temb, at_c = net.temb_saved
-    B = emb_c.shape[0]
+    emb, e0, a0, temb, at_c = net.temb_saved
+    B = emb.shape[0]
     nd = net.d_dense.shape[1]
     td = self.td
     dd = net.d_dense
@@ -636,13 +643,11 @@ class TimeEmbedding:
     d_at = ops.gemm_nn(dd_c, P.c_region('dense_w').view(nd, td), td, out_dtype=torch.float32)
     d_temb = ops.silu_bwd(temb, d_at)
     ops.colsum(d_temb, 1, B, td, P.g(self.l1 + 'bias'), accumulate=True)
-    d_temb_c = ops.cast(d_temb, cd) if cd != torch.float32 else d_temb
-    ops.gemm_tn(d_temb_c, a0_c, td, td, B, out=P.g(self.l1 + 'weight'), accumulate=True, split_k=1)
-    d_a0 = ops.gemm_nn(d_temb_c, P.c(self.l1 + 'weight'), td, out_dtype=torch.float32)
+    ops.gemm_tn(d_temb, a0, td, td, B, out=P.g(self.l1 + 'weight'), accumulate=True, split_k=1)
+    d_a0 = ops.gemm_nn(d_temb, P.f(self.l1 + 'weight'), td, out_dtype=torch.float32)
     d_e0 = ops.silu_bwd(e0, d_a0)
     ops.colsum(d_e0, 1, B, td, P.g(self.l0 + 'bias'), accumulate=True)
-    d_e0_c = ops.cast(d_e0, cd) if cd != torch.float32 else d_e0
-    ops.gemm_tn(d_e0_c, emb_c, td, self.embed_dim, B, out=P.g(self.l0 + 'weight'), accumulate=True, split_k=1)
+    ops.gemm_tn(d_e0, emb, td, self.embed_dim, B, out=P.g(self.l0 + 'weight'), accumulate=True, split_k=1)
 
 
 # ===================================================================================== parameter access

@@ -472,6 +472,22 @@ def softmax_bwd(p, dp, L, scale):
   return ds
 
 
+_ATTN_FUSED = os.environ.get('ST_ATTN_FUSED', '1') != '0'
+
+
+def attn_fused_ok(L, C, dtype):
+  """True when the one-kernel attention core (st_attn_fwd) runs this shape."""
+  return _ATTN_FUSED and dtype == torch.bfloat16 and bool(lib.st_attn_fwd_supported(int(L), int(C), BF16))
+
+
+def attn_fwd(qkv, B, L, C, scale, save_p):
+  """o = softmax(q k^T * scale) v from the packed (B*L, 3C) projections; returns (o (B, L, C), p (B, L, L) or None)."""
+  o = torch.empty((B, L, C), dtype=qkv.dtype, device=qkv.device)
+  p = torch.empty((B, L, L), dtype=qkv.dtype, device=qkv.device) if save_p else None
+  check(lib.st_attn_fwd(ptr(qkv), ptr(o), ptr(p), B, L, C, float(scale), stream()))
+  return o, p
+
+
 _FREQS = {}
 
 

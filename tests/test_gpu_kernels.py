@@ -613,8 +613,13 @@ def test_fused_adam_ema_matches_torch():
     acc.zero_()
     check(lib.st_sumsq(ops.ptr(g), n, ops.ptr(acc), ops.stream()))
     assert abs(acc.item() - (g.double() ** 2).sum().item()) < 1e-4 * acc.item()
-    check(lib.st_adam_ema(ops.ptr(p), ops.ptr(g), ops.ptr(m), ops.ptr(v), ops.ptr(ema), None, ops.ptr(p16), n, ops.ptr(acc),
-                          1.0, 1e-2, 0.9, 0.999, 1e-8, 0.0, 1 - 0.9 ** t, 1 - 0.999 ** t, d, ops.stream()))
+    if t % 2:     # step scalars by value ...
+      check(lib.st_adam_ema(ops.ptr(p), ops.ptr(g), ops.ptr(m), ops.ptr(v), ops.ptr(ema), None, ops.ptr(p16), n, ops.ptr(acc),
+                            1.0, 1e-2, 0.9, 0.999, 1e-8, 0.0, 1 - 0.9 ** t, 1 - 0.999 ** t, d, None, ops.stream()))
+    else:         # ... or from device memory (what a captured training graph replays with), by-value ones ignored
+      dyn = torch.tensor([1e-2, 1 - 0.9 ** t, 1 - 0.999 ** t, d], dtype=torch.float32, device=dev())
+      check(lib.st_adam_ema(ops.ptr(p), ops.ptr(g), ops.ptr(m), ops.ptr(v), ops.ptr(ema), None, ops.ptr(p16), n, ops.ptr(acc),
+                            1.0, 123., 0.9, 0.999, 1e-8, 0.0, 0., 0., 0., ops.ptr(dyn), ops.stream()))
     assert rel_l2(p, p_ref.detach()) < 1e-6
     assert rel_l2(ema, ema_ref) < 1e-6
     assert torch.equal(p16, p.to(torch.bfloat16))

@@ -36,8 +36,9 @@ def conv_shapes(B):
 
 def main():
   B = int(os.environ.get('GB_BATCH', '512'))
-  configs = [('v1', dict(ST_TC_VARIANT='1')), ('v2', dict(ST_TC_VARIANT='2', ST_TC_CLUSTER='1', ST_TC_MH='2')), ('v2 mh1', dict(ST_TC_VARIANT='2', ST_TC_CLUSTER='1', ST_TC_MH='1')),
-             ('hybrid', dict(ST_TC_VARIANT='0', ST_TC_CLUSTER='1', ST_TC_MH='2'))]
+  # single-CTA tcgen05.mma (round 1) against CTA pairs (cta_group::2), with and without programmatic dependent launch
+  configs = [('cg1', dict(ST_TC_CG='1')), ('cg2', dict(ST_TC_CG='2', ST_TC_CG2_MASK='3', ST_TC_PDL2='1')),
+             ('cg2 nopdl', dict(ST_TC_CG='2', ST_TC_CG2_MASK='3', ST_TC_PDL2='0'))]
   rows = []
   for name, H, C1, C2, Co, k in conv_shapes(B):
     Ci = C1 + C2
