@@ -381,10 +381,24 @@ def run_b200(args):
     if args.mode == 'sampler':
       sde_w = _sampler_sde(sde_lib, cfg, 6)          # short warm-up call (captures the graph, fills the allocator)
       sampling.get_sampling_fn(cfg, sde_w, (SB, 3, R, R), lambda v: v, cfg.sampling.truncation_time)(model)
+      fn(model)                                     # first full call captures this schedule's graph: untimed
       with ClockSampler(local) as clk_s:
-        fn(model)                                   # first full call captures this schedule's graph: untimed
-        ms_s = timed(lambda: fn(model), 1)
-      ms_s_e2e = timed(lambda: fn(model)[0].cpu(), 1)
+        # ONE timed call: CUDA events around sampling_fn(model) for `value`; the host clock around the same call plus the
+        # device->host copy of the samples for e2e (the prior draw on the CPU and its H2D copy are inside the call)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        xs, _ = fn(model)
+        e1.record()
+        xs = xs.cpu()
+        wall = time.perf_counter() - t0
+        barrier()
+        tms = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=dev)
+        if world > 1:
+          dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms_s, ms_s_e2e = tms[0].item(), tms[1].item()
+        assert torch.isfinite(xs).all(), 'non-finite samples'
     else:
       fn(model)
       ms_s = timed(lambda: fn(model), 1)

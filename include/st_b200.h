@@ -92,6 +92,13 @@ typedef struct st_gemm_args {
   const void* residual;   /* in_dtype, [b][m][n] with strides sRb, sRm or NULL */
   int64_t sRm, sRb;
   float alpha;
+  /* GroupNorm statistics of C as a by-product of the epilogue (optional; tcgen05 backend, bf16 C, rows = pixels of
+   * NHWC images of gn_hw pixels each): per block of R = min(gn_hw, 128) rows and per 4 adjacent channels, the sum and the
+   * sum of squares of the stored values -> gn_part[M / R][N / 4][2] (fp32).  *gn_rows_out (HOST int, optional) receives
+   * R when the launch emits them and 0 when it cannot (the caller then runs st_gn_stats).  st_gn_apply consumes them. */
+  float* gn_part;
+  int32_t gn_hw;
+  int32_t* gn_rows_out;
 } st_gemm_args;
 
 int st_gemm(const st_gemm_args* args, void* stream);
@@ -127,11 +134,14 @@ int st_gn_finalize(const float* part, int n_img, int splits, int G, int64_t coun
  * when non-NULL, else if p > 0 a counter-based RNG keyed by (seed, element index).  `keepbits` (optional,
  * n_img*hw*C/8 bytes) receives the drawn keep flags, one bit per element, for the backward kernels.
  * `part` != NULL (with `splits`, `count` = hw*(C/G), `eps`): the statistics are finalised inside the kernel from the
- * partial sums of st_gn_stats - no st_gn_finalize launch - and mean / rstd are OUTPUTS (kept for the backward). */
+ * partial sums of st_gn_stats - no st_gn_finalize launch - and mean / rstd are OUTPUTS (kept for the backward).
+ * `q1` != NULL (instead of `part`; with `qrows`, `count`, `eps`; `q2` for the second source): the statistics come from
+ * the per-(qrows rows, 4 channels) sums the GEMMs that produced x1 / x2 emitted (st_gemm_args.gn_part) - no pass
+ * over x for the statistics at all. */
 int st_gn_apply(const void* x1, const void* x2, int dtype, int n_img, int hw, int C1, int C2, int G,
                 const float* gamma, const float* beta, float* mean, float* rstd, int act,
                 float p_drop, uint64_t seed, const void* mask, uint8_t* keepbits, void* y, const float* part,
-                int splits, int64_t count, float eps, void* stream);
+                int splits, int64_t count, float eps, const float* q1, const float* q2, int qrows, void* stream);
 /* Device-resident 64-bit addend of the `seed` argument of every st_gn_apply / st_gn_fwd_fused launch that draws its own
  * dropout mask (NULL = none, the default): the kernel keys its generator with seed + *ptr.  A training step captured
  * in a CUDA graph bakes `seed` into the launch; the host advances *ptr between replays so that every step draws a

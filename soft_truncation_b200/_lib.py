@@ -29,6 +29,7 @@ class GemmArgs(ctypes.Structure):
       ('bias', c_p), ('rowbias', c_p), ('rows_per_rb', ctypes.c_int32), ('ld_rb', c_i64),
       ('residual', c_p), ('sRm', c_i64), ('sRb', c_i64),
       ('alpha', c_f),
+      ('gn_part', c_p), ('gn_hw', ctypes.c_int32), ('gn_rows_out', ctypes.POINTER(ctypes.c_int32)),
   ]
 
 
@@ -41,7 +42,7 @@ SIGNATURES = {
     'st_gn_stats': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p],
     'st_gn_finalize': [c_p, c_int, c_int, c_int, c_i64, c_f, c_p, c_p, c_p],
     'st_gn_apply': [c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f, c_u64, c_p,
-                    c_p, c_p, c_p, c_int, c_i64, c_f, c_p],
+                    c_p, c_p, c_p, c_int, c_i64, c_f, c_p, c_p, c_int, c_p],
     'st_gn_bwd_reduce': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f,
                          c_u64, c_p, c_p, c_int, c_p, c_p],
     'st_gn_bwd_params': [c_p, c_int, c_int, c_p, c_p, c_p],

@@ -48,6 +48,7 @@ extern "C" __attribute__((visibility("default"))) int st_gemm(const st_gemm_args
     ST_CHECK_ARG(a->split_k <= 1, "st_gemm: split_k needs accumulate");
   }
   ST_CHECK_ARG(!a->rowbias || a->rows_per_rb > 0, "st_gemm: rows_per_rb");
+  if (a->gn_rows_out) *a->gn_rows_out = 0;      // set by the tcgen05 backend when it emits GroupNorm partial sums
 
   int backend = a->backend;
   if (backend == ST_BACKEND_AUTO) {

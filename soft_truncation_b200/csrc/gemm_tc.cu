@@ -62,6 +62,10 @@ struct TcParams {
   int m_tiles, n_tiles;
   int epi_tma;            // epilogue writes the tile through shared memory with TMA stores (mapC / mapR are valid)
   int rb_rows;            // distinct rowbias rows (images) one tile spans (1..4) when epi_tma
+  // GroupNorm by-product (TMA epilogue, bf16 output, 256-column accumulators): per (gn_rows output rows, 4 channels) the
+  // sum and sum of squares of the STORED values -> gn_part[row / gn_rows][N / 4][2]; nullptr = off
+  float* gn_part;
+  int gn_rows;            // 16, 64 or 128: min(pixels per image, 128)
 };
 
 // ------------------------------------------------------------------------------------ kernel
@@ -303,6 +307,54 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
 //     its slice into every CTA of the cluster (L2 -> SM traffic for B drops by `cluster`),
 //   * weight gradients run transposed (A = shifted NHWC boxes MN-major, B = dY MN-major, C stored transposed) so
 //     that the big dimension taps*Cin is M and the dY tile is the multicast operand.
+// GroupNorm by-product of the TMA epilogue: column sums over a half-group's staged 128 x 128 bf16 tile (two SWIZZLE_128B
+// boxes of 64 columns), per 4-channel quad and per 128 / NP rows.  A warp owns 32 columns (4 swizzle chunks of one box);
+// lane = (row within an 8-row block) x (chunk): one LDS.128 per lane covers 8 rows x 64 bytes = every bank once per
+// wavefront (the swizzle spreads the 8 rows), 16 loads per lane for the tile, then three shuffles over the row lanes.
+template <int NP>
+__device__ __forceinline__ void gn_quad_pass(uint32_t region, int w4, int lane, float* part, long long qn, int gq, int grow0,
+                                             int M, bool col_ok) {
+  const uint32_t rs = (uint32_t)(lane >> 2);
+  const uint32_t c16 = (uint32_t)((w4 & 1) * 4 + (lane & 3));
+  const uint32_t addr0 = region + (uint32_t)((w4 >> 1) * 16384) + rs * 128u + ((c16 ^ rs) << 4);
+  float sm[NP][2], sq[NP][2];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) { sm[i][0] = sm[i][1] = sq[i][0] = sq[i][1] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    uint4 t;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(addr0 + (uint32_t)(i * 1024)));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.y));
+    const float2 c = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.z));
+    const float2 d = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.w));
+    constexpr int PER = 16 / NP;
+    const int k = i / PER;
+    sm[k][0] += (a.x + a.y) + (b.x + b.y);
+    sq[k][0] += fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(b.x, b.x, b.y * b.y)));
+    sm[k][1] += (c.x + c.y) + (d.x + d.y);
+    sq[k][1] += fmaf(c.x, c.x, fmaf(c.y, c.y, fmaf(d.x, d.x, d.y * d.y)));
+  }
+#pragma unroll
+  for (int k = 0; k < NP; ++k)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int o = 4; o <= 16; o <<= 1) {
+        sm[k][h] += __shfl_xor_sync(0xffffffffu, sm[k][h], o);
+        sq[k][h] += __shfl_xor_sync(0xffffffffu, sq[k][h], o);
+      }
+  if (rs == 0 && col_ok) {
+    constexpr int PR = 128 / NP;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const int row = grow0 + k * PR;
+      if (row < M)
+        *reinterpret_cast<float4*>(part + ((long long)(row / PR) * qn + gq) * 2) = make_float4(sm[k][0], sq[k][0], sm[k][1], sq[k][1]);
+    }
+  }
+}
+
 constexpr int NUM_THREADS2 = 352;     // warp 0 TMA (A operand), warp 1 MMA, warps 2..9 epilogue, warp 10 TMA (B operand)
 
 // MH = number of 128-row accumulators per CTA tile: the tile is (128*MH) x BN with MH*BN <= 256 TMEM columns per
@@ -791,6 +843,19 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
             }
             bulk_commit();
           }
+          if constexpr (TC == 256) {
+            if (p.gn_part && !f32) {
+              // GroupNorm statistics of the consumer as a by-product: sums over this half-group's 128 x 128 staged bf16
+              // values (what the store writes), per 4-channel quad and per gn_rows rows.
+              const int w4 = (warp - 2) & 3;
+              const bool col_ok = n0 + colbase + w4 * 32 + (lane & 3) * 8 < p.N;
+              const int gq = ((n0 + colbase) >> 2) + w4 * 8 + (lane & 3) * 2;
+              if (p.gn_rows == 128) gn_quad_pass<1>(region, w4, lane, p.gn_part, p.N >> 2, gq, m0 + rowbase, p.M, col_ok);
+              else if (p.gn_rows == 64) gn_quad_pass<2>(region, w4, lane, p.gn_part, p.N >> 2, gq, m0 + rowbase, p.M, col_ok);
+              else gn_quad_pass<8>(region, w4, lane, p.gn_part, p.N >> 2, gq, m0 + rowbase, p.M, col_ok);
+              named_bar(bar_id, 128);       // everyone has read the boxes before the leader lets them be refilled
+            }
+          }
         }
         if (res_mode && leader && st + n_clusters < total) {
           int m2, n2, b2, k2, nk2;
@@ -1203,7 +1268,9 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   int CG = 1;
   {
     const int want = env_int("ST_TC_CG", 2), mask = env_int("ST_TC_CG2_MASK", 3);
-    const bool big = (BN == 256 && MH == 1 && (mask & 1)) || (BN == 128 && MH == 2 && (mask & 2));
+    // bit 2: transposed weight gradients of <= 128-output-channel layers as 256 x 128 pair tiles (with ST_TC_WGRAD_NT=0)
+    const bool big = (BN == 256 && MH == 1 && (mask & 1)) || (BN == 128 && MH == 2 && (mask & 2)) ||
+                     (BN == 128 && MH == 1 && wgrad && (mask & 4));
     if (want == 2 && big && p.m_tiles >= 2) { CG = 2; cs = 2; }
   }
   p.cluster = cs;
@@ -1295,12 +1362,23 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
       p.rb_rows = rb_rows;
     }
   }
+  // ---------------- GroupNorm partial sums as a by-product (see TcParams::gn_part)
+  if (a->gn_rows_out) *a->gn_rows_out = 0;
+  if (a->gn_part && a->gn_hw >= 16 && p.epi_tma && p.out_bf16 && BN * MH == 256 && p.split_k == 1 && a->batch == 1 &&
+      a->N % 128 == 0 && a->M % a->gn_hw == 0 && (a->gn_hw & (a->gn_hw - 1)) == 0 && !a->accumulate &&
+      env_int("ST_TC_GN_STATS", 1) == 1) {
+    p.gn_part = a->gn_part;
+    p.gn_rows = a->gn_hw < 128 ? a->gn_hw : 128;
+    if (p.gn_rows != 16 && p.gn_rows != 64 && p.gn_rows != 128) p.gn_part = nullptr;
+    else if (a->gn_rows_out) *a->gn_rows_out = p.gn_rows;
+  }
 
   const int m_groups = (p.m_tiles + cs - 1) / cs;
   const long long total = (long long)p.batch * p.split_k * p.n_tiles * m_groups;
   ST_CHECK_ARG(total < (1LL << 30), "st_gemm(tc2): too many tiles");
   if (CG == 2 && BN == 256) return launch2<256, 1, 4, 2>(maps, p, (int)total, stream);
-  if (CG == 2) return launch2<128, 2, 4, 2>(maps, p, (int)total, stream);
+  if (CG == 2 && MH == 2) return launch2<128, 2, 4, 2>(maps, p, (int)total, stream);
+  if (CG == 2) return launch2<128, 1, 6, 2>(maps, p, (int)total, stream);
   if (BN == 256) return launch2<256, 1, 3, 1>(maps, p, (int)total, stream);
   if (BN == 128 && MH == 2) return launch2<128, 2, 3, 1>(maps, p, (int)total, stream);
   if (BN == 128) return launch2<128, 1, 5, 1>(maps, p, (int)total, stream);

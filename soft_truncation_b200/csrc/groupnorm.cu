@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(Src2<T> s, int hw, int
                                                           const T* mask, uint8_t* keepbits, T* y,
                                                           const float* __restrict__ part, int splits, double inv_count,
                                                           float eps, float* mean_out, float* rstd_out,
-                                                          const uint64_t* __restrict__ seed_off) {
+                                                          const uint64_t* __restrict__ seed_off,
+                                                          const float* __restrict__ q1, const float* __restrict__ q2, int qrows) {
   extern __shared__ __align__(16) uint8_t gsm[];
   pdl_wait();
   pdl_trigger();
@@ -91,12 +92,26 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(Src2<T> s, int hw, int
   const int n = blockIdx.y;
   const Walk w(Ct, n, hw, blockIdx.x, gridDim.x);
   ChanConst k;
-  if (part) {
-    // statistics straight from the partial sums of st_gn_stats (same arithmetic as gn_finalize_kernel); the first
-    // chunk of every image publishes mean / rstd for the backward passes
+  if (part || q1) {
+    // statistics straight from the partial sums of st_gn_stats (same arithmetic as gn_finalize_kernel) or from the
+    // per-(qrows rows, 4 channels) sums the producing GEMMs emitted (st_gemm gn_part; one buffer per concatenated
+    // source); the first chunk of every image publishes mean / rstd for the backward passes
     __shared__ float s_mean[64], s_rstd[64];
     if (threadIdx.x < G) {
       double a = 0., b = 0.;
+      if (q1) {
+        const int nch = hw / qrows;
+        for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; c += 4) {
+          const bool first = c < s.C1;
+          const float2* q = reinterpret_cast<const float2*>(first ? q1 : q2);
+          const int qn = (first ? s.C1 : s.C2) >> 2, cc = (first ? c : c - s.C1) >> 2;
+          for (int ch = 0; ch < nch; ++ch) {
+            const float2 v = q[((long long)n * nch + ch) * qn + cc];
+            a += (double)v.x;
+            b += (double)v.y;
+          }
+        }
+      } else
       for (int sp = 0; sp < splits; ++sp) {
         const float* o = part + (((long long)n * splits + sp) * G + threadIdx.x) * 2;
         a += (double)o[0];
@@ -255,10 +270,12 @@ extern "C" __attribute__((visibility("default"))) int st_gn_finalize(const float
 extern "C" __attribute__((visibility("default"))) int st_gn_apply(const void* x1, const void* x2, int dtype, int n_img, int hw, int C1, int C2, int G,
                            const float* gamma, const float* beta, float* mean, float* rstd, int act,
                            float p_drop, uint64_t seed, const void* mask, uint8_t* keepbits, void* y, const float* part, int splits,
-                           int64_t count, float eps, void* stream) {
+                           int64_t count, float eps, const float* q1, const float* q2, int qrows, void* stream) {
   if (int e = check_geom(C1, C2, G)) return e;
   ST_CHECK_ARG(n_img <= 65535, "st_gn_apply: more than 65535 images");
   ST_CHECK_ARG(!part || (splits >= 1 && count > 0 && mean && rstd), "st_gn_apply: partial sums need splits, count and mean/rstd outputs");
+  ST_CHECK_ARG(!q1 || (!part && qrows > 0 && hw % qrows == 0 && count > 0 && mean && rstd && (C2 == 0 || q2) && C1 % 4 == 0),
+               "st_gn_apply: quad sums need qrows dividing hw, count, mean/rstd outputs and one buffer per source");
   const int V = (C1 + C2) / 8;
   const int drop = mask ? DROP_SLOW : (p_drop > 0.f ? DROP_FAST : DROP_NONE);
   int rc = 0;
@@ -272,7 +289,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_apply(const void* x1
       if (!smem_ok) { if (!allow_smem(gn_apply_kernel<T, ACT, DROP>, smem)) { rc = ST_ERR_CUDA; return; } smem_ok = true; }
       st_launch(gn_apply_kernel<T, ACT, DROP>, dim3(chunks_for(n_img, hw, V), n_img), dim3(256), smem, (cudaStream_t)stream,
           s, hw, G, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, (T*)y, part, splits,
-          part ? 1.0 / (double)count : 0.0, eps, mean, rstd, st_seed_offset());
+          (part || q1) ? 1.0 / (double)count : 0.0, eps, mean, rstd, st_seed_offset(), q1, q2, qrows);
     });
   });
   if (rc) return rc;

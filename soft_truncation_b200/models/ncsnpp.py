@@ -78,11 +78,12 @@ class Tape:
 
 
 class Act:
-  """An activation tensor plus its tape id."""
-  __slots__ = ('t', 'id')
+  """An activation tensor plus its tape id and, when the GEMM that produced it emitted them, its GroupNorm partial
+  sums (ops.Quads): the next GroupNorm then needs no statistics pass over the tensor."""
+  __slots__ = ('t', 'id', 'q')
 
-  def __init__(self, t, tape):
-    self.t, self.id = t, tape.new_id()
+  def __init__(self, t, tape, q=None):
+    self.t, self.id, self.q = t, tape.new_id(), q
 
 
 class NetCtx:
@@ -188,14 +189,15 @@ class ResBlock:
     x1, x2 = xa.t, (xb.t if xb is not None else None)
     if x2 is not None and (self.up or self.down) and self.fir:
       raise NotImplementedError('FIR resampling of a concatenated input')
-    a0, st0 = ops.gn_norm_act(x1, x2, self.G0, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), act=1)
+    a0, st0 = ops.gn_norm_act(x1, x2, self.G0, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), act=1,
+                              quads=(xa.q, xb.q if xb is not None else None))
     xr = None
     if self.up or self.down:
       a0 = self._resample(net, a0, None)
       xr = self._resample(net, x1, x2)
     B, H, W, _ = a0.shape
-    h1 = ops.conv_fwd(a0, P.c(pre + 'Conv_0.weight'), self.cout, bias=P.f(pre + 'Conv_0.bias'),
-                      rowbias=net.dense[:, self.dense_off:], rowbias_ld=net.dense.shape[1])
+    h1, q_h1 = ops.conv_fwd(a0, P.c(pre + 'Conv_0.weight'), self.cout, bias=P.f(pre + 'Conv_0.bias'),
+                            rowbias=net.dense[:, self.dense_off:], rowbias_ld=net.dense.shape[1], want_quads=True)
     p_drop, seed, mask, keepbits = 0., 0, None, None
     if net.train and m.dropout > 0:
       mask = m._mask_for(self.idx, h1)
@@ -204,7 +206,7 @@ class ResBlock:
         if net.tape.enabled:      # keep flags (1 bit per element) for the two backward passes
           keepbits = torch.empty(h1.numel() // 8, dtype=torch.uint8, device=h1.device)
     a1, st1 = ops.gn_norm_act(h1, None, self.G1, P.f(pre + 'GroupNorm_1.weight'), P.f(pre + 'GroupNorm_1.bias'), act=1,
-                              p_drop=p_drop, seed=seed, mask=mask, keepbits=keepbits)
+                              p_drop=p_drop, seed=seed, mask=mask, keepbits=keepbits, quads=(q_h1, None))
     if self.shortcut:
       if xr is not None:
         sc = ops.conv_fwd(xr, P.c(pre + 'Conv_2.weight'), self.cout, 1, 1, bias=P.f(pre + 'Conv_2.bias'))
@@ -212,9 +214,9 @@ class ResBlock:
         sc = ops.conv_fwd(x1, P.c(pre + 'Conv_2.weight'), self.cout, 1, 1, x2=x2, bias=P.f(pre + 'Conv_2.bias'))
     else:
       sc = x1
-    out = ops.conv_fwd(a1, P.c(pre + 'Conv_1.weight'), self.cout, bias=P.f(pre + 'Conv_1.bias'), residual=sc,
-                       alpha=self.scale)
-    y = Act(out, net.tape)
+    out, q_out = ops.conv_fwd(a1, P.c(pre + 'Conv_1.weight'), self.cout, bias=P.f(pre + 'Conv_1.bias'), residual=sc,
+                              alpha=self.scale, want_quads=True)
+    y = Act(out, net.tape, q_out)
     if net.tape.enabled:
       saved = (x1, x2, st0, a0, xr, h1, st1, a1, p_drop, seed, mask, keepbits)
       net.tape.record(lambda g, acc, gs: self.bwd(net, saved, g, acc, gs),
@@ -309,7 +311,8 @@ class AttnBlock:
     x = xa.t
     B, H, W, _ = x.shape
     L, npix = H * W, B * H * W
-    h, st = ops.gn_norm_act(x, None, self.G, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), act=0)
+    h, st = ops.gn_norm_act(x, None, self.G, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), act=0,
+                            quads=(xa.q, None))
     wqkv, bqkv = P.c_group(self.names_w), P.f_group(self.names_b)        # (3C, C), (3C,)
     qkv = ops.gemm_nt(h.view(npix, C), wqkv, bias=bqkv)                 # (npix, 3C)
     if ops.attn_fused_ok(L, C, qkv.dtype):
@@ -324,9 +327,10 @@ class AttnBlock:
       del logits
       o = ops.gemm_nn(p, qkv[:, 2 * C:], C, M=L, K=L, lda=L, ldb=3 * C, batch=B, sAb=L * L, sBb=L * 3 * C,
                       sCb=L * C)                                          # (B, L, C)
-    out = ops.gemm_nt(o.view(npix, C), P.c(pre + 'NIN_3.W'), bias=P.f(pre + 'NIN_3.b'), residual=x.view(npix, C),
-                      alpha=self.scale).view(B, H, W, C)
-    y = Act(out, net.tape)
+    out, q_out = ops.gemm_nt(o.view(npix, C), P.c(pre + 'NIN_3.W'), bias=P.f(pre + 'NIN_3.b'), residual=x.view(npix, C),
+                             alpha=self.scale, quads_hw=L)
+    out = out.view(B, H, W, C)
+    y = Act(out, net.tape, q_out)
     if net.tape.enabled:
       saved = (x, st, h, qkv, p, o)
       net.tape.record(lambda g, acc, gs: self.bwd(net, saved, g, acc, gs), (xa.id,), y.id)
@@ -390,8 +394,9 @@ class ConvBlock:
 
   def fwd(self, net, xa, record_tap=True):
     P = net.m.P
-    out = ops.conv_fwd(xa.t, P.c(self.pre + 'weight'), self.cout, self.k, self.k, bias=P.f(self.pre + 'bias'))
-    y = Act(out, net.tape)
+    out, q_out = ops.conv_fwd(xa.t, P.c(self.pre + 'weight'), self.cout, self.k, self.k, bias=P.f(self.pre + 'bias'),
+                              want_quads=True)
+    y = Act(out, net.tape, q_out)
     if net.tape.enabled:
       x = xa.t
       net.tape.record(lambda g, acc, gs: self.bwd(net, x, g, acc, need_dx=net.need_dx or not self.is_input, gs=gs),
@@ -429,7 +434,7 @@ class NormActConv:
     """`res`: optional Act added to the output (the up-sampled output pyramid, ncsnpp.py:391-396)."""
     P = net.m.P
     x = xa.t
-    a, st = ops.gn_norm_act(x, None, self.G, P.f(self.pg + 'weight'), P.f(self.pg + 'bias'), act=1)
+    a, st = ops.gn_norm_act(x, None, self.G, P.f(self.pg + 'weight'), P.f(self.pg + 'bias'), act=1, quads=(xa.q, None))
     out = ops.conv_fwd(a, P.c(self.conv.pre + 'weight'), self.conv.cout, bias=P.f(self.conv.pre + 'bias'),
                        residual=res.t if res is not None else None)
     y = Act(out, net.tape)
@@ -502,8 +507,9 @@ class CombineBlock:
 
   def fwd(self, net, pyr, ha):
     P, c = net.m.P, self.conv
-    out = ops.conv_fwd(pyr.t, P.c(c.pre + 'weight'), c.cout, 1, 1, bias=P.f(c.pre + 'bias'), residual=ha.t)
-    y = Act(out, net.tape)
+    out, q_out = ops.conv_fwd(pyr.t, P.c(c.pre + 'weight'), c.cout, 1, 1, bias=P.f(c.pre + 'bias'), residual=ha.t,
+                              want_quads=True)
+    y = Act(out, net.tape, q_out)
     if net.tape.enabled:
       x = pyr.t
       net.tape.record(lambda g, acc, gs: self.bwd(net, x, g, acc, gs), (pyr.id, ha.id), y.id)
@@ -540,9 +546,10 @@ class PyramidDownConv:
     B, H, W, C = x.shape
     y = ops.upfirdn2d_nhwc(x, m._fir_down, pad=(2, 2)) if self.fir else x
     cols = ops.im2col(y, 3, 3, 2, 0, H // 2, W // 2)
-    out = ops.gemm_nt(cols, P.c(self.pre + 'weight'), bias=P.f(self.pre + 'bias'),
-                      residual=ha.t.view(-1, self.cout), alpha=self.scale).view(B, H // 2, W // 2, self.cout)
-    o = Act(out, net.tape)
+    out, q_out = ops.gemm_nt(cols, P.c(self.pre + 'weight'), bias=P.f(self.pre + 'bias'),
+                             residual=ha.t.view(-1, self.cout), alpha=self.scale, quads_hw=(H // 2) * (W // 2))
+    o = Act(out.view(B, H // 2, W // 2, self.cout), net.tape, q_out)
+    out = o.t
     if net.tape.enabled:
       net.tape.record(lambda g, acc, gs: self.bwd(net, (cols, x.shape, y.shape), g, acc, gs), (pyr.id, ha.id), o.id)
     if net.taps is not None:
@@ -595,6 +602,7 @@ class TimeEmbedding:
       # MLP (and every Dense_0 input) is 4*embedding_dim wide (reference models/ncsnpp.py:86-91,135,279-283)
       self.embed_dim = m.embedding_dim if getattr(m, 'lsgm', False) else nf
     td = self.td = model.temb_dim
+    self.fp32 = bool(getattr(m, 'temb_fp32', False))
     self.l0, self.l1 = f'all_modules.{i}.', f'all_modules.{i + 1}.'
     model._add_param(self.l0 + 'weight', (td, self.embed_dim), 'linear', init=init_conv(1.))
     model._add_param(self.l0 + 'bias', (td,), init=init_zeros)
@@ -603,32 +611,37 @@ class TimeEmbedding:
     self.next_idx = i + 2
 
   def fwd(self, net, time_cond):
-    """The two Linear layers of the embedding MLP run in fp32 on the master weights in every mode (the
-    sin / cos features of arguments up to 999 and what is computed from them must stay fp32; these are two
-    B x 512 x 512 GEMMs, 0.03 % of the step's flops); only the Dense_0 projections of all res-blocks - one
-    (B, 512) x (512, sum Cout) GEMM - run in the compute dtype."""
+    """Embedding features (sin / cos of arguments up to 999) are always computed in fp32.  The two Linear
+    layers of the MLP run in the compute dtype on the tensor cores by default; `model.temb_fp32 = True` keeps them in
+    fp32 on the master weights instead (five B x 512 x 512 fp32-FMA GEMMs per step, +0.3 ms at B = 512: measured to make
+    no difference to the bf16 gradient error, which is dominated by the 55 blocks behind them)."""
     m, P = net.m, net.m.P
     cd = m.compute_dtype
+    f32 = cd == torch.float32 or self.fp32
     if self.fourier:
       emb = ops.fourier_embedding(time_cond, P.f(self.w_name))
     else:
       emb = ops.timestep_embedding(time_cond, self.embed_dim)
-    e0 = ops.gemm_nt(emb, P.f(self.l0 + 'weight'), out_dtype=torch.float32, bias=P.f(self.l0 + 'bias'))
+    W = P.f if f32 else P.c
+    emb_c = emb if f32 else ops.cast(emb, cd)
+    e0 = ops.gemm_nt(emb_c, W(self.l0 + 'weight'), out_dtype=torch.float32, bias=P.f(self.l0 + 'bias'))
     a0 = ops.silu(e0)
-    temb = ops.gemm_nt(a0, P.f(self.l1 + 'weight'), out_dtype=torch.float32, bias=P.f(self.l1 + 'bias'))
+    a0_c = a0 if f32 else ops.cast(a0, cd)
+    temb = ops.gemm_nt(a0_c, W(self.l1 + 'weight'), out_dtype=torch.float32, bias=P.f(self.l1 + 'bias'))
     at = ops.silu(temb)
     at_c = ops.cast(at, cd) if cd != torch.float32 else at
     wd, bd = P.c_region('dense_w').view(-1, self.td), P.f_region('dense_b')
     net.dense = ops.gemm_nt(at_c, wd, out_dtype=torch.float32, bias=bd)      # (B, sum Cout)
     if net.tape.enabled:
       net.d_dense = torch.zeros_like(net.dense)
-      net.temb_saved = (emb, e0, a0, temb, at_c)
+      net.temb_saved = (emb_c, e0, a0_c, temb, at_c)
 
   def bwd(self, net):
     m, P = net.m, net.m.P
     cd = m.compute_dtype
-    emb, e0, a0, temb, at_c = net.temb_saved
-    B = emb.shape[0]
+    f32 = cd == torch.float32 or self.fp32
+    emb_c, e0, a0_c, temb, at_c = net.temb_saved
+    B = emb_c.shape[0]
     nd = net.d_dense.shape[1]
     td = self.td
     dd = net.d_dense
@@ -643,11 +656,14 @@ class TimeEmbedding:
     d_at = ops.gemm_nn(dd_c, P.c_region('dense_w').view(nd, td), td, out_dtype=torch.float32)
     d_temb = ops.silu_bwd(temb, d_at)
     ops.colsum(d_temb, 1, B, td, P.g(self.l1 + 'bias'), accumulate=True)
-    ops.gemm_tn(d_temb, a0, td, td, B, out=P.g(self.l1 + 'weight'), accumulate=True, split_k=1)
-    d_a0 = ops.gemm_nn(d_temb, P.f(self.l1 + 'weight'), td, out_dtype=torch.float32)
+    d_temb_c = d_temb if f32 else ops.cast(d_temb, cd)
+    W = P.f if f32 else P.c
+    ops.gemm_tn(d_temb_c, a0_c, td, td, B, out=P.g(self.l1 + 'weight'), accumulate=True, split_k=1)
+    d_a0 = ops.gemm_nn(d_temb_c, W(self.l1 + 'weight'), td, out_dtype=torch.float32)
     d_e0 = ops.silu_bwd(e0, d_a0)
     ops.colsum(d_e0, 1, B, td, P.g(self.l0 + 'bias'), accumulate=True)
-    ops.gemm_tn(d_e0, emb, td, self.embed_dim, B, out=P.g(self.l0 + 'weight'), accumulate=True, split_k=1)
+    d_e0_c = d_e0 if f32 else ops.cast(d_e0, cd)
+    ops.gemm_tn(d_e0_c, emb_c, td, self.embed_dim, B, out=P.g(self.l0 + 'weight'), accumulate=True, split_k=1)
 
 
 # ===================================================================================== parameter access

@@ -57,6 +57,31 @@ def _gemm(**kw):
   check(lib.st_gemm(ctypes.byref(a), stream()))
 
 
+# GroupNorm statistics as a by-product of the GEMM that produces a tensor (st_gemm_args.gn_part): `Quads` travels with
+# the activation; gn_norm_act consumes it instead of reading the tensor for its statistics.  ST_GN_QUADS=0 turns it off.
+GN_QUADS = os.environ.get('ST_GN_QUADS', '1') != '0'
+
+
+class Quads:
+  """Per-(rows block, 4 channels) sum / sum of squares of an NHWC tensor: `t` fp32 (M // rows, C // 4, 2)."""
+  __slots__ = ('t', 'rows')
+
+  def __init__(self, t, rows):
+    self.t, self.rows = t, rows
+
+
+def _quads_request(kw, out, hw):
+  """Adds the gn_part request to a GEMM call; returns a closure that yields the Quads (or None) after the call."""
+  if not (GN_QUADS and out.dtype == torch.bfloat16 and hw >= 16):
+    return lambda: None
+  M, N = kw['M'], kw['N']
+  rows = min(hw, 128)
+  part = torch.empty((M // rows, max(N // 4, 1), 2), dtype=torch.float32, device=out.device)
+  got = ctypes.c_int32(0)
+  kw.update(gn_part=part, gn_hw=hw, gn_rows_out=ctypes.pointer(got))
+  return lambda: Quads(part, got.value) if got.value == rows else None
+
+
 def _split_k(M, N, K):
   """Split the reduction so that a weight-gradient GEMM (few output tiles, huge K) fills the GPU."""
   tiles = ((M + 127) // 128) * ((N + 127) // 128)
@@ -65,20 +90,23 @@ def _split_k(M, N, K):
 
 
 def conv_fwd(x, w, cout, kh=3, kw=3, x2=None, bias=None, rowbias=None, rowbias_ld=0, residual=None, alpha=1.0,
-             out_dtype=None, out=None):
+             out_dtype=None, out=None, want_quads=False):
   """'same' convolution of NHWC x (optionally channel-concatenated with x2) with packed weights
-  w[cout][kh*kw][cin] (contiguous, same dtype as x).  rowbias: fp32 [B][rowbias_ld] slice added per image."""
+  w[cout][kh*kw][cin] (contiguous, same dtype as x).  rowbias: fp32 [B][rowbias_ld] slice added per image.
+  want_quads: returns (out, Quads | None) - the GroupNorm partial sums of `out` emitted by the epilogue."""
   B, H, W, C1 = x.shape
   C2 = 0 if x2 is None else x2.shape[3]
   K = kh * kw * (C1 + C2)
   od = out_dtype or x.dtype
   if out is None:
     out = torch.empty((B, H, W, cout), dtype=od, device=x.device)
-  _gemm(a_mode=OP_GATHER, b_mode=OP_STRIDED, in_dtype=dt(x), out_dtype=_DT[od], M=B * H * W, N=cout, K=K,
-        A=x, A2=x2, B=w, C=out, sBn=K, sBk=1, sCm=cout, n_img=B, H=H, W=W, C1=C1, C2=C2, kh=kh, kw=kw,
-        bias=bias, rowbias=rowbias, rows_per_rb=H * W, ld_rb=rowbias_ld, residual=residual, sRm=cout,
-        alpha=alpha)
-  return out
+  kwargs = dict(a_mode=OP_GATHER, b_mode=OP_STRIDED, in_dtype=dt(x), out_dtype=_DT[od], M=B * H * W, N=cout, K=K,
+                A=x, A2=x2, B=w, C=out, sBn=K, sBk=1, sCm=cout, n_img=B, H=H, W=W, C1=C1, C2=C2, kh=kh, kw=kw,
+                bias=bias, rowbias=rowbias, rows_per_rb=H * W, ld_rb=rowbias_ld, residual=residual, sRm=cout,
+                alpha=alpha)
+  q = _quads_request(kwargs, out, H * W) if want_quads else None
+  _gemm(**kwargs)
+  return (out, q()) if want_quads else out
 
 
 def conv_dgrad(dy, w, cin, kh=3, kw=3, alpha=1.0, out=None):
@@ -106,9 +134,10 @@ def conv_wgrad(dy, x, dw, kh=3, kw=3, x2=None, alpha=1.0):
 
 
 def gemm_nt(a, b, out=None, out_dtype=None, bias=None, residual=None, alpha=1.0, lda=None, ldb=None, ldc=None,
-            M=None, N=None, K=None, batch=1, sAb=0, sBb=0, sCb=0, sRb=0, ldr=None):
+            M=None, N=None, K=None, batch=1, sAb=0, sBb=0, sCb=0, sRb=0, ldr=None, quads_hw=0):
   """C[m][n] = alpha*(sum_k a[m][k] b[n][k] + bias[n] + residual[m][n]); a, b row-major with leading
-  dimensions lda/ldb (K contiguous)."""
+  dimensions lda/ldb (K contiguous).  quads_hw > 0 (rows are pixels of images of quads_hw pixels): returns
+  (C, Quads | None) with the GroupNorm partial sums of C emitted by the epilogue."""
   M = M if M is not None else a.shape[-2]
   K = K if K is not None else a.shape[-1]
   N = N if N is not None else b.shape[-2]
@@ -116,9 +145,13 @@ def gemm_nt(a, b, out=None, out_dtype=None, bias=None, residual=None, alpha=1.0,
   if out is None:
     out = torch.empty((M, N) if batch == 1 else (batch, M, N), dtype=od, device=a.device)
   ldc = ldc or N
-  _gemm(a_mode=OP_STRIDED, b_mode=OP_STRIDED, in_dtype=dt(a), out_dtype=dt(out), M=M, N=N, K=K, batch=batch, A=a,
-        B=b, C=out, sAm=lda or K, sAk=1, sAb=sAb, sBn=ldb or K, sBk=1, sBb=sBb, sCm=ldc, sCb=sCb, bias=bias,
-        residual=residual, sRm=ldr or ldc, sRb=sRb, alpha=alpha)
+  kwargs = dict(a_mode=OP_STRIDED, b_mode=OP_STRIDED, in_dtype=dt(a), out_dtype=dt(out), M=M, N=N, K=K, batch=batch, A=a,
+                B=b, C=out, sAm=lda or K, sAk=1, sAb=sAb, sBn=ldb or K, sBk=1, sBb=sBb, sCm=ldc, sCb=sCb, bias=bias,
+                residual=residual, sRm=ldr or ldc, sRb=sRb, alpha=alpha)
+  q = _quads_request(kwargs, out, quads_hw) if (quads_hw and batch == 1 and ldc == N) else None
+  _gemm(**kwargs)
+  if quads_hw:
+    return out, (q() if q is not None else None)
   return out
 
 
@@ -205,27 +238,43 @@ def gn_stats(x, x2, G, eps=1e-6, finalize=True):
   return GnStats(stats)
 
 
-def gn_apply(x, x2, G, gamma, beta, stats, act, p_drop=0., seed=0, mask=None, keepbits=None):
-  """`keepbits`: optional uint8 tensor (B*H*W*C/8 bytes) that receives the dropout keep flags drawn by the kernel."""
+def gn_apply(x, x2, G, gamma, beta, stats, act, p_drop=0., seed=0, mask=None, keepbits=None, quads=None, eps=1e-6):
+  """`keepbits`: optional uint8 tensor (B*H*W*C/8 bytes) that receives the dropout keep flags drawn by the kernel.
+  `quads` = (Quads of x, Quads of x2 | None): the statistics are finalised inside the kernel from the sums the
+  producing GEMMs emitted (`stats` is then the (2, B, G) tensor that receives mean / rstd)."""
   B, H, W, C1 = x.shape
   C2 = 0 if x2 is None else x2.shape[3]
   y = torch.empty((B, H, W, C1 + C2), dtype=x.dtype, device=x.device)
   pending = isinstance(stats, GnStats) and stats.part is not None
   t = stats.t if isinstance(stats, GnStats) else stats
+  q1 = q2 = None
+  qrows, count = 0, stats.count if pending else 0
+  if quads is not None:
+    q1, q2, qrows = quads[0].t, (quads[1].t if x2 is not None else None), quads[0].rows
+    count = H * W * ((C1 + C2) // G)
   check(lib.st_gn_apply(ptr(x), ptr(x2), dt(x), B, H * W, C1, C2, G, ptr(gamma), ptr(beta), ptr(t[0]),
                         ptr(t[1]), int(act), float(p_drop), int(seed), ptr(mask), ptr(keepbits), ptr(y),
                         ptr(stats.part) if pending else None, stats.splits if pending else 0,
-                        stats.count if pending else 0, float(stats.eps) if pending else 0., stream()))
+                        count, float(stats.eps) if pending else float(eps), ptr(q1), ptr(q2), int(qrows), stream()))
   if pending:
     stats.part = None          # finalised by the kernel
   return y
 
 
-def gn_norm_act(x, x2, G, gamma, beta, act, p_drop=0., seed=0, mask=None, keepbits=None, eps=1e-6, fused_chunks=None):
-  """GroupNorm (+SiLU, +dropout) forward: returns (y, GnStats).  One cluster launch with the image resident in shared
-  memory when it fits (st_gn_fwd_fused), else st_gn_stats followed by st_gn_apply (which finalises the statistics)."""
+def gn_norm_act(x, x2, G, gamma, beta, act, p_drop=0., seed=0, mask=None, keepbits=None, eps=1e-6, fused_chunks=None,
+                quads=None):
+  """GroupNorm (+SiLU, +dropout) forward: returns (y, GnStats).  `quads` = (Quads | None of x, of x2): when every source
+  carries the partial sums its producing GEMM emitted, ONE streaming apply launch (1 read + 1 write at copy speed, no
+  statistics pass).  Otherwise one cluster launch with the image resident in shared memory when it fits
+  (st_gn_fwd_fused), else st_gn_stats followed by st_gn_apply (which finalises the statistics)."""
   B, H, W, C1 = x.shape
   C2 = 0 if x2 is None else x2.shape[3]
+  if (quads is not None and fused_chunks is None and quads[0] is not None and (x2 is None or quads[1] is not None)
+      and (x2 is None or quads[1].rows == quads[0].rows) and (H * W) % quads[0].rows == 0):
+    stats = torch.empty((2, B, G), dtype=torch.float32, device=x.device)
+    y = gn_apply(x, x2, G, gamma, beta, stats, act, p_drop=p_drop, seed=seed, mask=mask, keepbits=keepbits,
+                 quads=quads, eps=eps)
+    return y, GnStats(stats)
   if fused_chunks is not None:
     fc = int(fused_chunks)
   elif p_drop > 0. and mask is None and not _GN_FWD_FUSED_DROP:

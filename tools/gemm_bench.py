@@ -37,8 +37,8 @@ def conv_shapes(B):
 def main():
   B = int(os.environ.get('GB_BATCH', '512'))
   # single-CTA tcgen05.mma (round 1) against CTA pairs (cta_group::2), with and without programmatic dependent launch
-  configs = [('cg1', dict(ST_TC_CG='1')), ('cg2', dict(ST_TC_CG='2', ST_TC_CG2_MASK='3', ST_TC_PDL2='1')),
-             ('cg2 nopdl', dict(ST_TC_CG='2', ST_TC_CG2_MASK='3', ST_TC_PDL2='0'))]
+  configs = [('cg1', dict(ST_TC_CG='1', ST_TC_WGRAD_NT='1')), ('cg2', dict(ST_TC_CG='2', ST_TC_CG2_MASK='3', ST_TC_PDL2='1', ST_TC_WGRAD_NT='1')),
+             ('cg2 wgrad-pair', dict(ST_TC_CG='2', ST_TC_CG2_MASK='7', ST_TC_PDL2='1', ST_TC_WGRAD_NT='0'))]
   rows = []
   for name, H, C1, C2, Co, k in conv_shapes(B):
     Ci = C1 + C2
