@@ -368,7 +368,14 @@ constexpr int NUM_THREADS2 = 352;     // warp 0 TMA (A operand), warp 1 MMA, war
 // Protocol: both CTAs' producers arm and signal the LEADER's full barrier (4 arrivals + the bytes of both CTAs); the
 // leader's MMA thread issues for the pair and commits with .multicast::cluster to the empty / accumulator-full
 // barriers of both CTAs; every epilogue warp of the pair arrives on the leader's accumulator-empty barrier.
-template <int BN, int MH, int STAGES, int CG>
+//
+// HALO (3x3 convolutions whose row tile lies inside one image and spans >= 4 image rows; CTA pairs only): the three
+// vertical taps (dy = -1, 0, +1) of one (dx, channel block) read the SAME pixels shifted by whole image rows, so the
+// producer loads ONE box of (tile rows + 2) image rows and the tensor core reads the three taps from it through
+// descriptor start offsets of dy * W * 128 bytes (a multiple of the 1024-byte swizzle period for W >= 8): the A operand
+// costs (rows + 2) / (3 rows) of the bytes (1/2 at 32x32, 3/8 at 16x16) in shared-memory writes and L2 reads.  A stage
+// is then one such box plus the three weight slabs and feeds 12 (x MH) tensor-core instructions.
+template <int BN, int MH, int STAGES, int CG, bool HALO = false>
 __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0,
                                                                    const __grid_constant__ CUtensorMap mapA1,
                                                                    const __grid_constant__ CUtensorMap mapB0,
@@ -381,7 +388,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
   constexpr int BMT = BM * MH;                // tile rows of this CTA
   constexpr int A_BYTES = A_STAGE_BYTES * MH;
   constexpr int B_STAGE_BYTES = BN * 128 / CG;     // this CTA's share of the B tile
-  constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
+  constexpr int A_SLOT_BYTES = HALO ? A_BYTES * 3 / 2 : A_BYTES;     // halo box: at most 1.5 x the tile (>= 4 rows + 2)
+  constexpr int STAGE_BYTES = A_SLOT_BYTES + (HALO ? 3 : 1) * B_STAGE_BYTES;
   constexpr int TC = BN * MH;                 // TMEM columns per accumulator buffer
   constexpr int TMEM_COLS = 2 * TC;
   constexpr int CH = TC / 64;                 // 32-column chunks per epilogue warp
@@ -391,7 +399,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
   {
     uint32_t dyn;
     asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-    constexpr uint32_t NEED = STAGES * STAGE_BYTES + TC * 256 + (2 * STAGES + 6) * 8 + 16 + 4 * BN * 4;
+    constexpr uint32_t NEED = STAGES * STAGE_BYTES + TC * 256 + (2 * STAGES + 6) * 8 + 16 + 4 * BN * 4;     // (see launch2)
     if ((uint32_t)(smem - smem_raw) + NEED > dyn) __trap();     // launched without re-alignment slack and misaligned
   }
   uint8_t* res_stage = smem + STAGES * STAGE_BYTES;
@@ -473,7 +481,40 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
     // (a single elected thread cannot issue the 4-6 boxes per K block of the MN-major forms fast enough);
     // the whole warp walks the loop, one elected lane issues
     const bool do_a = (warp == 0);
-    {
+    if constexpr (HALO) {
+      int s = 0;
+      uint32_t par = 1;
+      const int lw = p.logW, lhw = p.logW + p.logH, Hm = p.H - 1;
+      const int nsb = p.nk / 3;                           // (dx, channel block) super-blocks of three taps each
+      const uint32_t a_bytes = (uint32_t)(BMT + 2 * p.W) * 128u;
+      for (int st = cluster_id; st < total; st += n_clusters) {
+        int m0, n0, b, kt0, nkt;
+        decode(st, m0, n0, b, kt0, nkt);
+        const int gy = (m0 >> lw) & Hm, gn = m0 >> lhw;   // the tile starts at column 0 of image row gy
+        int dxi = 0, cb = 0;
+        for (int i = 0; i < nsb; ++i) {
+          mbar_wait(empty0 + 8 * s, par);
+          const uint32_t bar = CG == 2 ? ((full0 + 8 * s) & PEER_MASK) : (full0 + 8 * s);
+          const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_SLOT_BYTES;
+          if (elect_one()) {
+            const uint32_t bytes = do_a ? a_bytes : 3u * B_STAGE_BYTES;
+            if constexpr (CG == 2) mbar_expect_tx_cluster(bar, bytes);
+            else mbar_expect_tx(bar, bytes);
+            if (do_a) {
+              if (cb < p.c1blocks) ld4<CG>(sa, &mapA0, bar, cb * 64, dxi - 1, gy - 1, gn);
+              else ld4<CG>(sa, &mapA1, bar, (cb - p.c1blocks) * 64, dxi - 1, gy - 1, gn);
+            } else {
+#pragma unroll
+              for (int dyi = 0; dyi < 3; ++dyi)
+                ld3<CG>(sb + dyi * B_STAGE_BYTES, &mapB0, bar, ((dyi * 3 + dxi) * p.cblocks + cb) * 64, n0 + rank * (BN / CG), b);
+            }
+          }
+          __syncwarp();
+          if (++cb == p.cblocks) { cb = 0; ++dxi; }
+          if (++s == STAGES) { s = 0; par ^= 1; }
+        }
+      }
+    } else {
       int s = 0;
       uint32_t par = 1;                 // parity to wait on empty[s]: a fresh barrier passes parity 1 immediately
       const int pw = (p.kw - 1) / 2, ph = (p.kh - 1) / 2;
@@ -636,6 +677,52 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
       int s = 0, tl = 0;
       uint32_t par = 0;
       uint32_t a_lo = a_lo0, b_lo = b_lo0;
+      if constexpr (HALO) {
+        // both operands K-major; per stage: three taps x four K=16 steps x MH row blocks
+        const uint32_t hb_lo0 = ((smem_base + A_SLOT_BYTES) >> 4) | (1u << 16);
+        const uint32_t dy_step = (uint32_t)(p.W * 128) >> 4;
+        const int nsb = p.nk / 3;
+        b_lo = hb_lo0;
+        for (int st = cluster_id; st < total; st += n_clusters) {
+          const int buf = tl & 1;
+          if (tl >= 2) mbar_wait(tempty0 + 8 * buf, ((tl >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tacc = tmem_base + (uint32_t)(buf * TC);
+          uint32_t accum = 0;
+          for (int i = 0; i < nsb; ++i) {
+            mbar_wait(full0 + 8 * s, par);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+#pragma unroll
+              for (int dyi = 0; dyi < 3; ++dyi)
+#pragma unroll
+                for (int j = 0; j < BK / 16; ++j) {
+                  const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + dyi * (B_STAGE_BYTES >> 4) + j * 2);
+#pragma unroll
+                  for (int h = 0; h < MH; ++h) {
+                    const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + dyi * dy_step + h * (A_STAGE_BYTES >> 4) + j * 2);
+                    if constexpr (CG == 2) umma_f16_2sm(tacc + (uint32_t)(h * BN), ad, bd, idesc, accum);
+                    else umma_f16(tacc + (uint32_t)(h * BN), ad, bd, idesc, accum);
+                  }
+                  accum = 1;
+                }
+              if constexpr (CG == 2) umma_commit_2sm(empty0 + 8 * s, 3);
+              else umma_commit(empty0 + 8 * s);
+            }
+            __syncwarp();
+            accum = 1;
+            a_lo += STAGE_BYTES >> 4;
+            b_lo += STAGE_BYTES >> 4;
+            if (++s == STAGES) { s = 0; par ^= 1; a_lo = a_lo0; b_lo = hb_lo0; }
+          }
+          if (elect_one()) {
+            if constexpr (CG == 2) umma_commit_2sm(tfull0 + 8 * buf, 3);
+            else umma_commit(tfull0 + 8 * buf);
+          }
+          __syncwarp();
+          ++tl;
+        }
+      } else
       for (int st = cluster_id; st < total; st += n_clusters) {
         int m0, n0, b, kt0, nkt;
         decode(st, m0, n0, b, kt0, nkt);
@@ -1146,16 +1233,17 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-template <int BN, int MH, int STAGES, int CG>
+template <int BN, int MH, int STAGES, int CG, bool HALO = false>
 int launch2(const CUtensorMap* maps, TcParams& p, int total_super, cudaStream_t stream) {
-  constexpr int need = STAGES * (A_STAGE_BYTES * MH + BN * 128 / CG) + BN * MH * 256 + (2 * STAGES + 6) * 8 + 16 + 4 * BN * 4;
+  constexpr int stage = HALO ? (A_STAGE_BYTES * MH * 3 / 2 + 3 * BN * 128 / CG) : (A_STAGE_BYTES * MH + BN * 128 / CG);
+  constexpr int need = STAGES * stage + BN * MH * 256 + (2 * STAGES + 6) * 8 + 16 + 4 * BN * 4;
   // 1 KB of slack for re-aligning the dynamic shared-memory base to 1024 bytes (SWIZZLE_128B) - dropped when the
   // configuration only fits without it: the base is 1024-aligned in practice (the kernel traps if it is not)
   constexpr int smem = need + 1024 <= 232448 ? need + 1024 : need;
   static_assert(smem <= 232448, "shared memory budget");
   static bool configured = false;
   static int max_clusters[5] = {0, 0, 0, 0, 0};
-  auto kern = gemm_tc2_kernel<BN, MH, STAGES, CG>;
+  auto kern = gemm_tc2_kernel<BN, MH, STAGES, CG, HALO>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { st_set_error("st_gemm(tc2): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return ST_ERR_CUDA; }
@@ -1274,6 +1362,7 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
     if (want == 2 && big && p.m_tiles >= 2) { CG = 2; cs = 2; }
   }
   p.cluster = cs;
+  bool halo = false;
 
   // ---------------- A
   if (wgrad) {
@@ -1281,7 +1370,21 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
     if (!gather_maps(&maps[0], &maps[1], a->B, a->B2, a->C1, a->C2, a->W, a->H, a->n_img, 64)) return ST_ERR_CUDA;
   } else if (a->a_mode == ST_OP_GATHER) {
     p.a_kind = GATHER_K;
-    if (!gather_maps(&maps[0], &maps[1], a->A, a->A2, a->C1, a->C2, a->W, a->H, a->n_img, 128)) return ST_ERR_CUDA;
+    // halo form (see the kernel): 3x3, K-major weights, CTA pair, the row tile inside one image and >= 4 image rows tall
+    const int BMT = BM * MH;
+    halo = CG == 2 && !wgrad_any && a->kh == 3 && a->kw == 3 && b_kmajor && p.split_k == 1 && a->batch == 1 && a->W >= 8 &&
+           a->W * 4 <= BMT && ((long long)a->H * a->W) % BMT == 0 && env_int("ST_TC_HALO", 1) == 1;
+    if (halo) {
+      const uint32_t box[4] = {64, (uint32_t)a->W, (uint32_t)(BMT / a->W + 2), 1};
+      const void* src[2] = {a->A, a->A2};
+      const int Cs[2] = {a->C1, a->C2};
+      for (int k = 0; k < 2; ++k) {
+        if (Cs[k] <= 0) continue;
+        const uint64_t dims[4] = {(uint64_t)Cs[k], (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+        const uint64_t str[3] = {(uint64_t)Cs[k] * 2, (uint64_t)a->W * Cs[k] * 2, (uint64_t)a->H * a->W * Cs[k] * 2};
+        if (!encode_map(&maps[k], src[k], 4, dims, str, box)) return ST_ERR_CUDA;
+      }
+    } else if (!gather_maps(&maps[0], &maps[1], a->A, a->A2, a->C1, a->C2, a->W, a->H, a->n_img, 128)) return ST_ERR_CUDA;
   } else if (a->sAk == 1) {
     p.a_kind = KMAJOR;
     const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->batch};
@@ -1376,6 +1479,8 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   const int m_groups = (p.m_tiles + cs - 1) / cs;
   const long long total = (long long)p.batch * p.split_k * p.n_tiles * m_groups;
   ST_CHECK_ARG(total < (1LL << 30), "st_gemm(tc2): too many tiles");
+  if (halo && BN == 256) return launch2<256, 1, 2, 2, true>(maps, p, (int)total, stream);
+  if (halo) return launch2<128, 2, 2, 2, true>(maps, p, (int)total, stream);
   if (CG == 2 && BN == 256) return launch2<256, 1, 4, 2>(maps, p, (int)total, stream);
   if (CG == 2 && MH == 2) return launch2<128, 2, 4, 2>(maps, p, (int)total, stream);
   if (CG == 2) return launch2<128, 1, 6, 2>(maps, p, (int)total, stream);

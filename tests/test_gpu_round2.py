@@ -389,6 +389,42 @@ def test_tcgen05_grads_at_bench_shapes_vs_simt(case):
     assert rel_l2(got, want) < (3e-3 if name == 'wgrad' else 6e-3), (name, rel_l2(got, want))
 
 
+@pytest.mark.parametrize('case', [(256, 32, 128, 0, 128), (128, 32, 128, 128, 128), (256, 16, 256, 0, 256), (128, 16, 256, 256, 256),
+                                  (32, 64, 128, 0, 128), (64, 32, 64, 0, 128), (256, 16, 256, 128, 256)])
+def test_conv_halo_form_vs_plain_form(case):
+  """The halo form of the 3x3 convolution (one (rows + 2)-row box feeds the three vertical taps through descriptor
+  offsets, CTA pairs) against the plain one-box-per-tap form of the same kernel (ST_TC_HALO=0) and against the fp32-FMA
+  kernel, on identical bf16 inputs, with bias + per-image bias + residual epilogues and channel-concatenated inputs:
+  only the fp32 accumulation order differs -> rel-L2 <= 2e-5 between the two tensor-core forms (bf16 output rounding
+  flips), <= 6e-3 against SIMT."""
+  from soft_truncation_b200 import ops
+  if not ops.tc_available():
+    pytest.skip('tcgen05 backend unavailable on this device')
+  B, H, C1, C2, Co = case
+  gen = torch.Generator().manual_seed(B + H + C2)
+  Ci = C1 + C2
+  x1 = torch.randn(B, H, H, C1, generator=gen).to(DEV).to(torch.bfloat16)
+  x2 = torch.randn(B, H, H, C2, generator=gen).to(DEV).to(torch.bfloat16) if C2 else None
+  w = (torch.randn(Co, 9 * Ci, generator=gen) / math.sqrt(9 * Ci)).to(DEV).to(torch.bfloat16)
+  bias, rb = torch.randn(Co, generator=gen).to(DEV), torch.randn(B, Co, generator=gen).to(DEV)
+  resid = torch.randn(B, H, H, Co, generator=gen).to(DEV).to(torch.bfloat16)
+  outs = {}
+  try:
+    for name, backend, halo in (('halo', 'tcgen05', '1'), ('plain', 'tcgen05', '0'), ('simt', 'simt', '1')):
+      ops.gemm_backend = backend
+      os.environ['ST_TC_HALO'] = halo
+      a = ops.conv_fwd(x1, w, Co, 3, 3, x2=x2, bias=bias, rowbias=rb, rowbias_ld=Co)
+      b = ops.conv_fwd(x1, w, Co, 3, 3, x2=x2, bias=bias, residual=resid, alpha=0.7)
+      outs[name] = (a.float(), b.float())
+  finally:
+    ops.gemm_backend = 'auto'
+    os.environ.pop('ST_TC_HALO', None)
+  for i in range(2):
+    _note(f'conv halo vs plain {case} [{i}]: {rel_l2(outs["halo"][i], outs["plain"][i]):.2e}; vs simt {rel_l2(outs["halo"][i], outs["simt"][i]):.2e}')
+    assert rel_l2(outs['halo'][i], outs['plain'][i]) < 2e-3
+    assert rel_l2(outs['halo'][i], outs['simt'][i]) < 6e-3
+
+
 # ------------------------------------------------------------------------------------------------ reference checkpoint
 def test_checkpoint_written_by_the_reference_restores_and_continues(golden, tmp_path):
   """tests/golden/ref_checkpoint.pth was written by the reference's utils.save_checkpoint from its own NCSNpp

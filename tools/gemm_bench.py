@@ -37,8 +37,9 @@ def conv_shapes(B):
 def main():
   B = int(os.environ.get('GB_BATCH', '512'))
   # single-CTA tcgen05.mma (round 1) against CTA pairs (cta_group::2), with and without programmatic dependent launch
-  configs = [('cg1', dict(ST_TC_CG='1', ST_TC_WGRAD_NT='1')), ('cg2', dict(ST_TC_CG='2', ST_TC_CG2_MASK='3', ST_TC_PDL2='1', ST_TC_WGRAD_NT='1')),
-             ('cg2 wgrad-pair', dict(ST_TC_CG='2', ST_TC_CG2_MASK='7', ST_TC_PDL2='1', ST_TC_WGRAD_NT='0'))]
+  # single-CTA tcgen05.mma (round 1) / CTA pairs (cta_group::2) / CTA pairs + halo form of the 3x3 convolutions
+  configs = [('cg1', dict(ST_TC_CG='1', ST_TC_HALO='0')), ('cg2', dict(ST_TC_CG='2', ST_TC_HALO='0')),
+             ('cg2 halo', dict(ST_TC_CG='2', ST_TC_HALO='1'))]
   rows = []
   for name, H, C1, C2, Co, k in conv_shapes(B):
     Ci = C1 + C2
@@ -50,6 +51,7 @@ def main():
     res = torch.randn(B, H, H, Co, device=DEV).to(BF)
     dy = torch.randn(B, H, H, Co, device=DEV).to(BF)
     dw = torch.zeros(Co, k * k * Ci, device=DEV)
+    wt = (torch.randn(Ci, k * k * Co, device=DEV) * 0.02).to(BF)      # transposed weight copy: the bf16 path's data gradient
     out = torch.empty(B, H, H, Co, device=DEV, dtype=BF)
     dx = torch.empty(B, H, H, Ci, device=DEV, dtype=BF)
     flops = 2.0 * B * H * H * Co * k * k * Ci
@@ -57,10 +59,11 @@ def main():
         'fwd+rowbias': lambda: ops.conv_fwd(x1, w, Co, k, k, x2=x2, bias=bias, rowbias=rb, rowbias_ld=Co, out=out),
         'fwd+residual': lambda: ops.conv_fwd(x1, w, Co, k, k, x2=x2, bias=bias, residual=res, alpha=0.7, out=out),
         'dgrad': lambda: ops.conv_dgrad(dy, w, Ci, k, k, out=dx),
+        'dgrad (as conv)': lambda: ops.conv_fwd(dy, wt, Ci, k, k, out=dx),
         'wgrad': lambda: ops.conv_wgrad(dy, x1, dw, k, k, x2=x2),
     }
     for cname, fn in cases.items():
-      line = [f'{name:18s} {cname:13s}']
+      line = [f'{name:18s} {cname:15s}']
       for vname, env in configs:
         os.environ.update(env)
         t = timeit(fn)

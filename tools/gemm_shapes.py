@@ -8,6 +8,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault('ST_STEP_GRAPH', '0')      # the instrumented step must run eagerly (same kernels as the captured graphs)
 
 
 def main():

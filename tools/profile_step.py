@@ -8,6 +8,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault('ST_STEP_GRAPH', '0')      # profile the eager step: the captured graphs replay the same kernels
 
 
 def main():
