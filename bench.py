@@ -40,8 +40,8 @@ if ROOT not in sys.path:
 
 # DRAM bytes per GEMM launch (average over the GEMM launches of one B=512 bf16 c2 step), from the ncu launch list
 # committed under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum); see profiles/README.md for the file
-GEMM_DRAM_BYTES_PER_LAUNCH = 54.166e9 / 430
-TRAFFIC_SOURCE = 'profiles/r01_launches_train_step.md'
+GEMM_DRAM_BYTES_PER_LAUNCH = 52.07e9 / 420
+TRAFFIC_SOURCE = 'profiles/r02_launches_train_step.md'
 
 # name -> config path under the reference's configs/, per-GPU train batch, sampler batch, forward GF / image
 # (2 x MACs of conv / linear / NIN / attention products; None = not surveyed)
@@ -338,6 +338,9 @@ def run_b200(args):
     losses._STEP_GRAPH = False
     l1 = _lib.launches
     try:
+      # head start for the host: ~45 ms of device spin first, so that the (slower, eager) launch stream stays ahead of the
+      # GPU and every event pair brackets a kernel that starts as soon as its predecessor ends - as in the captured graph
+      torch.cuda._sleep(int(0.045 * 1.7e9))
       step_fn(state, batch_dev)
       torch.cuda.synchronize()
     finally:

@@ -2,6 +2,8 @@
 // Replaces reference op/upfirdn2d_kernel.cu:49-207 (index arithmetic :182-203) behind the same
 // argument list as op/upfirdn2d.cpp:12-19.  Inside the network the tensors are NHWC, i.e.
 // major = batch and minor = channels, so consecutive threads walk the contiguous channel axis.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -70,6 +72,131 @@ __global__ void __launch_bounds__(256) upfirdn2d_kernel(const T* __restrict__ x,
   }
 }
 
+// ---------------------------------------------------------------- fast path: the three FIR shapes the networks use
+// (4x4 taps; upsample_2d = up 2 / pad0 2, downsample_2d = down 2 / pad0 1, conv_downsample_2d
+// pre-filter = 1:1 / pad0 2), NHWC with the channel count a multiple of the 16-byte vector.  HBM-bound work: one thread
+// produces a BY x BX block of output pixels for one 16-byte channel vector, loading every input vector of the block's
+// footprint ONCE (12 loads for 8 outputs when up-sampling, 36 for 4 when down-sampling, 25 for 4 at 1:1 - instead of 4 /
+// 16 / 16 per output) and applying it to every output whose window contains it; which tap that is, is a compile-time
+// function of the unrolled loop indices, so the inner loop is loads and FMAs only.
+__device__ __forceinline__ void ld8(const bf16* p, float v[8]) {
+  uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+__device__ __forceinline__ void ld8(const float*, float*) {}
+__device__ __forceinline__ void st8(bf16* p, const float v[8]) {
+  uint4 t;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+__device__ __forceinline__ void st8(float*, const float*) {}
+
+template <int UP, int DOWN, int PAD0, int K>
+struct FirGeom {
+  // output index j (relative to a block origin that is a multiple of UP) -> first input index (relative) and first tap
+  static __host__ __device__ constexpr int fdiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+  static __host__ __device__ constexpr int mid(int j) { return j * DOWN + UP - 1 - PAD0; }       // + origin * DOWN
+  static __host__ __device__ constexpr int in0(int j) { return fdiv(mid(j), UP); }                 // + origin * DOWN / UP
+  static __host__ __device__ constexpr int k0(int j) { return (in0(j) + 1) * UP - mid(j) - 1; }
+  static constexpr int TAPS = K / UP;
+};
+
+template <typename T, int UP, int DOWN, int PAD0, int BY, int BX>
+__global__ void __launch_bounds__(256) upfirdn2d_fast_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ k,
+                                                             int in_h, int in_w, int minor, int out_h, int out_w, long long total) {
+  constexpr int K = 4, V = 16 / (int)sizeof(T);
+  using G = FirGeom<UP, DOWN, PAD0, K>;
+  constexpr int R0 = G::in0(0), RY = G::in0(BY - 1) + G::TAPS - R0, RX = G::in0(BX - 1) + G::TAPS - R0;
+  static_assert(BY % UP == 0 && BX % UP == 0, "block origin must keep the tap phase compile-time");
+  pdl_wait();
+  pdl_trigger();
+  float w[K * K];                               // flipped taps (reference upfirdn2d_kernel.cu:137)
+#pragma unroll
+  for (int i = 0; i < K * K; ++i) w[i] = __ldg(k + (K * K - 1 - i));
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int mq = minor / V, bxn = (out_w + BX - 1) / BX, byn = (out_h + BY - 1) / BY;
+  const int m = (int)(i % mq) * V;
+  long long t = i / mq;
+  const int ox0 = (int)(t % bxn) * BX;
+  t /= bxn;
+  const int oy0 = (int)(t % byn) * BY;
+  const long long mj = t / byn;
+  const int iy0 = oy0 * DOWN / UP + R0, ix0 = ox0 * DOWN / UP + R0;      // first input row / column of the footprint
+  float acc[BY][BX][V];
+#pragma unroll
+  for (int a = 0; a < BY; ++a)
+#pragma unroll
+    for (int b = 0; b < BX; ++b)
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[a][b][v] = 0.f;
+  const T* src0 = x + (mj * in_h * (long long)in_w) * minor + m;
+  // Branch-free footprint walk: out-of-image rows / columns are clamped to a valid address and their contribution is
+  // zeroed through the weight, so that every load of a footprint row can be in flight at once.
+  int colo[RX];
+  float colm[RX];
+#pragma unroll
+  for (int c = 0; c < RX; ++c) {
+    const int ix = ix0 + c;
+    colm[c] = (ix >= 0 && ix < in_w) ? 1.f : 0.f;
+    colo[c] = min(max(ix, 0), in_w - 1) * minor;
+  }
+#pragma unroll
+  for (int r = 0; r < RY; ++r) {
+    const int iy = iy0 + r;
+    const float rowm = (iy >= 0 && iy < in_h) ? 1.f : 0.f;
+    const T* row = src0 + (long long)min(max(iy, 0), in_h - 1) * in_w * minor;
+    float v[RX][V];
+#pragma unroll
+    for (int c = 0; c < RX; ++c) {
+      if constexpr (V == 8) ld8(row + colo[c], v[c]);
+      else load4(row + colo[c], v[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < RX; ++c) {
+      const float msk = rowm * colm[c];
+#pragma unroll
+      for (int a = 0; a < BY; ++a) {
+        const int dy = r - (G::in0(a) - R0);
+        if (dy < 0 || dy >= G::TAPS) continue;
+#pragma unroll
+        for (int b = 0; b < BX; ++b) {
+          const int dx = c - (G::in0(b) - R0);
+          if (dx < 0 || dx >= G::TAPS) continue;
+          const float wt = w[(G::k0(a) + dy * UP) * K + G::k0(b) + dx * UP] * msk;
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[a][b][e] = fmaf(v[c][e], wt, acc[a][b][e]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < BY; ++a)
+#pragma unroll
+    for (int b = 0; b < BX; ++b) {
+      if (oy0 + a >= out_h || ox0 + b >= out_w) continue;
+      T* dst = y + ((mj * out_h + oy0 + a) * (long long)out_w + ox0 + b) * minor + m;
+      if constexpr (V == 8) st8(dst, acc[a][b]);
+      else store4(dst, acc[a][b]);
+    }
+}
+
+template <typename T, int UP, int DOWN, int PAD0, int BY, int BX>
+int launch_fast(const void* x, void* y, const float* k, int major, int in_h, int in_w, int minor, int out_h, int out_w,
+                cudaStream_t stream) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const long long total = (long long)major * ((out_h + BY - 1) / BY) * ((out_w + BX - 1) / BX) * (minor / V);
+  const long long blocks = (total + 255) / 256;
+  if (blocks > 0x7fffffffLL) return -1;
+  cudaError_t e = st_launch(upfirdn2d_fast_kernel<T, UP, DOWN, PAD0, BY, BX>, dim3((unsigned)blocks), dim3(256), 0, stream,
+                            (const T*)x, (T*)y, k, in_h, in_w, minor, out_h, out_w, total);
+  return e == cudaSuccess ? 0 : -1;
+}
+
 }  // namespace
 
 extern "C" __attribute__((visibility("default"))) int st_upfirdn2d(const void* x, void* y, int dtype, const float* k, int major, int in_h, int in_w, int minor,
@@ -83,6 +210,27 @@ extern "C" __attribute__((visibility("default"))) int st_upfirdn2d(const void* x
   p.out_h = (in_h * up_y + pad_y0 + pad_y1 - kh + down_y) / down_y;   // op/upfirdn2d_kernel.cu:237-240
   p.out_w = (in_w * up_x + pad_x0 + pad_x1 - kw + down_x) / down_x;
   ST_CHECK_ARG(p.out_h > 0 && p.out_w > 0, "st_upfirdn2d: empty output");
+  // ---- fast path for the networks' FIR shapes
+  {
+    const int V = dtype == ST_BF16 ? 8 : 4;
+    const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    const char* env = getenv("ST_UPFIRDN_FAST");
+    const bool on = !env || atoi(env) != 0;
+    if (on && al && kh == 4 && kw == 4 && up_x == up_y && down_x == down_y && pad_x0 == pad_y0 && minor % V == 0 &&
+        (dtype == ST_BF16 || dtype == ST_F32)) {
+      int rc = 1;
+      ST_DISPATCH_DTYPE(dtype, T, {
+        if (up_x == 2 && down_x == 1 && pad_x0 == 2)
+          rc = launch_fast<T, 2, 1, 2, 2, 4>(x, y, k, major, in_h, in_w, minor, p.out_h, p.out_w, (cudaStream_t)stream);
+        else if (up_x == 1 && down_x == 2 && pad_x0 == 1)
+          rc = launch_fast<T, 1, 2, 1, 2, 2>(x, y, k, major, in_h, in_w, minor, p.out_h, p.out_w, (cudaStream_t)stream);
+        else if (up_x == 1 && down_x == 1 && pad_x0 == 2)
+          rc = launch_fast<T, 1, 1, 2, 2, 2>(x, y, k, major, in_h, in_w, minor, p.out_h, p.out_w, (cudaStream_t)stream);
+      });
+      if (rc == 0) { ST_CHECK_LAUNCH("st_upfirdn2d"); return 0; }
+      if (rc < 0) { cudaGetLastError(); }
+    }
+  }
   const bool vec = (minor % 4 == 0);
   long long total = (long long)major * p.out_h * p.out_w * (vec ? minor / 4 : minor);
   long long blocks = (total + 255) / 256;

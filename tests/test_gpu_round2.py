@@ -425,6 +425,34 @@ def test_conv_halo_form_vs_plain_form(case):
     assert rel_l2(outs['halo'][i], outs['simt'][i]) < 6e-3
 
 
+@pytest.mark.parametrize('mode', ['up2', 'down2', 'pre'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_upfirdn2d_fast_path_vs_generic_kernel(mode, dtype):
+  """The register-blocked FIR kernel of the three network shapes (up 2 / pad (2,1), down 2 / pad (1,1), 1:1 / pad (2,2),
+  4x4 taps, NHWC) against the generic kernel (which the reference fixture ops_golden.npz pins) on the same inputs, incl.
+  odd image sizes: same taps, same fp32 FMA order per output up to association -> 1e-6 (fp32) / equal up to bf16
+  rounding (bf16)."""
+  from soft_truncation_b200 import ops
+  kw = dict(up2=dict(up=2, pad=(2, 1)), down2=dict(down=2, pad=(1, 1)), pre=dict(pad=(2, 2)))[mode]
+  k1 = np.asarray([1., 3., 3., 1.], dtype=np.float32)
+  k = np.outer(k1, k1)
+  k = torch.tensor(k / k.sum() * (4. if mode == 'up2' else 1.), device=DEV)
+  k = k + 0.01 * torch.arange(16, device=DEV).float().view(4, 4)      # asymmetric: catches a flipped / transposed tap
+  for shape in ((3, 16, 16, 64), (2, 10, 14, 32), (1, 64, 64, 128), (2, 7, 9, 8)):
+    if mode == 'down2' and (shape[1] % 2 or shape[2] % 2):
+      continue
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(sum(shape))).to(DEV).to(dtype)
+    try:
+      os.environ['ST_UPFIRDN_FAST'] = '1'
+      fast = ops.upfirdn2d_nhwc(x, k, **kw)
+      os.environ['ST_UPFIRDN_FAST'] = '0'
+      ref = ops.upfirdn2d_nhwc(x, k, **kw)
+    finally:
+      os.environ.pop('ST_UPFIRDN_FAST', None)
+    assert fast.shape == ref.shape
+    assert rel_l2(fast.float(), ref.float()) < (1e-6 if dtype == torch.float32 else 3e-3), (mode, shape)
+
+
 # ------------------------------------------------------------------------------------------------ reference checkpoint
 def test_checkpoint_written_by_the_reference_restores_and_continues(golden, tmp_path):
   """tests/golden/ref_checkpoint.pth was written by the reference's utils.save_checkpoint from its own NCSNpp

@@ -42,6 +42,9 @@ def main():
            int(kw.get('residual') is not None), int(kw.get('C2', 0) > 0))
     recs.append((key, a, b, 2.0 * kw['M'] * kw['N'] * kw['K'] * kw.get('batch', 1)))
   ops._gemm = spy
+  # head start for the host (45 ms of device spin): the eager launch stream stays ahead of the GPU, so every event pair
+  # brackets a kernel that starts when its predecessor ends, as in the captured graph
+  torch.cuda._sleep(int(0.045 * 1.7e9))
   step_fn(state, batch)
   torch.cuda.synchronize()
   ops._gemm = orig

@@ -49,6 +49,10 @@ def main(path):
     for key, label in METRICS:
       if key in idx and r[idx[key]] != '':
         print(f'| {label} (`{key}`) | {r[idx[key]]} {units[idx[key]]} |')
+    # tensor-pipe activity: the metric's name differs between ncu versions / architectures (tcgen05 on sm_100)
+    for h in hdr:
+      if 'pipe_tensor' in h and 'cycles_active' in h and ('pct' in h or h.endswith('.avg')) and r[idx[h]] != '':
+        print(f'| tensor pipe (`{h}`) | {r[idx[h]]} {units[idx[h]]} |')
     top = sorted(((float(r[idx[h]] or 0), h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')])
                   for h in stall), reverse=True)[:5]
     print('| top stall reasons (warps per issue) | ' + ', '.join(f'{k} {v:.2f}' for v, k in top) + ' |\n')
