@@ -99,6 +99,27 @@ typedef struct st_gemm_args {
   float* gn_part;
   int32_t gn_hw;
   int32_t* gn_rows_out;
+  /* GroupNorm BACKWARD, phase 1, as the epilogue of the data-gradient GEMM (optional; tcgen05 backend, bf16 C, no bias /
+   * residual / accumulate).  With dz_x set, the GEMM result dy = alpha * A B is the gradient with respect to
+   * y = dropout(act(GroupNorm(x))) and the epilogue stores, instead of dy,
+   *     dz = dy * keep * act'(u),   u = x * cst.x + cst.y   (the GroupNorm output before the activation)
+   * and emits, per block of 32 rows and per 4 adjacent channels, the two sums the GroupNorm backward needs of the
+   * STORED dz:  gn_part[M / 32][N / 4][2] = (sum gamma * dz, sum dz * (u - beta))  [= sum gamma*dz*xhat].
+   * st_gn_bwd_dz_apply turns dz and these sums into dx: the reduction pass over (x, dy) of the two-pass backward
+   * and all of its activation / dropout arithmetic run under the GEMM's main loop.
+   *   dz_x     bf16 [M][N] rows of stride dz_ldx: the GroupNorm input (rows = pixels, gn_hw per image)
+   *   dz_cst   fp32 [M / gn_hw][N][4]: (rstd*gamma, beta - mean*rstd*gamma, gamma, beta) per (image, channel)
+   *            (st_gn_bwd_consts writes it)
+   *   dz_keep  dropout keep flags, 1 bit per element ([M][N / 8] bytes, as st_gn_apply wrote them) or NULL
+   *   dz_inv_keep  1 / (1 - p_drop) (1 without dropout);  dz_act  0 none, 1 SiLU
+   * *gn_rows_out receives 32 when the launch did all this and 0 when it cannot (C then holds the plain dy and the
+   * caller runs the ordinary backward). */
+  const void* dz_x;
+  int64_t dz_ldx;
+  const float* dz_cst;
+  const uint8_t* dz_keep;
+  float dz_inv_keep;
+  int32_t dz_act;
 } st_gemm_args;
 
 int st_gemm(const st_gemm_args* args, void* stream);
@@ -203,6 +224,21 @@ int st_gn_bwd_resident(const void* x1, const void* x2, const void* dy, int dtype
                        const float* rstd, int act, float p_drop, uint64_t seed, const void* mask,
                        const uint8_t* keepbits, int chunks, float* red, const void* extra, float extra_scale,
                        void* dx1, void* dx2, float* csum, void* stream);
+
+/* The backward behind a data-gradient GEMM that already produced dz and its quad sums (st_gemm_args.dz_x):
+ * st_gn_bwd_consts writes the per-(image, channel) table that epilogue reads, cst[n_img][C][4] =
+ * (rstd*gamma, beta - mean*rstd*gamma, gamma, beta); st_gn_bwd_dz_apply is the ONE streaming pass that is left:
+ *   dx = rstd*(gamma*dz - mean_g(gamma*dz) - xhat*mean_g(gamma*dz*xhat)) + extra_scale*extra  (split / accumulated as
+ * in st_gn_bwd_apply), with qpart [n_img*hw/32][C/4][2] the sums the GEMM emitted.  It also leaves
+ * red[n_img][chunks][C][2] = (sum dz, sum dz*xhat) per pixel chunk (parameter gradients via st_gn_bwd_params or a
+ * batched column sum; NULL = not wanted) and csum[n_img][chunks][C] (optional) as st_gn_bwd_apply does.
+ * hw must be a multiple of 32, C <= 1024. */
+int st_gn_bwd_consts(const float* gamma, const float* beta, const float* mean, const float* rstd, int n_img, int C,
+                     int G, float* cst, void* stream);
+int st_gn_bwd_dz_apply(const void* x1, const void* x2, const void* dz, int dtype, int n_img, int hw, int C1, int C2,
+                       int G, const float* gamma, const float* mean, const float* rstd, const float* qpart,
+                       const void* extra, float extra_scale, void* dx1, int accum1, void* dx2, int accum2, int chunks,
+                       float* red, float* csum, void* stream);
 
 /* ------------------------------------------------------------------ training-batch preparation
  * Replaces the float pipeline of datasets.py:56-62,117,311-326 + run_lib.py:73-75: src uint8 [n_img][H][W][C] ->

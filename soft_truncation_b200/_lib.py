@@ -30,6 +30,8 @@ class GemmArgs(ctypes.Structure):
       ('residual', c_p), ('sRm', c_i64), ('sRb', c_i64),
       ('alpha', c_f),
       ('gn_part', c_p), ('gn_hw', ctypes.c_int32), ('gn_rows_out', ctypes.POINTER(ctypes.c_int32)),
+      ('dz_x', c_p), ('dz_ldx', c_i64), ('dz_cst', c_p), ('dz_keep', c_p), ('dz_inv_keep', c_f),
+      ('dz_act', ctypes.c_int32),
   ]
 
 
@@ -58,6 +60,9 @@ SIGNATURES = {
     'st_gn_bwd_fused_chunks': [c_int, c_int, c_int, c_int, c_int],
     'st_gn_bwd_fused': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f,
                         c_u64, c_p, c_p, c_int, c_p, c_p, c_f, c_p, c_int, c_p, c_int, c_p, c_p],
+    'st_gn_bwd_consts': [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p],
+    'st_gn_bwd_dz_apply': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_f, c_p,
+                           c_int, c_p, c_int, c_int, c_p, c_p, c_p],
     'st_prep_batch': [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_f, c_f, c_p],
     'st_cast': [c_p, c_int, c_p, c_int, c_i64, c_p],
     'st_axpby': [c_p, c_p, c_p, c_int, c_f, c_f, c_i64, c_p],

@@ -537,29 +537,60 @@ __global__ void dsm_perturb_kernel(const float* __restrict__ x0, const float* __
     xt[i] = fmaf(sd[n], z[i], mc[n] * x0[i]);
   }
 }
-// one block per sample
+// grid (parts, B): a thread-block cluster of `parts` CTAs per sample (1 for the 32x32 / 64x64 images, 8 for 256x256 where
+// 16 single blocks would run alone on the GPU); the slices' sums meet in CTA 0 through distributed shared memory, in
+// rank order (deterministic)
 __global__ void __launch_bounds__(256) dsm_loss_kernel(const float* __restrict__ out, const float* __restrict__ z,
                                                        const float* __restrict__ a, const float* __restrict__ b,
                                                        const float* __restrict__ w, float* loss, float* dout,
                                                        const float* __restrict__ gvec, long long D, int reduce_mean) {
-  const long long n = blockIdx.x;
+  const long long n = blockIdx.y;
+  const int parts = gridDim.x, rank = blockIdx.x;
   const float an = a[n], bn = b[n], wn = w[n];
   const float gscale = (dout && gvec) ? gvec[n] : 1.f;
   const float red = reduce_mean ? 1.f / (float)D : 0.5f;
+  const long long per = (D + parts - 1) / parts, i0 = rank * per, i1 = i0 + per < D ? i0 + per : D;
   float acc = 0.f;
-  for (long long i = threadIdx.x; i < D; i += 256) {
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
     float e = fmaf(an, out[n * D + i], bn * z[n * D + i]);
     acc = fmaf(e, e, acc);
     if (dout) dout[n * D + i] = gscale * wn * red * 2.f * e * an;
   }
   acc = warp_sum(acc);
   __shared__ float sm[8];
+  __shared__ float s_tot;
   if (threadIdx.x % 32 == 0) sm[threadIdx.x / 32] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.;
     for (int i = 0; i < 8; ++i) t += (double)sm[i];
+    s_tot = (float)t;
+  }
+  if (parts > 1) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && rank == 0) {
+    double t = 0.;
+    for (int r = 0; r < parts; ++r) {
+      float v;
+      if (parts > 1) {
+        uint32_t la = (uint32_t)__cvta_generic_to_shared(&s_tot), ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"((uint32_t)r));
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+      } else {
+        v = s_tot;
+      }
+      t += (double)v;
+    }
     loss[n] = wn * red * (float)t;
+  }
+  // no CTA may exit while CTA 0 can still read its s_tot
+  if (parts > 1) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
 }
 
@@ -844,7 +875,23 @@ extern "C" __attribute__((visibility("default"))) int st_dsm_perturb(const float
 }
 extern "C" __attribute__((visibility("default"))) int st_dsm_loss(const float* out, const float* z, const float* a, const float* b, const float* w, float* loss,
                            float* dout, const float* gvec, int B, int64_t D, int reduce_mean, void* stream) {
-  dsm_loss_kernel<<<B, 256, 0, S>>>(out, z, a, b, w, loss, dout, gvec, D, reduce_mean);
+  ST_CHECK_ARG(B > 0 && B <= 65535 && D > 0, "st_dsm_loss: bad shape");
+  int parts = 1;
+  if (D >= 32768) { parts = (int)(D / 16384); if (parts > 8) parts = 8; }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(parts, B);
+  cfg.blockDim = dim3(256);
+  cfg.stream = S;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = parts;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, dsm_loss_kernel, out, z, a, b, w, loss, dout, gvec, (long long)D, reduce_mean);
+  if (e != cudaSuccess) { st_set_error("st_dsm_loss: launch: %s", cudaGetErrorString(e)); return ST_ERR_CUDA; }
   ST_CHECK_LAUNCH("st_dsm_loss");
   return 0;
 }

@@ -66,7 +66,49 @@ struct TcParams {
   // sum and sum of squares of the STORED values -> gn_part[row / gn_rows][N / 4][2]; nullptr = off
   float* gn_part;
   int gn_rows;            // 16, 64 or 128: min(pixels per image, 128)
+  // GroupNorm backward phase 1 in the epilogue (st_gemm_args::dz_x; TMA epilogue, bf16 output, 256-column accumulators):
+  // the tile of x arrives like a residual tile (mapR), dz replaces dy in the staged tile, and every epilogue warp emits
+  // the (sum gamma*dz, sum dz*(u-beta)) of its 32 rows per 4-channel quad -> gn_part[row / 32][N / 4][2]
+  const float4* dz_cst;   // nullptr = off
+  const uint8_t* dz_keep;
+  float dz_ks;            // alpha / (1 - p_drop)
+  int dz_act, dz_loghw;
 };
+
+// 16 per-lane values -> their sums over the 32 lanes of the warp, value i left in lanes 2i and 2i+1 (recursive halving:
+// 8 + 4 + 2 + 1 + 1 shuffles)
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float send = hi ? v[k] : v[8 + k], keep = hi ? v[8 + k] : v[k];
+      a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float send = hi ? a[k] : a[4 + k], keep = hi ? a[4 + k] : a[k];
+      b[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float send = hi ? b[k] : b[2 + k], keep = hi ? b[2 + k] : b[k];
+      c[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  const bool hi = lane & 2;
+  const float send = hi ? c[0] : c[1], keep = hi ? c[1] : c[0];
+  float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
+}
 
 // ------------------------------------------------------------------------------------ kernel
 template <int BN, int STAGES>
@@ -793,7 +835,8 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
       const uint32_t rfull = rfull0 + 8 * half;
       const int bar_id = 1 + half;
       const bool has_bias = p.bias || p.rowbias;
-      const bool res_mode = p.residual != nullptr;
+      const bool dz_mode = TC == 256 && p.dz_cst != nullptr;
+      const bool res_mode = p.residual != nullptr || dz_mode;      // dz: the x tile arrives like a residual tile
       const int nb_vals = p.rb_rows * BN;                 // staged bias values per tile
       const int my_rb = (p.rowbias && p.rows_per_rb < BMT) ? row / p.rows_per_rb : 0;
       const int colbase = (MH == 2 ? 0 : half * (BN / 2));
@@ -848,6 +891,22 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
             load_bias(m2, n2);                            // lands while this tile is processed
           }
         }
+        // dz: this row's dropout keep flags (1 bit per element, 16 bytes for its 128 columns) and its image's constants
+        uint4 kw4 = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        const float4* cst_row = nullptr;
+        float* part_row = nullptr;
+        if (dz_mode) {
+          const long long grow = (long long)m0 + rowbase + q * 32 + lane;      // (the host guarantees M % 256 == 0, N % 128 == 0)
+          const int ncol0 = n0 + colbase;
+          const long long row0 = grow - lane;             // first row of this warp: one image per 32 rows (hw % 32 == 0)
+          if (row0 < p.M) {                               // (the odd last tile of a CTA pair lies past M)
+            if (p.dz_keep) kw4 = __ldg(reinterpret_cast<const uint4*>(p.dz_keep + (grow * p.N + ncol0) / 8));
+            cst_row = p.dz_cst + (row0 >> p.dz_loghw) * p.N + ncol0;
+            part_row = p.gn_part + ((row0 >> 5) * (p.N >> 2) + (ncol0 >> 2)) * 2;
+          } else {
+            cst_row = p.dz_cst + ncol0;
+          }
+        }
         if (res_mode) mbar_wait(rfull, tl & 1);
         mbar_wait(tfull0 + 8 * buf, (tl >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -884,6 +943,50 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
             if (!f32) {
               const uint32_t base = rowaddr + (uint32_t)((cc >> 1) * 16384);
               const uint32_t pb = (uint32_t)((cc & 1) * 4);
+              if (dz_mode) {
+                // ---- GroupNorm backward phase 1: dz = dy * keep * act'(u) replaces dy; quad sums of the stored values
+                const uint32_t kword = cc == 0 ? kw4.x : cc == 1 ? kw4.y : cc == 2 ? kw4.z : kw4.w;
+                float qs[16];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  const uint32_t addr = base + (((pb + g) ^ sw) << 4);
+                  uint4 t;
+                  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(addr));
+                  const uint32_t xw[4] = {t.x, t.y, t.z, t.w};
+                  const uint32_t kb = kword >> (8 * g);
+                  const float4* ct = cst_row + cc * 32 + g * 8;
+                  float dzv[8], gm[8], ub[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float4 k = __ldg(ct + e);
+                    const float xf = __uint_as_float((e & 1) ? (xw[e >> 1] & 0xffff0000u) : (xw[e >> 1] << 16));
+                    const float u = fmaf(xf, k.x, k.y);
+                    float d = v[g * 8 + e] * (((kb >> e) & 1u) ? p.dz_ks : 0.f);
+                    if (p.dz_act) d *= silu_grad_t<bf16>(u);
+                    dzv[e] = d; gm[e] = k.z; ub[e] = u - k.w;
+                  }
+                  uint4 o;
+                  __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) ho[e] = __floats2bfloat162_rn(dzv[2 * e], dzv[2 * e + 1]);
+                  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                  const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                  for (int h2 = 0; h2 < 2; ++h2) {
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int e = 4 * h2; e < 4 * h2 + 4; ++e) {
+                      const float r = __uint_as_float((e & 1) ? (ow[e >> 1] & 0xffff0000u) : (ow[e >> 1] << 16));
+                      s1 = fmaf(gm[e], r, s1);
+                      s2 = fmaf(r, ub[e], s2);
+                    }
+                    qs[(2 * g + h2) * 2] = s1;
+                    qs[(2 * g + h2) * 2 + 1] = s2;
+                  }
+                }
+                const float tot = warp_reduce16(qs, lane);
+                if ((lane & 1) == 0 && part_row) part_row[cc * 16 + (lane >> 1)] = tot;
+              } else
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 const uint32_t addr = base + (((pb + g) ^ sw) << 4);
@@ -931,7 +1034,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm_tc2_kernel(const __grid_
             bulk_commit();
           }
           if constexpr (TC == 256) {
-            if (p.gn_part && !f32) {
+            if (p.gn_part && !f32 && !dz_mode) {
               // GroupNorm statistics of the consumer as a by-product: sums over this half-group's 128 x 128 staged bf16
               // values (what the store writes), per 4-channel quad and per gn_rows rows.
               const int w4 = (warp - 2) & 3;
@@ -1323,7 +1426,10 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
   int BN = (N >= 256 && (N % 256 == 0 || wgrad_nt)) ? 256 : (N > 64 ? 128 : 64);
   if (BN == 256 && env_int("ST_TC_BN", 256) == 128) BN = 128;
   // too few 128x256 tiles to occupy the SMs (4x4 level of the U-Net): halve the tile instead of idling half the GPU
-  if (BN == 256 && !wgrad && env_int("ST_TC_SMALL", 1) == 1) {
+  // a dz request (GroupNorm backward phase 1 in the epilogue) needs 256-column accumulators: keep / form them
+  const bool want_dz = a->dz_x && a->dz_cst && a->gn_part && !wgrad_any && a->N % 128 == 0 && a->M % 256 == 0 &&
+                       env_int("ST_TC_GN_DZ", 1) == 1;
+  if (BN == 256 && !wgrad && !want_dz && env_int("ST_TC_SMALL", 1) == 1) {
     const long long tiles256 = (long long)((M + BM - 1) / BM) * (N / 256) * p.batch * p.split_k;
     if (tiles256 * 10 < (long long)st_num_sms() * 7) BN = 128;
   }
@@ -1333,7 +1439,7 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
     const long long tiles2 = (long long)((M + 255) / 256) * ((N + BN - 1) / BN) * p.batch * p.split_k;
     // weight gradients with a short M' = taps*Cin axis keep 128-row tiles (4 gathered A boxes per K block would
     // make the A producer the bottleneck, and 1152 rows quantise badly into 256-row tiles)
-    if (tiles2 >= 120 && !(wgrad && M < env_int("ST_TC_WGRAD_MH_MIN", 2048))) MH = 2;
+    if ((tiles2 >= 120 || want_dz) && !(wgrad && M < env_int("ST_TC_WGRAD_MH_MIN", 2048))) MH = 2;
   }
   p.m_tiles = (M + BM * MH - 1) / (BM * MH);
   p.n_tiles = (N + BN - 1) / BN;
@@ -1444,6 +1550,12 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
     ok = ok && !((a->residual || has_vec) && p.split_k > 1);
     if (a->residual)
       ok = ok && p.out_bf16 && aligned16(a->residual) && a->sRm % 8 == 0 && (a->batch == 1 || a->sRb % 8 == 0);
+    // GroupNorm backward phase 1 in the epilogue (st_gemm_args::dz_x): needs the TMA epilogue over 256-column accumulators
+    const bool dz = ok && a->dz_x && a->dz_cst && a->gn_part && p.out_bf16 && !a->residual && !has_vec && !a->accumulate &&
+                    p.split_k == 1 && a->batch == 1 && BN * MH == 256 && a->N % 128 == 0 && a->M % 256 == 0 &&
+                    a->gn_hw >= 32 && (a->gn_hw & (a->gn_hw - 1)) == 0 && a->M % a->gn_hw == 0 && aligned16(a->dz_x) &&
+                    a->dz_ldx % 8 == 0 && aligned16(a->dz_cst) && (!a->dz_keep || aligned16(a->dz_keep)) &&
+                    env_int("ST_TC_GN_DZ", 1) == 1;
     int rb_rows = 1;
     if (a->rowbias) {
       if (p.rows_per_rb % BMT == 0) rb_rows = 1;
@@ -1461,13 +1573,27 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
         const uint32_t rbox[3] = {64, 128, 1};
         if (!encode_map(&maps[5], a->residual, 3, dims, rstr, rbox)) return ST_ERR_CUDA;
       }
+      if (dz) {
+        const uint64_t rstr[2] = {(uint64_t)a->dz_ldx * 2, (uint64_t)a->M * a->dz_ldx * 2};
+        const uint32_t rbox[3] = {64, 128, 1};
+        if (!encode_map(&maps[5], a->dz_x, 3, dims, rstr, rbox)) return ST_ERR_CUDA;
+        p.dz_cst = reinterpret_cast<const float4*>(a->dz_cst);
+        p.dz_keep = a->dz_keep;
+        p.dz_ks = a->alpha * (a->dz_inv_keep > 0.f ? a->dz_inv_keep : 1.f);
+        p.dz_act = a->dz_act;
+        for (p.dz_loghw = 0; (1 << p.dz_loghw) < a->gn_hw; ++p.dz_loghw) {}
+        p.gn_part = a->gn_part;
+        p.gn_rows = 32;
+      }
       p.epi_tma = 1;
       p.rb_rows = rb_rows;
     }
   }
   // ---------------- GroupNorm partial sums as a by-product (see TcParams::gn_part)
   if (a->gn_rows_out) *a->gn_rows_out = 0;
-  if (a->gn_part && a->gn_hw >= 16 && p.epi_tma && p.out_bf16 && BN * MH == 256 && p.split_k == 1 && a->batch == 1 &&
+  if (p.dz_cst) {
+    if (a->gn_rows_out) *a->gn_rows_out = 32;
+  } else if (!a->dz_x && a->gn_part && a->gn_hw >= 16 && p.epi_tma && p.out_bf16 && BN * MH == 256 && p.split_k == 1 && a->batch == 1 &&
       a->N % 128 == 0 && a->M % a->gn_hw == 0 && (a->gn_hw & (a->gn_hw - 1)) == 0 && !a->accumulate &&
       env_int("ST_TC_GN_STATS", 1) == 1) {
     p.gn_part = a->gn_part;

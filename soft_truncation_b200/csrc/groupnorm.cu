@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(Src2<T> s, int hw, int
                                                           const float* __restrict__ part, int splits, double inv_count,
                                                           float eps, float* mean_out, float* rstd_out,
                                                           const uint64_t* __restrict__ seed_off,
-                                                          const float* __restrict__ q1, const float* __restrict__ q2, int qrows) {
+                                                          const float* __restrict__ q1, const float* __restrict__ q2, int qrows,
+                                                          int rev) {
   extern __shared__ __align__(16) uint8_t gsm[];
   pdl_wait();
   pdl_trigger();
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(Src2<T> s, int hw, int
   using P = Pipe<T, 1, GN_DEPTH>;
   const P pipe(gsm);
   const int Ct = s.C1 + s.C2, cpg = Ct / G;
-  const int n = blockIdx.y;
+  const int n = img_of(blockIdx.y, gridDim.y, rev);
   const Walk w(Ct, n, hw, blockIdx.x, gridDim.x);
   ChanConst k;
   if (part || q1) {
@@ -97,9 +98,48 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(Src2<T> s, int hw, int
     // per-(qrows rows, 4 channels) sums the producing GEMMs emitted (st_gemm gn_part; one buffer per concatenated
     // source); the first chunk of every image publishes mean / rstd for the backward passes
     __shared__ float s_mean[64], s_rstd[64];
+    // The partial sums of one image are summed by the whole block - 256 threads = (row lane, column) over the
+    // [rows][columns] partial array, then one thread per group adds its columns - so that the dependent-load chain in
+    // front of the streaming loop stays a few loads long even when an image has hundreds of row blocks (256x256 images).
+    __shared__ float s_pa[256], s_pb[256];
+    const int NQ = q1 ? Ct >> 2 : G;                    // columns of the partial array: quads or groups
+    const bool par = NQ <= 256;
+    if (par) {
+      const int rows = q1 ? hw / qrows : splits, lanes_q = 256 / NQ;
+      const int col = threadIdx.x % NQ, ln = threadIdx.x / NQ;
+      if (ln < lanes_q) {
+        float a = 0.f, b = 0.f;
+        const float2* src;
+        int ld;
+        if (q1) {
+          const int c = col << 2;
+          const bool first = c < s.C1;
+          ld = (first ? s.C1 : s.C2) >> 2;
+          src = reinterpret_cast<const float2*>(first ? q1 : q2) + (long long)n * rows * ld + ((first ? c : c - s.C1) >> 2);
+        } else {
+          ld = G;
+          src = reinterpret_cast<const float2*>(part) + (long long)n * rows * G + col;
+        }
+        for (int r = ln; r < rows; r += lanes_q) {
+          const float2 v = src[(long long)r * ld];
+          a += v.x;
+          b += v.y;
+        }
+        s_pa[ln * NQ + col] = a;
+        s_pb[ln * NQ + col] = b;
+      }
+      __syncthreads();
+    }
     if (threadIdx.x < G) {
       double a = 0., b = 0.;
-      if (q1) {
+      if (par) {
+        const int lanes_q = 256 / NQ, per = q1 ? cpg >> 2 : 1;
+        for (int l = 0; l < lanes_q; ++l)
+          for (int k = 0; k < per; ++k) {
+            a += (double)s_pa[l * NQ + threadIdx.x * per + k];
+            b += (double)s_pb[l * NQ + threadIdx.x * per + k];
+          }
+      } else if (q1) {
         const int nch = hw / qrows;
         for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; c += 4) {
           const bool first = c < s.C1;
@@ -176,11 +216,11 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(Src2<T> s, const 
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             float p_drop, uint64_t seed, const T* mask,
-                                                            const uint8_t* __restrict__ keepbits, float* red) {
+                                                            const uint8_t* __restrict__ keepbits, float* red, int rev) {
   pdl_wait();
   pdl_trigger();
   gn_bwd_reduce_body<T, ACT, DROP>(s, dy, hw, G, splits, gamma, beta, mean, rstd, p_drop, seed, mask, keepbits, red,
-                                   blockIdx.x, blockIdx.y);
+                                   img_of(blockIdx.x, gridDim.x, rev), blockIdx.y);
 }
 
 // dgamma[c] += sum_rows red[row][c][1]; dbeta[c] += sum_rows red[row][c][0]
@@ -289,7 +329,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_apply(const void* x1
       if (!smem_ok) { if (!allow_smem(gn_apply_kernel<T, ACT, DROP>, smem)) { rc = ST_ERR_CUDA; return; } smem_ok = true; }
       st_launch(gn_apply_kernel<T, ACT, DROP>, dim3(chunks_for(n_img, hw, V), n_img), dim3(256), smem, (cudaStream_t)stream,
           s, hw, G, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, (T*)y, part, splits,
-          (part || q1) ? 1.0 / (double)count : 0.0, eps, mean, rstd, st_seed_offset(), q1, q2, qrows);
+          (part || q1) ? 1.0 / (double)count : 0.0, eps, mean, rstd, st_seed_offset(), q1, q2, qrows, gn_order_bits() & 1);
     });
   });
   if (rc) return rc;
@@ -313,7 +353,8 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_reduce(const voi
       static bool smem_ok = false;
       if (!smem_ok) { if (!allow_smem(gn_bwd_reduce_kernel<T, ACT, DROP>, smem)) { rc = ST_ERR_CUDA; return; } smem_ok = true; }
       st_launch(gn_bwd_reduce_kernel<T, ACT, DROP>, dim3(n_img, splits), dim3(256), smem, (cudaStream_t)stream,
-          s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, red);
+          s, (const T*)dy, hw, G, splits, gamma, beta, mean, rstd, p_drop, seed, (const T*)mask, keepbits, red,
+          (gn_order_bits() >> 2) & 1);
     });
   });
   if (rc) return rc;

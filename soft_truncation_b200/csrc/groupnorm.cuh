@@ -353,18 +353,41 @@ __device__ __forceinline__ void gn_bwd_apply_body(const Src2<T>& s, const T* dy,
       __syncthreads();
     }
   }
-  if (threadIdx.x < G) {
-    const int g = threadIdx.x;
-    double a = 0., b = 0.;
-    for (int sp = 0; sp < splits; ++sp)
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        const float* o = red + (((long long)n * splits + sp) * Ct + c) * 2;
-        a += (double)gamma[c] * (double)__ldcg(o);
-        b += (double)gamma[c] * (double)__ldcg(o + 1);
+  {
+    // gamma-weighted sums of `red` over the splits: per channel by the whole block (256 threads = (split lane, channel),
+    // a short chain of independent loads each; through the not yet used pipeline memory), then per group
+    float* s_ch = reinterpret_cast<float*>(gsm);           // [lanes_c][Ct][2]
+    const int lanes_c = Ct <= 256 ? 256 / Ct : 1;
+    auto channel = [&](int c, int ln) {
+      float a = 0.f, b = 0.f;
+      const float2* o = reinterpret_cast<const float2*>(red) + (long long)n * splits * Ct + c;
+      for (int sp = ln; sp < splits; sp += lanes_c) {
+        const float2 v = __ldcg(o + (long long)sp * Ct);
+        a += v.x;
+        b += v.y;
       }
-    const double inv = 1.0 / ((double)hw * cpg);
-    sh1[g] = (float)(a * inv);
-    sh2[g] = (float)(b * inv);
+      const float gm = gamma[c];
+      s_ch[((size_t)ln * Ct + c) * 2] = gm * a;
+      s_ch[((size_t)ln * Ct + c) * 2 + 1] = gm * b;
+    };
+    if (lanes_c > 1) {
+      if ((int)threadIdx.x < lanes_c * Ct) channel(threadIdx.x % Ct, threadIdx.x / Ct);
+    } else {
+      for (int c = threadIdx.x; c < Ct; c += 256) channel(c, 0);
+    }
+    __syncthreads();
+    if (threadIdx.x < G) {
+      const int g = threadIdx.x;
+      double a = 0., b = 0.;
+      for (int l = 0; l < lanes_c; ++l)
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+          a += (double)s_ch[((size_t)l * Ct + c) * 2];
+          b += (double)s_ch[((size_t)l * Ct + c) * 2 + 1];
+        }
+      const double inv = 1.0 / ((double)hw * cpg);
+      sh1[g] = (float)(a * inv);
+      sh2[g] = (float)(b * inv);
+    }
   }
   __syncthreads();
   Walk w(Ct, n, hw, chunk, chunks);
@@ -451,6 +474,19 @@ __device__ __forceinline__ void gn_bwd_apply_body(const Src2<T>& s, const T* dy,
     }
   }
 }
+
+// Image order of a launch.  Consecutive kernels of the step stream the same activation tensors (134-268 MB at B=512,
+// L2 = 126 MB): a kernel that walks the images in the order OPPOSITE to its producer starts on what the producer left
+// in L2.  The GEMMs walk their row tiles upwards, so the GroupNorm passes that follow a GEMM walk the images downwards
+// (ST_GN_ORDER bit 0: forward apply / resident forward, bit 1: single-launch backward forms, bit 2: backward reduction
+// of the two-kernel form, whose apply pass then walks upwards again over what the reduction just read).  Measured at
+// B=512 (10-step bench lines, one box): forward passes reversed 44.94 ms/step and sampler 26.52 ms/step against 45.43-45.63
+// and 26.71 unreversed; reversing the backward forms as well measured 45.21-45.34 -> default 1.
+inline int gn_order_bits() {
+  static const int v = getenv("ST_GN_ORDER") ? atoi(getenv("ST_GN_ORDER")) : 1;
+  return v;
+}
+__device__ __forceinline__ int img_of(int idx, int n_img, int rev) { return rev ? n_img - 1 - idx : idx; }
 
 // opt a kernel in to more than 48 KB of dynamic shared memory (once per kernel instance)
 template <typename K>

@@ -17,10 +17,10 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_fused_kernel(Src2<T> s, const T
                                                            float p_drop, uint64_t seed, const T* mask,
                                                            const uint8_t* __restrict__ keepbits,
                                                            float* red, const T* extra, float extra_scale,
-                                                           T* dx1, int accum1, T* dx2, int accum2, float* csum) {
+                                                           T* dx1, int accum1, T* dx2, int accum2, float* csum, int rev) {
   pdl_wait();
   pdl_trigger();
-  const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  const int n = img_of(blockIdx.y, gridDim.y, rev), chunk = blockIdx.x, chunks = gridDim.x;
   gn_bwd_reduce_body<T, ACT, DROP>(s, dy, hw, G, chunks, gamma, beta, mean, rstd, p_drop, seed, mask, keepbits, red, n, chunk);
   __threadfence();
   __syncthreads();
@@ -105,7 +105,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_fused(const void
         cfg.numAttrs = st_pdl_on((cudaStream_t)stream) ? 2 : 1;
         cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, s, (const T*)dy, hw, G, gamma, beta, mean, rstd, p_drop, seed,
                                            (const T*)mask, keepbits, red, (const T*)extra, extra_scale, (T*)dx1, accum1,
-                                           (T*)dx2, accum2, csum);
+                                           (T*)dx2, accum2, csum, (gn_order_bits() >> 1) & 1);
         if (e != cudaSuccess) { st_set_error("st_gn_bwd_fused: launch: %s", cudaGetErrorString(e)); rc = ST_ERR_CUDA; }
       };
       if (csum) launch(std::true_type{}); else launch(std::false_type{});
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256, 3) gn_fwd_fused_kernel(Src2<T> s, int hw,
                                                               const float* __restrict__ beta, double inv_count, float eps,
                                                               float p_drop, uint64_t seed, const T* mask, uint8_t* keepbits,
                                                               T* y, float* mean_out, float* rstd_out,
-                                                              const uint64_t* __restrict__ seed_off) {
+                                                              const uint64_t* __restrict__ seed_off, int rev) {
   extern __shared__ __align__(16) uint8_t gsm[];
   __shared__ float s_sum[512], s_sq[512];
   __shared__ float s_part[128];               // this CTA's per-group (sum, sum of squares): read by the whole cluster
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256, 3) gn_fwd_fused_kernel(Src2<T> s, int hw,
   using P = Pipe<T, 1, GN_RES>;
   const P pipe(gsm);
   const int Ct = s.C1 + s.C2, cpg = Ct / G;
-  const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  const int n = img_of(blockIdx.y, gridDim.y, rev), chunk = blockIdx.x, chunks = gridDim.x;
   const Walk w(Ct, n, hw, chunk, chunks);
   const int V = w.V, lanes = w.lanes;
   const bool active = w.lane < lanes;
@@ -353,7 +353,7 @@ extern "C" __attribute__((visibility("default"))) int st_gn_fwd_fused(const void
       cfg.attrs = attr;
       cfg.numAttrs = st_pdl_on((cudaStream_t)stream) ? 2 : 1;
       cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, s, hw, G, gamma, beta, inv_count, eps, p_drop, seed, (const T*)mask,
-                                         keepbits, (T*)y, mean, rstd, st_seed_offset());
+                                         keepbits, (T*)y, mean, rstd, st_seed_offset(), gn_order_bits() & 1);
       if (e != cudaSuccess) { st_set_error("st_gn_fwd_fused: launch: %s", cudaGetErrorString(e)); rc = ST_ERR_CUDA; }
     });
   });
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_resident_kernel(Src2<T> s, cons
                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                  float p_drop, uint64_t seed, const T* mask,
                                                                  const uint8_t* __restrict__ keepbits, float* red, T* dx1,
-                                                                 T* dx2, float* csum) {
+                                                                 T* dx2, float* csum, int rev) {
   extern __shared__ __align__(16) uint8_t gsm[];
   __shared__ float s_red[256 * 8];
   __shared__ float s_gpart[128];             // gamma-weighted per-group (sum dz, sum dz*xhat) of this CTA's chunk
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_resident_kernel(Src2<T> s, cons
   using P = Pipe<T, NS, GN_BRES>;
   const P pipe(gsm);
   const int Ct = s.C1 + s.C2, cpg = Ct / G;
-  const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  const int n = img_of(blockIdx.y, gridDim.y, rev), chunk = blockIdx.x, chunks = gridDim.x;
   Walk w(Ct, n, hw, chunk, chunks);
   const int V = w.V, lanes = w.lanes, v = w.v, lane = w.lane;
   const bool active = lane < lanes;
@@ -642,7 +642,8 @@ extern "C" __attribute__((visibility("default"))) int st_gn_bwd_resident(const v
         cfg.attrs = attr;
         cfg.numAttrs = st_pdl_on((cudaStream_t)stream) ? 2 : 1;
         cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, s, (const T*)dy, (const T*)extra, extra_scale, hw, G, gamma, beta, mean,
-                                           rstd, p_drop, seed, (const T*)mask, keepbits, red, (T*)dx1, (T*)dx2, csum);
+                                           rstd, p_drop, seed, (const T*)mask, keepbits, red, (T*)dx1, (T*)dx2, csum,
+                                           (gn_order_bits() >> 1) & 1);
         if (e != cudaSuccess) { st_set_error("st_gn_bwd_resident: launch: %s", cudaGetErrorString(e)); rc = ST_ERR_CUDA; }
       };
       auto with_ns = [&](auto CS) {

@@ -100,12 +100,27 @@ class NetCtx:
 USE_WT = os.environ.get('ST_DGRAD_WT', '1') != '0'    # data gradients as forward convs over transposed weight copies
 
 
-def conv_dgrad_w(P, dy, name, cin, kh=3, kw=3, alpha=1.0):
-  """Data gradient of the convolution whose weight is `name`."""
+def conv_dgrad_w(P, dy, name, cin, kh=3, kw=3, alpha=1.0, dz=None):
+  """Data gradient of the convolution whose weight is `name`.  dz (ops.DzRequest): returns (gradient, qpart | None);
+  with qpart the gradient already is dz of the GroupNorm that fed the convolution (ops.conv_fwd)."""
   wt = P.ct(name)
   if wt is not None and dy.shape[3] % 64 == 0:
-    return ops.conv_fwd(dy, wt, cin, kh, kw, alpha=alpha)
-  return ops.conv_dgrad(dy, P.c(name), cin, kh, kw, alpha=alpha)
+    return ops.conv_fwd(dy, wt, cin, kh, kw, alpha=alpha, dz=dz)
+  out = ops.conv_dgrad(dy, P.c(name), cin, kh, kw, alpha=alpha)
+  return (out, None) if dz is not None else out
+
+
+def gn_backward_after(P, pre_gn, dy, qpart, x, x2, G, stats, act, **kw):
+  """GroupNorm backward of `pre_gn` behind a data-gradient convolution: the one-pass form when the convolution's
+  epilogue produced dz (qpart), the two-phase form otherwise.  kw: p_drop / seed / mask / keepbits (two-phase form only)
+  and the common extra / destination / csum / queue arguments."""
+  gamma, beta = P.f(pre_gn + '.weight'), P.f(pre_gn + '.bias')
+  dgamma, dbeta = P.g(pre_gn + '.weight'), P.g(pre_gn + '.bias')
+  if qpart is not None:
+    for k in ('p_drop', 'seed', 'mask', 'keepbits'):
+      kw.pop(k, None)
+    return ops.gn_backward_dz(x, x2, dy, qpart, G, gamma, stats, dgamma, dbeta, **kw)
+  return ops.gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, **kw)
 
 
 CSQ = ops.ColsumQueue()      # reductions deferred to the end of NCSNpp._backward (destinations are distinct parameters)
@@ -237,11 +252,16 @@ class ResBlock:
     # ---- Conv_1 (and the 1/sqrt2 output scale)
     bias_grad(P.g(pre + 'Conv_1.bias'), g2, gs, s)
     ops.conv_wgrad(g, a1, P.g(pre + 'Conv_1.weight'), alpha=s)
-    da1 = conv_dgrad_w(P, g, pre + 'Conv_1.weight', Co, alpha=s)
-    # ---- GroupNorm_1 + SiLU + dropout
-    r1 = ops.gn_backward(h1, None, da1, self.G1, P.f(pre + 'GroupNorm_1.weight'), P.f(pre + 'GroupNorm_1.bias'), st1, 1,
-                         P.g(pre + 'GroupNorm_1.weight'), P.g(pre + 'GroupNorm_1.bias'), p_drop=p_drop, seed=seed,
-                         mask=mask, keepbits=keepbits, want_csum=FUSE_CSUM, queue=CSQ)
+    # ---- GroupNorm_1 + SiLU + dropout: dz and its group sums come out of the data-gradient GEMM's epilogue where the
+    # shape allows (ops.dz_applicable), leaving one streaming pass
+    req1 = None
+    if ops.dz_applicable(h1, None, mask, p_drop, keepbits):
+      req1 = ops.DzRequest(h1, self.G1, P.f(pre + 'GroupNorm_1.weight'), P.f(pre + 'GroupNorm_1.bias'), st1, 1, p_drop,
+                           keepbits)
+    da1 = conv_dgrad_w(P, g, pre + 'Conv_1.weight', Co, alpha=s, dz=req1)
+    da1, qp1 = da1 if req1 is not None else (da1, None)
+    r1 = gn_backward_after(P, pre + 'GroupNorm_1', da1, qp1, h1, None, self.G1, st1, 1, p_drop=p_drop, seed=seed,
+                           mask=mask, keepbits=keepbits, want_csum=FUSE_CSUM, queue=CSQ)
     dh1 = r1[0]
     del da1
     # ---- temb projection gradient = per-image column sums of dh1 (by-product of the kernel above, or an explicit
@@ -255,7 +275,11 @@ class ResBlock:
       ops.colsum(dh1.view(npix, Co), B, H * W, Co, dd)
       net.d_dense[:, self.dense_off:self.dense_off + Co].copy_(dd)
     ops.conv_wgrad(dh1, a0, P.g(pre + 'Conv_0.weight'))
-    da0 = conv_dgrad_w(P, dh1, pre + 'Conv_0.weight', self.cin)
+    req0 = None
+    if not (self.up or self.down) and ops.dz_applicable(x1, x2, None, 0., None):
+      req0 = ops.DzRequest(x1, self.G0, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st0, 1)
+    da0 = conv_dgrad_w(P, dh1, pre + 'Conv_0.weight', self.cin, dz=req0)
+    da0, qp0 = da0 if req0 is not None else (da0, None)
     del dh1
     # ---- shortcut
     extra, extra_scale = None, 1.0
@@ -274,10 +298,9 @@ class ResBlock:
     # ---- GroupNorm_0 + SiLU, plus the shortcut gradient, split over the two inputs
     a1_acc = acc[0]
     a2_acc = acc[1] if x2 is not None else None
-    r0 = ops.gn_backward(x1, x2, da0, self.G0, P.f(pre + 'GroupNorm_0.weight'), P.f(pre + 'GroupNorm_0.bias'), st0, 1,
-                         P.g(pre + 'GroupNorm_0.weight'), P.g(pre + 'GroupNorm_0.bias'), extra=extra,
-                         extra_scale=extra_scale, dx1=a1_acc, accum1=a1_acc is not None, dx2=a2_acc,
-                         accum2=a2_acc is not None, want_csum=FUSE_CSUM, queue=CSQ)
+    r0 = gn_backward_after(P, pre + 'GroupNorm_0', da0, qp0, x1, x2, self.G0, st0, 1, extra=extra,
+                           extra_scale=extra_scale, dx1=a1_acc, accum1=a1_acc is not None, dx2=a2_acc,
+                           accum2=a2_acc is not None, want_csum=FUSE_CSUM, queue=CSQ)
     dx1, dx2 = r0[0], r0[1]
     c1, c2 = _split_csum(r0[2], x1.shape[3], 0 if x2 is None else x2.shape[3]) if FUSE_CSUM else (None, None)
     return ((dx1,), (c1,)) if x2 is None else ((dx1, dx2), (c1, c2))

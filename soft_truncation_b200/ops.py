@@ -89,11 +89,57 @@ def _split_k(M, N, K):
   return int(max(1, min(want, K // 1024 if K >= 2048 else 1, 64)))
 
 
+# GroupNorm backward phase 1 inside the data-gradient GEMM (st_gemm_args.dz_x).  Parity-tested but OFF by default
+# (ST_GN_DZ=1 turns it on): measured on B200 at B=512 it removes 0.8 ms of GroupNorm kernels per step and adds 3.3 ms to
+# the GEMMs - ~20 ALU instructions per element in 8 epilogue warps outlast the 9216 tensor-core cycles of a 128-channel
+# tile.
+GN_DZ = os.environ.get('ST_GN_DZ', '0') != '0'
+
+
+class DzRequest:
+  """What the dz epilogue needs: the GroupNorm input `x` (B,H,W,C) whose output the convolution consumed, the
+  statistics / parameters of that GroupNorm, the activation flag and the dropout keep bits (or None)."""
+  __slots__ = ('x', 'G', 'gamma', 'beta', 'stats', 'act', 'p_drop', 'keepbits')
+
+  def __init__(self, x, G, gamma, beta, stats, act, p_drop=0., keepbits=None):
+    self.x, self.G, self.gamma, self.beta, self.stats, self.act = x, G, gamma, beta, stats, act
+    self.p_drop, self.keepbits = p_drop, keepbits
+
+
+def dz_applicable(x, x2, mask, p_drop, keepbits):
+  """Shapes / modes the dz epilogue covers (everything else keeps the two-phase GroupNorm backward)."""
+  if not GN_DZ or x2 is not None or mask is not None or x.dtype != torch.bfloat16 or gemm_backend == 'simt':
+    return False
+  B, H, W, C = x.shape
+  hw = H * W
+  if p_drop > 0. and keepbits is None:
+    return False
+  return hw >= 32 and (hw & (hw - 1)) == 0 and C % 128 == 0 and C <= 1024 and (B * hw) % 256 == 0
+
+
+def _dz_request(kw, req, out):
+  """Adds the dz request to a (data-gradient) convolution call; returns a closure that yields the quad sums the
+  epilogue emitted (fp32 (M/32, N/4, 2)) or None when the launch could not take the request (out is then plain dy)."""
+  B, H, W, C = req.x.shape
+  M, N = kw['M'], kw['N']
+  assert N == C and M == B * H * W
+  cst = torch.empty((B, C, 4), dtype=torch.float32, device=out.device)
+  check(lib.st_gn_bwd_consts(ptr(req.gamma), ptr(req.beta), ptr(req.stats[0]), ptr(req.stats[1]), B, C, req.G, ptr(cst),
+                             stream()))
+  part = torch.empty((M // 32, N // 4, 2), dtype=torch.float32, device=out.device)
+  got = ctypes.c_int32(0)
+  kw.update(gn_part=part, gn_hw=H * W, gn_rows_out=ctypes.pointer(got), dz_x=req.x, dz_ldx=C, dz_cst=cst,
+            dz_keep=req.keepbits if req.p_drop > 0. else None, dz_inv_keep=1.0 / (1.0 - req.p_drop), dz_act=int(req.act))
+  return lambda: part if got.value == 32 else None
+
+
 def conv_fwd(x, w, cout, kh=3, kw=3, x2=None, bias=None, rowbias=None, rowbias_ld=0, residual=None, alpha=1.0,
-             out_dtype=None, out=None, want_quads=False):
+             out_dtype=None, out=None, want_quads=False, dz=None):
   """'same' convolution of NHWC x (optionally channel-concatenated with x2) with packed weights
   w[cout][kh*kw][cin] (contiguous, same dtype as x).  rowbias: fp32 [B][rowbias_ld] slice added per image.
-  want_quads: returns (out, Quads | None) - the GroupNorm partial sums of `out` emitted by the epilogue."""
+  want_quads: returns (out, Quads | None) - the GroupNorm partial sums of `out` emitted by the epilogue.
+  dz (DzRequest; data gradients run as forward convolutions): returns (out, qpart | None) - with qpart, `out` holds
+  dz of the GroupNorm whose output this convolution's forward consumed and gn_backward_dz finishes the job."""
   B, H, W, C1 = x.shape
   C2 = 0 if x2 is None else x2.shape[3]
   K = kh * kw * (C1 + C2)
@@ -105,8 +151,10 @@ def conv_fwd(x, w, cout, kh=3, kw=3, x2=None, bias=None, rowbias=None, rowbias_l
                 bias=bias, rowbias=rowbias, rows_per_rb=H * W, ld_rb=rowbias_ld, residual=residual, sRm=cout,
                 alpha=alpha)
   q = _quads_request(kwargs, out, H * W) if want_quads else None
+  if dz is not None:
+    q = _dz_request(kwargs, dz, out)
   _gemm(**kwargs)
-  return (out, q()) if want_quads else out
+  return (out, q()) if (want_quads or dz is not None) else out
 
 
 def conv_dgrad(dy, w, cin, kh=3, kw=3, alpha=1.0, out=None):
@@ -356,6 +404,36 @@ def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0.,
     csum = torch.empty((B, chunks, Ct), dtype=torch.float32, device=x.device)
   check(lib.st_gn_bwd_apply(*common, ptr(extra), float(extra_scale), ptr(dx1), int(accum1), ptr(dx2), int(accum2),
                             chunks, ptr(csum), ptr(dgamma), ptr(dbeta), stream()))
+  return (dx1, dx2, csum) if want_csum else (dx1, dx2)
+
+
+def gn_backward_dz(x, x2, dz, qpart, G, gamma, stats, dgamma, dbeta, extra=None, extra_scale=1.0, dx1=None,
+                   accum1=False, dx2=None, accum2=False, want_csum=False, queue=None):
+  """The GroupNorm backward that is left when the data-gradient GEMM already produced dz and its quad sums
+  (conv_fwd(dz=...)): one streaming pass.  Same returns / parameter-gradient handling as gn_backward."""
+  B, H, W, C1 = x.shape
+  C2 = 0 if x2 is None else x2.shape[3]
+  hw, Ct = H * W, C1 + C2
+  if dx1 is None:
+    dx1 = torch.empty_like(x)
+    accum1 = False
+  if x2 is not None and dx2 is None:
+    dx2 = torch.empty_like(x2)
+    accum2 = False
+  if not PARAM_GRADS:
+    dgamma = dbeta = None
+  chunks = lib.st_gn_chunks(B, hw, Ct)
+  red = torch.empty((B, chunks, Ct, 2), dtype=torch.float32, device=x.device) if dgamma is not None else None
+  csum = torch.empty((B, chunks, Ct), dtype=torch.float32, device=x.device) if want_csum else None
+  check(lib.st_gn_bwd_dz_apply(ptr(x), ptr(x2), ptr(dz), dt(x), B, hw, C1, C2, G, ptr(gamma), ptr(stats[0]), ptr(stats[1]),
+                               ptr(qpart), ptr(extra), float(extra_scale), ptr(dx1), int(accum1), ptr(dx2), int(accum2),
+                               chunks, ptr(red), ptr(csum), stream()))
+  if dgamma is None:
+    pass
+  elif queue is not None:
+    queue.add_gn_params(dgamma, dbeta, red.view(B * chunks, Ct, 2))
+  else:
+    check(lib.st_gn_bwd_params(ptr(red), B * chunks, Ct, ptr(dgamma), ptr(dbeta), stream()))
   return (dx1, dx2, csum) if want_csum else (dx1, dx2)
 
 

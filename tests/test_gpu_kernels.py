@@ -572,9 +572,10 @@ def test_fused_leaky_relu_matches_reference_fixture(golden):
 
 
 # ------------------------------------------------------------------------------------------------ loss / optimizer / sampler
-def test_dsm_perturb_and_loss():
+@pytest.mark.parametrize('D', [3 * 32 * 32, 3 * 128 * 128 + 5, 3 * 256 * 256])      # 1 / 3 / 8 CTAs per sample
+def test_dsm_perturb_and_loss(D):
   from soft_truncation_b200._lib import check, lib
-  B, D = 5, 3 * 32 * 32
+  B = 5
   x0, z, out = rnd(B, D, seed=1), rnd(B, D, seed=2), rnd(B, D, seed=3)
   mc, sd = torch.rand(B, generator=gen(4)).to(dev()), torch.rand(B, generator=gen(5)).to(dev())
   xt = torch.empty_like(x0)
@@ -676,3 +677,62 @@ def test_prepare_batch_matches_reference_pipeline(centered, dequant, flip):
     assert not torch.equal(ev, datasets.prepare_batch(cfg, u8.to(dev()), train=False, seed=6))
   else:
     assert torch.allclose(inv, base, atol=1e-6)
+
+
+@pytest.mark.parametrize('shape', [(4, 32, 32, 128, 128, 3, 0.1, True), (2, 16, 16, 256, 256, 3, 0.1, False),
+                                   (8, 8, 8, 256, 256, 3, 0.0, True), (2, 32, 32, 256, 128, 3, 0.0, True),
+                                   (4, 16, 16, 512, 256, 3, 0.1, True), (2, 32, 32, 128, 256, 1, 0.0, False)])
+def test_groupnorm_backward_phase1_in_the_dgrad_gemm_epilogue(shape, monkeypatch):
+  """st_gemm_args.dz_x: the data-gradient convolution stores dz = dy * keep * silu'(u) and emits the quad sums; with
+  st_gn_bwd_dz_apply that must reproduce conv -> st_gn_backward (two-phase form) on the same inputs: dx, the
+  parameter gradients, the column sums; and an fp64 PyTorch reference bounds the error of both."""
+  B, H, W, C, Co, k, p_drop, with_extra = shape
+  bf = torch.bfloat16
+  G = min(C // 4, 32)
+  monkeypatch.setattr(ops, 'GN_DZ', True)                         # (off by default: slower than the two-phase form)
+  x = nhwc(rnd(B, C, H, W, seed=1) * 1.5 + 0.3).to(bf)
+  g = nhwc(rnd(B, Co, H, W, seed=2)).to(bf)                       # gradient arriving at the convolution's output
+  wt = rnd(C, k * k, Co, seed=3, scale=1. / math.sqrt(k * k * Co)).to(bf)     # [cin][tap][cout]: the dgrad-as-forward weights
+  gamma, beta = rnd(C, seed=5) * 0.2 + 1., rnd(C, seed=6) * 0.2
+  extra = nhwc(rnd(B, C, H, W, seed=4)).to(bf) if with_extra else None
+  bits = torch.empty(B * H * W * C // 8, dtype=torch.uint8, device=dev()) if p_drop > 0 else None
+  y, st = ops.gn_norm_act(x, None, G, gamma, beta, 1, p_drop=p_drop, seed=77, keepbits=bits)
+  alpha = 0.7
+  res = []
+  for fused in (False, True):
+    dg, db = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
+    q = ops.ColsumQueue()
+    base = torch.ones_like(x) if not with_extra else None          # accumulate-into-destination variant
+    if fused:
+      assert ops.dz_applicable(x, None, None, p_drop, bits)
+      req = ops.DzRequest(x, G, gamma, beta, st, 1, p_drop, bits)
+      dz, qp = ops.conv_fwd(g, wt, C, k, k, alpha=alpha, dz=req)
+      assert qp is not None, 'the tcgen05 epilogue did not take the dz request'
+      d1, _, cs = ops.gn_backward_dz(x, None, dz, qp, G, gamma, st, dg, db, extra=extra, extra_scale=0.5, dx1=base,
+                                     accum1=base is not None, want_csum=True, queue=q)
+    else:
+      dy = ops.conv_fwd(g, wt, C, k, k, alpha=alpha)
+      d1, _, cs = ops.gn_backward(x, None, dy, G, gamma, beta, st, 1, dg, db, p_drop=p_drop, seed=77, keepbits=bits,
+                                  extra=extra, extra_scale=0.5, dx1=base, accum1=base is not None, want_csum=True, queue=q)
+    q.flush()
+    res.append((d1.float(), cs.sum(1), dg, db))
+  # fp64 reference from the same bf16 inputs (dy kept in fp64: neither path's bf16 rounding of dy / dz)
+  xd = nchw(x.double()).requires_grad_(True)
+  gam, bet = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+  keep = torch.ones_like(xd)
+  if p_drop > 0:
+    kb = bits.view(B, H, W, C // 8).cpu().numpy()
+    keep = torch.from_numpy(np.unpackbits(kb, axis=-1, bitorder='little')).to(dev()).double().permute(0, 3, 1, 2) / (1 - p_drop)
+  yr = F.group_norm(xd, G, gam, bet, eps=1e-6)
+  yr = yr * torch.sigmoid(yr) * keep
+  w4 = wt.double().view(C, k, k, Co).permute(0, 3, 1, 2)         # OIHW of the forward-form convolution
+  dyr = alpha * F.conv2d(nchw(g.double()), w4, padding=k // 2)
+  yr.backward(dyr)
+  want = xd.grad + (0.5 * nchw(extra.double()) if with_extra else 1.0)
+  two, one = res
+  e2, e1 = rel_l2(nchw(two[0]).double(), want), rel_l2(nchw(one[0]).double(), want)
+  assert e2 < 8e-3 and e1 < 8e-3 and e1 < 1.5 * e2 + 1e-3, (e1, e2)
+  assert rel_l2(one[0], two[0]) < 1e-2
+  assert rel_l2(one[1], two[1]) < 5e-3
+  assert rel_l2(one[2].double(), gam.grad) < 5e-3 and rel_l2(one[3].double(), bet.grad) < 5e-3
+  assert rel_l2(one[2], two[2]) < 5e-3 and rel_l2(one[3], two[3]) < 5e-3

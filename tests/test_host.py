@@ -31,7 +31,7 @@ def test_gemm_args_struct_matches_header_layout():
   header = open(os.path.join(ROOT, 'include', 'st_b200.h')).read()
   body = header[header.index('typedef struct st_gemm_args {'):header.index('} st_gemm_args;')]
   fields = []
-  for decl in re.findall(r'^\s*(?:const\s+)?(?:int32_t|int64_t|float|void\*|float\*|void)\W[^;]*;', body, flags=re.M):
+  for decl in re.findall(r'^\s*(?:const\s+)?(?:int32_t|int64_t|uint8_t|float|void\*|float\*|void)\W[^;]*;', body, flags=re.M):
     decl = decl.split('/*')[0].strip().rstrip(';')
     names = decl.replace('const', '').replace('*', ' ').split(None, 1)[1]
     fields += [n.strip() for n in names.split(',')]

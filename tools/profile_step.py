@@ -17,11 +17,12 @@ def main():
   ap.add_argument('--dtype', default='bf16')
   ap.add_argument('--warm', type=int, default=2)
   ap.add_argument('--mode', default='train', choices=['train', 'forward'])
+  ap.add_argument('--config', default='vp/CIFAR10/ddpmpp_nll_st', help='config path under the reference configs/ tree')
   args = ap.parse_args()
   from soft_truncation_b200 import configs, losses, sde_lib
   from soft_truncation_b200.models import utils as mutils
   from soft_truncation_b200.models.ema import ExponentialMovingAverage
-  cfg = configs.cifar10_ddpmpp_nll_st()
+  cfg = configs.get_config(args.config)
   cfg.device = torch.device('cuda:0')
   cfg.model.compute_dtype = args.dtype
   torch.manual_seed(42)
@@ -31,7 +32,10 @@ def main():
   state = dict(model=model, optimizer=losses.get_optimizer(cfg, model.parameters()),
                ema=ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate), step=0)
   step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
-  batch = torch.rand(args.batch, 3, 32, 32, device=cfg.device) * 2 - 1
+  R = cfg.data.image_size
+  batch = torch.rand(args.batch, 3, R, R, device=cfg.device)
+  if cfg.data.centered:
+    batch = batch * 2 - 1
   t = torch.rand(args.batch, device=cfg.device) * 999
 
   def run():
