@@ -225,6 +225,24 @@ int st_gn_bwd_resident(const void* x1, const void* x2, const void* dy, int dtype
                        const uint8_t* keepbits, int chunks, float* red, const void* extra, float extra_scale,
                        void* dx1, void* dx2, float* csum, void* stream);
 
+/* Both backward passes in ONE persistent launch whose phases chase each other through L2 (groupnorm_wave.cu): the work
+ * items of the reduction pass and of the apply pass come from one queue, ordered so that the apply items of a group of
+ * images (x + dy of a group = a fraction of L2) run while the reduction items of the next group stream from HBM; an
+ * apply item waits on a per-image counter for the reduction items of its image.  HBM sees x and dy once and dx once
+ * (3 passes instead of 5), without the load -> barrier -> store chain of the cluster-resident form.  Arguments as for
+ * st_gn_bwd_fused, plus
+ *   chunks, group  the plan st_gn_bwd_wave_plan returns (pixel chunks per image; images per group via *group_out);
+ *                  chunks = 0: the tensor is too small to gain (or ST_GN_WAVE=0) - use the other forms
+ *   red            [n_img][chunks][C][2] (required), csum [n_img][chunks][C] (optional)
+ *   work           int32 [n_img + 2] counters, ZERO on entry; the kernel leaves them zero again.  reset != 0: the
+ *                  library zeroes them first (cudaMemsetAsync on the stream). */
+int st_gn_bwd_wave_plan(int n_img, int hw, int C, int dtype, int* group_out);
+int st_gn_bwd_wave(const void* x1, const void* x2, const void* dy, int dtype, int n_img, int hw, int C1, int C2, int G,
+                   const float* gamma, const float* beta, const float* mean, const float* rstd, int act, float p_drop,
+                   uint64_t seed, const void* mask, const uint8_t* keepbits, int chunks, int group, float* red,
+                   const void* extra, float extra_scale, void* dx1, int accum1, void* dx2, int accum2, float* csum,
+                   int* work, int reset, void* stream);
+
 /* The backward behind a data-gradient GEMM that already produced dz and its quad sums (st_gemm_args.dz_x):
  * st_gn_bwd_consts writes the per-(image, channel) table that epilogue reads, cst[n_img][C][4] =
  * (rstd*gamma, beta - mean*rstd*gamma, gamma, beta); st_gn_bwd_dz_apply is the ONE streaming pass that is left:

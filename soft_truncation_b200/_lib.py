@@ -60,6 +60,9 @@ SIGNATURES = {
     'st_gn_bwd_fused_chunks': [c_int, c_int, c_int, c_int, c_int],
     'st_gn_bwd_fused': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f,
                         c_u64, c_p, c_p, c_int, c_p, c_p, c_f, c_p, c_int, c_p, c_int, c_p, c_p],
+    'st_gn_bwd_wave_plan': [c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32)],
+    'st_gn_bwd_wave': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_int, c_f, c_u64, c_p,
+                       c_p, c_int, c_int, c_p, c_p, c_f, c_p, c_int, c_p, c_int, c_p, c_p, c_int, c_p],
     'st_gn_bwd_consts': [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p],
     'st_gn_bwd_dz_apply': [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_f, c_p,
                            c_int, c_p, c_int, c_int, c_p, c_p, c_p],

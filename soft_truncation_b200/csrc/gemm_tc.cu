@@ -1453,8 +1453,9 @@ int st_gemm_tc2(const st_gemm_args* a, cudaStream_t stream) {
 
   // B kind first (it bounds the cluster size)
   const bool b_kmajor = !wgrad && a->b_mode == ST_OP_STRIDED && a->sBk == 1;
-  int cs = env_int("ST_TC_CLUSTER", 1);
-  if (cs != 1 && cs != 2 && cs != 4) cs = 2;
+  // (round 1's B-tile multicast across 2 / 4 single-MMA CTAs is superseded by the CTA-pair form and no longer maintained:
+  // with the round-2 barrier counts it produces wrong tiles - the ST_TC_CLUSTER switch is therefore gone)
+  int cs = 1;
   while (cs > 1 && cs > p.m_tiles) cs >>= 1;
   if (!b_kmajor) while (cs > 1 && cs > BN / 64) cs >>= 1;
   // CTA pairs (tcgen05.mma.cta_group::2): the big tiles, whenever there are at least two row blocks to pair

@@ -340,14 +340,28 @@ def gn_norm_act(x, x2, G, gamma, beta, act, p_drop=0., seed=0, mask=None, keepbi
   return y, GnStats(stats)
 
 
+_WAVE_WORK = {}
+
+
+def _wave_work(device, n_img):
+  """Zeroed int32 counters of st_gn_bwd_wave (the kernel hands them back zeroed), one buffer per device."""
+  w = _WAVE_WORK.get(device)
+  if w is None or w.numel() < n_img + 2:
+    w = torch.zeros(max(n_img + 2, 1024), dtype=torch.int32, device=device)
+    _WAVE_WORK[device] = w
+  return w
+
+
 def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0., seed=0, mask=None, extra=None,
                 extra_scale=1.0, dx1=None, accum1=False, dx2=None, accum2=False, keepbits=None, want_csum=False,
-                queue=None, fused_chunks=None, resident=None):
+                queue=None, fused_chunks=None, resident=None, wave=None):
   """Returns (dx1, dx2[, csum]); accumulates dgamma/dbeta (fp32 views into the flat gradient buffer).
   csum (want_csum): fp32 (B, chunks, C1+C2) column sums of the gradient this call contributed.
   `queue`: a ColsumQueue that takes the dgamma/dbeta reduction of the fused (single-launch) form; `fused_chunks`:
   cluster size override (0 = two-kernel form, None = the library decides); `resident`: cluster size of the form that
-  keeps x / dy in shared memory between the two phases (2-stream calls only; None = the library decides, 0 = off)."""
+  keeps x / dy in shared memory between the two phases (2-stream calls only; None = the library decides, 0 = off);
+  `wave`: the persistent two-phase form (st_gn_bwd_wave; None = whenever no other form is forced and the tensor is
+  large enough to gain, False = off)."""
   B, H, W, C1 = x.shape
   C2 = 0 if x2 is None else x2.shape[3]
   hw, Ct = H * W, C1 + C2
@@ -362,6 +376,24 @@ def gn_backward(x, x2, dy, G, gamma, beta, stats, act, dgamma, dbeta, p_drop=0.,
   head = (ptr(x), ptr(x2), ptr(dy), dt(x), B, hw, C1, C2, G, ptr(gamma), ptr(beta), ptr(stats[0]), ptr(stats[1]),
           int(act), float(p_drop), int(seed), ptr(mask), ptr(keepbits))
   n_streams = 2 + (extra is not None) + bool(accum1 or accum2)
+  if wave is None:
+    wave = fused_chunks is None and resident is None
+  if wave:
+    # one persistent launch, reduction items of the next group of images overlapping the apply items of this one
+    group = ctypes.c_int32(0)
+    wc = lib.st_gn_bwd_wave_plan(B, hw, Ct, dt(x), ctypes.byref(group))
+    if wc > 0:
+      red = torch.empty((B, wc, Ct, 2), dtype=torch.float32, device=x.device)
+      csum = torch.empty((B, wc, Ct), dtype=torch.float32, device=x.device) if want_csum else None
+      check(lib.st_gn_bwd_wave(*head, int(wc), int(group.value), ptr(red), ptr(extra), float(extra_scale), ptr(dx1), int(accum1),
+                               ptr(dx2), int(accum2), ptr(csum), ptr(_wave_work(x.device, B)), 0, stream()))
+      if dgamma is None:
+        pass
+      elif queue is not None:
+        queue.add_gn_params(dgamma, dbeta, red.view(B * wc, Ct, 2))
+      else:
+        check(lib.st_gn_bwd_params(ptr(red), B * wc, Ct, ptr(dgamma), ptr(dbeta), stream()))
+      return (dx1, dx2, csum) if want_csum else (dx1, dx2)
   if resident is None:
     ok = fused_chunks is None and not (accum1 or accum2)
     resident = lib.st_gn_bwd_resident_chunks(B, hw, Ct, n_streams) if ok else 0

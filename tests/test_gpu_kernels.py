@@ -736,3 +736,55 @@ def test_groupnorm_backward_phase1_in_the_dgrad_gemm_epilogue(shape, monkeypatch
   assert rel_l2(one[1], two[1]) < 5e-3
   assert rel_l2(one[2].double(), gam.grad) < 5e-3 and rel_l2(one[3].double(), bet.grad) < 5e-3
   assert rel_l2(one[2], two[2]) < 5e-3 and rel_l2(one[3], two[3]) < 5e-3
+
+
+@pytest.mark.parametrize('shape', [(50, 64, 64, 128, 0, 0.1, 'extra'), (200, 32, 32, 128, 0, 0.1, 'plain'),
+                                   (37, 32, 32, 256, 128, 0.0, 'accum'), (130, 16, 16, 256, 256, 0.1, 'extra'),
+                                   (3, 256, 256, 128, 0, 0.0, 'extra')])
+def test_groupnorm_backward_wave_form_matches_two_pass(shape):
+  """st_gn_bwd_wave (one persistent launch, apply items of one group of images behind the reduction items of the next)
+  against the two-kernel form on the same inputs: several groups, a short last group, concatenated sources, in-kernel
+  dropout bits, extra / accumulated destinations, column sums, parameter gradients; and the counters come back zeroed
+  (two calls in a row)."""
+  from soft_truncation_b200._lib import lib
+  import ctypes
+  B, H, W, C1, C2, p_drop, mode = shape
+  C, bf = C1 + C2, torch.bfloat16
+  G = min(C // 4, 32)
+  grp = ctypes.c_int32(0)
+  chunks = lib.st_gn_bwd_wave_plan(B, H * W, C, 1, ctypes.byref(grp))
+  if chunks == 0:
+    pytest.skip('the wave form is off by default (measured slower): run with ST_GN_WAVE=1')
+  assert 1 <= grp.value <= B
+  x1 = nhwc(rnd(B, C1, H, W, seed=1)).to(bf)
+  x2 = nhwc(rnd(B, C2, H, W, seed=2)).to(bf) if C2 else None
+  dy = nhwc(rnd(B, C, H, W, seed=3)).to(bf)
+  extra = nhwc(rnd(B, C, H, W, seed=4)).to(bf) if mode == 'extra' else None
+  gamma, beta = rnd(C, seed=5) * 0.2 + 1., rnd(C, seed=6) * 0.2
+  bits = torch.empty(B * H * W * C // 8, dtype=torch.uint8, device=dev()) if p_drop > 0 else None
+  st = ops.gn_stats(x1, x2, G)
+  ops.gn_apply(x1, x2, G, gamma, beta, st, 1, p_drop=p_drop, seed=77, keepbits=bits)
+  res = []
+  for form in ('two_pass', 'wave', 'wave'):
+    dg, db = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
+    q = ops.ColsumQueue()
+    b1 = torch.ones_like(x1) if mode == 'accum' else None
+    b2 = torch.ones_like(x2) if (mode == 'accum' and C2) else None
+    kw = dict(fused_chunks=0) if form == 'two_pass' else dict(wave=True)
+    d1, d2, cs = ops.gn_backward(x1, x2, dy, G, gamma, beta, st, 1, dg, db, p_drop=p_drop, seed=77, keepbits=bits,
+                                 extra=extra, extra_scale=0.7, dx1=b1, accum1=b1 is not None, dx2=b2, accum2=b2 is not None,
+                                 want_csum=True, queue=q, **kw)
+    q.flush()
+    if form == 'wave':
+      assert cs.shape[1] == chunks
+    res.append((d1.float(), d2.float() if C2 else None, cs.sum(1), dg, db))
+  torch.cuda.synchronize()
+  assert int(ops._wave_work(dev(), B).abs().sum()) == 0
+  two = res[0]
+  for one in res[1:]:
+    assert torch.equal(two[0], one[0]) or rel_l2(one[0], two[0]) < 3e-3     # bf16 outputs, fp32 sums in another order
+    if C2:
+      assert rel_l2(one[1], two[1]) < 3e-3
+    assert rel_l2(one[2], two[2]) < 1e-3
+    assert rel_l2(one[3], two[3]) < 1e-4 and rel_l2(one[4], two[4]) < 1e-4
+  assert two[3].abs().sum() > 0
