@@ -1,8 +1,6 @@
-# GPU run 19 (one B200): full GPU suite, smoke, default bench line (with the reference legs), reference arm
+# GPU run 20 (one B200): FIR kernel with batched footprint loads
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1; echo "build rc=$?"
-timeout 1500 python -m pytest tests -q -m gpu --timeout=900 > gpurun_out/t_gpu_final.log 2>&1; echo "pytest -m gpu rc=$?"; tail -n 4 gpurun_out/t_gpu_final.log
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_final.log 2>&1; echo "smoke rc=$?"; tail -n 3 gpurun_out/smoke_final.log
-timeout 900 python bench.py > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; echo "bench rc=$?"; cut -c1-400 gpurun_out/r02_bench_1gpu.json; tail -3 gpurun_out/r02_bench_1gpu.err
-timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench_reference_arm.err; echo "reference arm rc=$?"; cut -c1-300 gpurun_out/r02_bench_reference_arm.json
+timeout 600 python -m pytest tests/test_gpu_round2.py tests/test_gpu_kernels.py tests/test_gpu_parity.py -q -k "upfirdn or fir or full_width" --timeout=300 > gpurun_out/t_fir.log 2>&1; echo "fir tests rc=$?"; tail -n 3 gpurun_out/t_fir.log
+timeout 300 python tools/upfirdn_bench.py > gpurun_out/r02_upfirdn_bench.txt 2>&1; echo "upfirdn rc=$?"; cat gpurun_out/r02_upfirdn_bench.txt

@@ -145,54 +145,31 @@ __global__ void __launch_bounds__(256) upfirdn2d_fast_kernel(const T* __restrict
     colm[c] = (ix >= 0 && ix < in_w) ? 1.f : 0.f;
     colo[c] = min(max(ix, 0), in_w - 1) * minor;
   }
-  // rows in batches of RB: the raw 16-byte vectors of a whole batch (<= 12 loads) are requested before the first of them
-  // is used, so that a thread keeps ~190 bytes in flight instead of one footprint row
-  constexpr int RB = (12 / RX) > 0 ? (12 / RX) : 1;
 #pragma unroll
-  for (int r0 = 0; r0 < RY; r0 += RB) {
-    uint4 raw[RB][RX];
-    float rowm[RB];
+  for (int r = 0; r < RY; ++r) {
+    const int iy = iy0 + r;
+    const float rowm = (iy >= 0 && iy < in_h) ? 1.f : 0.f;
+    const T* row = src0 + (long long)min(max(iy, 0), in_h - 1) * in_w * minor;
+    float v[RX][V];
 #pragma unroll
-    for (int rr = 0; rr < RB; ++rr) {
-      const int r = r0 + rr;
-      if (r >= RY) continue;
-      const int iy = iy0 + r;
-      rowm[rr] = (iy >= 0 && iy < in_h) ? 1.f : 0.f;
-      const T* row = src0 + (long long)min(max(iy, 0), in_h - 1) * in_w * minor;
-#pragma unroll
-      for (int c = 0; c < RX; ++c) {
-        if constexpr (V == 8) raw[rr][c] = __ldg(reinterpret_cast<const uint4*>(row + colo[c]));
-        else raw[rr][c] = __ldg(reinterpret_cast<const uint4*>(row + colo[c]));
-      }
+    for (int c = 0; c < RX; ++c) {
+      if constexpr (V == 8) ld8(row + colo[c], v[c]);
+      else load4(row + colo[c], v[c]);
     }
 #pragma unroll
-    for (int rr = 0; rr < RB; ++rr) {
-      const int r = r0 + rr;
-      if (r >= RY) continue;
+    for (int c = 0; c < RX; ++c) {
+      const float msk = rowm * colm[c];
 #pragma unroll
-      for (int c = 0; c < RX; ++c) {
-        float v[V];
-        if constexpr (V == 8) {
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[rr][c]);
+      for (int a = 0; a < BY; ++a) {
+        const int dy = r - (G::in0(a) - R0);
+        if (dy < 0 || dy >= G::TAPS) continue;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
-        } else {
-          v[0] = __uint_as_float(raw[rr][c].x); v[1] = __uint_as_float(raw[rr][c].y);
-          v[2] = __uint_as_float(raw[rr][c].z); v[3] = __uint_as_float(raw[rr][c].w);
-        }
-        const float msk = rowm[rr] * colm[c];
+        for (int b = 0; b < BX; ++b) {
+          const int dx = c - (G::in0(b) - R0);
+          if (dx < 0 || dx >= G::TAPS) continue;
+          const float wt = w[(G::k0(a) + dy * UP) * K + G::k0(b) + dx * UP] * msk;
 #pragma unroll
-        for (int a = 0; a < BY; ++a) {
-          const int dy = r - (G::in0(a) - R0);
-          if (dy < 0 || dy >= G::TAPS) continue;
-#pragma unroll
-          for (int b = 0; b < BX; ++b) {
-            const int dx = c - (G::in0(b) - R0);
-            if (dx < 0 || dx >= G::TAPS) continue;
-            const float wt = w[(G::k0(a) + dy * UP) * K + G::k0(b) + dx * UP] * msk;
-#pragma unroll
-            for (int e = 0; e < V; ++e) acc[a][b][e] = fmaf(v[e], wt, acc[a][b][e]);
-          }
+          for (int e = 0; e < V; ++e) acc[a][b][e] = fmaf(v[c][e], wt, acc[a][b][e]);
         }
       }
     }
