@@ -383,6 +383,11 @@ class _StepGraph:
     self.graph_a = self.graph_b = None
     self.losses = None
     self.pinned = []
+    # the per-sample losses leave the device on a side stream as soon as graph A has produced them: the host gets them
+    # (and starts enqueueing the next step) while the gradient all-reduce and graph B are still running
+    self.side = torch.cuda.Stream(device=dev)
+    self.losses_host = torch.empty(B, dtype=torch.float32).pin_memory()
+    self.ev_a, self.ev_copy = torch.cuda.Event(), torch.cuda.Event()
 
   @staticmethod
   def _key(state, batch_shape):
@@ -396,7 +401,9 @@ class _StepGraph:
     return (id(net), id(opt), id(ema), tuple(batch_shape), tuple(ptrs), _world())
 
   def _dynamic_t_min(self):
-    return isinstance(self.sde, VPSDE) and bool(self.config.training.st)
+    # every VP step reads its t_min-dependent scalars from device memory, soft-truncated or not: the eager expressions
+    # mix 0-dim HOST tensors (Z, A) into device arithmetic, which stream capture refuses (ImageNet32 / C4 ran eagerly)
+    return isinstance(self.sde, VPSDE)
 
   # ---- the step body (runs once, under capture)
   def _body_a(self):
@@ -468,13 +475,21 @@ class _StepGraph:
       lr, bc1, bc2 = opt.hyper()
       self.hp_f32[4:8] = torch.tensor([lr, bc1, bc2, ema.next_decay()], dtype=torch.float32)
     self.graph_a.replay()
+    main = torch.cuda.current_stream(self.dev)
+    self.ev_a.record(main)
+    with torch.cuda.stream(self.side):
+      self.side.wait_event(self.ev_a)
+      self.losses_host.copy_(self.losses, non_blocking=True)
+      self.ev_copy.record(self.side)
     sync_gradients(state['model'])
     if self.fused_opt:
       self.graph_b.replay()
       state['step'] += 1
     else:
       finish(state, state['model'], reduced=True)
-    return self.losses
+    main.wait_event(self.ev_copy)                       # the next replay of graph A overwrites self.losses
+    self.ev_copy.synchronize()
+    return self.losses_host.clone()
 
 
 def _graph_eligible(config, sde, state, batch, injected):
@@ -566,7 +581,7 @@ def get_step_fn(config, sde, train, optimize_fn=None):
     if batch.is_cuda:
       losses = _graph_step(state, batch, injected)
       if losses is not None:
-        return losses.cpu()
+        return losses.cpu() if losses.is_cuda else losses
     _zero_grad(state)
     B = batch.shape[0]
     nmb = config.optim.num_micro_batch

@@ -118,15 +118,19 @@ def test_step_graph_matches_eager(dtype, dropout):
     assert not torch.allclose(ls[3], ls[4], rtol=1e-4)
 
 
-def test_step_graph_is_used_and_keeps_rng_stream():
+@pytest.mark.parametrize('st', [True, False])
+def test_step_graph_is_used_and_keeps_rng_stream(st):
   """Without injected draws the graph step consumes torch's CUDA generator exactly like the eager step (u = rand(B), then
-  z = randn) - the per-step losses of both modes agree - and the captured graphs are really what runs."""
+  z = randn) - the per-step losses of both modes agree - and the captured graphs are really what runs, with and without
+  soft truncation (st=False: the ImageNet32 / C4 recipe, fixed t_min)."""
   from soft_truncation_b200 import losses
+  import warnings
   B = 8
   batch = (torch.rand(B, 3, 32, 32, generator=torch.Generator().manual_seed(1)) * 2 - 1).to(DEV)
   out = {}
   for mode in ('eager', 'graph'):
     cfg = _small(_cfg(dropout=0.))
+    cfg.training.st = st
     cfg.optim.warmup = 0
     cfg.optim.cuda_graph = (mode == 'graph')
     model, sde, _ = _model(cfg, 6, torch.float32)
@@ -137,7 +141,9 @@ def test_step_graph_is_used_and_keeps_rng_stream():
     torch.cuda.manual_seed(7)
     from soft_truncation_b200 import _lib
     l0 = _lib.launches
-    ls = [step_fn(state, batch) for _ in range(5)]
+    with warnings.catch_warnings():
+      warnings.filterwarnings('error', message='.*CUDA-graph capture.*')      # a failed capture only warns
+      ls = [step_fn(state, batch) for _ in range(5)]
     out[mode] = (torch.stack(ls), _lib.launches - l0)
   assert rel_l2(out['graph'][0], out['eager'][0]) < 2e-5
   # two eager steps + one capture pass instead of five eager steps worth of C-ABI calls
