@@ -40,7 +40,7 @@ if ROOT not in sys.path:
 
 # DRAM bytes per GEMM launch (average over the GEMM launches of one B=512 bf16 c2 step), from the ncu launch list
 # committed under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum); see profiles/README.md for the file
-GEMM_DRAM_BYTES_PER_LAUNCH = 52.07e9 / 420
+GEMM_DRAM_BYTES_PER_LAUNCH = 52.16e9 / 420
 TRAFFIC_SOURCE = 'profiles/r02_launches_train_step.md'
 
 # name -> config path under the reference's configs/, per-GPU train batch, sampler batch, forward GF / image

@@ -1,6 +1,6 @@
 """Runs one GEMM case of the bench workload a few times (for `ncu --set full --import-source on`).
-GP_CASE in {fwd128, fwd256, dgrad128, wgrad128, attn_qk, attn_pv, nin768, nin256}; kernel variant / cluster via
-ST_TC_VARIANT / ST_TC_CLUSTER."""
+GP_CASE in {fwd128, fwd256, dgrad128, wgrad128, attn_qk, attn_pv, nin768, nin256}; kernel variant / pair form via
+ST_TC_VARIANT / ST_TC_CG."""
 import os
 import sys
 
