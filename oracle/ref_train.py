@@ -7,6 +7,7 @@ network, with all randomness INJECTED:
 * time sampling + soft truncation    - reference sde_lib.py:180-207 (VP), 314-332 (VE), 421-430 (RVE)
 * score wrapper                      - reference models/utils.py:128-190
 * DSM loss (IS / plain / likelihood-weighted branches) - reference losses.py:101-132
+* reconstruction (decoder) term    - reference losses.py:80-100, 134-164
 * step_fn / step_fn_mixed            - reference losses.py:262-293, 295-320
 * warm-up / clip / Adam              - reference losses.py:44-58, torch.optim.Adam
 * EMA                                - reference models/ema.py:32-51
@@ -14,7 +15,7 @@ network, with all randomness INJECTED:
                                      - reference sampling.py:185-210, 263-292, 402-431
 
 Parity pin: tests/golden/train_golden.npz, sampler_golden.npz, variants_golden.npz, deepest_golden.npz and
-lossbranch_golden.npz (made from the untouched reference by tests/golden/make_golden.py) are checked in
+lossbranch_golden.npz, recon_golden.npz (made from the untouched reference by tests/golden/make_golden.py) are checked in
 tests/test_oracle.py.
 """
 import math
@@ -142,8 +143,40 @@ def score_fn(sd, cfg, sde, x, t, train=False, drop_masks=None):
   return sde.score_from_out(out, t)
 
 
-def dsm_losses(sd, cfg, sde, batch, u, z, t_min, train=True, drop_masks=None, importance_sampling=None):
-  """Per-sample losses of reference losses.py:101-132 for injected uniforms `u` and noise `z`.
+def reconstruction_term(sd, cfg, sde, batch, t_min, z2, train=True, variance='scoreflow'):
+  """Decoder term of reference losses.py:134-164 for the injected second noise `z2`: second score evaluation at
+  t = t_min, q(x | x_tmin) = N((x_t + beta^2 s) / alpha, q_std^2) with q_std = beta ('ddpm') or beta / alpha
+  ('scoreflow'); 'lossless' data: minus the discretised Gaussian log-likelihood (:83-100), otherwise the Gaussian
+  cross-entropy minus the entropy of the perturbation kernel at t_min (:139 re-binds `std`)."""
+  B = batch.shape[0]
+  eps_vec = torch.ones(B) * t_min
+  alpha, beta = sde.mean_coeff(eps_vec), sde.std(eps_vec)
+  x_t = alpha[:, None, None, None] * batch + beta[:, None, None, None] * z2
+  score = score_fn(sd, cfg, sde, x_t, eps_vec, train=train)
+  q_mean = x_t / alpha[:, None, None, None] + beta[:, None, None, None] ** 2 * score / alpha[:, None, None, None]
+  q_std = beta if variance == 'ddpm' else beta / alpha
+  if cfg.data.dequantization == 'lossless':
+    cdf = lambda v: 0.5 * (1.0 + torch.tanh(np.sqrt(2.0 / np.pi) * (v + 0.044715 * (v ** 3))))
+    inv = 1. / q_std[:, None, None, None]
+    plus, minus = cdf(inv * (batch - q_mean + 1. / 255.)), cdf(inv * (batch - q_mean - 1. / 255.))
+    lo = torch.tensor(1e-12)
+    ll = torch.where(batch < -0.999, torch.log(torch.max(plus, lo)),
+                     torch.where(batch > 0.999, torch.log(torch.max(1. - minus, lo)), torch.log(torch.max(plus - minus, lo))))
+    rec = -ll.sum(dim=(1, 2, 3))
+  else:
+    n = float(np.prod(batch.shape[1:]))
+    p_entropy = n / 2. * (np.log(2 * np.pi) + 2 * torch.log(beta) + 1.)
+    rec = n / 2. * (np.log(2 * np.pi) + 2 * torch.log(q_std)) + 0.5 / q_std ** 2 * torch.square(batch - q_mean).sum(dim=(1, 2, 3)) \
+        - p_entropy
+  if cfg.training.reduce_mean:
+    rec = rec / float(np.prod(batch.shape[1:]))
+  return rec
+
+
+def dsm_losses(sd, cfg, sde, batch, u, z, t_min, train=True, drop_masks=None, importance_sampling=None, z2=None,
+               variance='scoreflow'):
+  """Per-sample losses of reference losses.py:101-132 (+ the reconstruction term :134-164 when the config asks for it)
+  for injected uniforms `u` and noise `z` (`z2`: the second perturbation of the reconstruction term).
   `importance_sampling` (the loss_fn ARGUMENT, :101,112) only selects how the times are drawn; the loss formula is keyed
   on the config (:122) - the two differ inside step_fn_mixed."""
   tr = cfg.training
@@ -152,6 +185,11 @@ def dsm_losses(sd, cfg, sde, batch, u, z, t_min, train=True, drop_masks=None, im
   x_t = sde.mean_coeff(t)[:, None, None, None] * batch + std[:, None, None, None] * z
   score = score_fn(sd, cfg, sde, x_t, t, train=train, drop_masks=drop_masks)
   reduce = (lambda v: v.mean(dim=-1)) if tr.reduce_mean else (lambda v: 0.5 * v.sum(dim=-1))
+  if tr.reconstruction_loss:
+    assert tr.importance_sampling or not tr.likelihood_weighting
+    sq = torch.square(score * std[:, None, None, None] + z)
+    return 0.5 * Z * reduce(sq.reshape(sq.shape[0], -1)) + \
+        reconstruction_term(sd, cfg, sde, batch, t_min, z2, train=train, variance=variance)
   if tr.importance_sampling or not tr.likelihood_weighting:
     sq = torch.square(score * std[:, None, None, None] + z)
     return 0.5 * Z * reduce(sq.reshape(sq.shape[0], -1))

@@ -237,11 +237,52 @@ def get_sde_loss_fn(config, sde, train, variance='scoreflow'):
   """loss_fn(model, batch, importance_sampling, t_min=None) -> per-sample losses
   (reference losses.py:61-168, core :101-132)."""
   tr = config.training
-  if tr.reconstruction_loss:
-    raise NotImplementedError('training.reconstruction_loss (off in every BASELINE config) is not built')
+  if variance not in ('ddpm', 'scoreflow'):
+    raise ValueError(f'unknown decoder variance {variance!r}')
+
+  def _std_normal_cdf(v):      # tanh approximation of the standard normal CDF (reference :80-81)
+    return 0.5 * (1.0 + torch.tanh(np.sqrt(2.0 / np.pi) * (v + 0.044715 * (v ** 3))))
+
+  def _discretized_gaussian_ll(x, means, log_scales):
+    """log-likelihood of 8-bit data rescaled to [-1, 1] under a Gaussian discretised to bins of width 2/255, with the
+    open-ended first / last bin (reference losses.py:83-100)."""
+    centered, inv = x - means, torch.exp(-log_scales)
+    cdf_plus, cdf_min = _std_normal_cdf(inv * (centered + 1. / 255.)), _std_normal_cdf(inv * (centered - 1. / 255.))
+    floor = torch.tensor(1e-12, device=x.device)
+    log_plus = torch.log(torch.max(cdf_plus, floor))
+    log_one_minus_min = torch.log(torch.max(1. - cdf_min, floor))
+    log_mid = torch.log(torch.max(cdf_plus - cdf_min, floor))
+    return torch.where(x < -0.999, log_plus, torch.where(x > 0.999, log_one_minus_min, log_mid))
+
+  def _reconstruction_term(model, batch, t_min, z2):
+    """The decoder term of the NELBO at t_min added to the DSM losses when training.reconstruction_loss is set
+    (reference losses.py:134-164): a second network evaluation at t = t_min on a fresh perturbation, the Gaussian
+    decoder q(x | x_{t_min}) with mean (x_t + beta^2 score) / alpha and deviation beta [/ alpha for 'scoreflow'], scored
+    either by the discretised Gaussian likelihood ('lossless' dequantisation) or by the cross-entropy minus the
+    entropy of the perturbation kernel at t_min."""
+    B, dev = batch.shape[0], batch.device
+    eps_vec = torch.ones(B, device=dev) * t_min
+    mean, std = sde.marginal_prob(batch, eps_vec)
+    xt = mean + std[:, None, None, None] * z2
+    score = mutils.get_score_fn(config, sde, model, train=train, continuous=tr.continuous)(xt, eps_vec)
+    alpha, beta = sde.marginal_prob(torch.ones_like(batch), eps_vec)
+    q_mean = xt / alpha + beta[:, None, None, None] ** 2 * score / alpha
+    q_std = beta if variance == 'ddpm' else beta / torch.mean(alpha, dim=(1, 2, 3))
+    if config.data.dequantization == 'lossless':
+      rec = -_discretized_gaussian_ll(batch, q_mean, torch.log(q_std)[:, None, None, None]).sum(dim=(1, 2, 3))
+    else:
+      n_dim = float(np.prod(batch.shape[1:]))
+      p_entropy = n_dim / 2. * (np.log(2 * np.pi) + 2 * torch.log(std) + 1.)
+      q_recon = n_dim / 2. * (np.log(2 * np.pi) + 2 * torch.log(q_std)) + \
+          0.5 / (q_std ** 2) * torch.square(batch - q_mean).sum(dim=(1, 2, 3))
+      rec = q_recon - p_entropy
+    if tr.reduce_mean:
+      rec = rec / float(np.prod(batch.shape[1:]))
+    return rec
 
   def loss_fn(model, batch, importance_sampling, t_min=None, injected=None):
-    """`injected` = dict(u=..., z=...) replaces the two random draws (parity tests)."""
+    """`injected` = dict(u=..., z=...[, z2=...]) replaces the random draws (parity tests); z2 is the noise of
+    the reconstruction term's second perturbation."""
     if t_min is None:
       t_min = sde.get_t_min(config)
     B, dev = batch.shape[0], batch.device
@@ -255,7 +296,11 @@ def get_sde_loss_fn(config, sde, train, variance='scoreflow'):
     xt, labels, a, b, w = _dsm_inputs(config, sde, batch, t, Z, z)
     model_fn = mutils.get_model_fn(model, train=train)
     out = model_fn(xt, labels)
-    return _DsmLoss.apply(out, z, a, b, w, bool(tr.reduce_mean))
+    losses = _DsmLoss.apply(out, z, a, b, w, bool(tr.reduce_mean))
+    if tr.reconstruction_loss:
+      z2 = injected['z2'].to(dev).float() if injected is not None and 'z2' in injected else torch.randn_like(batch)
+      losses = losses + _reconstruction_term(model, batch, t_min, z2)
+    return losses
 
   return loss_fn
 
@@ -500,6 +545,8 @@ def _graph_eligible(config, sde, state, batch, injected):
     return False
   if config.optim.num_micro_batch != 1 or int(getattr(config.optim, 'l2_blocks', 1) or 1) != 1 or config.training.mixed:
     return False
+  if config.training.reconstruction_loss:
+    return False                                      # second network evaluation at t_min: eager autograd path
   if net.drop_masks is not None or net._taps is not None:
     return False                                      # injected dropout masks / activation taps: eager parity paths
   if injected is not None and any(k not in ('t_min', 'u', 'z') for k in injected):

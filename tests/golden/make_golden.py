@@ -418,6 +418,39 @@ def golden_lossbranches(R):
   np.savez_compressed(os.path.join(HERE, 'lossbranch_golden.npz'), **out)
 
 
+def golden_recon(R):
+  """The reconstruction (decoder) term of the loss (reference losses.py:134-164), which no shipped config switches on:
+  reduced CIFAR VP net, importance-sampled DSM loss + decoder term, for 'uniform' data (Gaussian cross-entropy minus the
+  perturbation entropy; both decoder variances) and 'lossless' data (discretised Gaussian likelihood).  The three torch
+  draws of loss_fn (u, z, second z) are replayed from the seed."""
+  out = {}
+  for tag, deq, variance, reduce_mean in (('uni_sf', 'uniform', 'scoreflow', False), ('uni_ddpm', 'uniform', 'ddpm', True),
+                                          ('lossless', 'lossless', 'scoreflow', False)):
+    cfg = reduced_cifar(ref_config('vp/CIFAR10/ddpmpp_nll_st'))
+    cfg.model.dropout = 0.
+    cfg.training.reconstruction_loss = True
+    cfg.training.reduce_mean = reduce_mean
+    cfg.data.dequantization = deq
+    model, sde, _ = build_ref_model(R, cfg, seed=23)
+    g = torch.Generator().manual_seed(43)
+    x = torch.rand(2, 3, 32, 32, generator=g)
+    if deq == 'lossless':
+      x = torch.round(x * 255.) / 255.
+      x[0, 0, 0, :4] = torch.tensor([0., 1., 0., 1.])        # exercise the open-ended first / last bins
+    x = x * 2. - 1.
+    loss_fn = R.losses.get_sde_loss_fn(cfg, sde, train=True, variance=variance)
+    t_min = 2e-3
+    torch.manual_seed(10)
+    u, z, z2 = torch.rand(2), torch.randn(2, 3, 32, 32), torch.randn(2, 3, 32, 32)
+    torch.manual_seed(10)
+    losses = loss_fn(model, x, importance_sampling=True, t_min=t_min)
+    torch.mean(losses).backward()
+    gnorm = np.array([0. if p.grad is None else p.grad.double().norm().item() for p in model.parameters()])
+    out.update({f'{tag}_x': x.numpy(), f'{tag}_u': u.numpy(), f'{tag}_z': z.numpy(), f'{tag}_z2': z2.numpy(),
+                f'{tag}_tmin': t_min, f'{tag}_losses': losses.detach().numpy(), f'{tag}_gnorm': gnorm, f'{tag}_seed': 23})
+  np.savez_compressed(os.path.join(HERE, 'recon_golden.npz'), **out)
+
+
 def golden_sde_reverse(R):
   """a6-a9 on every SDE class incl. subVPSDE: sde / marginal_prob / prior_logp / discretize and the reverse-time SDE
   (lambda 1), a lambda 0.5 interpolation and the probability-flow ODE (lambda 0) built by SDE.reverse with a fixed
@@ -675,7 +708,7 @@ def main(which):
   R = import_reference()
   jobs = dict(configs=golden_configs, ops=golden_ops, sde=golden_sde, unet=golden_unet_cifar,
               variants=golden_variants, sampler=golden_sampler, train=golden_train, deepest=golden_deepest,
-              likelihood=golden_likelihood, lossbranches=golden_lossbranches,
+              likelihood=golden_likelihood, lossbranches=golden_lossbranches, recon=golden_recon,
               sde_reverse=golden_sde_reverse, score_fn=golden_score_fn,
               predictors=golden_predictors, checkpoint=golden_checkpoint, fullwidth=golden_fullwidth,
               traj100=golden_traj100)

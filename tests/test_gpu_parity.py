@@ -474,6 +474,39 @@ def test_likelihood_weighted_loss_branch_vs_reference_fixture(golden, tag):
   np.testing.assert_allclose(gn, g[f'{tag}_gnorm'], rtol=2e-3, atol=1e-6 * g[f'{tag}_gnorm'].max())
 
 
+@pytest.mark.parametrize('tag,deq,variance,reduce_mean', [('uni_sf', 'uniform', 'scoreflow', False), ('uni_ddpm', 'uniform', 'ddpm', True),
+                                                         ('lossless', 'lossless', 'scoreflow', False)])
+def test_reconstruction_loss_term_vs_reference_fixture(golden, tag, deq, variance, reduce_mean):
+  """reference losses.py:134-164 (training.reconstruction_loss): the DSM loss plus the decoder term at t_min - a second
+  network evaluation inside one backward pass - against the reference fixture: losses and every gradient norm; and one
+  optimizer step through step_fn (the captured-graph path must stand aside for it)."""
+  from soft_truncation_b200 import losses
+  from soft_truncation_b200.models import utils as mutils
+  from soft_truncation_b200.models.ema import ExponentialMovingAverage
+  g = golden('recon_golden.npz')
+  cfg = _cfg(dropout=0.)
+  cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks = 32, (1, 2), 1
+  cfg.training.reconstruction_loss, cfg.training.reduce_mean, cfg.data.dequantization = True, reduce_mean, deq
+  model, sde, _ = _model(cfg, int(g[f'{tag}_seed']), torch.float32)
+  net = mutils.unwrap(model)
+  loss_fn = losses.get_sde_loss_fn(cfg, sde, train=True, variance=variance)
+  net.zero_grad()
+  inj = dict(u=torch.tensor(g[f'{tag}_u']), z=torch.tensor(g[f'{tag}_z']), z2=torch.tensor(g[f'{tag}_z2']))
+  ls = loss_fn(model, torch.tensor(g[f'{tag}_x'], device=DEV), importance_sampling=True, t_min=float(g[f'{tag}_tmin']), injected=inj)
+  np.testing.assert_allclose(ls.detach().cpu().numpy(), g[f'{tag}_losses'], rtol=3e-4)
+  torch.mean(ls).backward()
+  gn = np.array([p.grad.double().norm().item() if p.requires_grad else 0. for _, p in net.named_parameters()])
+  np.testing.assert_allclose(gn, g[f'{tag}_gnorm'], rtol=3e-3, atol=1e-6 * g[f'{tag}_gnorm'].max())
+  if variance == 'scoreflow':       # what step_fn builds (get_sde_loss_fn's default decoder variance)
+    state = dict(optimizer=losses.get_optimizer(cfg, model.parameters()), model=model,
+                 ema=ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate), step=0)
+    step_fn = losses.get_step_fn(cfg, sde, train=True, optimize_fn=losses.optimization_manager(cfg))
+    before = net._flat.clone()
+    for _ in range(4):              # past the point where an eligible step would have been captured
+      got = step_fn(state, torch.tensor(g[f'{tag}_x'], device=DEV), injected=dict(inj, t_min=float(g[f'{tag}_tmin'])))
+    assert state['step'] == 4 and torch.isfinite(got).all() and not torch.equal(before, net._flat)
+
+
 def test_pc_sampler_ve_langevin_vs_reference_fixture(golden):
   """4-step reverse-diffusion predictor + Langevin corrector (VE) on the reduced C5 network: pins the
   ReverseDiffusionPredictor / LangevinCorrector updates, the on-device batch norms and the final VE denoise step."""

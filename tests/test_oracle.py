@@ -258,6 +258,33 @@ def test_likelihood_weighted_loss_branch_oracle_vs_reference(golden, tag):
   np.testing.assert_allclose(gn, g[f'{tag}_gnorm'], rtol=2e-3, atol=1e-6 * g[f'{tag}_gnorm'].max())
 
 
+_RECON = {'uni_sf': ('uniform', 'scoreflow', False), 'uni_ddpm': ('uniform', 'ddpm', True), 'lossless': ('lossless', 'scoreflow', False)}
+
+
+@pytest.mark.parametrize('tag', sorted(_RECON))
+def test_reconstruction_term_oracle_vs_reference(golden, tag):
+  """losses.py:134-164 (training.reconstruction_loss, off in every shipped config): DSM loss + decoder term, both decoder
+  variances, Gaussian cross-entropy and discretised-likelihood forms - losses and every gradient norm."""
+  g = golden('recon_golden.npz')
+  deq, variance, reduce_mean = _RECON[tag]
+  cfg = configs.cifar10_ddpmpp_nll_st()
+  cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks = 32, (1, 2), 1
+  cfg.model.dropout = 0.
+  cfg.training.reconstruction_loss, cfg.training.reduce_mean, cfg.data.dequantization = True, reduce_mean, deq
+  sde = ref_train.make_sde(cfg)
+  state = ref_train.TrainState(ref_model.make_state_dict(cfg, seed=int(g[f'{tag}_seed'])))
+  for k in state.trainable:
+    state.sd[k].requires_grad_(True)
+  losses = ref_train.dsm_losses(state.sd, cfg, sde, torch.tensor(g[f'{tag}_x']), torch.tensor(g[f'{tag}_u']),
+                                torch.tensor(g[f'{tag}_z']), float(g[f'{tag}_tmin']), importance_sampling=True,
+                                z2=torch.tensor(g[f'{tag}_z2']), variance=variance)
+  np.testing.assert_allclose(losses.detach().numpy(), g[f'{tag}_losses'], rtol=2e-4)
+  torch.mean(losses).backward()
+  names = [k for k in state.sd if k != 'sigmas']
+  gn = np.array([0. if state.sd[k].grad is None else state.sd[k].grad.double().norm().item() for k in names])
+  np.testing.assert_allclose(gn, g[f'{tag}_gnorm'], rtol=2e-3, atol=1e-6 * g[f'{tag}_gnorm'].max())
+
+
 class _OracleNet(torch.nn.Module):
   """The oracle U-Net behind the model call convention, so that the host-side estimators can run on the CPU."""
 
