@@ -557,6 +557,8 @@ def _graph_eligible(config, sde, state, batch, injected):
 def get_step_fn(config, sde, train, optimize_fn=None):
   """One optimizer step (reference losses.py:218-325): returns the per-sample losses on the CPU."""
   if not config.training.continuous:
+    # (the reference's discrete path cannot run either: its step_fn calls loss_fn(model, batch, importance_sampling=...,
+    # t_min=...) (losses.py:287) while get_smld_loss_fn / get_ddpm_loss_fn return loss_fn(model, batch) (:181,201) -> TypeError)
     raise NotImplementedError('only continuous-time training (every BASELINE config) is built')
   loss_fn = get_sde_loss_fn(config, sde, train)
   tr = config.training
