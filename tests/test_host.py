@@ -401,3 +401,31 @@ def test_reference_is_staged_and_importable():
           "print('ok', R.root)" % ROOT)
   r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
   assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
+
+
+def test_committed_bench_lines_keep_the_contract():
+  """The bench lines committed under profiles/ are what DESIGN.md quotes: every one must carry the contract's keys and be
+  self-consistent (value = batch * GPUs / time per step; e2e not faster than value beyond run-to-run noise; roofline fraction = achieved / peak)."""
+  import glob
+  files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r02_bench_*.json')))
+  assert len(files) >= 10
+  for f in files:
+    lines = [l for l in open(f).read().splitlines() if l.strip().startswith('{')]
+    assert len(lines) == 1, f
+    d = json.loads(lines[0])
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'dtype', 'data', 'config'):
+      assert k in d, (f, k)
+    assert 'workload' in d['config'] and 'model' not in d['config'], f
+    assert d['value'] > 0 and d['ms_per_step'] > 0
+    if d.get('impl') == 'reference':
+      assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['e2e']['h2d_bytes_per_step'] == 0
+      continue
+    assert d['gpu_launches'] > 0 and d['clocks']['sm_mhz'] > 0, f
+    assert not set(d['clocks'].get('reasons', [])) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}, f
+    r = d.get('roofline')
+    if r and r.get('frac') is not None:
+      assert abs(r['frac'] - r['achieved'] / r['peak']) < 1e-6 and 0. < r['frac'] < 1., f
+    if d['unit'] == 'images/s':
+      B = int(re.search(r'batch (\d+)/GPU', d['config']['workload']).group(1))
+      assert abs(d['value'] - B * d['n_gpus'] / (d['ms_per_step'] * 1e-3)) < 1e-3 * d['value'], f
+      assert d['e2e']['value'] <= d['value'] * 1.03 and d['e2e']['h2d_bytes_per_step'] > 0, f
