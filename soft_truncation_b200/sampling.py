@@ -363,14 +363,17 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
           torch.cuda.current_stream().wait_stream(side)
           torch.cuda.set_rng_state(rng, device)
           try:
+            from . import _lib
             graph = torch.cuda.CUDAGraph()
+            calls0 = _lib.launches
             with torch.cuda.graph(graph):
               vec_t = torch.ones(B, device=device) * sts.index_select(0, step)
               nx, nx_mean = one_step(sx, vec_t)
               sx.copy_(nx)
               sx_mean.copy_(nx_mean)
               step.add_(1)
-            g = dict(key=key, graph=graph, step=step, sx=sx, sx_mean=sx_mean, sts=sts)
+            # `calls`: C-ABI calls one replay stands for (each enqueued >= 1 of the library's kernels at capture)
+            g = dict(key=key, graph=graph, step=step, sx=sx, sx_mean=sx_mean, sts=sts, calls=_lib.launches - calls0)
           except Exception as ex:                    # a predictor / corrector that cannot be captured: eager loop
             import warnings
             warnings.warn(f'soft_truncation_b200: CUDA-graph capture of the reverse step failed ({ex!r}); sampling eagerly')
@@ -393,6 +396,7 @@ def get_pc_sampler(config, sde, shape, predictor, corrector, inverse_scaler, snr
       x_mean = x = denoise_update_fn(model, x_mean if denoise else x)
       return inverse_scaler(x_mean if denoise else x), sde.N * (n_steps + 1)
 
+  pc_sampler.graph_cache = graph_cache      # (bench.py reads the per-replay launch count from it)
   return pc_sampler
 
 
