@@ -105,8 +105,8 @@ struct FirGeom {
   static constexpr int TAPS = K / UP;
 };
 
-template <typename T, int UP, int DOWN, int PAD0, int BY, int BX>
-__global__ void __launch_bounds__(256) upfirdn2d_fast_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ k,
+template <typename T, int UP, int DOWN, int PAD0, int BY, int BX, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) upfirdn2d_fast_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ k,
                                                              int in_h, int in_w, int minor, int out_h, int out_w, long long total) {
   constexpr int K = 4, V = 16 / (int)sizeof(T);
   using G = FirGeom<UP, DOWN, PAD0, K>;
@@ -185,14 +185,14 @@ __global__ void __launch_bounds__(256) upfirdn2d_fast_kernel(const T* __restrict
     }
 }
 
-template <typename T, int UP, int DOWN, int PAD0, int BY, int BX>
+template <typename T, int UP, int DOWN, int PAD0, int BY, int BX, int MINB = 1>
 int launch_fast(const void* x, void* y, const float* k, int major, int in_h, int in_w, int minor, int out_h, int out_w,
                 cudaStream_t stream) {
   constexpr int V = 16 / (int)sizeof(T);
   const long long total = (long long)major * ((out_h + BY - 1) / BY) * ((out_w + BX - 1) / BX) * (minor / V);
   const long long blocks = (total + 255) / 256;
   if (blocks > 0x7fffffffLL) return -1;
-  cudaError_t e = st_launch(upfirdn2d_fast_kernel<T, UP, DOWN, PAD0, BY, BX>, dim3((unsigned)blocks), dim3(256), 0, stream,
+  cudaError_t e = st_launch(upfirdn2d_fast_kernel<T, UP, DOWN, PAD0, BY, BX, MINB>, dim3((unsigned)blocks), dim3(256), 0, stream,
                             (const T*)x, (T*)y, k, in_h, in_w, minor, out_h, out_w, total);
   return e == cudaSuccess ? 0 : -1;
 }
@@ -219,13 +219,14 @@ extern "C" __attribute__((visibility("default"))) int st_upfirdn2d(const void* x
     if (on && al && kh == 4 && kw == 4 && up_x == up_y && down_x == down_y && pad_x0 == pad_y0 && minor % V == 0 &&
         (dtype == ST_BF16 || dtype == ST_F32)) {
       int rc = 1;
+      // Registers, not bytes, decide these kernels: uncapped, the down-sampling / 1:1 kernels take 170-220 registers
+      // (ONE CTA of 8 warps per SM).  Measured per shape (profiles/r02_upfirdn_variants.txt): up-sampling is fastest
+      // uncapped (128 registers, 2 CTAs per SM), down-sampling capped at 2 CTAs per SM (-20 %), the 1:1 pre-filter at 3 (-22 %).
+      auto args = [&](auto fn) { return fn(x, y, k, major, in_h, in_w, minor, p.out_h, p.out_w, (cudaStream_t)stream); };
       ST_DISPATCH_DTYPE(dtype, T, {
-        if (up_x == 2 && down_x == 1 && pad_x0 == 2)
-          rc = launch_fast<T, 2, 1, 2, 2, 4>(x, y, k, major, in_h, in_w, minor, p.out_h, p.out_w, (cudaStream_t)stream);
-        else if (up_x == 1 && down_x == 2 && pad_x0 == 1)
-          rc = launch_fast<T, 1, 2, 1, 2, 2>(x, y, k, major, in_h, in_w, minor, p.out_h, p.out_w, (cudaStream_t)stream);
-        else if (up_x == 1 && down_x == 1 && pad_x0 == 2)
-          rc = launch_fast<T, 1, 1, 2, 2, 2>(x, y, k, major, in_h, in_w, minor, p.out_h, p.out_w, (cudaStream_t)stream);
+        if (up_x == 2 && down_x == 1 && pad_x0 == 2) rc = args(launch_fast<T, 2, 1, 2, 2, 4, 1>);
+        else if (up_x == 1 && down_x == 2 && pad_x0 == 1) rc = args(launch_fast<T, 1, 2, 1, 2, 2, 2>);
+        else if (up_x == 1 && down_x == 1 && pad_x0 == 2) rc = args(launch_fast<T, 1, 1, 2, 2, 2, 3>);
       });
       if (rc == 0) { ST_CHECK_LAUNCH("st_upfirdn2d"); return 0; }
       if (rc < 0) { cudaGetLastError(); }
