@@ -1,7 +1,9 @@
-# GPU run 29 (one B200): final full GPU suite + smoke on the round's last build
+# GPU run 30 (one B200): FIR tap loop with packed fp32 FMAs (FFMA2)
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-rm -f gpurun_out/test_stats.txt
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1; echo "build rc=$?"
-timeout 900 python -m pytest tests -q -m gpu --timeout=600 > gpurun_out/t_gpu_final.log 2>&1; echo "pytest -m gpu rc=$?"; tail -n 2 gpurun_out/t_gpu_final.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_final.log 2>&1; echo "smoke rc=$?"; tail -n 2 gpurun_out/smoke_final.log
+for v in 0 1; do
+echo "== ST_FIR_FFMA2=$v"; ST_FIR_FFMA2=$v timeout 150 python tools/upfirdn_bench.py 2>&1 | grep -v "^st_upfirdn2d" | cut -c1-130
+done > gpurun_out/fir_ffma2.txt 2>&1
+cat gpurun_out/fir_ffma2.txt
+ST_FIR_FFMA2=1 timeout 200 python -m pytest tests/test_gpu_round2.py tests/test_gpu_kernels.py tests/test_gpu_parity.py -q -k "upfirdn or fir or full_width" --timeout=150 2>&1 | tail -1

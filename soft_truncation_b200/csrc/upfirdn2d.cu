@@ -95,6 +95,16 @@ __device__ __forceinline__ void st8(bf16* p, const float v[8]) {
 }
 __device__ __forceinline__ void st8(float*, const float*) {}
 
+// packed fp32 FMA (sm_100 FFMA2): two accumulator lanes per issued instruction, same rounding as two FFMAs
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+
 template <int UP, int DOWN, int PAD0, int K>
 struct FirGeom {
   // output index j (relative to a block origin that is a multiple of UP) -> first input index (relative) and first tap
@@ -105,7 +115,7 @@ struct FirGeom {
   static constexpr int TAPS = K / UP;
 };
 
-template <typename T, int UP, int DOWN, int PAD0, int BY, int BX, int MINB = 1>
+template <typename T, int UP, int DOWN, int PAD0, int BY, int BX, int MINB = 1, bool F2 = false>
 __global__ void __launch_bounds__(256, MINB) upfirdn2d_fast_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ k,
                                                              int in_h, int in_w, int minor, int out_h, int out_w, long long total) {
   constexpr int K = 4, V = 16 / (int)sizeof(T);
@@ -127,7 +137,7 @@ __global__ void __launch_bounds__(256, MINB) upfirdn2d_fast_kernel(const T* __re
   const int oy0 = (int)(t % byn) * BY;
   const long long mj = t / byn;
   const int iy0 = oy0 * DOWN / UP + R0, ix0 = ox0 * DOWN / UP + R0;      // first input row / column of the footprint
-  float acc[BY][BX][V];
+  float acc[BY][BX][V];                         // (F2: read as V / 2 adjacent pairs by the packed FMA)
 #pragma unroll
   for (int a = 0; a < BY; ++a)
 #pragma unroll
@@ -168,8 +178,18 @@ __global__ void __launch_bounds__(256, MINB) upfirdn2d_fast_kernel(const T* __re
           const int dx = c - (G::in0(b) - R0);
           if (dx < 0 || dx >= G::TAPS) continue;
           const float wt = w[(G::k0(a) + dy * UP) * K + G::k0(b) + dx * UP] * msk;
+          if constexpr (F2) {
+            const float2 w2 = make_float2(wt, wt);
 #pragma unroll
-          for (int e = 0; e < V; ++e) acc[a][b][e] = fmaf(v[c][e], wt, acc[a][b][e]);
+            for (int e = 0; e < V; e += 2) {
+              const float2 r = ffma2(make_float2(v[c][e], v[c][e + 1]), w2, make_float2(acc[a][b][e], acc[a][b][e + 1]));
+              acc[a][b][e] = r.x;
+              acc[a][b][e + 1] = r.y;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[a][b][e] = fmaf(v[c][e], wt, acc[a][b][e]);
+          }
         }
       }
     }
@@ -185,14 +205,14 @@ __global__ void __launch_bounds__(256, MINB) upfirdn2d_fast_kernel(const T* __re
     }
 }
 
-template <typename T, int UP, int DOWN, int PAD0, int BY, int BX, int MINB = 1>
+template <typename T, int UP, int DOWN, int PAD0, int BY, int BX, int MINB = 1, bool F2 = false>
 int launch_fast(const void* x, void* y, const float* k, int major, int in_h, int in_w, int minor, int out_h, int out_w,
                 cudaStream_t stream) {
   constexpr int V = 16 / (int)sizeof(T);
   const long long total = (long long)major * ((out_h + BY - 1) / BY) * ((out_w + BX - 1) / BX) * (minor / V);
   const long long blocks = (total + 255) / 256;
   if (blocks > 0x7fffffffLL) return -1;
-  cudaError_t e = st_launch(upfirdn2d_fast_kernel<T, UP, DOWN, PAD0, BY, BX, MINB>, dim3((unsigned)blocks), dim3(256), 0, stream,
+  cudaError_t e = st_launch(upfirdn2d_fast_kernel<T, UP, DOWN, PAD0, BY, BX, MINB, F2>, dim3((unsigned)blocks), dim3(256), 0, stream,
                             (const T*)x, (T*)y, k, in_h, in_w, minor, out_h, out_w, total);
   return e == cudaSuccess ? 0 : -1;
 }
@@ -223,10 +243,15 @@ extern "C" __attribute__((visibility("default"))) int st_upfirdn2d(const void* x
       // (ONE CTA of 8 warps per SM).  Measured per shape (profiles/r02_upfirdn_variants.txt): up-sampling is fastest
       // uncapped (128 registers, 2 CTAs per SM), down-sampling capped at 2 CTAs per SM (-20 %), the 1:1 pre-filter at 3 (-22 %).
       auto args = [&](auto fn) { return fn(x, y, k, major, in_h, in_w, minor, p.out_h, p.out_w, (cudaStream_t)stream); };
+      // packed fp32 FMAs (FFMA2) in the tap loop: 3-10 % faster on every shape (profiles/r02_upfirdn_variants.txt); =0: scalar FFMAs
+      static const int f2 = getenv("ST_FIR_FFMA2") ? atoi(getenv("ST_FIR_FFMA2")) : 1;
       ST_DISPATCH_DTYPE(dtype, T, {
-        if (up_x == 2 && down_x == 1 && pad_x0 == 2) rc = args(launch_fast<T, 2, 1, 2, 2, 4, 1>);
-        else if (up_x == 1 && down_x == 2 && pad_x0 == 1) rc = args(launch_fast<T, 1, 2, 1, 2, 2, 2>);
-        else if (up_x == 1 && down_x == 1 && pad_x0 == 2) rc = args(launch_fast<T, 1, 1, 2, 2, 2, 3>);
+        if (up_x == 2 && down_x == 1 && pad_x0 == 2)
+          rc = f2 ? args(launch_fast<T, 2, 1, 2, 2, 4, 1, true>) : args(launch_fast<T, 2, 1, 2, 2, 4, 1>);
+        else if (up_x == 1 && down_x == 2 && pad_x0 == 1)
+          rc = f2 ? args(launch_fast<T, 1, 2, 1, 2, 2, 2, true>) : args(launch_fast<T, 1, 2, 1, 2, 2, 2>);
+        else if (up_x == 1 && down_x == 1 && pad_x0 == 2)
+          rc = f2 ? args(launch_fast<T, 1, 1, 2, 2, 2, 3, true>) : args(launch_fast<T, 1, 1, 2, 2, 2, 3>);
       });
       if (rc == 0) { ST_CHECK_LAUNCH("st_upfirdn2d"); return 0; }
       if (rc < 0) { cudaGetLastError(); }
